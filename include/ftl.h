@@ -1,0 +1,259 @@
+/*
+ * ftl.h -- C-ABI of the B200-native batched "follow the leader" simulator (libftl.so).
+ *
+ * The reference (sag111/ContiniousEnvironment_Follower_Leader) is pure Python and has no FFI; the
+ * entry points below are what a binding of its hot path would need.  Each one names the reference
+ * interface it stands in for (paths relative to the reference root):
+ *
+ *   ENV = src/continuous_grid_arctic/follow_the_leader_continuous_env.py
+ *   CLS = src/continuous_grid_arctic/utils/classes.py
+ *   SEN = src/continuous_grid_arctic/utils/sensors.py
+ *   WRP = src/continuous_grid_arctic/utils/wrappers.py
+ *
+ * Conventions: plain pointers and sizes, no torch types.  Pointers suffixed _dev are device
+ * pointers on the handle's GPU; everything else is host memory.  All calls return 0 on success or
+ * a negative FtlStatus; ftl_last_error() gives the text.  A handle is not re-entrant; different
+ * handles may be driven from different threads.  Nothing here allocates per step.
+ *
+ * The same POD structs (FtlConfig, FtlScenarioPool, FtlEnvState) are consumed by the CPU oracle in
+ * oracle/ftl_oracle.c so that tests can compare the two implementations field by field.
+ */
+#ifndef FTL_H_
+#define FTL_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FTL_ABI_VERSION 1
+
+#define FTL_MAX_BEARS 4
+#define FTL_MAX_RAY_SENSORS 4
+#define FTL_MAX_REGIME 16
+#define FTL_MAX_HIST 8 /* upper bound for max_prev_obs */
+
+typedef enum FtlStatus {
+    FTL_OK = 0,
+    FTL_ERR_INVALID = -1,     /* bad argument / unsupported configuration (ValueError in the reference) */
+    FTL_ERR_CUDA = -2,        /* CUDA runtime error, text in ftl_last_error() */
+    FTL_ERR_STATE = -3,       /* call order (e.g. step before upload_scenarios/reset) */
+    FTL_ERR_NOMEM = -4
+} FtlStatus;
+
+/* info dict codes (ENV:951-955 and the places that overwrite them) */
+enum { FTL_MISSION_IN_PROGRESS = 0, FTL_MISSION_FAIL = 1, FTL_MISSION_SUCCESS = 2, FTL_MISSION_FINISHED_BY_TIME = 3 };
+enum { FTL_AGENT_MOVING = 0, FTL_AGENT_CRASH = 1, FTL_AGENT_FINISHED = 2, FTL_AGENT_LOW_REWARD = 3, FTL_AGENT_TOO_FAR = 4 };
+enum { FTL_LEADER_MOVING = 0, FTL_LEADER_FINISHED = 1, FTL_LEADER_CRASH = 2 };
+
+/* react_to_obstacles of the ray sensors (SEN:650-661) */
+enum { FTL_REACT_NONE = 0, FTL_REACT_ALL = 1, FTL_REACT_STATIC = 2, FTL_REACT_DYNAMIC = 3 };
+
+/* action layouts accepted by ftl_step (ENV:908-933) */
+enum {
+    FTL_ACTION_CONTINUOUS = 0, /* float[N][2] = (v px/frame, w deg/frame)                      ENV:927-933 */
+    FTL_ACTION_CONST_SPEED = 1, /* float[N][1] = w; v is forced to 0.25 as in the reference     ENV:924-925 */
+    FTL_ACTION_DISCRETE = 2    /* int32[N] in 0..4 -> (max_speed, table[a])                    ENV:363-367, 918-922 */
+};
+
+/* One robot class (leader / follower / bear): constructor arguments of AbstractRobot, CLS:60-105,
+ * already converted to pixels and frames exactly as ENV:330-357, 704-714 do it. */
+typedef struct FtlRobotConfig {
+    double min_speed;
+    double max_speed;
+    double max_rotation_speed;
+    double max_speed_change;
+    double max_rotation_speed_change;
+    int32_t width;  /* integer sprite size after transform.scale, CLS:42 */
+    int32_t height;
+} FtlRobotConfig;
+
+/* One history ray sensor = LeaderCorridor_Prev_lasers_v2 (SEN:867-968); the retired class name
+ * LaserPrevSensor maps onto it with corridor/green-zone off and offset 0 (SEN:847-851). */
+typedef struct FtlRaySensorConfig {
+    int32_t lasers_count;
+    int32_t max_prev_obs;            /* H */
+    int32_t pad_sectors;             /* SEN:932-953: output is 4*R wide and float64 in the reference */
+    int32_t react_to_safe_corridor;
+    int32_t react_to_green_zone;
+    int32_t react_to_obstacles;      /* FTL_REACT_* */
+    double laser_length;
+    double first_laser_angle_offset; /* SEN:873, default -45 */
+} FtlRaySensorConfig;
+
+typedef struct FtlConfig {
+    int32_t abi_version;
+    /* geometry and stepping, ENV:45-105 */
+    int32_t game_width, game_height;
+    int32_t frames_per_step;
+    int32_t max_steps;
+    int32_t warm_start;
+    int32_t trajectory_saving_period;  /* ENV:262, always 5 */
+    int32_t aggregate_reward;
+    int32_t ignore_follower_collisions;
+    int32_t action_mode;               /* FTL_ACTION_* */
+    double leader_pos_epsilon;
+    double min_distance, max_distance, max_dev;  /* pixels, ENV:283-285 */
+    double const_speed_action;          /* 0.25, ENV:925 */
+    double discrete_rotation_table[5];  /* ENV:363-367 */
+    FtlRobotConfig follower, leader, bear;
+    int32_t n_bears;                    /* 0 when add_bear is false */
+    int32_t move_bear_v4;
+    /* Reward dataclass, utils/reward_constructor.py:4-15 with leader_movement_reward forced to 0 by ENV:279 */
+    double reward_in_box, reward_on_track, reward_in_dev, leader_movement_reward;
+    double crash_penalty, not_on_track_penalty, too_close_penalty, leader_stop_penalty;
+    /* early_stopping dict, ENV:1088-1107 */
+    int32_t es_has_low_reward, es_has_max_distance_coef;
+    double es_low_reward, es_max_distance_coef;
+    /* leader_speed_regime / leader_acceleration_regime, ENV:1143-1174 (keys in insertion order) */
+    int32_t n_speed_regime;
+    int32_t speed_regime_key[FTL_MAX_REGIME];
+    int32_t speed_regime_is_range[FTL_MAX_REGIME];
+    double speed_regime_lo[FTL_MAX_REGIME], speed_regime_hi[FTL_MAX_REGIME];
+    int32_t n_accel_regime;
+    int32_t accel_regime_key[FTL_MAX_REGIME];
+    double accel_regime_val[FTL_MAX_REGIME];
+    /* LeaderPositionsTracker_v2, SEN:231-327 (eat_close_points=False, generate_corridor=True) */
+    int32_t tracker_enabled;
+    int32_t saving_period;
+    int32_t start_corridor_behind_follower;
+    int32_t tracker_scans_per_step;     /* 2: the double-scan quirk of CLS:263-286 */
+    double corridor_length, corridor_width;
+    /* ray sensors, in follower_sensors dict order */
+    int32_t n_ray_sensors;
+    FtlRaySensorConfig ray[FTL_MAX_RAY_SENSORS];
+    /* capacities of the per-env rings (design parameters of this library, not of the reference) */
+    int32_t trail_cap;     /* leader_factual_trajectory points */
+    int32_t corridor_cap;  /* tracker history / corridor ring, power of two */
+    int32_t route_cap;     /* waypoints per scenario */
+    int32_t static_cap;    /* static rectangles per scenario (2 bridge walls + rocks) */
+    int32_t auto_reset;    /* 1: envs that finished are re-initialised at the end of the step */
+    int32_t reserved[7];
+} FtlConfig;
+
+/* Scenario pool = what Game.reset() builds (ENV:434-543) before the first sensor scan, as data.
+ * Scenario generation (random placement + D-star/A-star planning, ENV:545-677, 1493-1712) is a host
+ * pre-pass; the kernels only ever consume this. */
+typedef struct FtlScenarioPool {
+    int32_t n_scenarios;
+    int32_t static_cap, route_cap;
+    const int32_t* static_rects;   /* [S][static_cap][4]  x,y,w,h in game_object_list order (ENV:675-677) */
+    const int32_t* n_static;       /* [S] */
+    const int32_t* route;          /* [S][route_cap][2]   trajectory waypoints (python ints) */
+    const int32_t* n_route;        /* [S] */
+    const float* leader_pos;       /* [S][2] */
+    const double* leader_dir;      /* [S]    angle_to_point(leader, trajectory[1]), ENV:525 */
+    const float* follower_pos;     /* [S][2] after _pos_follower_behind_leader, ENV:598-611 */
+    const double* follower_dir;    /* [S] */
+    const uint8_t* found_target_point; /* [S] what SkipBadSeeds looks at, WRP:823; may be NULL */
+} FtlScenarioPool;
+
+/* ---- canonical per-env state record used by get/set_state and by the oracle ----------------- */
+typedef struct FtlRobotState {
+    float pos[2];          /* np.float32 position, CLS:47 */
+    int32_t rect[4];       /* pygame.Rect x,y,w,h */
+    double dir;            /* degrees */
+    double speed, rot_speed;
+    double des_speed, des_rot_speed;
+    int32_t rot_dir, des_rot_dir;
+} FtlRobotState;
+
+typedef struct FtlSnapshot {   /* one entry of history_obstacles_list, SEN:894-895, by reference */
+    int32_t valid;             /* 0 = the degenerate zero segment of SEN:964-968 */
+    int32_t corr_tail, corr_head;  /* absolute corridor-ring indices [tail, head) live at that scan */
+    int32_t pad_;
+    int32_t dyn_rect[1 + FTL_MAX_BEARS][4];  /* leader, bears at that scan */
+} FtlSnapshot;
+
+typedef struct FtlEnvState {
+    FtlRobotState follower, leader, bear[FTL_MAX_BEARS];
+    double bear_target[FTL_MAX_BEARS][2]; /* cur_points_for_bear, ENV:717 */
+    int32_t bear_index[FTL_MAX_BEARS];    /* dynamics_index, ENV:718 */
+    double accumulated_penalty, overall_reward, last_reward;
+    double cur_speed_multiplier, cur_leader_acceleration, cur_leader_cumulative_speed;
+    int32_t accel_consumed;  /* bitmask of consumed leader_acceleration_regime keys (ENV:1170) */
+    int32_t scenario_id;
+    int32_t cur_target_id, leader_finished;
+    int32_t step_count;      /* counts FRAMES, ENV:1127 */
+    int32_t finish_timer;    /* finish_position_framestimer, -1 = None */
+    int32_t done, crash, is_in_box, is_on_trace, too_close;
+    int32_t mission_status, agent_status, leader_status; /* of the last frame */
+    int32_t trail_len;       /* len(leader_factual_trajectory) */
+    int32_t saving_counter;  /* tracker, SEN:200 */
+    int32_t ring_tail, ring_head; /* absolute indices of the live tracker history/corridor deque */
+    int32_t hist_f64_end;    /* absolute index one past the last float64-typed history point */
+    int32_t snap_pushes;     /* number of sensor scans since reset (saturates) */
+    int32_t episode_count;
+    int32_t overflow;        /* bit0 trail, bit1 corridor ring */
+    int32_t pad_;
+    FtlSnapshot snap[FTL_MAX_HIST]; /* snap[0] oldest ... snap[FTL_MAX_HIST-1] newest */
+} FtlEnvState;
+
+/* Host-side view of everything ftl_get_state/ftl_set_state moves, n = number of envs addressed. */
+typedef struct FtlStateBuffers {
+    FtlEnvState* env;   /* [n] */
+    float* trail;       /* [n][trail_cap][2]      leader_factual_trajectory, ENV:533-539, 1075 */
+    double* hist;       /* [n][corridor_cap][2]   tracker leader_positions_hist ring (slot = abs index % cap) */
+    float* corridor;    /* [n][corridor_cap][4]   (right.x, right.y, left.x, left.y) rounded to f32 as SEN:672 */
+} FtlStateBuffers;
+
+/* Per-step outputs (device pointers for ftl_step, host pointers for ftl_step_host). */
+typedef struct FtlOutputs {
+    float* numerical_features; /* [N][10]  ENV:1793-1802 */
+    int32_t* leader_target;    /* [N][2]   obs["leader_target_point"], ENV:1803-1806 */
+    float* rays;               /* [N][rays_per_env]  sensors concatenated, each [H][R] (or [H][4R]) row-major */
+    float* reward;             /* [N] */
+    uint8_t* done;             /* [N] */
+    uint8_t* status;           /* [N][4]  mission, agent, leader, crash */
+} FtlOutputs;
+
+/* Episode statistics accumulated on the device (summed over envs), the vector reduced with NCCL. */
+enum {
+    FTL_STAT_EPISODES = 0, FTL_STAT_RETURN_SUM, FTL_STAT_LENGTH_SUM, FTL_STAT_CRASH, FTL_STAT_SUCCESS,
+    FTL_STAT_TIMEOUT, FTL_STAT_LEADER_CRASH, FTL_STAT_ENV_STEPS, FTL_STAT_OVERFLOW, FTL_STAT_COUNT = 16
+};
+
+typedef struct FtlHandle_* ftl_handle;
+
+/* ---- lifecycle: replaces Game.__init__ (ENV:45-416) ------------------------------------------ */
+int ftl_abi_version(void);
+const char* ftl_last_error(void);
+/* Validates the configuration the way check_parameters/sensor constructors do (ENV:419-427,
+ * SEN:761) and allocates every device buffer for n_envs environments on CUDA device `device`.
+ * env_id_base: global index of this handle's first env (rank offset for multi-GPU sharding). */
+int ftl_create(const FtlConfig* cfg, int32_t n_envs, int32_t device, int64_t env_id_base, ftl_handle* out);
+int ftl_destroy(ftl_handle h);
+int ftl_rays_per_env(ftl_handle h);      /* floats per env in FtlOutputs.rays */
+int ftl_num_envs(ftl_handle h);
+
+/* ---- scenarios + reset: replaces Game.reset (ENV:434-543) ------------------------------------- */
+int ftl_upload_scenarios(ftl_handle h, const FtlScenarioPool* pool);
+/* mask_dev: uint8[N] device pointer or NULL (= all envs).  scenario_ids_dev: int32[N] device
+ * pointer or NULL (= keep the env's own round-robin cursor).  Runs the initial sensor scan
+ * (ENV:541) and fills `out` (may be NULL) with the initial observation. */
+int ftl_reset(ftl_handle h, const uint8_t* mask_dev, const int32_t* scenario_ids_dev,
+              const FtlOutputs* out_dev, void* cuda_stream);
+
+/* ---- step: replaces Game.step (ENV:908-945) ---------------------------------------------------- */
+int ftl_step(ftl_handle h, const void* actions_dev, const FtlOutputs* out_dev, void* cuda_stream);
+/* Same call with HOST buffers (pinned or pageable): copies actions in, steps, copies outputs back,
+ * and synchronises the stream.  This is the end-to-end path a gym-style caller sees. */
+int ftl_step_host(ftl_handle h, const void* actions_host, const FtlOutputs* out_host, void* cuda_stream);
+int ftl_reset_host(ftl_handle h, const uint8_t* mask_host, const int32_t* scenario_ids_host,
+                   const FtlOutputs* out_host, void* cuda_stream);
+
+/* ---- state access: teacher forcing, snapshots, the attribute reads of WRP:180-212 ------------- */
+int ftl_get_state(ftl_handle h, int32_t first_env, int32_t n, const FtlStateBuffers* host_out);
+int ftl_set_state(ftl_handle h, int32_t first_env, int32_t n, const FtlStateBuffers* host_in);
+
+/* ---- statistics -------------------------------------------------------------------------------- */
+/* Copies the FTL_STAT_COUNT running sums (double) to stats_dev; optionally zeroes them. */
+int ftl_stats(ftl_handle h, double* stats_dev, int32_t reset_after, void* cuda_stream);
+/* Number of kernel launches issued by this handle so far (for bench.py's gpu_launches). */
+int64_t ftl_launch_count(ftl_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FTL_H_ */
