@@ -1,0 +1,509 @@
+// ftl_capi.cu -- the C-ABI of include/ftl.h (libftl.so), the ray kernel and the state-exchange kernels.
+//
+// Launch structure of one ftl_step():
+//   k_step<NB>   (ftl_step_nb.cu) one thread per env: the F sub-frames fused in registers, tracker scans,
+//                history snapshot, non-ray outputs, episode statistics, optional in-place auto-reset
+//   k_rays       one thread per (env, ray): history ray casting with static/corridor de-duplication
+// Both are HBM/ALU streaming kernels without tensor-core work (ray casting is not a contraction).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false (see build.py); fused
+// multiply-adds are written explicitly where wanted so float results match the reference's rounding.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "ftl_launch.h"
+#include "ftl_rays.cuh"
+#include "ftl_step.cuh"
+#include "ftl_state_io.cuh"
+
+using namespace ftl;
+
+// =================================================================================================
+// kernels
+// =================================================================================================
+__global__ void __launch_bounds__(128)
+k_rays(const __grid_constant__ DevCfg cfg, const DevState s, const DevPool pool, float* __restrict__ rays_out,
+       int rays_total) {
+    long long flat = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int i = (int)(flat / rays_total);
+    if (i >= s.n) return;
+    int sensor, k, offset;
+    if (!locate_ray(cfg.c, (int)(flat % rays_total), &sensor, &k, &offset)) return;
+    RayEnv re;
+    ray_env_load(s, i, re);
+    float rows[FTL_MAX_HIST];
+    cast_ray(cfg, s, pool, i, re, cfg.c.ray[sensor], k, rows);
+    store_ray_rows(cfg.c.ray[sensor], rays_out + (size_t)i * cfg.rays_per_env + offset, k, rows);
+}
+
+// ---- state exchange: SoA <-> FtlEnvState (AoS) ----------------------------------------------------
+__global__ void k_pack_state(const DevState s, int first, int count, FtlEnvState* __restrict__ dst) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    pack_env(s, first + j, dst[j]);
+}
+
+__global__ void k_unpack_state(const __grid_constant__ DevCfg cfg, const DevState s, int first, int count,
+                               const FtlEnvState* __restrict__ src) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    unpack_env(cfg, s, first + j, src[j]);
+}
+
+// =================================================================================================
+// host side: handle, C-ABI
+// =================================================================================================
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t err__ = (expr);                                                                      \
+        if (err__ != cudaSuccess)                                                                        \
+            return fail(FTL_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(err__));            \
+    } while (0)
+
+struct FtlHandle_ {
+    DevCfg cfg;
+    int n = 0, device = 0;
+    int n_robots = 2;
+    DevState st{};
+    DevPool pool{};
+    bool have_pool = false, was_reset = false;
+    std::vector<void*> allocs, pool_allocs;
+    double* d_stats = nullptr;
+    // device-side staging for the host-buffer entry points
+    void* d_actions = nullptr;
+    uint8_t* d_mask = nullptr;
+    int* d_scen_ids = nullptr;
+    DevOutputs d_out{};
+    FtlEnvState* d_state_stage = nullptr;
+    int state_stage_cap = 0;
+    int64_t launches = 0;
+    int rays_total = 0;
+    // optional per-kernel timing (ftl_profile): three events per step on the launching stream
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;
+    size_t prof_used = 0;
+};
+
+static cudaEvent_t prof_event(FtlHandle_* h, cudaStream_t st) {
+    if (h->prof_used == h->prof_events.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        h->prof_events.push_back(e);
+    }
+    cudaEvent_t e = h->prof_events[h->prof_used++];
+    cudaEventRecord(e, st);
+    return e;
+}
+
+static float sq_threshold(double limit) {
+    // largest float x with sqrtf(x) <= (float)limit: the reference compares float32 square roots
+    float lim = (float)limit;
+    if (!(lim >= 0.f)) return -1.f;
+    float x = lim * lim;
+    while (sqrtf(x) > lim) x = nextafterf(x, 0.f);
+    for (;;) {
+        float y = nextafterf(x, INFINITY);
+        if (sqrtf(y) <= lim) x = y; else break;
+    }
+    return x;
+}
+
+template <typename T>
+static cudaError_t dalloc(FtlHandle_* h, T** p, size_t count, std::vector<void*>* list = nullptr) {
+    void* q = nullptr;
+    size_t bytes = (count ? count : 1) * sizeof(T);
+    cudaError_t e = cudaMalloc(&q, bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaMemset(q, 0, bytes);
+    if (e != cudaSuccess) return e;
+    (list ? *list : h->allocs).push_back(q);
+    *p = (T*)q;
+    return cudaSuccess;
+}
+
+static int validate(const FtlConfig* c, int n_envs) {
+    if (!c) return fail(FTL_ERR_INVALID, "config is NULL");
+    if (c->abi_version != FTL_ABI_VERSION) return fail(FTL_ERR_INVALID, "FtlConfig.abi_version mismatch");
+    if (n_envs <= 0) return fail(FTL_ERR_INVALID, "n_envs must be positive");
+    if (c->frames_per_step < 1) return fail(FTL_ERR_INVALID, "frames_per_step must be >= 1");
+    if (c->n_bears < 0 || c->n_bears > FTL_MAX_BEARS) return fail(FTL_ERR_INVALID, "n_bears out of range");
+    if (c->n_ray_sensors < 0 || c->n_ray_sensors > FTL_MAX_RAY_SENSORS)
+        return fail(FTL_ERR_INVALID, "n_ray_sensors out of range");
+    if (c->n_ray_sensors > 0 && !c->tracker_enabled)
+        return fail(FTL_ERR_INVALID, "ray sensors need LeaderPositionsTracker_v2 (CLS:263-280)");
+    if (c->corridor_cap < 2 || (c->corridor_cap & (c->corridor_cap - 1)) || c->corridor_cap > 512)
+        return fail(FTL_ERR_INVALID, "corridor_cap must be a power of two in [2, 512]");
+    if (c->static_cap < 1 || c->static_cap > 64) return fail(FTL_ERR_INVALID, "static_cap must be in [1, 64]");
+    if (c->route_cap < 2) return fail(FTL_ERR_INVALID, "route_cap must be >= 2");
+    if (c->trail_cap < 8) return fail(FTL_ERR_INVALID, "trail_cap too small");
+    if (c->tracker_enabled && (c->saving_period < 1 || c->tracker_scans_per_step < 1))
+        return fail(FTL_ERR_INVALID, "tracker saving_period / scans_per_step must be positive");
+    if (c->n_speed_regime > FTL_MAX_REGIME || c->n_accel_regime > FTL_MAX_REGIME)
+        return fail(FTL_ERR_INVALID, "too many regime keys");
+    for (int s = 0; s < c->n_ray_sensors; s++) {
+        const FtlRaySensorConfig& r = c->ray[s];
+        if (r.lasers_count < 1) return fail(FTL_ERR_INVALID, "lasers_count must be positive (SEN:761)");
+        if (r.max_prev_obs < 1 || r.max_prev_obs > FTL_MAX_HIST)
+            return fail(FTL_ERR_INVALID, "max_prev_obs must be in [1, FTL_MAX_HIST] (SEN:876)");
+        if (r.react_to_obstacles < 0 || r.react_to_obstacles > 3)
+            return fail(FTL_ERR_INVALID, "react_to_obstacles must be True/'all'/'static'/'dynamic'/False (SEN:650-661)");
+    }
+    return FTL_OK;
+}
+
+static DevOutputs to_dev_outputs(const FtlOutputs* o) {
+    DevOutputs d{};
+    if (o) {
+        d.numerical_features = o->numerical_features; d.leader_target = o->leader_target; d.rays = o->rays;
+        d.reward = o->reward; d.done = o->done; d.status = o->status;
+    }
+    return d;
+}
+
+static int launch_rays(ftl_handle h, float* rays, cudaStream_t st) {
+    if (!rays || h->rays_total == 0) return FTL_OK;
+    long long total = (long long)h->n * h->rays_total;
+    int threads = 128;
+    long long blocks = (total + threads - 1) / threads;
+    k_rays<<<(unsigned)blocks, threads, 0, st>>>(h->cfg, h->st, h->pool, rays, h->rays_total);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return FTL_OK;
+}
+
+static int copy_outputs_to_host(ftl_handle h, const FtlOutputs* o, cudaStream_t st) {
+    const size_t n = h->n;
+    const DevOutputs& d = h->d_out;
+    if (o->numerical_features) CUDA_TRY(cudaMemcpyAsync(o->numerical_features, d.numerical_features, 40 * n, cudaMemcpyDeviceToHost, st));
+    if (o->leader_target) CUDA_TRY(cudaMemcpyAsync(o->leader_target, d.leader_target, 8 * n, cudaMemcpyDeviceToHost, st));
+    if (o->rays && h->cfg.rays_per_env) CUDA_TRY(cudaMemcpyAsync(o->rays, d.rays, sizeof(float) * h->cfg.rays_per_env * n, cudaMemcpyDeviceToHost, st));
+    if (o->reward) CUDA_TRY(cudaMemcpyAsync(o->reward, d.reward, 4 * n, cudaMemcpyDeviceToHost, st));
+    if (o->done) CUDA_TRY(cudaMemcpyAsync(o->done, d.done, n, cudaMemcpyDeviceToHost, st));
+    if (o->status) CUDA_TRY(cudaMemcpyAsync(o->status, d.status, 4 * n, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return FTL_OK;
+}
+
+static FtlOutputs staged_outputs(ftl_handle h, const FtlOutputs* want) {
+    // only compute what the caller asked for
+    FtlOutputs o{};
+    const DevOutputs& d = h->d_out;
+    if (want) {
+        if (want->numerical_features) o.numerical_features = d.numerical_features;
+        if (want->leader_target) o.leader_target = d.leader_target;
+        if (want->rays) o.rays = d.rays;
+        if (want->reward) o.reward = d.reward;
+        if (want->done) o.done = d.done;
+        if (want->status) o.status = d.status;
+    }
+    return o;
+}
+
+static int ensure_stage(ftl_handle h, int count) {
+    if (h->state_stage_cap >= count) return FTL_OK;
+    if (h->d_state_stage) cudaFree(h->d_state_stage);
+    h->d_state_stage = nullptr;
+    h->state_stage_cap = 0;
+    CUDA_TRY(cudaMalloc((void**)&h->d_state_stage, sizeof(FtlEnvState) * (size_t)count));
+    h->state_stage_cap = count;
+    return FTL_OK;
+}
+
+extern "C" {
+
+int ftl_abi_version(void) { return FTL_ABI_VERSION; }
+const char* ftl_last_error(void) { return g_err.c_str(); }
+
+int ftl_create(const FtlConfig* cfg, int32_t n_envs, int32_t device, int64_t env_id_base, ftl_handle* out) {
+    if (!out) return fail(FTL_ERR_INVALID, "out handle is NULL");
+    *out = nullptr;
+    int rc = validate(cfg, n_envs);
+    if (rc) return rc;
+    CUDA_TRY(cudaSetDevice(device));
+    FtlHandle_* h = new FtlHandle_();
+    h->n = n_envs;
+    h->device = device;
+    const FtlConfig& c = *cfg;
+    DevCfg& d = h->cfg;
+    memset(&d, 0, sizeof d);
+    d.c = c;
+    d.env_id_base = env_id_base;
+    d.rays_per_env = 0;
+    for (int s = 0; s < c.n_ray_sensors; s++) d.rays_per_env += sensor_width(c.ray[s]);
+    h->rays_total = total_rays(c);
+    d.eps2_f32 = sq_threshold(c.leader_pos_epsilon);
+    d.dev2_f32 = sq_threshold(c.max_dev);
+    d.min_dist2_f32 = sq_threshold(c.min_distance);
+    d.max_distance_f32 = (float)c.max_distance;
+    d.es_far_f32 = (float)(c.max_distance * c.es_max_distance_coef);
+    d.trail_seed_denom_f32 = (float)(c.trajectory_saving_period * c.leader.max_speed);
+    d.corridor_length_f32 = (float)c.corridor_length;
+    d.corridor_width_f32 = (float)c.corridor_width;
+    auto inflate = [&](const FtlRobotConfig& r) {
+        double half_diag = 0.5 * std::sqrt((double)r.width * r.width + (double)r.height * r.height);
+        return (float)(half_diag + c.frames_per_step * std::fabs(r.max_speed) + 4.0);
+    };
+    d.static_inflate[0] = inflate(c.follower);
+    d.static_inflate[1] = inflate(c.leader);
+
+    const size_t n = n_envs;
+    const int nb = c.n_bears, nr = 2 + nb;
+    h->n_robots = nr;
+    DevState& s = h->st;
+    s.n = n_envs;
+    s.n_bears = nb;
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+    ok(dalloc(h, &s.gd, GD_COUNT * n));
+    ok(dalloc(h, &s.rd, (size_t)nr * RD_COUNT * n));
+    ok(dalloc(h, &s.bear_tgt, (size_t)nb * 2 * n));
+    ok(dalloc(h, &s.gi, GI_COUNT * n));
+    ok(dalloc(h, &s.ri, (size_t)nr * n));
+    ok(dalloc(h, &s.bear_idx, (size_t)nb * n));
+    ok(dalloc(h, &s.gf, GF_COUNT * n));
+    ok(dalloc(h, &s.pos, (size_t)nr * n));
+    ok(dalloc(h, &s.rect, (size_t)nr * n));
+    ok(dalloc(h, &s.trail, n * c.trail_cap));
+    ok(dalloc(h, &s.hist, n * c.corridor_cap));
+    ok(dalloc(h, &s.corridor, n * c.corridor_cap));
+    ok(dalloc(h, &s.snap_range, (size_t)FTL_MAX_HIST * n));
+    ok(dalloc(h, &s.snap_rect, (size_t)FTL_MAX_HIST * (1 + nb) * n));
+    ok(dalloc(h, &h->d_stats, (size_t)FTL_STAT_COUNT));
+    size_t action_bytes = c.action_mode == FTL_ACTION_CONTINUOUS ? 8 : 4;
+    ok(dalloc(h, (char**)&h->d_actions, action_bytes * n));
+    ok(dalloc(h, &h->d_mask, n));
+    ok(dalloc(h, &h->d_scen_ids, n));
+    ok(dalloc(h, &h->d_out.numerical_features, 10 * n));
+    ok(dalloc(h, &h->d_out.leader_target, 2 * n));
+    ok(dalloc(h, &h->d_out.rays, (size_t)(d.rays_per_env ? d.rays_per_env : 1) * n));
+    ok(dalloc(h, &h->d_out.reward, n));
+    ok(dalloc(h, &h->d_out.done, n));
+    ok(dalloc(h, &h->d_out.status, 4 * n));
+    if (e != cudaSuccess) {
+        for (void* p : h->allocs) cudaFree(p);
+        delete h;
+        return fail(e == cudaErrorMemoryAllocation ? FTL_ERR_NOMEM : FTL_ERR_CUDA,
+                    std::string("device allocation failed: ") + cudaGetErrorString(e));
+    }
+    *out = h;
+    return FTL_OK;
+}
+
+int ftl_destroy(ftl_handle h) {
+    if (!h) return FTL_OK;
+    cudaSetDevice(h->device);
+    for (void* p : h->allocs) cudaFree(p);
+    for (void* p : h->pool_allocs) cudaFree(p);
+    if (h->d_state_stage) cudaFree(h->d_state_stage);
+    for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
+    delete h;
+    return FTL_OK;
+}
+
+int ftl_rays_per_env(ftl_handle h) { return h ? h->cfg.rays_per_env : 0; }
+int ftl_num_envs(ftl_handle h) { return h ? h->n : 0; }
+int64_t ftl_launch_count(ftl_handle h) { return h ? h->launches : 0; }
+
+int ftl_upload_scenarios(ftl_handle h, const FtlScenarioPool* p) {
+    if (!h || !p) return fail(FTL_ERR_INVALID, "NULL argument");
+    const FtlConfig& c = h->cfg.c;
+    if (p->n_scenarios <= 0) return fail(FTL_ERR_INVALID, "scenario pool is empty");
+    if (p->static_cap != c.static_cap || p->route_cap != c.route_cap)
+        return fail(FTL_ERR_INVALID, "pool static_cap/route_cap differ from the configuration");
+    const int32_t* ns = p->n_static;
+    const int32_t* nr = p->n_route;
+    for (int s = 0; s < p->n_scenarios; s++) {
+        if (ns[s] < 0 || ns[s] > c.static_cap) return fail(FTL_ERR_INVALID, "n_static out of range");
+        if (nr[s] < 2 || nr[s] > c.route_cap) return fail(FTL_ERR_INVALID, "a route needs 2..route_cap waypoints");
+    }
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    for (void* q : h->pool_allocs) cudaFree(q);
+    h->pool_allocs.clear();
+    const size_t S = p->n_scenarios;
+    DevPool& d = h->pool;
+    d.n_scenarios = p->n_scenarios;
+    int4* sr; int* dns; int2* rt; int* dnr; float2* lp; double* ld; float2* fp; double* fd;
+    CUDA_TRY(dalloc(h, &sr, S * c.static_cap, &h->pool_allocs));
+    CUDA_TRY(dalloc(h, &dns, S, &h->pool_allocs));
+    CUDA_TRY(dalloc(h, &rt, S * c.route_cap, &h->pool_allocs));
+    CUDA_TRY(dalloc(h, &dnr, S, &h->pool_allocs));
+    CUDA_TRY(dalloc(h, &lp, S, &h->pool_allocs));
+    CUDA_TRY(dalloc(h, &ld, S, &h->pool_allocs));
+    CUDA_TRY(dalloc(h, &fp, S, &h->pool_allocs));
+    CUDA_TRY(dalloc(h, &fd, S, &h->pool_allocs));
+    CUDA_TRY(cudaMemcpy(sr, p->static_rects, S * c.static_cap * sizeof(int4), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(dns, p->n_static, S * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(rt, p->route, S * c.route_cap * sizeof(int2), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(dnr, p->n_route, S * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(lp, p->leader_pos, S * sizeof(float2), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(ld, p->leader_dir, S * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(fp, p->follower_pos, S * sizeof(float2), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(fd, p->follower_dir, S * sizeof(double), cudaMemcpyHostToDevice));
+    d.static_rects = sr; d.n_static = dns; d.route = rt; d.n_route = dnr;
+    d.leader_pos = lp; d.leader_dir = ld; d.follower_pos = fp; d.follower_dir = fd;
+    h->have_pool = true;
+    return FTL_OK;
+}
+
+int ftl_reset(ftl_handle h, const uint8_t* mask_dev, const int32_t* scenario_ids_dev, const FtlOutputs* out_dev,
+              void* cuda_stream) {
+    if (!h) return fail(FTL_ERR_INVALID, "NULL handle");
+    if (!h->have_pool) return fail(FTL_ERR_STATE, "ftl_upload_scenarios must be called before ftl_reset");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    DevOutputs o = to_dev_outputs(out_dev);
+    switch (h->cfg.c.n_bears) {
+        case 0: ftl_launch_reset_nb0(h->cfg, h->st, h->pool, mask_dev, scenario_ids_dev, o, st); break;
+        case 1: ftl_launch_reset_nb1(h->cfg, h->st, h->pool, mask_dev, scenario_ids_dev, o, st); break;
+        case 2: ftl_launch_reset_nb2(h->cfg, h->st, h->pool, mask_dev, scenario_ids_dev, o, st); break;
+        case 3: ftl_launch_reset_nb3(h->cfg, h->st, h->pool, mask_dev, scenario_ids_dev, o, st); break;
+        default: ftl_launch_reset_nb4(h->cfg, h->st, h->pool, mask_dev, scenario_ids_dev, o, st); break;
+    }
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    h->was_reset = true;
+    return launch_rays(h, o.rays, st);
+}
+
+int ftl_step(ftl_handle h, const void* actions_dev, const FtlOutputs* out_dev, void* cuda_stream) {
+    if (!h || !actions_dev) return fail(FTL_ERR_INVALID, "NULL argument");
+    if (!h->was_reset) return fail(FTL_ERR_STATE, "ftl_reset must be called before ftl_step");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    DevOutputs o = to_dev_outputs(out_dev);
+    if (h->profiling) prof_event(h, st);
+    switch (h->cfg.c.n_bears) {
+        case 0: ftl_launch_step_nb0(h->cfg, h->st, h->pool, actions_dev, o, h->d_stats, st); break;
+        case 1: ftl_launch_step_nb1(h->cfg, h->st, h->pool, actions_dev, o, h->d_stats, st); break;
+        case 2: ftl_launch_step_nb2(h->cfg, h->st, h->pool, actions_dev, o, h->d_stats, st); break;
+        case 3: ftl_launch_step_nb3(h->cfg, h->st, h->pool, actions_dev, o, h->d_stats, st); break;
+        default: ftl_launch_step_nb4(h->cfg, h->st, h->pool, actions_dev, o, h->d_stats, st); break;
+    }
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    if (h->profiling) prof_event(h, st);
+    int rc = launch_rays(h, o.rays, st);
+    if (h->profiling) prof_event(h, st);
+    return rc;
+}
+
+int ftl_step_host(ftl_handle h, const void* actions_host, const FtlOutputs* out_host, void* cuda_stream) {
+    if (!h || !actions_host) return fail(FTL_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    size_t action_bytes = (h->cfg.c.action_mode == FTL_ACTION_CONTINUOUS ? 8 : 4) * (size_t)h->n;
+    CUDA_TRY(cudaMemcpyAsync(h->d_actions, actions_host, action_bytes, cudaMemcpyHostToDevice, st));
+    FtlOutputs o = staged_outputs(h, out_host);
+    int rc = ftl_step(h, h->d_actions, &o, cuda_stream);
+    if (rc) return rc;
+    if (!out_host) { CUDA_TRY(cudaStreamSynchronize(st)); return FTL_OK; }
+    return copy_outputs_to_host(h, out_host, st);
+}
+
+int ftl_reset_host(ftl_handle h, const uint8_t* mask_host, const int32_t* scenario_ids_host, const FtlOutputs* out_host,
+                   void* cuda_stream) {
+    if (!h) return fail(FTL_ERR_INVALID, "NULL handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (mask_host) CUDA_TRY(cudaMemcpyAsync(h->d_mask, mask_host, h->n, cudaMemcpyHostToDevice, st));
+    if (scenario_ids_host) CUDA_TRY(cudaMemcpyAsync(h->d_scen_ids, scenario_ids_host, 4 * (size_t)h->n, cudaMemcpyHostToDevice, st));
+    FtlOutputs o = staged_outputs(h, out_host);
+    int rc = ftl_reset(h, mask_host ? h->d_mask : nullptr, scenario_ids_host ? h->d_scen_ids : nullptr, &o, cuda_stream);
+    if (rc) return rc;
+    if (!out_host) { CUDA_TRY(cudaStreamSynchronize(st)); return FTL_OK; }
+    return copy_outputs_to_host(h, out_host, st);
+}
+
+int ftl_get_state(ftl_handle h, int32_t first, int32_t count, const FtlStateBuffers* b) {
+    if (!h || !b) return fail(FTL_ERR_INVALID, "NULL argument");
+    if (first < 0 || count < 0 || first + count > h->n) return fail(FTL_ERR_INVALID, "env range out of bounds");
+    if (count == 0) return FTL_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    const FtlConfig& c = h->cfg.c;
+    if (b->env) {
+        int rc = ensure_stage(h, count);
+        if (rc) return rc;
+        k_pack_state<<<(count + 127) / 128, 128>>>(h->st, first, count, h->d_state_stage);
+        h->launches++;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpy(b->env, h->d_state_stage, sizeof(FtlEnvState) * (size_t)count, cudaMemcpyDeviceToHost));
+    }
+    if (b->trail) CUDA_TRY(cudaMemcpy(b->trail, h->st.trail + (size_t)first * c.trail_cap, sizeof(float2) * (size_t)c.trail_cap * count, cudaMemcpyDeviceToHost));
+    if (b->hist) CUDA_TRY(cudaMemcpy(b->hist, h->st.hist + (size_t)first * c.corridor_cap, sizeof(double2) * (size_t)c.corridor_cap * count, cudaMemcpyDeviceToHost));
+    if (b->corridor) CUDA_TRY(cudaMemcpy(b->corridor, h->st.corridor + (size_t)first * c.corridor_cap, sizeof(float4) * (size_t)c.corridor_cap * count, cudaMemcpyDeviceToHost));
+    return FTL_OK;
+}
+
+int ftl_set_state(ftl_handle h, int32_t first, int32_t count, const FtlStateBuffers* b) {
+    if (!h || !b) return fail(FTL_ERR_INVALID, "NULL argument");
+    if (first < 0 || count < 0 || first + count > h->n) return fail(FTL_ERR_INVALID, "env range out of bounds");
+    if (!b->env || !b->trail) return fail(FTL_ERR_INVALID, "set_state needs at least env and trail");
+    if (count == 0) return FTL_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    const FtlConfig& c = h->cfg.c;
+    CUDA_TRY(cudaMemcpy(h->st.trail + (size_t)first * c.trail_cap, b->trail, sizeof(float2) * (size_t)c.trail_cap * count, cudaMemcpyHostToDevice));
+    if (b->hist) CUDA_TRY(cudaMemcpy(h->st.hist + (size_t)first * c.corridor_cap, b->hist, sizeof(double2) * (size_t)c.corridor_cap * count, cudaMemcpyHostToDevice));
+    if (b->corridor) CUDA_TRY(cudaMemcpy(h->st.corridor + (size_t)first * c.corridor_cap, b->corridor, sizeof(float4) * (size_t)c.corridor_cap * count, cudaMemcpyHostToDevice));
+    int rc = ensure_stage(h, count);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpy(h->d_state_stage, b->env, sizeof(FtlEnvState) * (size_t)count, cudaMemcpyHostToDevice));
+    k_unpack_state<<<(count + 127) / 128, 128>>>(h->cfg, h->st, first, count, h->d_state_stage);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaDeviceSynchronize());
+    h->was_reset = true;
+    return FTL_OK;
+}
+
+int ftl_stats(ftl_handle h, double* stats_dev, int32_t reset_after, void* cuda_stream) {
+    if (!h || !stats_dev) return fail(FTL_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    CUDA_TRY(cudaMemcpyAsync(stats_dev, h->d_stats, sizeof(double) * FTL_STAT_COUNT, cudaMemcpyDeviceToDevice, st));
+    if (reset_after) CUDA_TRY(cudaMemsetAsync(h->d_stats, 0, sizeof(double) * FTL_STAT_COUNT, st));
+    return FTL_OK;
+}
+
+int ftl_profile(ftl_handle h, int32_t enable) {
+    if (!h) return fail(FTL_ERR_INVALID, "NULL handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    h->profiling = enable != 0;
+    h->prof_used = 0;
+    return FTL_OK;
+}
+
+int ftl_profile_read(ftl_handle h, double* step_kernel_ms, double* ray_kernel_ms, int64_t* steps) {
+    if (!h) return fail(FTL_ERR_INVALID, "NULL handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    double a = 0, b = 0;
+    size_t n = h->prof_used / 3;
+    for (size_t k = 0; k < n; k++) {
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, h->prof_events[3 * k], h->prof_events[3 * k + 1]));
+        a += ms;
+        CUDA_TRY(cudaEventElapsedTime(&ms, h->prof_events[3 * k + 1], h->prof_events[3 * k + 2]));
+        b += ms;
+    }
+    if (step_kernel_ms) *step_kernel_ms = a;
+    if (ray_kernel_ms) *ray_kernel_ms = b;
+    if (steps) *steps = (int64_t)n;
+    h->prof_used = 0;
+    return FTL_OK;
+}
+
+}  // extern "C"

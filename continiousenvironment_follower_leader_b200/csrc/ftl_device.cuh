@@ -1,0 +1,717 @@
+// ftl_device.cuh -- per-environment logic of the batched "follow the leader" simulator.
+//
+// Everything here is FTL_HD (host + device) inline code: the kernels in ftl_kernels.cu call it with
+// one thread per environment, and tests/hostsim compiles the very same functions for the CPU so the
+// kernel logic is unit-tested in a container without a GPU.  (The host build is a test target; the
+// product path is libftl.so only.)
+//
+// What each block restates (paths relative to the reference root, ENV/CLS/SEN/MSC as in
+// include/ftl.h): the arithmetic TYPES are chosen so that results match the reference bit for bit
+// wherever the reference's own result is type-stable: python floats -> double, np.float32 arrays ->
+// float with separately rounded operations (the translation unit is compiled with -fmad=false;
+// fused operations are written explicitly).
+//
+// The structure is NOT the reference's: state is structure-of-arrays in HBM, the F sub-frames of a
+// step run in registers, the O(trail) green-zone searches are replaced by cached exact bounds
+// (see GreenCache), and static-obstacle collision tests are pre-filtered once per step.
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/ftl.h"
+
+#if defined(__CUDACC__)
+#define FTL_HD __host__ __device__ __forceinline__
+#define FTL_HD_NOINLINE static __host__ __device__ __noinline__
+#else
+#define FTL_HD inline
+#define FTL_HD_NOINLINE static
+#include <cstring>
+struct float2 { float x, y; };
+struct float4 { float x, y, z, w; };
+struct double2 { double x, y; };
+struct int2 { int x, y; };
+struct int4 { int x, y, z, w; };
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+static inline double2 make_double2(double x, double y) { return double2{x, y}; }
+static inline int2 make_int2(int x, int y) { return int2{x, y}; }
+static inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
+#endif
+
+namespace ftl {
+
+constexpr int kMaxRobots = 2 + FTL_MAX_BEARS;  // follower, leader, bears
+constexpr double kDeg2Rad = 3.14159265358979323846 / 180.0;
+constexpr double kRad2Deg = 180.0 / 3.14159265358979323846;
+
+// ---- state layout (structure of arrays, env index fastest) ---------------------------------------
+enum GlobalF64 { GD_ACC_PENALTY, GD_OVERALL, GD_LAST_REWARD, GD_SPEED_MULT, GD_LEAD_ACC, GD_LEAD_CUM, GD_COUNT };
+enum RobotF64 { RD_DIR, RD_SPEED, RD_ROT, RD_DES_SPEED, RD_DES_ROT, RD_COUNT };
+enum GlobalI32 {
+    GI_STEP_COUNT, GI_TARGET_ID, GI_FINISH_TIMER, GI_FLAGS, GI_TRAIL_LEN, GI_SAVING_COUNTER, GI_RING_TAIL,
+    GI_RING_HEAD, GI_HIST_F64_END, GI_SNAP_PUSHES, GI_SCENARIO, GI_EPISODE, GI_OVERFLOW, GI_ACCEL_CONSUMED,
+    // derived caches (not part of FtlEnvState; invalidated by set_state/reset)
+    GI_G_LO, GI_A_STAR, GI_B_STAR, GI_COUNT
+};
+enum GlobalF32 { GF_LB_GREEN, GF_LB_ALL, GF_COUNT };
+
+// flag bits of GI_FLAGS
+enum {
+    FL_DONE = 1, FL_CRASH = 2, FL_LEADER_FINISHED = 4, FL_IN_BOX = 8, FL_ON_TRACE = 16, FL_TOO_CLOSE = 32,
+    FL_MISSION_SHIFT = 8, FL_AGENT_SHIFT = 10, FL_LEADER_SHIFT = 13
+};
+
+struct DevState {
+    int n;
+    int n_bears;
+    double* gd;        // [GD_COUNT][n]
+    double* rd;        // [2+n_bears][RD_COUNT][n]
+    double* bear_tgt;  // [n_bears][2][n]
+    int* gi;           // [GI_COUNT][n]
+    int* ri;           // [2+n_bears][n]   (rot_dir+1) | (des_rot_dir+1)<<2
+    int* bear_idx;     // [n_bears][n]
+    float* gf;         // [GF_COUNT][n]
+    float2* pos;       // [2+n_bears][n]
+    int4* rect;        // [2+n_bears][n]
+    float2* trail;     // [n][trail_cap]
+    double2* hist;     // [n][corridor_cap]
+    float4* corridor;  // [n][corridor_cap]   (right.x, right.y, left.x, left.y)
+    int2* snap_range;  // [FTL_MAX_HIST][n]   ring slot = push index % FTL_MAX_HIST
+    int4* snap_rect;   // [FTL_MAX_HIST][1+n_bears][n]
+};
+
+struct DevPool {  // scenario pool in device (or host, for hostsim) memory
+    int n_scenarios;
+    const int4* static_rects;  // [S][static_cap]
+    const int* n_static;       // [S]
+    const int2* route;         // [S][route_cap]
+    const int* n_route;        // [S]
+    const float2* leader_pos;
+    const double* leader_dir;
+    const float2* follower_pos;
+    const double* follower_dir;
+};
+
+struct DevOutputs {
+    float* numerical_features;
+    int* leader_target;
+    float* rays;
+    float* reward;
+    uint8_t* done;
+    uint8_t* status;
+};
+
+// Configuration as the kernels want it: the user's FtlConfig plus values derived once on the host.
+struct DevCfg {
+    FtlConfig c;
+    int64_t env_id_base;
+    int rays_per_env;
+    // float32 thresholds on SQUARED distances, exactly equivalent to the reference's comparisons of
+    // float32 square roots (largest x with sqrtf(x) <= (float)limit)
+    float eps2_f32, dev2_f32, min_dist2_f32;
+    float max_distance_f32;      // (float)max_distance for the green-zone walk
+    float es_far_f32;            // (float)(max_distance * max_distance_coef)
+    float trail_seed_denom_f32;  // (float)(trajectory_saving_period * leader.max_speed)
+    float corridor_length_f32;
+    float corridor_width_f32;
+    float static_inflate[2];     // pre-filter margin for follower / leader static collisions
+};
+
+// ---- tiny helpers -----------------------------------------------------------------------------------
+FTL_HD double angle_correction(double a) {  // MSC:6-13
+    if (a >= 360) return a - 360;
+    if (a < 0) return 360 + a;
+    return a;
+}
+
+FTL_HD double angle_to_point(double cx, double cy, double tx, double ty) {  // MSC:16-26
+    double rx = tx - cx, ry = ty - cy, res;
+    if (rx > 0)
+        res = atan(ry / rx) * kRad2Deg;
+    else if (rx < 0)
+        res = atan(ry / rx) * kRad2Deg + 180;
+    else
+        res = 0;
+    return angle_correction(res);
+}
+
+FTL_HD float d2_f32(float ax, float ay, float bx, float by) {  // float32 (a-b)^2 summed, numpy order
+    float dx = ax - bx, dy = ay - by;
+    float sx = dx * dx, sy = dy * dy;
+    return sx + sy;
+}
+FTL_HD double dist_f64(double ax, double ay, double bx, double by) {
+    double dx = ax - bx, dy = ay - by;
+    double sx = dx * dx, sy = dy * dy;
+    return sqrt(sx + sy);
+}
+
+FTL_HD void sincos_deg(double deg, double* s, double* c) {
+    double th = deg * kDeg2Rad;
+#if defined(__CUDA_ARCH__)
+    sincos(th, s, c);
+#else
+    *s = sin(th);
+    *c = cos(th);
+#endif
+}
+
+// ---- robots -------------------------------------------------------------------------------------------
+struct Robot {
+    float px, py;
+    int rx, ry, rw, rh;
+    double dir, speed, rot, des_speed, des_rot;
+    int rot_dir, des_rot_dir;
+};
+
+FTL_HD void robot_load(const DevState& s, int k, int i, Robot& r) {
+    float2 p = s.pos[(size_t)k * s.n + i];
+    int4 q = s.rect[(size_t)k * s.n + i];
+    r.px = p.x; r.py = p.y;
+    r.rx = q.x; r.ry = q.y; r.rw = q.z; r.rh = q.w;
+    const double* d = s.rd + (size_t)k * RD_COUNT * s.n + i;
+    r.dir = d[(size_t)RD_DIR * s.n];
+    r.speed = d[(size_t)RD_SPEED * s.n];
+    r.rot = d[(size_t)RD_ROT * s.n];
+    r.des_speed = d[(size_t)RD_DES_SPEED * s.n];
+    r.des_rot = d[(size_t)RD_DES_ROT * s.n];
+    int f = s.ri[(size_t)k * s.n + i];
+    r.rot_dir = (f & 3) - 1;
+    r.des_rot_dir = ((f >> 2) & 3) - 1;
+}
+FTL_HD void robot_store(const DevState& s, int k, int i, const Robot& r) {
+    s.pos[(size_t)k * s.n + i] = make_float2(r.px, r.py);
+    s.rect[(size_t)k * s.n + i] = make_int4(r.rx, r.ry, r.rw, r.rh);
+    double* d = s.rd + (size_t)k * RD_COUNT * s.n + i;
+    d[(size_t)RD_DIR * s.n] = r.dir;
+    d[(size_t)RD_SPEED * s.n] = r.speed;
+    d[(size_t)RD_ROT * s.n] = r.rot;
+    d[(size_t)RD_DES_SPEED * s.n] = r.des_speed;
+    d[(size_t)RD_DES_ROT * s.n] = r.des_rot;
+    s.ri[(size_t)k * s.n + i] = (r.rot_dir + 1) | ((r.des_rot_dir + 1) << 2);
+}
+
+FTL_HD void robot_init(Robot& r, const FtlRobotConfig& c, float x, float y, double dir) {
+    r.px = x; r.py = y;
+    r.rw = c.width; r.rh = c.height;
+    r.rx = (int)x - (c.width >> 1);   // image.get_rect(center=position), CLS:50/56
+    r.ry = (int)y - (c.height >> 1);
+    r.dir = dir;
+    r.speed = r.rot = r.des_speed = r.des_rot = 0.0;
+    r.rot_dir = r.des_rot_dir = 0;
+}
+
+// pygame 2.1.2 transform.rotate bounding box (third party; see oracle/shims/pygame/transform.py)
+FTL_HD void rotated_size(int w, int h, double angle_py, int* ow, int* oh) {
+    float angle = (float)angle_py;
+    double q = rint((double)angle / 90.0);
+    if ((double)angle == 90.0 * q) {  // fmod(angle, 90) == 0
+        int turns = ((int)angle / 90) % 4;
+        if (turns < 0) turns += 4;
+        if (turns & 1) { *ow = h; *oh = w; } else { *ow = w; *oh = h; }
+        return;
+    }
+    double rad = angle * .01745329251994329, sn, cs;
+#if defined(__CUDA_ARCH__)
+    sincos(rad, &sn, &cs);
+#else
+    sn = sin(rad); cs = cos(rad);
+#endif
+    double cx = cs * w, cy = cs * h, sx = sn * w, sy = sn * h;
+    double mx = fmax(fmax(fmax(fabs(cx + sy), fabs(cx - sy)), fabs(-cx + sy)), fabs(-cx - sy));
+    double my = fmax(fmax(fmax(fabs(sx + cy), fabs(sx - cy)), fabs(-sx + cy)), fabs(-sx - cy));
+    *ow = (int)mx;
+    *oh = (int)my;
+}
+
+FTL_HD void command_turn(Robot& r, const FtlRobotConfig& c, double des, int dir) {  // CLS:109-117
+    r.des_rot = (c.max_rotation_speed < des) ? c.max_rotation_speed : des;
+    r.des_rot_dir = dir;
+}
+FTL_HD void command_forward(Robot& r, const FtlRobotConfig& c, double des) {  // CLS:119-127
+    if (des > c.max_speed) des = c.max_speed;
+    if (des < c.min_speed) des = c.min_speed;
+    r.des_speed = des;
+}
+
+FTL_HD void robot_move(Robot& r, const FtlRobotConfig& c) {  // CLS:129-182
+    double change;
+    if (r.rot_dir == 0) r.rot_dir = r.des_rot_dir;
+    if (r.rot_dir == r.des_rot_dir) {
+        double needed = fabs(r.rot - r.des_rot);
+        change = (c.max_rotation_speed_change < needed) ? c.max_rotation_speed_change : needed;
+        if (r.des_rot < r.rot) change = -change;
+    } else {
+        double needed = fabs(r.des_rot + r.rot);
+        change = -((c.max_rotation_speed_change < needed) ? c.max_rotation_speed_change : needed);
+    }
+    double nrs = r.rot + change;
+    if (nrs < 0) r.rot_dir = -r.rot_dir;
+    r.rot = fabs(nrs);
+    double needed = fabs(r.speed - r.des_speed);
+    double sc = (needed < c.max_speed_change) ? needed : c.max_speed_change;
+    if (r.speed > r.des_speed) sc = -sc;
+    r.speed = r.speed + sc;
+
+    if (r.rot != 0) {
+        r.dir = angle_correction(r.dir + r.rot_dir * r.rot);
+        int cx = r.rx + (r.rw >> 1), cy = r.ry + (r.rh >> 1);
+        int nw, nh;
+        rotated_size(c.width, c.height, -r.dir, &nw, &nh);
+        r.rw = nw; r.rh = nh;
+        r.rx = cx - (nw >> 1);
+        r.ry = cy - (nh >> 1);
+    }
+    double sn, cs;
+    sincos_deg(r.dir, &sn, &cs);
+    float mx = (float)(cs * r.speed), my = (float)(sn * r.speed);
+    r.px = r.px + mx;
+    r.py = r.py + my;
+    double dx = (double)r.px - (double)(r.rx + (r.rw >> 1));
+    double dy = (double)r.py - (double)(r.ry + (r.rh >> 1));
+    r.rx += (int)dx;  // move_ip truncates toward zero; (0, 0) is a no-op
+    r.ry += (int)dy;
+}
+
+FTL_HD void move_to_the_point(Robot& r, const FtlRobotConfig& c, double tx, double ty, bool has_speed,
+                              double speed) {  // CLS:184-215
+    double new_speed = has_speed ? speed : dist_f64((double)r.px, (double)r.py, tx, ty);
+    int desirable_angle = (int)angle_to_point((double)r.px, (double)r.py, tx, ty);
+    int cur = (int)r.dir;
+    int delta, nrd;
+    if (desirable_angle - cur > 0) {
+        if (desirable_angle - cur > 180) { delta = cur + (360 - desirable_angle); nrd = -1; }
+        else { delta = desirable_angle - cur; nrd = 1; }
+    } else {
+        if (cur - desirable_angle > 180) { nrd = 1; delta = (360 - cur) + desirable_angle; }
+        else { nrd = -1; delta = cur - desirable_angle; }
+    }
+    command_turn(r, c, (double)delta, nrd);
+    command_forward(r, c, new_speed);
+    robot_move(r, c);
+}
+
+// ---- collisions -----------------------------------------------------------------------------------------
+FTL_HD bool rects_collide(int ax, int ay, int aw, int ah, int bx, int by, int bw, int bh) {  // pygame colliderect
+    if (aw == 0 || ah == 0 || bw == 0 || bh == 0) return false;
+    return ax < bx + bw && ay < by + bh && ax + aw > bx && ay + ah > by;
+}
+FTL_HD bool robots_collide(const Robot& a, const Robot& b) {
+    return rects_collide(a.rx, a.ry, a.rw, a.rh, b.rx, b.ry, b.rw, b.rh);
+}
+FTL_HD bool out_of_bounds(const FtlConfig& c, const Robot& r) {  // ENV:1182-1183
+    return r.px > (float)c.game_width || r.py > (float)c.game_height || r.px < 0 || r.py < 0;
+}
+
+// Static rectangles that the robot could possibly touch during one step: those whose box, grown by
+// `inflate` (half the largest hit-box diagonal + the distance covered in F frames + slack), contains
+// the robot's position at the start of the step.  Exact: the per-frame test still uses the integer
+// rectangles, the mask only skips rectangles that are provably out of reach.
+FTL_HD uint64_t near_static_mask(const int4* rects, int n_static, float px, float py, float inflate) {
+    uint64_t m = 0;
+    for (int k = 0; k < n_static; k++) {
+        int4 q = rects[k];
+        if (px >= (float)q.x - inflate && px <= (float)(q.x + q.z) + inflate && py >= (float)q.y - inflate &&
+            py <= (float)(q.y + q.w) + inflate)
+            m |= (uint64_t)1 << k;
+    }
+    return m;
+}
+FTL_HD bool collide_static_masked(const Robot& r, const int4* rects, uint64_t mask) {
+    while (mask) {
+#if defined(__CUDA_ARCH__)
+        int k = __ffsll((long long)mask) - 1;
+#else
+        int k = __builtin_ctzll(mask);
+#endif
+        mask &= mask - 1;
+        int4 q = rects[k];
+        if (rects_collide(r.rx, r.ry, r.rw, r.rh, q.x, q.y, q.z, q.w)) return true;
+    }
+    return false;
+}
+
+// ---- green zone: exact flags from cached bounds ------------------------------------------------------------
+// The reference recomputes, every frame, (1) the "green" suffix of the leader trail whose arc length
+// from the newest point stays <= max_distance and (2) the nearest green point to the follower, and,
+// when that is farther than max_dev, (3) the nearest point of the WHOLE trail (ENV:1828-1843,
+// 1906-1937; half of the reference's run time).  The flags only depend on whether those minima are
+// below two thresholds, so this implementation keeps
+//   * g_lo: first green index, recomputed (same float32 accumulation order) only when the trail grows;
+//   * for each of the two searches a witness index (a point known to be in the set: its exact distance
+//     is an upper bound of the minimum) and a lower bound of the minimum that is decreased every frame
+//     by the follower's displacement (triangle inequality) and folded with each newly added point.
+// A full scan (bit-identical arithmetic to the reference) is only done when the bounds cannot decide a
+// comparison, so the flags are always exactly those of the reference.
+struct GreenCache {
+    int g_lo;      // first green trail index; green = [g_lo, trail_len-2]
+    int a_star;    // witness for the green minimum (-1 = none)
+    int b_star;    // witness for the whole-trail minimum (-1 = none)
+    float lb_g;    // lower bound of min distance follower -> green points (negative = unknown)
+    float lb_all;  // lower bound of min distance follower -> all trail points
+};
+
+constexpr float kBoundSlack = 2e-3f;  // covers float32 rounding of positions/distances up to ~4000 px
+
+// _trajectory_in_box, ENV:1828-1843 (float32 accumulation from the newest point backwards)
+FTL_HD int green_lo(const float2* trail, int n, float max_distance_f32) {
+    int lo = n - 1;  // empty
+    float acc = 0.f;
+    float2 newer = n > 0 ? trail[n - 1] : make_float2(0.f, 0.f);
+    for (int i = n - 2; i >= 0; i--) {
+        float2 p = trail[i];
+        acc = acc + sqrtf(d2_f32(newer.x, newer.y, p.x, p.y));
+        if (acc <= max_distance_f32)
+            lo = i;
+        else
+            break;
+        newer = p;
+    }
+    return lo;
+}
+
+FTL_HD float scan_min_d2(const float2* trail, int lo, int hi, float fx, float fy, int* arg) {
+    // min over [lo, hi] of the reference's float32 squared distance; first minimum in the reference's
+    // list order does not matter for the value
+    float best = 3.0e38f;
+    int bi = -1;
+    for (int i = hi; i >= lo; i--) {
+        float2 p = trail[i];
+        float d2 = d2_f32(p.x, p.y, fx, fy);
+        if (d2 < best) { best = d2; bi = i; }
+    }
+    *arg = bi;
+    return best;
+}
+
+// returns 1 if min <= thr, 0 if min > thr, -1 if the bounds cannot tell
+FTL_HD int bound_decide(float ub2, float lb, float thr2) {
+    if (ub2 <= thr2) return 1;
+    if (lb > 0.f) {
+        float l2 = lb * lb * 0.999999f;
+        if (l2 > thr2) return 0;
+    }
+    return -1;
+}
+
+FTL_HD void green_flags(const DevCfg& cfg, const float2* trail, int n, float fx, float fy, GreenCache& gc,
+                        bool* in_box, bool* on_trace) {  // ENV:1906-1931
+    *in_box = false;
+    *on_trace = false;
+    int hi = n - 2;
+    int n_green = hi - gc.g_lo + 1;
+    if (n_green <= 2) return;
+    // upper bound from the witness
+    float ub2 = 3.0e38f;
+    if (gc.a_star >= gc.g_lo && gc.a_star <= hi) {
+        float2 p = trail[gc.a_star];
+        ub2 = d2_f32(p.x, p.y, fx, fy);
+    }
+    int le_eps = bound_decide(ub2, gc.lb_g, cfg.eps2_f32);
+    int le_dev = le_eps == 1 ? 1 : bound_decide(ub2, gc.lb_g, cfg.dev2_f32);
+    if (le_eps < 0 || (le_eps == 0 && le_dev < 0)) {
+        float m = scan_min_d2(trail, gc.g_lo, hi, fx, fy, &gc.a_star);
+        gc.lb_g = sqrtf(m) - kBoundSlack;
+        le_eps = m <= cfg.eps2_f32;
+        le_dev = m <= cfg.dev2_f32;
+    }
+    if (le_eps == 1) {
+        *in_box = true;
+        *on_trace = true;
+        return;
+    }
+    if (le_dev == 1) {
+        *in_box = true;
+        return;
+    }
+    // whole-trail fallback, ENV:1924-1931
+    float ub2a = 3.0e38f;
+    if (gc.b_star >= 0 && gc.b_star < n) {
+        float2 p = trail[gc.b_star];
+        ub2a = d2_f32(p.x, p.y, fx, fy);
+    }
+    int le = bound_decide(ub2a, gc.lb_all, cfg.eps2_f32);
+    if (le < 0) {
+        float m = scan_min_d2(trail, 0, n - 1, fx, fy, &gc.b_star);
+        gc.lb_all = sqrtf(m) - kBoundSlack;
+        le = m <= cfg.eps2_f32;
+    }
+    *on_trace = le == 1;
+}
+
+// bookkeeping of the cache when the follower moved by at most `moved` pixels
+FTL_HD void green_cache_moved(GreenCache& gc, float moved) {
+    gc.lb_g -= moved;
+    gc.lb_all -= moved;
+}
+// ... and when the trail grew: trail[n-1] is new (n = new length).  trail[n-2] enters the green set.
+FTL_HD void green_cache_appended(const DevCfg& cfg, const float2* trail, int n, float fx, float fy, GreenCache& gc) {
+    gc.g_lo = green_lo(trail, n, cfg.max_distance_f32);
+    float2 p = trail[n - 1];
+    float d = sqrtf(d2_f32(p.x, p.y, fx, fy)) - kBoundSlack;
+    if (d < gc.lb_all) gc.lb_all = d;
+    if (n >= 2) {
+        float2 q = trail[n - 2];
+        float dq = sqrtf(d2_f32(q.x, q.y, fx, fy)) - kBoundSlack;
+        if (dq < gc.lb_g) gc.lb_g = dq;
+    }
+}
+FTL_HD void green_cache_invalidate(const DevCfg& cfg, const float2* trail, int n, GreenCache& gc) {
+    gc.g_lo = green_lo(trail, n, cfg.max_distance_f32);
+    gc.a_star = -1;
+    gc.b_star = -1;
+    gc.lb_g = -1.f;
+    gc.lb_all = -1.f;
+}
+
+// ---- Philox4x32-10 for list-valued speed regimes (same keying as the oracle) --------------------------------
+FTL_HD uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+FTL_HD double regime_uniform(int64_t env_global, int episode, int frame) {
+    uint32_t c0 = (uint32_t)frame, c1 = (uint32_t)episode, c2 = 0x46544c31u, c3 = 0u;
+    uint32_t k0 = (uint32_t)env_global, k1 = (uint32_t)((uint64_t)env_global >> 32);
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0 = mulhi32(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = mulhi32(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return (double)c0 * (1.0 / 4294967296.0);
+}
+
+// ---- episode scalars kept in registers during a step --------------------------------------------------------
+struct Episode {
+    int step_count, cur_target_id, finish_timer, flags, trail_len, scenario, episode, overflow, accel_consumed;
+    double acc_penalty, overall, last_reward, speed_mult, lead_acc, lead_cum;
+};
+
+FTL_HD double reward_of(const FtlConfig& c, const Episode& e, bool too_close, bool in_box, bool on_trace) {  // ENV:1869-1904
+    double r = 0;
+    r += c.leader_movement_reward;
+    if (too_close) {
+        r += c.too_close_penalty;
+    } else {
+        if (in_box && on_trace) r += c.reward_in_box;
+        else if (in_box) r += c.reward_in_dev;
+        else if (on_trace) r += c.reward_on_track;
+        else if (e.step_count > c.warm_start) r += c.not_on_track_penalty;
+    }
+    if (e.flags & FL_CRASH) r += c.crash_penalty;
+    return r;
+}
+
+FTL_HD double leader_speed(const DevCfg& cfg, Episode& e, int env_index) {  // ENV:1143-1157
+    const FtlConfig& c = cfg.c;
+    int sel = -1;
+    for (int k = 0; k < c.n_speed_regime; k++)
+        if (c.speed_regime_key[k] <= e.step_count) sel = k;
+    if (sel >= 0) {
+        if (c.speed_regime_is_range[sel]) {
+            double u = regime_uniform(cfg.env_id_base + env_index, e.episode, e.step_count);
+            e.speed_mult = c.speed_regime_lo[sel] + (c.speed_regime_hi[sel] - c.speed_regime_lo[sel]) * u;
+        } else {
+            e.speed_mult = c.speed_regime_lo[sel];
+        }
+    }
+    return c.leader.max_speed * e.speed_mult;
+}
+FTL_HD double leader_accel(const DevCfg& cfg, Episode& e) {  // ENV:1159-1174
+    const FtlConfig& c = cfg.c;
+    for (int k = 0; k < c.n_accel_regime; k++) {
+        if (e.accel_consumed & (1 << k)) continue;
+        if (c.accel_regime_key[k] <= e.step_count) {
+            e.lead_acc = c.accel_regime_val[k];
+            e.lead_cum = e.lead_acc;
+            e.accel_consumed |= (1 << k);
+        }
+    }
+    e.lead_cum += e.lead_acc;
+    return e.lead_cum * c.leader.max_speed;
+}
+
+// bear target, ENV:722-758 and 819-837
+FTL_HD void bear_target(const FtlConfig& c, int idx, const Robot& bear, const Robot& leader, double* tx, double* ty,
+                        int* index) {
+    double d = dist_f64((double)bear.px, (double)bear.py, *tx, *ty);
+    double radius, ang;
+    if (c.move_bear_v4 && (idx & 1)) {
+        if (d < c.leader_pos_epsilon) *index += 1;
+        if (*index > 3) *index = 0;
+        // order[idx][k] -> which of p1..p4: idx1 [p4,p3,p1,p2], idx3 [p3,p1,p2,p4]
+        int which;
+        if (idx == 1) which = (*index == 0) ? 3 : (*index == 1) ? 2 : (*index == 2) ? 0 : 1;
+        else which = (*index == 0) ? 2 : (*index == 1) ? 0 : (*index == 2) ? 1 : 3;
+        radius = which < 2 ? 150.0 : 250.0;
+        ang = which == 0 ? leader.dir + 140 : which == 1 ? leader.dir - 140 : which == 2 ? leader.dir - 160 : leader.dir + 160;
+    } else {
+        if (d < c.leader_pos_epsilon) {
+            *index += 1;
+            if (*index > 1) *index = 0;
+        }
+        radius = 100.0 * (idx + 1);
+        ang = *index == 0 ? leader.dir - 130 : leader.dir + 130;
+    }
+    double sn, cs;
+    sincos_deg(ang, &sn, &cs);
+    *tx = (double)leader.px + cs * radius;
+    *ty = (double)leader.py + sn * radius;
+}
+
+// ---- tracker (LeaderPositionsTracker_v2.scan, SEN:243-327) ---------------------------------------------------
+struct Tracker {
+    int saving_counter, ring_tail, ring_head, hist_f64_end;
+};
+
+// numpy add.reduce (pairwise_sum) order, generated on the fly over k = 0..n-1 of f(k)
+template <typename T, typename F>
+FTL_HD T np_pairwise_sum(int n, int base, F f) {
+    if (n < 8) {
+        T r = 0;
+        for (int i = 0; i < n; i++) r += f(base + i);
+        return r;
+    }
+    T r0 = f(base + 0), r1 = f(base + 1), r2 = f(base + 2), r3 = f(base + 3), r4 = f(base + 4), r5 = f(base + 5),
+      r6 = f(base + 6), r7 = f(base + 7);
+    int i;
+    for (i = 8; i < n - (n % 8); i += 8) {
+        r0 += f(base + i); r1 += f(base + i + 1); r2 += f(base + i + 2); r3 += f(base + i + 3);
+        r4 += f(base + i + 4); r5 += f(base + i + 5); r6 += f(base + i + 6); r7 += f(base + i + 7);
+    }
+    T res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+    for (; i < n; i++) res += f(base + i);
+    return res;
+}
+template <typename T, typename F>
+FTL_HD T np_sum(int n, F f) {  // n <= 512 here (corridor_cap): at most two levels of blocking
+    if (n <= 128) return np_pairwise_sum<T>(n, 0, f);
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    T a, b;
+    if (n2 <= 128) a = np_pairwise_sum<T>(n2, 0, f);
+    else { int m = n2 / 2; m -= m % 8; a = np_pairwise_sum<T>(m, 0, f) + np_pairwise_sum<T>(n2 - m, m, f); }
+    int nr = n - n2;
+    if (nr <= 128) b = np_pairwise_sum<T>(nr, n2, f);
+    else { int m = nr / 2; m -= m % 8; b = np_pairwise_sum<T>(m, n2, f) + np_pairwise_sum<T>(nr - m, n2 + m, f); }
+    return a + b;
+}
+
+FTL_HD bool tracker_too_long(const DevCfg& cfg, const Tracker& t, const double2* hist, int cap) {  // SEN:283-287
+    int n = t.ring_head - t.ring_tail;
+    if (n < 2) return false;
+    int mask = cap - 1, tail = t.ring_tail;
+    if (tail < t.hist_f64_end) {
+        double len = np_sum<double>(n - 1, [&](int k) {
+            double2 a = hist[(tail + k) & mask], b = hist[(tail + k + 1) & mask];
+            return dist_f64(a.x, a.y, b.x, b.y);
+        });
+        return len > cfg.c.corridor_length;
+    } else {
+        float len = np_sum<float>(n - 1, [&](int k) {
+            double2 a = hist[(tail + k) & mask], b = hist[(tail + k + 1) & mask];
+            return sqrtf(d2_f32((float)a.x, (float)a.y, (float)b.x, (float)b.y));
+        });
+        return len > cfg.corridor_length_f32;
+    }
+}
+
+FTL_HD float4 corridor_entry(const DevCfg& cfg, const Tracker& t, const double2* hist, int cap, int ia, int ib,
+                             int ianchor) {  // SEN:302-317
+    int mask = cap - 1;
+    double2 pa = hist[ia & mask], pb = hist[ib & mask], pc = hist[ianchor & mask];
+    double vx, vy;
+    if (ia < t.hist_f64_end || ib < t.hist_f64_end) {
+        vx = pb.x - pa.x;
+        vy = pb.y - pa.y;
+        double nrm = sqrt(fma(vy, vy, vx * vx));
+        double s = cfg.c.corridor_width / nrm;
+        vx *= s;
+        vy *= s;
+    } else {
+        float fx = (float)pb.x - (float)pa.x, fy = (float)pb.y - (float)pa.y;
+        float sx = fx * fx, sy = fy * fy;
+        float ss = sx + sy;
+        float s = cfg.corridor_width_f32 / sqrtf(ss);
+        float gx = fx * s, gy = fy * s;
+        vx = gx;
+        vy = gy;
+    }
+    const double c90 = 6.123233995736766e-17;
+    double rx = fma(c90, vx, -1.0 * vy), ry = fma(1.0, vx, c90 * vy);
+    double lx = fma(c90, vx, 1.0 * vy), ly = fma(-1.0, vx, c90 * vy);
+    rx += pc.x; ry += pc.y;
+    lx += pc.x; ly += pc.y;
+    return make_float4((float)rx, (float)ry, (float)lx, (float)ly);
+}
+
+struct TrackerInput {  // what the tracker reads from the robots, by value
+    float fpx, fpy, lpx, lpy;
+    double fdir;
+};
+
+FTL_HD_NOINLINE void tracker_scan(const DevCfg& cfg, Tracker& t, double2* hist, float4* corr, TrackerInput in,
+                                  int* overflow) {
+    struct { float px, py; double dir; } follower = {in.fpx, in.fpy, in.fdir};
+    struct { float px, py; } leader = {in.lpx, in.lpy};
+    const FtlConfig& c = cfg.c;
+    int cap = c.corridor_cap, mask = cap - 1;
+    if (t.saving_counter % c.saving_period == 0) {
+        int n = t.ring_head - t.ring_tail;
+        if (n > 0) {
+            double2 last = hist[(t.ring_head - 1) & mask];
+            if (last.x == (double)leader.px && last.y == (double)leader.py) return;  // SEN:247-251
+        }
+        if (n == 0 && t.saving_counter == 0) {
+            double lx = leader.px, ly = leader.py;
+            int m;
+            if (c.start_corridor_behind_follower) {  // SEN:257-272
+                double sn, cs;
+                sincos_deg(angle_correction(follower.dir + 180), &sn, &cs);
+                double sx = 50 * cs + (double)follower.px, sy = 50 * sn + (double)follower.py;
+                m = (int)(dist_f64(sx, sy, lx, ly) / (c.saving_period * 5 * c.leader.max_speed));
+                if (m > cap) { m = cap; *overflow |= 2; }
+                double stepx = m > 1 ? (lx - sx) / (m - 1) : 0, stepy = m > 1 ? (ly - sy) / (m - 1) : 0;
+                for (int i = 0; i < m; i++) {
+                    double tx = (double)i * stepx, ty = (double)i * stepy;
+                    hist[(t.ring_head + i) & mask] = make_double2(tx + sx, ty + sy);
+                }
+                t.hist_f64_end = t.ring_head + m;
+            } else {  // SEN:273-281, float32 linspace
+                float fsx = follower.px, fsy = follower.py, flx = leader.px, fly = leader.py;
+                float q = sqrtf(d2_f32(fsx, fsy, flx, fly)) / (float)(c.saving_period * 5 * c.leader.max_speed);
+                m = (int)q;
+                if (m > cap) { m = cap; *overflow |= 2; }
+                float ddx = flx - fsx, ddy = fly - fsy;
+                float stepx = m > 1 ? ddx / (float)(m - 1) : 0.f, stepy = m > 1 ? ddy / (float)(m - 1) : 0.f;
+                for (int i = 0; i < m; i++) {
+                    float tx = (float)i * stepx, ty = (float)i * stepy;
+                    float vx = tx + fsx, vy = ty + fsy;
+                    hist[(t.ring_head + i) & mask] = make_double2((double)vx, (double)vy);
+                }
+                t.hist_f64_end = t.ring_tail;
+            }
+            if (m > 1) hist[(t.ring_head + m - 1) & mask] = make_double2(lx, ly);
+            t.ring_head += m;
+        } else {
+            if (t.ring_head - t.ring_tail >= cap) { t.ring_tail++; *overflow |= 2; }
+            hist[t.ring_head & mask] = make_double2((double)leader.px, (double)leader.py);
+            t.ring_head++;
+        }
+        while (tracker_too_long(cfg, t, hist, cap)) t.ring_tail++;  // SEN:286-292
+        n = t.ring_head - t.ring_tail;
+        if (n > 1) {
+            if (t.saving_counter == 0) {  // SEN:300-308
+                for (int i = n - 1; i > 0; i--) {
+                    int anchor = t.ring_tail + (n - i - 1);
+                    corr[anchor & mask] = corridor_entry(cfg, t, hist, cap, t.ring_tail + i - 1, t.ring_tail + i, anchor);
+                }
+            }
+            corr[(t.ring_head - 1) & mask] =
+                corridor_entry(cfg, t, hist, cap, t.ring_head - 2, t.ring_head - 1, t.ring_head - 2);
+        }
+    }
+    t.saving_counter += 1;
+}
+
+}  // namespace ftl

@@ -1,0 +1,374 @@
+// ftl_step.cuh -- one environment step (F fused sub-frames + tracker + bookkeeping), reset and outputs.
+// Host+device like ftl_device.cuh; NB (number of dynamic obstacles) is a template parameter so that
+// the robots live in registers.
+#pragma once
+
+#include "ftl_device.cuh"
+
+namespace ftl {
+
+FTL_HD void episode_load(const DevState& s, int i, Episode& e) {
+    const int* g = s.gi + i;
+    size_t n = s.n;
+    e.step_count = g[GI_STEP_COUNT * n];
+    e.cur_target_id = g[GI_TARGET_ID * n];
+    e.finish_timer = g[GI_FINISH_TIMER * n];
+    e.flags = g[GI_FLAGS * n];
+    e.trail_len = g[GI_TRAIL_LEN * n];
+    e.scenario = g[GI_SCENARIO * n];
+    e.episode = g[GI_EPISODE * n];
+    e.overflow = g[GI_OVERFLOW * n];
+    e.accel_consumed = g[GI_ACCEL_CONSUMED * n];
+    const double* d = s.gd + i;
+    e.acc_penalty = d[GD_ACC_PENALTY * n];
+    e.overall = d[GD_OVERALL * n];
+    e.last_reward = d[GD_LAST_REWARD * n];
+    e.speed_mult = d[GD_SPEED_MULT * n];
+    e.lead_acc = d[GD_LEAD_ACC * n];
+    e.lead_cum = d[GD_LEAD_CUM * n];
+}
+FTL_HD void episode_store(const DevState& s, int i, const Episode& e) {
+    int* g = s.gi + i;
+    size_t n = s.n;
+    g[GI_STEP_COUNT * n] = e.step_count;
+    g[GI_TARGET_ID * n] = e.cur_target_id;
+    g[GI_FINISH_TIMER * n] = e.finish_timer;
+    g[GI_FLAGS * n] = e.flags;
+    g[GI_TRAIL_LEN * n] = e.trail_len;
+    g[GI_SCENARIO * n] = e.scenario;
+    g[GI_EPISODE * n] = e.episode;
+    g[GI_OVERFLOW * n] = e.overflow;
+    g[GI_ACCEL_CONSUMED * n] = e.accel_consumed;
+    double* d = s.gd + i;
+    d[GD_ACC_PENALTY * n] = e.acc_penalty;
+    d[GD_OVERALL * n] = e.overall;
+    d[GD_LAST_REWARD * n] = e.last_reward;
+    d[GD_SPEED_MULT * n] = e.speed_mult;
+    d[GD_LEAD_ACC * n] = e.lead_acc;
+    d[GD_LEAD_CUM * n] = e.lead_cum;
+}
+FTL_HD void cache_load(const DevState& s, int i, GreenCache& gc, Tracker& t, int* snap_pushes) {
+    const int* g = s.gi + i;
+    size_t n = s.n;
+    gc.g_lo = g[GI_G_LO * n];
+    gc.a_star = g[GI_A_STAR * n];
+    gc.b_star = g[GI_B_STAR * n];
+    gc.lb_g = s.gf[GF_LB_GREEN * n + i];
+    gc.lb_all = s.gf[GF_LB_ALL * n + i];
+    t.saving_counter = g[GI_SAVING_COUNTER * n];
+    t.ring_tail = g[GI_RING_TAIL * n];
+    t.ring_head = g[GI_RING_HEAD * n];
+    t.hist_f64_end = g[GI_HIST_F64_END * n];
+    *snap_pushes = g[GI_SNAP_PUSHES * n];
+}
+FTL_HD void cache_store(const DevState& s, int i, const GreenCache& gc, const Tracker& t, int snap_pushes) {
+    int* g = s.gi + i;
+    size_t n = s.n;
+    g[GI_G_LO * n] = gc.g_lo;
+    g[GI_A_STAR * n] = gc.a_star;
+    g[GI_B_STAR * n] = gc.b_star;
+    s.gf[GF_LB_GREEN * n + i] = gc.lb_g;
+    s.gf[GF_LB_ALL * n + i] = gc.lb_all;
+    g[GI_SAVING_COUNTER * n] = t.saving_counter;
+    g[GI_RING_TAIL * n] = t.ring_tail;
+    g[GI_RING_HEAD * n] = t.ring_head;
+    g[GI_HIST_F64_END * n] = t.hist_f64_end;
+    g[GI_SNAP_PUSHES * n] = snap_pushes;
+}
+
+FTL_HD int2 route_point(const DevPool& pool, const FtlConfig& c, int scenario, int k) {
+    return pool.route[(size_t)scenario * c.route_cap + k];
+}
+
+template <int NB>
+struct World {  // registers of one env during a step
+    Robot follower, leader;
+    Robot bear[NB > 0 ? NB : 1];
+    double btx[NB > 0 ? NB : 1], bty[NB > 0 ? NB : 1];
+    int bidx[NB > 0 ? NB : 1];
+};
+
+template <int NB>
+FTL_HD void world_load(const DevState& s, int i, World<NB>& w) {
+    robot_load(s, 0, i, w.follower);
+    robot_load(s, 1, i, w.leader);
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        robot_load(s, 2 + b, i, w.bear[b]);
+        w.btx[b] = s.bear_tgt[((size_t)b * 2 + 0) * s.n + i];
+        w.bty[b] = s.bear_tgt[((size_t)b * 2 + 1) * s.n + i];
+        w.bidx[b] = s.bear_idx[(size_t)b * s.n + i];
+    }
+}
+template <int NB>
+FTL_HD void world_store(const DevState& s, int i, const World<NB>& w) {
+    robot_store(s, 0, i, w.follower);
+    robot_store(s, 1, i, w.leader);
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        robot_store(s, 2 + b, i, w.bear[b]);
+        s.bear_tgt[((size_t)b * 2 + 0) * s.n + i] = w.btx[b];
+        s.bear_tgt[((size_t)b * 2 + 1) * s.n + i] = w.bty[b];
+        s.bear_idx[(size_t)b * s.n + i] = w.bidx[b];
+    }
+}
+
+// ---- sensors that are cheap and serial: tracker scans + history snapshot (CLS:255-288, SEN:894-895) ----------
+template <int NB>
+FTL_HD void sense_serial(const DevCfg& cfg, const DevState& s, int i, const World<NB>& w, Tracker& t, int* snap_pushes,
+                         int* overflow) {
+    const FtlConfig& c = cfg.c;
+    if (!c.tracker_enabled) return;
+    double2* hist = s.hist + (size_t)i * c.corridor_cap;
+    float4* corr = s.corridor + (size_t)i * c.corridor_cap;
+    TrackerInput in = {w.follower.px, w.follower.py, w.leader.px, w.leader.py, w.follower.dir};
+    for (int k = 0; k < c.tracker_scans_per_step; k++) tracker_scan(cfg, t, hist, corr, in, overflow);
+    if (c.n_ray_sensors > 0 && t.ring_head - t.ring_tail > 1) {
+        int slot = *snap_pushes % FTL_MAX_HIST;
+        s.snap_range[(size_t)slot * s.n + i] = make_int2(t.ring_tail, t.ring_head);
+        int4* sr = s.snap_rect + ((size_t)slot * (1 + NB)) * s.n + i;
+        sr[0] = make_int4(w.leader.rx, w.leader.ry, w.leader.rw, w.leader.rh);
+#pragma unroll
+        for (int b = 0; b < NB; b++)
+            sr[(size_t)(1 + b) * s.n] = make_int4(w.bear[b].rx, w.bear[b].ry, w.bear[b].rw, w.bear[b].rh);
+        *snap_pushes += 1;
+    }
+}
+
+template <int NB>
+FTL_HD void write_outputs(const DevCfg& cfg, const DevPool& pool, const DevOutputs& out, int i, const World<NB>& w,
+                          const Episode& e, bool obs_only) {
+    const FtlConfig& c = cfg.c;
+    if (out.numerical_features) {  // ENV:1793-1802
+        float* nf = out.numerical_features + (size_t)i * 10;
+        nf[0] = w.leader.px; nf[1] = w.leader.py;
+        nf[2] = (float)w.leader.speed; nf[3] = (float)w.leader.dir; nf[4] = (float)w.leader.rot;
+        nf[5] = w.follower.px; nf[6] = w.follower.py;
+        nf[7] = (float)w.follower.speed; nf[8] = (float)w.follower.dir; nf[9] = (float)w.follower.rot;
+    }
+    if (out.leader_target) {  // ENV:1803-1806
+        int n_route = pool.n_route[e.scenario];
+        int tid = e.cur_target_id < n_route ? e.cur_target_id : n_route - 1;
+        int2 p = route_point(pool, c, e.scenario, tid), last = route_point(pool, c, e.scenario, n_route - 1);
+        if (n_route > 1 && p.x == last.x && p.y == last.y) p = route_point(pool, c, e.scenario, n_route - 2);
+        out.leader_target[2 * (size_t)i] = p.x;
+        out.leader_target[2 * (size_t)i + 1] = p.y;
+    }
+    if (obs_only) return;
+    if (out.reward) out.reward[i] = (float)e.last_reward;
+    if (out.done) out.done[i] = (uint8_t)((e.flags & FL_DONE) != 0);
+    if (out.status) {
+        out.status[4 * (size_t)i + 0] = (uint8_t)((e.flags >> FL_MISSION_SHIFT) & 3);
+        out.status[4 * (size_t)i + 1] = (uint8_t)((e.flags >> FL_AGENT_SHIFT) & 7);
+        out.status[4 * (size_t)i + 2] = (uint8_t)((e.flags >> FL_LEADER_SHIFT) & 3);
+        out.status[4 * (size_t)i + 3] = (uint8_t)((e.flags & FL_CRASH) != 0);
+    }
+}
+
+// ---- reset: the tail of Game.reset once the scenario exists (ENV:495-543) ---------------------------------------
+template <int NB>
+FTL_HD void env_reset(const DevCfg& cfg, const DevState& s, const DevPool& pool, int i, int scenario, World<NB>& w,
+                      Episode& e) {
+    const FtlConfig& c = cfg.c;
+    float2 lp = pool.leader_pos[scenario], fp = pool.follower_pos[scenario];
+    robot_init(w.leader, c.leader, lp.x, lp.y, pool.leader_dir[scenario]);
+    robot_init(w.follower, c.follower, fp.x, fp.y, pool.follower_dir[scenario]);
+#pragma unroll
+    for (int b = 0; b < NB; b++) {  // ENV:687-718, 761-770
+        float bx = (b % 2 == 0) ? lp.x + 150.f : lp.x - 150.f;
+        float by = (b % 2 == 0) ? lp.y - 150.f : lp.y + 150.f;
+        robot_init(w.bear[b], c.bear, bx, by, 0.0);
+        w.btx[b] = (double)(lp.x - 150.f);
+        w.bty[b] = (double)(lp.y - 150.f);
+        w.bidx[b] = 0;
+    }
+    int accel_consumed = s.gi[(size_t)GI_ACCEL_CONSUMED * s.n + i];  // never restored by the reference, ENV:1170
+    int episodes = s.gi[(size_t)GI_EPISODE * s.n + i];
+    e.step_count = 0;
+    e.cur_target_id = 1;
+    e.finish_timer = -1;
+    e.flags = 0;
+    e.scenario = scenario;
+    e.episode = episodes + 1;
+    e.overflow = 0;
+    e.accel_consumed = accel_consumed;
+    e.acc_penalty = e.overall = e.last_reward = 0.0;
+    e.speed_mult = 1.0;
+    e.lead_acc = e.lead_cum = 0.0;
+    // seed the trail, ENV:533-539 (float32 linspace follower -> leader)
+    float2* trail = s.trail + (size_t)i * c.trail_cap;
+    float q = sqrtf(d2_f32(fp.x, fp.y, lp.x, lp.y)) / cfg.trail_seed_denom_f32;
+    int m = (int)q;
+    if (m > c.trail_cap) { m = c.trail_cap; e.overflow |= 1; }
+    if (m > 0) {
+        float dx = lp.x - fp.x, dy = lp.y - fp.y;
+        float stepx = m > 1 ? dx / (float)(m - 1) : 0.f, stepy = m > 1 ? dy / (float)(m - 1) : 0.f;
+        for (int k = 0; k < m; k++) {
+            float tx = (float)k * stepx, ty = (float)k * stepy;
+            trail[k] = make_float2(tx + fp.x, ty + fp.y);
+        }
+        if (m > 1) trail[m - 1] = lp;
+    }
+    e.trail_len = m;
+    GreenCache gc;
+    green_cache_invalidate(cfg, trail, m, gc);
+    Tracker t = {0, 0, 0, 0};
+    // ring indices restart at 0; old snapshots are dropped by zeroing the push counter
+    int snap_pushes = 0;
+    sense_serial<NB>(cfg, s, i, w, t, &snap_pushes, &e.overflow);
+    cache_store(s, i, gc, t, snap_pushes);
+}
+
+// ---- one step: Game.step without the ray sensors (ENV:908-945, 947-1141) ------------------------------------------
+template <int NB>
+FTL_HD void env_step(const DevCfg& cfg, const DevState& s, const DevPool& pool, int i, double a0, double a1,
+                     World<NB>& w, Episode& e) {
+    const FtlConfig& c = cfg.c;
+    GreenCache gc;
+    Tracker t;
+    int snap_pushes;
+    cache_load(s, i, gc, t, &snap_pushes);
+    float2* trail = s.trail + (size_t)i * c.trail_cap;
+    const int4* statics = pool.static_rects + (size_t)e.scenario * c.static_cap;
+    const int n_static = pool.n_static[e.scenario];
+    const int n_route = pool.n_route[e.scenario];
+
+    command_forward(w.follower, c.follower, a0);  // ENV:927-933
+    if (a1 < 0) command_turn(w.follower, c.follower, fabs(a1), -1);
+    else if (a1 > 0) command_turn(w.follower, c.follower, a1, 1);
+    else command_turn(w.follower, c.follower, 0, 0);
+
+    const uint64_t fmask = near_static_mask(statics, n_static, w.follower.px, w.follower.py, cfg.static_inflate[0]);
+    const uint64_t lmask = near_static_mask(statics, n_static, w.leader.px, w.leader.py, cfg.static_inflate[1]);
+
+    for (int f = 0; f < c.frames_per_step; f++) {
+        int mission = FTL_MISSION_IN_PROGRESS, agent = FTL_AGENT_MOVING, leader_st = FTL_LEADER_MOVING;
+        // (1) follower, ENV:957-964
+        robot_move(w.follower, c.follower);
+        green_cache_moved(gc, (float)fabs(w.follower.speed) + 2e-4f);
+        if (!c.ignore_follower_collisions) {
+            bool hit = robots_collide(w.follower, w.leader) || collide_static_masked(w.follower, statics, fmask) ||
+                       out_of_bounds(c, w.follower);
+#pragma unroll
+            for (int b = 0; b < NB; b++) hit = hit || robots_collide(w.follower, w.bear[b]);
+            if (hit) {
+                e.flags |= FL_CRASH | FL_DONE;
+                mission = FTL_MISSION_FAIL;
+                agent = FTL_AGENT_CRASH;
+            }
+        }
+        // (2) green zone + flags, ENV:966-973
+        bool in_box, on_trace;
+        green_flags(cfg, trail, e.trail_len, w.follower.px, w.follower.py, gc, &in_box, &on_trace);
+        bool too_close = d2_f32(w.leader.px, w.leader.py, w.follower.px, w.follower.py) <= cfg.min_dist2_f32;
+        // (3) waypoint advance, ENV:978-983
+        {
+            int tid = e.cur_target_id < n_route ? e.cur_target_id : n_route - 1;
+            int2 p = route_point(pool, c, e.scenario, tid);
+            if (dist_f64((double)w.leader.px, (double)w.leader.py, (double)p.x, (double)p.y) < c.leader_pos_epsilon) {
+                e.cur_target_id += 1;
+                if (e.cur_target_id >= n_route) e.flags |= FL_LEADER_FINISHED;
+            }
+        }
+        // (4) bears, ENV:987-995
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            bear_target(c, b, w.bear[b], w.leader, &w.btx[b], &w.bty[b], &w.bidx[b]);
+            move_to_the_point(w.bear[b], c.bear, w.btx[b], w.bty[b], false, 0.0);
+        }
+        // (5) leader, ENV:1048-1072
+        if (!(e.flags & FL_LEADER_FINISHED)) {
+            double speed = c.n_speed_regime > 0 ? leader_speed(cfg, e, i) : c.leader.max_speed;
+            double accel = c.n_accel_regime > 0 ? leader_accel(cfg, e) / c.frames_per_step : 0.0;
+            int2 p = route_point(pool, c, e.scenario, e.cur_target_id);
+            move_to_the_point(w.leader, c.leader, (double)p.x, (double)p.y, true, speed + accel);
+        } else {
+            command_forward(w.leader, c.leader, 0);
+            command_turn(w.leader, c.leader, 0, 0);
+            leader_st = FTL_LEADER_FINISHED;
+        }
+        if (robots_collide(w.leader, w.follower) || collide_static_masked(w.leader, statics, lmask) ||
+            out_of_bounds(c, w.leader)) {
+            e.flags |= FL_DONE;
+            mission = FTL_MISSION_FAIL;
+            leader_st = FTL_LEADER_CRASH;
+        }
+        // (6) trail append on the virtual clock, ENV:1074-1075
+        if (e.step_count % c.trajectory_saving_period == 0) {
+            if (e.trail_len < c.trail_cap) {
+                trail[e.trail_len] = make_float2(w.leader.px, w.leader.py);
+                e.trail_len++;
+                green_cache_appended(cfg, trail, e.trail_len, w.follower.px, w.follower.py, gc);
+            } else {
+                e.overflow |= 1;
+            }
+        }
+        // (7) finish timer, ENV:1077-1087
+        if ((e.flags & FL_LEADER_FINISHED) && in_box) {
+            if (e.finish_timer < 0) {
+                e.finish_timer = 0;
+            } else {
+                e.finish_timer += 1;
+                if (e.finish_timer > c.frames_per_step * 20) {
+                    mission = FTL_MISSION_SUCCESS;
+                    leader_st = FTL_LEADER_FINISHED;
+                    agent = FTL_AGENT_FINISHED;
+                    e.flags |= FL_DONE;
+                }
+            }
+        }
+        // (8) early stopping, ENV:1088-1107
+        if (e.step_count > c.warm_start) {
+            if (c.es_has_low_reward && e.acc_penalty < c.es_low_reward) {
+                mission = FTL_MISSION_FAIL; leader_st = FTL_LEADER_MOVING; agent = FTL_AGENT_LOW_REWARD;
+                e.flags |= FL_CRASH | FL_DONE;
+            }
+            if (c.es_has_max_distance_coef) {
+                float d = sqrtf(d2_f32(w.follower.px, w.follower.py, w.leader.px, w.leader.py));
+                if (d > cfg.es_far_f32) {
+                    mission = FTL_MISSION_FAIL; leader_st = FTL_LEADER_MOVING; agent = FTL_AGENT_TOO_FAR;
+                    e.flags |= FL_CRASH | FL_DONE;
+                }
+            }
+        }
+        // (9) reward + counters, ENV:1109-1139
+        double r = reward_of(c, e, too_close, in_box, on_trace);
+        if (r < 0) e.acc_penalty += r; else e.acc_penalty = 0;
+        e.overall += r;
+        e.step_count += 1;
+        if (e.step_count > c.max_steps) {
+            mission = FTL_MISSION_FINISHED_BY_TIME; leader_st = FTL_LEADER_MOVING; agent = FTL_AGENT_MOVING;
+            e.flags |= FL_DONE;
+        }
+        e.last_reward = c.aggregate_reward ? e.overall : r;
+        e.flags = (e.flags & (FL_DONE | FL_CRASH | FL_LEADER_FINISHED)) | (in_box ? FL_IN_BOX : 0) |
+                  (on_trace ? FL_ON_TRACE : 0) | (too_close ? FL_TOO_CLOSE : 0) | (mission << FL_MISSION_SHIFT) |
+                  (agent << FL_AGENT_SHIFT) | (leader_st << FL_LEADER_SHIFT);
+    }
+    sense_serial<NB>(cfg, s, i, w, t, &snap_pushes, &e.overflow);
+    cache_store(s, i, gc, t, snap_pushes);
+}
+
+// ---- action decode, ENV:918-925 -------------------------------------------------------------------------------
+FTL_HD void decode_action(const FtlConfig& c, const void* actions, int i, double* a0, double* a1) {
+    if (c.action_mode == FTL_ACTION_DISCRETE) {
+        int a = ((const int32_t*)actions)[i];
+        a = a < 0 ? 0 : a > 4 ? 4 : a;
+        *a0 = c.follower.max_speed;
+        *a1 = c.discrete_rotation_table[a];
+    } else if (c.action_mode == FTL_ACTION_CONST_SPEED) {
+        *a0 = c.const_speed_action;
+        *a1 = (double)((const float*)actions)[i];
+    } else {
+        *a0 = (double)((const float*)actions)[2 * (size_t)i];
+        *a1 = (double)((const float*)actions)[2 * (size_t)i + 1];
+    }
+}
+
+// the scenario an env moves to when nobody names one: same rule as the oracle's next_scenario()
+FTL_HD int next_scenario(const DevCfg& cfg, int n_scenarios, int i, int episode_count) {
+    int64_t g = cfg.env_id_base + i;
+    return (int)((g + (int64_t)episode_count * 7919) % n_scenarios);
+}
+
+}  // namespace ftl

@@ -252,6 +252,11 @@ int ftl_set_state(ftl_handle h, int32_t first_env, int32_t n, const FtlStateBuff
 int ftl_stats(ftl_handle h, double* stats_dev, int32_t reset_after, void* cuda_stream);
 /* Number of kernel launches issued by this handle so far (for bench.py's gpu_launches). */
 int64_t ftl_launch_count(ftl_handle h);
+/* Per-kernel device timing: while enabled, ftl_step records CUDA events on the launching stream around
+ * its two kernels; ftl_profile_read synchronises and returns the accumulated milliseconds of the fused
+ * step kernel and of the ray kernel over `steps` steps, then clears the accumulation. */
+int ftl_profile(ftl_handle h, int32_t enable);
+int ftl_profile_read(ftl_handle h, double* step_kernel_ms, double* ray_kernel_ms, int64_t* steps);
 
 #ifdef __cplusplus
 }

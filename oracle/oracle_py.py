@@ -42,29 +42,7 @@ def lib():
     return _LIB
 
 
-class HostOutputs:
-    """numpy buffers laid out as FtlOutputs."""
-
-    def __init__(self, n, rays_per_env):
-        self.numerical_features = np.zeros((n, 10), np.float32)
-        self.leader_target = np.zeros((n, 2), np.int32)
-        self.rays = np.zeros((n, max(rays_per_env, 1)), np.float32)
-        self.reward = np.zeros(n, np.float32)
-        self.done = np.zeros(n, np.uint8)
-        self.status = np.zeros((n, 4), np.uint8)
-        self.c = abi.FtlOutputs(abi.ptr(self.numerical_features), abi.ptr(self.leader_target), abi.ptr(self.rays),
-                                abi.ptr(self.reward), abi.ptr(self.done), abi.ptr(self.status))
-
-
-class HostState:
-    """numpy buffers laid out as FtlStateBuffers."""
-
-    def __init__(self, n, cfg):
-        self.env = np.zeros(n, abi.ENV_STATE_DTYPE)
-        self.trail = np.zeros((n, cfg.trail_cap, 2), np.float32)
-        self.hist = np.zeros((n, cfg.corridor_cap, 2), np.float64)
-        self.corridor = np.zeros((n, cfg.corridor_cap, 4), np.float32)
-        self.c = abi.FtlStateBuffers(abi.ptr(self.env), abi.ptr(self.trail), abi.ptr(self.hist), abi.ptr(self.corridor))
+from continiousenvironment_follower_leader_b200.capi import HostOutputs, HostState  # noqa: E402,F401
 
 
 class OracleEnv:

@@ -1,0 +1,218 @@
+"""GPU parity tests: libftl.so (CUDA, through the C-ABI) against the golden reference traces and the
+CPU oracle.  Run on the B200 box with `pytest -m gpu`.
+
+Bars (BASELINE.json north_star): collision/done/step-count and every other integer bit-exact;
+poses, rewards and ray distances within 1e-4 relative.  Ray values may additionally differ where a
+ray grazes a corner (the hit/no-hit predicate is discontinuous there); those are counted and must stay
+below 1e-4 of all ray values.
+"""
+import numpy as np
+import pytest
+
+import parity
+from continiousenvironment_follower_leader_b200 import abi, capi
+from continiousenvironment_follower_leader_b200.config import GameConfig, cfg3_sensors
+from continiousenvironment_follower_leader_b200.scenario import synthetic_pool
+
+pytestmark = pytest.mark.gpu
+
+FILES = parity.golden_files()
+
+
+def _cuda_env(gc, n, **kw):
+    return capi.HostEnv(gc, n, lib=capi.load(), **kw)   # raises if libftl.so is missing: no fallback
+
+
+@pytest.mark.parametrize("path", FILES, ids=[p.split("/")[-1][:-4] for p in FILES])
+def test_cuda_reproduces_reference_trace(path):
+    d, meta = parity.load_trace(path)
+    gc = parity.config_for(meta, _route_len=len(d["scen_route"]), _n_static=len(d["scen_static_rects"]))
+    env = _cuda_env(gc, 33)   # 33 copies: more than a warp, all must agree
+    env.upload_scenarios(parity.pool_for(d, gc))
+    n_vals = max(1, meta["n_env_steps"] * gc.rays_per_env)
+    budget = max(2, int(1e-4 * n_vals))
+    for idx in (0, 32):
+        T, outliers = parity.replay(env, d, gc, env_index=idx, float_rtol=parity.RTOL, ray_rtol=parity.RTOL,
+                                    ray_outlier_budget=budget)
+        assert T == meta["n_env_steps"]
+    parity.check_final_arrays(env.get_state(), d, gc, env_index=32)
+
+
+def _compare_states(a, b, gc, n, float_rtol):
+    """a: cuda HostState, b: oracle HostState.  Integers exact, floats within tolerance."""
+    ea, eb = a.env, b.env
+    int_fields = ["scenario_id", "cur_target_id", "leader_finished", "step_count", "finish_timer", "done", "crash",
+                  "is_in_box", "is_on_trace", "too_close", "mission_status", "agent_status", "leader_status",
+                  "trail_len", "saving_counter", "ring_tail", "ring_head", "hist_f64_end", "episode_count", "overflow",
+                  "accel_consumed"]
+    for f in int_fields:
+        assert np.array_equal(ea[f], eb[f]), "%s differs at envs %s" % (f, np.nonzero(ea[f] != eb[f])[0][:8])
+    robots = ["follower", "leader"]
+    for r in robots:
+        for f in ("rect", "rot_dir", "des_rot_dir"):
+            assert np.array_equal(ea[r][f], eb[r][f]), "%s.%s differs" % (r, f)
+        for f in ("pos", "dir", "speed", "rot_speed", "des_speed", "des_rot_speed"):
+            x, y = ea[r][f].astype(np.float64), eb[r][f].astype(np.float64)
+            assert np.all(np.abs(x - y) <= float_rtol * np.maximum(1, np.abs(y))), "%s.%s differs" % (r, f)
+    nb = gc.c.n_bears
+    if nb:
+        assert np.array_equal(ea["bear"]["rect"][:, :nb], eb["bear"]["rect"][:, :nb])
+        assert np.array_equal(ea["bear_index"][:, :nb], eb["bear_index"][:, :nb])
+        x, y = ea["bear"]["pos"][:, :nb].astype(np.float64), eb["bear"]["pos"][:, :nb].astype(np.float64)
+        assert np.all(np.abs(x - y) <= float_rtol * np.maximum(1, np.abs(y)))
+    for f in ("overall_reward", "accumulated_penalty", "last_reward"):
+        assert np.all(np.abs(ea[f] - eb[f]) <= float_rtol * np.maximum(1, np.abs(eb[f]))), f
+
+
+def _ray_outliers(got, want, rtol=parity.RTOL):
+    err = np.abs(got.astype(np.float64) - want.astype(np.float64))
+    return int(np.sum(err > rtol * np.maximum(1.0, np.abs(want))))
+
+
+@pytest.mark.parametrize("name,kwargs,n,steps", [
+    ("cfg2", dict(add_obstacles=False, add_bear=False,
+                  follower_sensors={"LeaderPositionsTracker_v2": cfg3_sensors()["LeaderPositionsTracker_v2"]}), 4096, 40),
+    ("cfg3", dict(bear_number=1, follower_sensors=cfg3_sensors()), 2048, 60),
+    ("cfg3_3bears_discrete", dict(bear_number=3, discrete_action_space=True, follower_sensors=cfg3_sensors(24, 20, 3)), 512, 40),
+])
+def test_cuda_matches_oracle_on_seeded_batch(name, kwargs, n, steps):
+    from oracle_py import OracleEnv
+    gc = GameConfig(**kwargs)
+    pool = synthetic_pool(gc, 64, seed=1)
+    cuda, orc = _cuda_env(gc, n), OracleEnv(gc, n, n_threads=8)
+    cuda.upload_scenarios(pool)
+    orc.upload_scenarios(pool)
+    ids = (np.arange(n) % pool.n).astype(np.int32)
+    oc, oo = cuda.reset(scenario_ids=ids), orc.reset(scenario_ids=ids)
+    rng = np.random.RandomState(7)
+    bounds = gc.action_bounds()
+    total_rays, bad_rays = 0, 0
+    for t in range(steps):
+        if gc.discrete_action_space:
+            a = rng.randint(0, 5, size=n).astype(np.int32)
+        else:
+            a = rng.uniform(bounds[0], bounds[1], size=(n, 2)).astype(np.float32)
+        oc, oo = cuda.step(a), orc.step(a)
+        assert np.array_equal(oc.done, oo.done), "done differs at step %d" % t
+        assert np.array_equal(oc.status, oo.status), "status differs at step %d" % t
+        assert np.allclose(oc.reward, oo.reward, rtol=1e-5, atol=1e-6), "reward differs at step %d" % t
+        assert np.array_equal(oc.leader_target, oo.leader_target)
+        assert np.allclose(oc.numerical_features, oo.numerical_features, rtol=parity.RTOL, atol=1e-4)
+        if gc.rays_per_env:
+            bad_rays += _ray_outliers(oc.rays, oo.rays)
+            total_rays += oc.rays.size
+        if t % 10 == 9 or t == steps - 1:
+            _compare_states(cuda.get_state(), orc.get_state(), gc, n, parity.RTOL)
+    if total_rays:
+        assert bad_rays <= max(2, 1e-4 * total_rays), "%d of %d ray values outside tolerance" % (bad_rays, total_rays)
+
+
+def test_auto_reset_matches_oracle():
+    from oracle_py import OracleEnv
+    gc = GameConfig(bear_number=1, follower_sensors=cfg3_sensors(), max_steps=300, auto_reset=True)
+    pool = synthetic_pool(gc, 32, seed=3)
+    n = 256
+    cuda, orc = _cuda_env(gc, n), OracleEnv(gc, n, n_threads=8)
+    cuda.upload_scenarios(pool)
+    orc.upload_scenarios(pool)
+    cuda.reset()
+    orc.reset()
+    rng = np.random.RandomState(11)
+    lo, hi = gc.action_bounds()
+    dones = 0
+    for t in range(80):
+        a = rng.uniform(lo, hi, size=(n, 2)).astype(np.float32)
+        oc, oo = cuda.step(a), orc.step(a)
+        assert np.array_equal(oc.done, oo.done)
+        assert np.allclose(oc.numerical_features, oo.numerical_features, rtol=parity.RTOL, atol=1e-4)
+        dones += int(oc.done.sum())
+    assert dones > n            # every env finished at least once (max_steps=300 frames = 30 steps)
+    sa, sb = cuda.get_state(), orc.get_state()
+    assert np.array_equal(sa.env["episode_count"], sb.env["episode_count"])
+    assert np.array_equal(sa.env["scenario_id"], sb.env["scenario_id"])
+    _compare_states(sa, sb, gc, n, parity.RTOL)
+
+
+def test_teacher_forced_state_injection():
+    """set_state(oracle state) then one step: single-step parity independent of trajectory history."""
+    from oracle_py import OracleEnv
+    gc = GameConfig(bear_number=1, follower_sensors=cfg3_sensors())
+    pool = synthetic_pool(gc, 16, seed=5)
+    n = 128
+    cuda, orc = _cuda_env(gc, n), OracleEnv(gc, n, n_threads=8)
+    cuda.upload_scenarios(pool)
+    orc.upload_scenarios(pool)
+    orc.reset()
+    cuda.reset()
+    rng = np.random.RandomState(2)
+    lo, hi = gc.action_bounds()
+    for t in range(25):
+        orc.step(rng.uniform(lo, hi, size=(n, 2)).astype(np.float32))
+    cuda.set_state(orc.get_state())
+    for t in range(5):
+        a = rng.uniform(lo, hi, size=(n, 2)).astype(np.float32)
+        oc, oo = cuda.step(a), orc.step(a)
+        assert np.array_equal(oc.done, oo.done)
+        assert _ray_outliers(oc.rays, oo.rays) <= 2
+        _compare_states(cuda.get_state(), orc.get_state(), gc, n, parity.RTOL)
+
+
+def test_full_size_properties():
+    """BASELINE.json configs[2] size (65536 envs): determinism, slice invariance, output ranges."""
+    import torch
+    from continiousenvironment_follower_leader_b200.batch_env import FtlBatchEnv
+    gc = GameConfig(bear_number=1, follower_sensors=cfg3_sensors(), auto_reset=True)
+    pool = synthetic_pool(gc, 128, seed=0)
+    n = 65536
+
+    def run(n_envs, base):
+        env = FtlBatchEnv(n_envs, game_config=gc, scenario_pool=pool, env_id_base=base)
+        env.reset()
+        g = torch.Generator(device="cuda").manual_seed(1)
+        lo, hi = [torch.tensor(x, device="cuda") for x in gc.action_bounds()]
+        acts = lo + (hi - lo) * torch.rand((20, n, 2), generator=g, device="cuda")
+        for t in range(20):
+            obs, rew, done, info = env.step(acts[t, base:base + n_envs].contiguous())
+        out = {k: v.clone() for k, v in obs.items()}
+        out["reward"], out["done"] = rew.clone(), done.clone()
+        st = env.get_state(0, min(n_envs, 512))
+        env.close()
+        return out, st
+
+    a, sa = run(n, 0)
+    b, sb = run(n, 0)
+    for k in a:
+        assert torch.equal(a[k], b[k]), "non-deterministic: " + k
+    c, sc = run(4096, 8192)     # a slice of the batch run on its own must give the same results
+    for k in a:
+        assert torch.equal(a[k][8192:8192 + 4096], c[k]), "batch composition changed results: " + k
+    for name, off, h, w in gc.ray_layout():
+        L = [r.laser_length for r in gc.c.ray[:gc.c.n_ray_sensors]][[x[0] for x in gc.ray_layout()].index(name)]
+        v = a[name]
+        assert float(v.min()) > 0 and float(v.max()) <= L * (1 + 1e-6)
+    nf = a["numerical_features"]
+    assert torch.isfinite(nf).all()
+    assert int(sa.env["overflow"].max()) == 0
+
+
+def test_device_and_host_entry_points_agree():
+    import torch
+    from continiousenvironment_follower_leader_b200.batch_env import FtlBatchEnv
+    gc = GameConfig(bear_number=1, follower_sensors=cfg3_sensors())
+    pool = synthetic_pool(gc, 8, seed=2)
+    n = 300
+    dev = FtlBatchEnv(n, game_config=gc, scenario_pool=pool)
+    host = _cuda_env(gc, n)
+    host.upload_scenarios(pool)
+    dev.reset()
+    host.reset()
+    rng = np.random.RandomState(0)
+    lo, hi = gc.action_bounds()
+    for t in range(12):
+        a = rng.uniform(lo, hi, size=(n, 2)).astype(np.float32)
+        obs, rew, done, info = dev.step(torch.from_numpy(a).cuda())
+        oh = host.step(a)
+        assert np.array_equal(obs["numerical_features"].cpu().numpy(), oh.numerical_features)
+        assert np.array_equal(dev.rays.cpu().numpy(), oh.rays)
+        assert np.array_equal(rew.cpu().numpy(), oh.reward)
+    assert dev.launch_count >= 24

@@ -1,0 +1,54 @@
+"""Device functions (host build) against the oracle on seeded synthetic batches, on the CPU: the same
+checks tests/test_gpu_parity.py applies to the CUDA build, at sizes that finish in seconds."""
+import numpy as np
+import pytest
+
+import parity
+from continiousenvironment_follower_leader_b200.config import GameConfig, cfg3_sensors, TEST_GAME_MANUAL_GAZEBO_KWARGS
+from continiousenvironment_follower_leader_b200.scenario import synthetic_pool
+from hostsim_py import make_env
+from oracle_py import OracleEnv
+from test_gpu_parity import _compare_states, _ray_outliers
+
+CASES = [
+    ("cfg2", dict(add_obstacles=False, add_bear=False,
+                  follower_sensors={"LeaderPositionsTracker_v2": cfg3_sensors()["LeaderPositionsTracker_v2"]}), 96, 60),
+    ("cfg3", dict(bear_number=1, follower_sensors=cfg3_sensors()), 96, 80),
+    ("cfg3_3bears_discrete", dict(bear_number=3, discrete_action_space=True, follower_sensors=cfg3_sensors(24, 20, 3)), 48, 50),
+    ("cfg3_autoreset", dict(bear_number=1, follower_sensors=cfg3_sensors(), max_steps=200, auto_reset=True), 64, 70),
+    ("gazebo_ranges", dict(TEST_GAME_MANUAL_GAZEBO_KWARGS, max_steps=600, auto_reset=True), 48, 150),
+]
+
+
+@pytest.mark.parametrize("name,kwargs,n,steps", CASES, ids=[c[0] for c in CASES])
+def test_hostsim_matches_oracle(name, kwargs, n, steps):
+    gc = GameConfig(**kwargs)
+    pool = synthetic_pool(gc, 24, seed=1)
+    sim, orc = make_env(gc, n), OracleEnv(gc, n, n_threads=4)
+    sim.upload_scenarios(pool)
+    orc.upload_scenarios(pool)
+    ids = (np.arange(n) % pool.n).astype(np.int32)
+    sim.reset(scenario_ids=ids)
+    orc.reset(scenario_ids=ids)
+    rng = np.random.RandomState(7)
+    bounds = gc.action_bounds()
+    bad, total = 0, 0
+    for t in range(steps):
+        if gc.discrete_action_space:
+            a = rng.randint(0, 5, size=n).astype(np.int32)
+        else:
+            a = rng.uniform(bounds[0], bounds[1], size=(n, 2)).astype(np.float32)
+            if t % 3 == 0:      # keep some followers moving straight so they stay near the trail
+                a[: n // 2, 0], a[: n // 2, 1] = bounds[1][0], 0.0
+        os_, oo = sim.step(a), orc.step(a)
+        assert np.array_equal(os_.done, oo.done), "done differs at step %d" % t
+        assert np.array_equal(os_.status, oo.status)
+        assert np.array_equal(os_.reward, oo.reward)
+        assert np.array_equal(os_.leader_target, oo.leader_target)
+        assert np.array_equal(os_.numerical_features, oo.numerical_features)
+        if gc.rays_per_env:
+            bad += _ray_outliers(os_.rays, oo.rays)
+            total += os_.rays.size
+        _compare_states(sim.get_state(), orc.get_state(), gc, n, 0.0)
+    assert bad == 0, "%d of %d ray values outside tolerance" % (bad, total)
+    assert int(sim.get_state().env["overflow"].max()) == 0
