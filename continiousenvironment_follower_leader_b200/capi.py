@@ -110,7 +110,6 @@ def pinned_alloc(shape, dtype):
     t = torch.empty(tuple(int(x) for x in shape), dtype=getattr(torch, np.dtype(dtype).name)).pin_memory()
     t.zero_()
     a = t.numpy()
-    a._ftl_keepalive = t if hasattr(a, "__dict__") else None  # numpy arrays take no attributes; keep below
     return a, t
 
 
