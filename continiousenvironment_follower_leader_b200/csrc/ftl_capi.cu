@@ -27,18 +27,14 @@ using namespace ftl;
 // kernels
 // =================================================================================================
 __global__ void __launch_bounds__(128)
-k_rays(const __grid_constant__ DevCfg cfg, const DevState s, const DevPool pool, float* __restrict__ rays_out,
-       int rays_total) {
-    long long flat = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    int i = (int)(flat / rays_total);
-    if (i >= s.n) return;
-    int sensor, k, offset;
-    if (!locate_ray(cfg.c, (int)(flat % rays_total), &sensor, &k, &offset)) return;
-    RayEnv re;
-    ray_env_load(s, i, re);
-    float rows[FTL_MAX_HIST];
-    cast_ray(cfg, s, pool, i, re, cfg.c.ray[sensor], k, rows);
-    store_ray_rows(cfg.c.ray[sensor], rays_out + (size_t)i * cfg.rays_per_env + offset, k, rows);
+k_rays(const __grid_constant__ DevCfg cfg, const DevState s, const DevPool pool, const double2* __restrict__ rot,
+       float* __restrict__ rays_out, int smem_per_warp) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warp = threadIdx.x >> 5;
+    const int i = blockIdx.x * (blockDim.x >> 5) + warp;  // one warp per env
+    if (i >= s.n_real) return;
+    RayShared& sh = *reinterpret_cast<RayShared*>(smem + (size_t)warp * smem_per_warp);
+    rays_warp(cfg, s, pool, rot, i, sh, rays_out);
 }
 
 // ---- state exchange: SoA <-> FtlEnvState (AoS) ----------------------------------------------------
@@ -72,7 +68,7 @@ static int fail(int code, const std::string& msg) {
 
 struct FtlHandle_ {
     DevCfg cfg;
-    int n = 0, device = 0;
+    int n = 0, n_pad = 0, device = 0;
     int n_robots = 2;
     DevState st{};
     DevPool pool{};
@@ -88,6 +84,8 @@ struct FtlHandle_ {
     int state_stage_cap = 0;
     int64_t launches = 0;
     int rays_total = 0;
+    bool rays_smem_opted = false;
+    double2* d_rot = nullptr;   // (cos, sin)(k * 360/R) per flat ray
     // optional per-kernel timing (ftl_profile): three events per step on the launching stream
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;
@@ -103,6 +101,16 @@ static cudaEvent_t prof_event(FtlHandle_* h, cudaStream_t st) {
     cudaEvent_t e = h->prof_events[h->prof_used++];
     cudaEventRecord(e, st);
     return e;
+}
+
+static std::vector<double2> ray_rotation_table(const FtlConfig& c) {
+    std::vector<double2> rot;
+    for (int s = 0; s < c.n_ray_sensors; s++)
+        for (int k = 0; k < c.ray[s].lasers_count; k++) {
+            double th = (k * (360.0 / c.ray[s].lasers_count)) * kDeg2Rad;
+            rot.push_back(make_double2(std::cos(th), std::sin(th)));
+        }
+    return rot;
 }
 
 static float sq_threshold(double limit) {
@@ -161,8 +169,9 @@ static int validate(const FtlConfig* c, int n_envs) {
     return FTL_OK;
 }
 
-static DevOutputs to_dev_outputs(const FtlOutputs* o) {
+static DevOutputs to_dev_outputs(const FtlOutputs* o, int n_real) {
     DevOutputs d{};
+    d.n = n_real;
     if (o) {
         d.numerical_features = o->numerical_features; d.leader_target = o->leader_target; d.rays = o->rays;
         d.reward = o->reward; d.done = o->done; d.status = o->status;
@@ -172,10 +181,15 @@ static DevOutputs to_dev_outputs(const FtlOutputs* o) {
 
 static int launch_rays(ftl_handle h, float* rays, cudaStream_t st) {
     if (!rays || h->rays_total == 0) return FTL_OK;
-    long long total = (long long)h->n * h->rays_total;
-    int threads = 128;
-    long long blocks = (total + threads - 1) / threads;
-    k_rays<<<(unsigned)blocks, threads, 0, st>>>(h->cfg, h->st, h->pool, rays, h->rays_total);
+    const int warps = 4, threads = warps * 32;
+    const int per_warp = (int)((ray_shared_bytes(h->rays_total) + 15) & ~(size_t)15);
+    const int smem = per_warp * warps;
+    if (smem > 48 * 1024 && !h->rays_smem_opted) {
+        CUDA_TRY(cudaFuncSetAttribute(k_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        h->rays_smem_opted = true;
+    }
+    int blocks = (h->n + warps - 1) / warps;
+    k_rays<<<blocks, threads, smem, st>>>(h->cfg, h->st, h->pool, h->d_rot, rays, per_warp);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return FTL_OK;
@@ -241,6 +255,9 @@ int ftl_create(const FtlConfig* cfg, int32_t n_envs, int32_t device, int64_t env
     d.rays_per_env = 0;
     for (int s = 0; s < c.n_ray_sensors; s++) d.rays_per_env += sensor_width(c.ray[s]);
     h->rays_total = total_rays(c);
+    d.rays_total = h->rays_total;
+    d.eps_f32 = (float)c.leader_pos_epsilon;
+    d.dev_f32 = (float)c.max_dev;
     d.eps2_f32 = sq_threshold(c.leader_pos_epsilon);
     d.dev2_f32 = sq_threshold(c.max_dev);
     d.min_dist2_f32 = sq_threshold(c.min_distance);
@@ -256,11 +273,13 @@ int ftl_create(const FtlConfig* cfg, int32_t n_envs, int32_t device, int64_t env
     d.static_inflate[0] = inflate(c.follower);
     d.static_inflate[1] = inflate(c.leader);
 
-    const size_t n = n_envs;
+    h->n_pad = (n_envs + 31) & ~31;   // whole warps: the step kernel uses warp-wide collectives
+    const size_t n = h->n_pad;
     const int nb = c.n_bears, nr = 2 + nb;
     h->n_robots = nr;
     DevState& s = h->st;
-    s.n = n_envs;
+    s.n = h->n_pad;
+    s.n_real = n_envs;
     s.n_bears = nb;
     cudaError_t e = cudaSuccess;
     auto ok = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
@@ -274,15 +293,23 @@ int ftl_create(const FtlConfig* cfg, int32_t n_envs, int32_t device, int64_t env
     ok(dalloc(h, &s.pos, (size_t)nr * n));
     ok(dalloc(h, &s.rect, (size_t)nr * n));
     ok(dalloc(h, &s.trail, n * c.trail_cap));
+    ok(dalloc(h, &s.trail_d, n * c.trail_cap));
+    ok(dalloc(h, &s.trail_s, n * c.trail_cap));
     ok(dalloc(h, &s.hist, n * c.corridor_cap));
     ok(dalloc(h, &s.corridor, n * c.corridor_cap));
     ok(dalloc(h, &s.snap_range, (size_t)FTL_MAX_HIST * n));
     ok(dalloc(h, &s.snap_rect, (size_t)FTL_MAX_HIST * (1 + nb) * n));
     ok(dalloc(h, &h->d_stats, (size_t)FTL_STAT_COUNT));
+    ok(dalloc(h, &h->d_rot, (size_t)h->rays_total));
+    if (e == cudaSuccess && h->rays_total > 0) {
+        std::vector<double2> rot = ray_rotation_table(c);
+        ok(cudaMemcpy(h->d_rot, rot.data(), sizeof(double2) * rot.size(), cudaMemcpyHostToDevice));
+    }
     size_t action_bytes = c.action_mode == FTL_ACTION_CONTINUOUS ? 8 : 4;
     ok(dalloc(h, (char**)&h->d_actions, action_bytes * n));
     ok(dalloc(h, &h->d_mask, n));
     ok(dalloc(h, &h->d_scen_ids, n));
+    h->d_out.n = n_envs;
     ok(dalloc(h, &h->d_out.numerical_features, 10 * n));
     ok(dalloc(h, &h->d_out.leader_target, 2 * n));
     ok(dalloc(h, &h->d_out.rays, (size_t)(d.rays_per_env ? d.rays_per_env : 1) * n));
@@ -362,13 +389,14 @@ int ftl_reset(ftl_handle h, const uint8_t* mask_dev, const int32_t* scenario_ids
     if (!h->have_pool) return fail(FTL_ERR_STATE, "ftl_upload_scenarios must be called before ftl_reset");
     CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    DevOutputs o = to_dev_outputs(out_dev);
+    DevOutputs o = to_dev_outputs(out_dev, h->n);
+    const int reset_filler = (!mask_dev || !h->was_reset) ? 1 : 0;
     switch (h->cfg.c.n_bears) {
-        case 0: ftl_launch_reset_nb0(h->cfg, h->st, h->pool, mask_dev, scenario_ids_dev, o, st); break;
-        case 1: ftl_launch_reset_nb1(h->cfg, h->st, h->pool, mask_dev, scenario_ids_dev, o, st); break;
-        case 2: ftl_launch_reset_nb2(h->cfg, h->st, h->pool, mask_dev, scenario_ids_dev, o, st); break;
-        case 3: ftl_launch_reset_nb3(h->cfg, h->st, h->pool, mask_dev, scenario_ids_dev, o, st); break;
-        default: ftl_launch_reset_nb4(h->cfg, h->st, h->pool, mask_dev, scenario_ids_dev, o, st); break;
+        case 0: ftl_launch_reset_nb0(h->cfg, h->st, h->pool, mask_dev, scenario_ids_dev, o, reset_filler, st); break;
+        case 1: ftl_launch_reset_nb1(h->cfg, h->st, h->pool, mask_dev, scenario_ids_dev, o, reset_filler, st); break;
+        case 2: ftl_launch_reset_nb2(h->cfg, h->st, h->pool, mask_dev, scenario_ids_dev, o, reset_filler, st); break;
+        case 3: ftl_launch_reset_nb3(h->cfg, h->st, h->pool, mask_dev, scenario_ids_dev, o, reset_filler, st); break;
+        default: ftl_launch_reset_nb4(h->cfg, h->st, h->pool, mask_dev, scenario_ids_dev, o, reset_filler, st); break;
     }
     h->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -381,7 +409,7 @@ int ftl_step(ftl_handle h, const void* actions_dev, const FtlOutputs* out_dev, v
     if (!h->was_reset) return fail(FTL_ERR_STATE, "ftl_reset must be called before ftl_step");
     CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    DevOutputs o = to_dev_outputs(out_dev);
+    DevOutputs o = to_dev_outputs(out_dev, h->n);
     if (h->profiling) prof_event(h, st);
     switch (h->cfg.c.n_bears) {
         case 0: ftl_launch_step_nb0(h->cfg, h->st, h->pool, actions_dev, o, h->d_stats, st); break;

@@ -40,6 +40,13 @@ static inline int2 make_int2(int x, int y) { return int2{x, y}; }
 static inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
 #endif
 
+#if defined(FTL_COUNT_RESCANS) && !defined(__CUDA_ARCH__)
+extern long long g_ftl_counters[8];   // test-only instrumentation (tests/hostsim)
+#define FTL_COUNT(k, v) (g_ftl_counters[k] += (v))
+#else
+#define FTL_COUNT(k, v) ((void)0)
+#endif
+
 namespace ftl {
 
 constexpr int kMaxRobots = 2 + FTL_MAX_BEARS;  // follower, leader, bears
@@ -53,9 +60,9 @@ enum GlobalI32 {
     GI_STEP_COUNT, GI_TARGET_ID, GI_FINISH_TIMER, GI_FLAGS, GI_TRAIL_LEN, GI_SAVING_COUNTER, GI_RING_TAIL,
     GI_RING_HEAD, GI_HIST_F64_END, GI_SNAP_PUSHES, GI_SCENARIO, GI_EPISODE, GI_OVERFLOW, GI_ACCEL_CONSUMED,
     // derived caches (not part of FtlEnvState; invalidated by set_state/reset)
-    GI_G_LO, GI_A_STAR, GI_B_STAR, GI_COUNT
+    GI_G_LO, GI_G_UNC, GI_A_STAR, GI_B_STAR, GI_NICE_FROM, GI_COUNT
 };
-enum GlobalF32 { GF_LB_GREEN, GF_LB_ALL, GF_COUNT };
+enum GlobalF32 { GF_LB_GREEN, GF_LB_ALL, GF_SCAN_GX, GF_SCAN_GY, GF_SCAN_AX, GF_SCAN_AY, GF_COUNT };
 
 // flag bits of GI_FLAGS
 enum {
@@ -64,7 +71,8 @@ enum {
 };
 
 struct DevState {
-    int n;
+    int n;             // padded to a multiple of 32 (array stride and grid size); envs >= n_real are filler
+    int n_real;        // environments the caller sees
     int n_bears;
     double* gd;        // [GD_COUNT][n]
     double* rd;        // [2+n_bears][RD_COUNT][n]
@@ -76,6 +84,8 @@ struct DevState {
     float2* pos;       // [2+n_bears][n]
     int4* rect;        // [2+n_bears][n]
     float2* trail;     // [n][trail_cap]
+    float* trail_d;    // [n][trail_cap]  float32 distance to the previous trail point (the reference's term)
+    double* trail_s;   // [n][trail_cap]  cumulative arc length in float64 (derived; decides the green window)
     double2* hist;     // [n][corridor_cap]
     float4* corridor;  // [n][corridor_cap]   (right.x, right.y, left.x, left.y)
     int2* snap_range;  // [FTL_MAX_HIST][n]   ring slot = push index % FTL_MAX_HIST
@@ -95,6 +105,7 @@ struct DevPool {  // scenario pool in device (or host, for hostsim) memory
 };
 
 struct DevOutputs {
+    int n;  // number of real envs: rows >= n are never written
     float* numerical_features;
     int* leader_target;
     float* rays;
@@ -108,9 +119,11 @@ struct DevCfg {
     FtlConfig c;
     int64_t env_id_base;
     int rays_per_env;
+    int rays_total;              // number of rays over all sensors
     // float32 thresholds on SQUARED distances, exactly equivalent to the reference's comparisons of
     // float32 square roots (largest x with sqrtf(x) <= (float)limit)
     float eps2_f32, dev2_f32, min_dist2_f32;
+    float eps_f32, dev_f32;      // (float)leader_pos_epsilon, (float)max_dev
     float max_distance_f32;      // (float)max_distance for the green-zone walk
     float es_far_f32;            // (float)(max_distance * max_distance_coef)
     float trail_seed_denom_f32;  // (float)(trajectory_saving_period * leader.max_speed)
@@ -346,37 +359,70 @@ FTL_HD bool collide_static_masked(const Robot& r, const int4* rects, uint64_t ma
 // A full scan (bit-identical arithmetic to the reference) is only done when the bounds cannot decide a
 // comparison, so the flags are always exactly those of the reference.
 struct GreenCache {
-    int g_lo;      // first green trail index; green = [g_lo, trail_len-2]
+    int g_lo;      // first trail index that is CERTAINLY green; green = [g_lo - (0..g_unc), trail_len-2]
+    int g_unc;     // how many points just below g_lo could not be decided without the exact float32 walk
     int a_star;    // witness for the green minimum (-1 = none)
     int b_star;    // witness for the whole-trail minimum (-1 = none)
-    float lb_g;    // lower bound of min distance follower -> green points (negative = unknown)
-    float lb_all;  // lower bound of min distance follower -> all trail points
+    float lb_g;    // lower bound of the distance from (sgx, sgy) to every green point (negative = unknown)
+    float lb_all;  // lower bound of the distance from (sax, say) to every trail point
+    float sgx, sgy, sax, say;  // follower positions at the last full scans
+    int nice_from;  // all trail_d[k], k >= nice_from, are multiples of 2^-15 (exact float32 sums)
 };
 
 constexpr float kBoundSlack = 2e-3f;  // covers float32 rounding of positions/distances up to ~4000 px
 
-// _trajectory_in_box, ENV:1828-1843 (float32 accumulation from the newest point backwards)
-FTL_HD int green_lo(const float2* trail, int n, float max_distance_f32) {
+// _trajectory_in_box, ENV:1828-1843, literally: float32 accumulation of the stored segment lengths from
+// the newest point backwards.  trail_d[k] = float32 |trail[k] - trail[k-1]|.
+FTL_HD int green_lo_exact(const float* trail_d, int n, float max_distance_f32) {
     int lo = n - 1;  // empty
     float acc = 0.f;
-    float2 newer = n > 0 ? trail[n - 1] : make_float2(0.f, 0.f);
+    FTL_COUNT(2, 1);
     for (int i = n - 2; i >= 0; i--) {
-        float2 p = trail[i];
-        acc = acc + sqrtf(d2_f32(newer.x, newer.y, p.x, p.y));
+        acc = acc + trail_d[i + 1];
         if (acc <= max_distance_f32)
             lo = i;
         else
             break;
-        newer = p;
     }
     return lo;
 }
 
+// The same index without the walk: the float32 running sum differs from the float64 cumulative length by at
+// most (#terms) * 0.5 ulp, so membership is decided from trail_s unless a point is that close to the threshold.
+// Such points (the leader covers 1.25 px per saved point and max_distance is 160 of those, so near-ties are the
+// rule on straight stretches) are kept as "uncertain" and only resolved with the exact walk if the flags ever
+// depend on them.  The window start only moves forward (float addition is monotone).
+FTL_HD void green_window_update(const double* trail_s, int n, float max_distance_f32, int nice_from, int* g_lo,
+                                int* g_unc) {
+    if (n < 2) { *g_lo = n - 1; *g_unc = 0; return; }
+    const double maxd = (double)max_distance_f32;
+    const double total = trail_s[n - 1];
+    int lo = *g_lo - *g_unc;
+    if (lo < 0) lo = 0;
+    int first_unc = -1;
+    for (; lo <= n - 2; lo++) {
+        double len = total - trail_s[lo];
+        double err = (double)(n - 1 - lo) * maxd * 1.2e-7 + 1e-9;
+        if (lo + 1 >= nice_from && maxd < 512.0) {
+            // every term of this window is a multiple of 2^-15 and the sum stays below 2^9: the float32
+            // running sum is exact, so the float64 length (snapped to the grid) decides, ties included
+            len = rint(len * 32768.0) * (1.0 / 32768.0);
+            err = 0.0;
+        }
+        if (len > maxd + err) continue;                                   // certainly outside
+        if (len > maxd - err) { if (first_unc < 0) first_unc = lo; continue; }  // too close to call
+        break;                                                            // certainly inside
+    }
+    *g_lo = lo;   // n-1 when nothing is certainly inside
+    *g_unc = first_unc < 0 ? 0 : lo - first_unc;
+}
+
 FTL_HD float scan_min_d2(const float2* trail, int lo, int hi, float fx, float fy, int* arg) {
-    // min over [lo, hi] of the reference's float32 squared distance; first minimum in the reference's
-    // list order does not matter for the value
+    // min over [lo, hi] of the reference's float32 squared distance
     float best = 3.0e38f;
     int bi = -1;
+    FTL_COUNT(0, 1);
+    FTL_COUNT(1, hi - lo + 1);
     for (int i = hi; i >= lo; i--) {
         float2 p = trail[i];
         float d2 = d2_f32(p.x, p.y, fx, fy);
@@ -386,84 +432,178 @@ FTL_HD float scan_min_d2(const float2* trail, int lo, int hi, float fx, float fy
     return best;
 }
 
-// returns 1 if min <= thr, 0 if min > thr, -1 if the bounds cannot tell
-FTL_HD int bound_decide(float ub2, float lb, float thr2) {
+// 1: min <= thr, 0: min > thr, -1: the bounds cannot tell.  ub2: squared distance to a witness inside the
+// set; lb: lower bound of the distances from the scan position; disp2: squared displacement since that scan.
+FTL_HD int bound_decide(float ub2, float lb, float disp2, float thr, float thr2) {
     if (ub2 <= thr2) return 1;
-    if (lb > 0.f) {
-        float l2 = lb * lb * 0.999999f;
-        if (l2 > thr2) return 0;
-    }
+    float m = lb - thr - kBoundSlack;
+    if (m > 0.f && m * m > disp2 * 1.0001f) return 0;
     return -1;
 }
 
-FTL_HD void green_flags(const DevCfg& cfg, const float2* trail, int n, float fx, float fy, GreenCache& gc,
-                        bool* in_box, bool* on_trace) {  // ENV:1906-1931
-    *in_box = false;
-    *on_trace = false;
-    int hi = n - 2;
-    int n_green = hi - gc.g_lo + 1;
-    if (n_green <= 2) return;
-    // upper bound from the witness
-    float ub2 = 3.0e38f;
-    if (gc.a_star >= gc.g_lo && gc.a_star <= hi) {
-        float2 p = trail[gc.a_star];
-        ub2 = d2_f32(p.x, p.y, fx, fy);
+// Full scans are requested, not performed, by the per-thread logic: on the GPU the 32 lanes of a warp serve
+// each request together (coalesced loads, ~60 warp instructions instead of a ~200-iteration serial loop in one
+// lane while 31 wait); the host build runs the same arithmetic serially.
+FTL_HD float warp_scan_min(bool need, const float2* trail, int lo, int hi, float fx, float fy, int* arg) {
+#if defined(__CUDA_ARCH__)
+    const unsigned full = 0xffffffffu;
+    const int lane = (int)(threadIdx.x & 31);
+    unsigned pending = __ballot_sync(full, need);
+    float my_best = 3.0e38f;
+    int my_arg = -1;
+    while (pending) {
+        const int src = __ffs((int)pending) - 1;
+        pending &= pending - 1;
+        const float2* t = (const float2*)(uintptr_t)__shfl_sync(full, (unsigned long long)(uintptr_t)trail, src);
+        const int blo = __shfl_sync(full, lo, src), bhi = __shfl_sync(full, hi, src);
+        const float bfx = __shfl_sync(full, fx, src), bfy = __shfl_sync(full, fy, src);
+        float best = 3.0e38f;
+        int bi = -1;
+        for (int k = bhi - lane; k >= blo; k -= 32) {
+            float2 p = t[k];
+            float d2 = d2_f32(p.x, p.y, bfx, bfy);
+            if (d2 < best) { best = d2; bi = k; }
+        }
+#pragma unroll
+        for (int off = 16; off; off >>= 1) {
+            float ob = __shfl_xor_sync(full, best, off);
+            int oi = __shfl_xor_sync(full, bi, off);
+            if (ob < best || (ob == best && oi > bi)) { best = ob; bi = oi; }
+        }
+        if (lane == src) { my_best = best; my_arg = bi; }
     }
-    int le_eps = bound_decide(ub2, gc.lb_g, cfg.eps2_f32);
-    int le_dev = le_eps == 1 ? 1 : bound_decide(ub2, gc.lb_g, cfg.dev2_f32);
-    if (le_eps < 0 || (le_eps == 0 && le_dev < 0)) {
-        float m = scan_min_d2(trail, gc.g_lo, hi, fx, fy, &gc.a_star);
-        gc.lb_g = sqrtf(m) - kBoundSlack;
-        le_eps = m <= cfg.eps2_f32;
-        le_dev = m <= cfg.dev2_f32;
-    }
-    if (le_eps == 1) {
-        *in_box = true;
-        *on_trace = true;
-        return;
-    }
-    if (le_dev == 1) {
-        *in_box = true;
-        return;
-    }
-    // whole-trail fallback, ENV:1924-1931
-    float ub2a = 3.0e38f;
-    if (gc.b_star >= 0 && gc.b_star < n) {
-        float2 p = trail[gc.b_star];
-        ub2a = d2_f32(p.x, p.y, fx, fy);
-    }
-    int le = bound_decide(ub2a, gc.lb_all, cfg.eps2_f32);
-    if (le < 0) {
-        float m = scan_min_d2(trail, 0, n - 1, fx, fy, &gc.b_star);
-        gc.lb_all = sqrtf(m) - kBoundSlack;
-        le = m <= cfg.eps2_f32;
-    }
-    *on_trace = le == 1;
+    *arg = my_arg;
+    return my_best;
+#else
+    if (!need) { *arg = -1; return 3.0e38f; }
+    return scan_min_d2(trail, lo, hi, fx, fy, arg);
+#endif
 }
 
-// bookkeeping of the cache when the follower moved by at most `moved` pixels
-FTL_HD void green_cache_moved(GreenCache& gc, float moved) {
-    gc.lb_g -= moved;
-    gc.lb_all -= moved;
+FTL_HD void green_resolve(const DevCfg& cfg, const float* trail_d, int n, GreenCache& gc) {
+    gc.g_lo = green_lo_exact(trail_d, n, cfg.max_distance_f32);
+    gc.g_unc = 0;
 }
-// ... and when the trail grew: trail[n-1] is new (n = new length).  trail[n-2] enters the green set.
-FTL_HD void green_cache_appended(const DevCfg& cfg, const float2* trail, int n, float fx, float fy, GreenCache& gc) {
-    gc.g_lo = green_lo(trail, n, cfg.max_distance_f32);
+
+FTL_HD void green_flags(const DevCfg& cfg, const float2* trail, const float* trail_d, int n, float fx, float fy,
+                        GreenCache& gc, bool* in_box, bool* on_trace) {  // ENV:1906-1931; all lanes of a warp call this
+    FTL_COUNT(3, 1);
+    const int hi = n - 2;
+    // len(green) > 2 ?  (only ambiguous in the first frames of an episode)
+    if (gc.g_unc > 0 && hi - gc.g_lo + 1 <= 2 && hi - gc.g_lo + 1 + gc.g_unc > 2) green_resolve(cfg, trail_d, n, gc);
+    const bool have_green = hi - gc.g_lo + 1 > 2;
+    int le_eps = 0, le_dev = 0;
+    bool need = false;
+    if (have_green) {
+        if (gc.a_star < gc.g_lo) gc.a_star = gc.g_lo;  // the witness left the window: its oldest certain point is the next guess
+        float ub2 = 3.0e38f;
+        if (gc.a_star <= hi) {
+            float2 p = trail[gc.a_star];
+            ub2 = d2_f32(p.x, p.y, fx, fy);
+        }
+        float disp2 = d2_f32(fx, fy, gc.sgx, gc.sgy);
+        le_eps = bound_decide(ub2, gc.lb_g, disp2, cfg.eps_f32, cfg.eps2_f32);
+        le_dev = le_eps == 1 ? 1 : bound_decide(ub2, gc.lb_g, disp2, cfg.dev_f32, cfg.dev2_f32);
+        need = le_eps < 0 || (le_eps == 0 && le_dev < 0);
+    }
+    {
+        int arg;
+        float m = warp_scan_min(need, trail, gc.g_lo, hi, fx, fy, &arg);
+        if (need) {
+            float m_low = m;   // lower bound material: certain and uncertain points together
+            for (int u = gc.g_lo - gc.g_unc; u < gc.g_lo; u++) {
+                float2 p = trail[u];
+                m_low = fminf(m_low, d2_f32(p.x, p.y, fx, fy));
+            }
+            if (m_low < m) {   // an undecided point would be the nearest one: now its membership matters
+                int old_lo = gc.g_lo;
+                green_resolve(cfg, trail_d, n, gc);
+                for (int u = gc.g_lo; u < old_lo; u++) {
+                    float2 p = trail[u];
+                    float d2 = d2_f32(p.x, p.y, fx, fy);
+                    if (d2 < m) { m = d2; arg = u; }
+                }
+                m_low = m;
+            }
+            gc.a_star = arg;
+            gc.lb_g = sqrtf(m_low) - kBoundSlack;
+            gc.sgx = fx; gc.sgy = fy;
+            le_eps = m <= cfg.eps2_f32;
+            le_dev = m <= cfg.dev2_f32;
+        }
+    }
+    // whole-trail fallback, ENV:1924-1931
+    const bool fallback = have_green && le_eps != 1 && le_dev != 1;
+    int le = 0;
+    need = false;
+    if (fallback) {
+        float ub2a = 3.0e38f;
+        if (gc.b_star >= 0 && gc.b_star < n) {
+            float2 p = trail[gc.b_star];
+            ub2a = d2_f32(p.x, p.y, fx, fy);
+        }
+        float disp2a = d2_f32(fx, fy, gc.sax, gc.say);
+        le = bound_decide(ub2a, gc.lb_all, disp2a, cfg.eps_f32, cfg.eps2_f32);
+        FTL_COUNT(4, 1);
+        need = le < 0;
+    }
+    {
+        int arg;
+        float m = warp_scan_min(need, trail, 0, n - 1, fx, fy, &arg);
+        if (need) {
+            FTL_COUNT(5, 1);
+            FTL_COUNT(6, n);
+            gc.b_star = arg;
+            gc.lb_all = sqrtf(m) - kBoundSlack;
+            gc.sax = fx; gc.say = fy;
+            le = m <= cfg.eps2_f32;
+        }
+    }
+    *in_box = have_green && (le_eps == 1 || le_dev == 1);
+    *on_trace = have_green && (le_eps == 1 || (fallback && le == 1));
+}
+
+// the trail grew: trail[n-1] is new (n = new length); trail[n-2] enters the green set.  New points are folded
+// into the bounds as distances from the respective scan positions.
+FTL_HD void green_cache_appended(const DevCfg& cfg, const float2* trail, const float* trail_d, const double* trail_s,
+                                 int n, GreenCache& gc) {
+    {
+        float d = trail_d[n - 1];
+        if (d * 32768.f != rintf(d * 32768.f)) gc.nice_from = n;  // term n-1 is not on the 2^-15 grid
+    }
+    green_window_update(trail_s, n, cfg.max_distance_f32, gc.nice_from, &gc.g_lo, &gc.g_unc);
     float2 p = trail[n - 1];
-    float d = sqrtf(d2_f32(p.x, p.y, fx, fy)) - kBoundSlack;
+    float d = sqrtf(d2_f32(p.x, p.y, gc.sax, gc.say)) - kBoundSlack;
     if (d < gc.lb_all) gc.lb_all = d;
     if (n >= 2) {
         float2 q = trail[n - 2];
-        float dq = sqrtf(d2_f32(q.x, q.y, fx, fy)) - kBoundSlack;
+        float dq = sqrtf(d2_f32(q.x, q.y, gc.sgx, gc.sgy)) - kBoundSlack;
         if (dq < gc.lb_g) gc.lb_g = dq;
     }
 }
-FTL_HD void green_cache_invalidate(const DevCfg& cfg, const float2* trail, int n, GreenCache& gc) {
-    gc.g_lo = green_lo(trail, n, cfg.max_distance_f32);
+FTL_HD void green_cache_invalidate(const DevCfg& cfg, const float* trail_d, int n, GreenCache& gc) {
+    gc.g_lo = green_lo_exact(trail_d, n, cfg.max_distance_f32);
+    gc.g_unc = 0;
+    gc.nice_from = n;  // conservative: nothing known about the existing terms
     gc.a_star = -1;
     gc.b_star = -1;
     gc.lb_g = -1.f;
     gc.lb_all = -1.f;
+    gc.sgx = gc.sgy = gc.sax = gc.say = 0.f;
+}
+
+// append one point to the trail and its derived arrays
+FTL_HD void trail_push(float2* trail, float* trail_d, double* trail_s, int k, float x, float y) {
+    trail[k] = make_float2(x, y);
+    if (k == 0) {
+        trail_d[0] = 0.f;
+        trail_s[0] = 0.0;
+    } else {
+        float2 prev = trail[k - 1];
+        float d = sqrtf(d2_f32(x, y, prev.x, prev.y));  // euclidean(newer, older) in float32, ENV:1838
+        trail_d[k] = d;
+        trail_s[k] = trail_s[k - 1] + (double)d;
+    }
 }
 
 // ---- Philox4x32-10 for list-valued speed regimes (same keying as the oracle) --------------------------------
@@ -488,8 +628,9 @@ struct Episode {
 };
 
 FTL_HD double reward_of(const FtlConfig& c, const Episode& e, bool too_close, bool in_box, bool on_trace) {  // ENV:1869-1904
-    double r = 0;
-    r += c.leader_movement_reward;
+    // (written as an initialisation, not as 0 + x: ptxas 12.9 -O3 dropped the zero initialiser of the
+    // accumulator in the NB=0 instantiation; tests/test_gpu_parity.py's no-bear golden trace guards this)
+    double r = c.leader_movement_reward;
     if (too_close) {
         r += c.too_close_penalty;
     } else {

@@ -6,14 +6,15 @@
 //     are cast ONCE per ray and merged into each valid history row; the corridor copies are sub-ranges
 //     [tail_j, head_j) of one ring, so every ring segment is cast once and merged into the rows whose
 //     range contains it.  Only the dynamic rectangles (leader + bears) and the end caps are cast per row.
-//   * static rectangles are culled with the ray's bounding box before their four edges are tested.
 //   * a history entry is stored by reference (ring range + dynamic rectangles), 8 + 16*(1+B) bytes instead
 //     of ~2.5 KB of edges.
+//   * edges are culled against the sensors' reach, rectangles reduced to their front-facing edges, and each
+//     surviving edge is only tested against the rays inside the angle it subtends from the follower.
 //
 // Arithmetic: float32, with the reference's own float32 operations reproduced where it uses float32
 // (edge vectors, the numerator of the intersection parameter, ccw(A,B,C)); the reference evaluates the
 // predicates that involve the ray end point in float64 -- here they are float32 cross products with
-// fused multiply-adds (documented tolerance: 1e-4 relative on the distances).
+// error-free products (documented tolerance: 1e-4 relative on the distances).
 #pragma once
 
 #include "ftl_device.cuh"
@@ -52,158 +53,370 @@ FTL_HD float seg_hit(float px, float py, float dx, float dy, float L, float ax, 
     return fabsf(t) * L;
 }
 
-FTL_HD float rect_hit(float px, float py, float dx, float dy, float L, int4 q, float lox, float hix, float loy,
-                      float hiy) {
-    float l = (float)q.x, t = (float)q.y, r = (float)(q.x + q.z), b = (float)(q.y + q.w);
-    if (r < lox || l > hix || b < loy || t > hiy) return kNoHit;  // outside the ray's bounding box
-    float m = seg_hit(px, py, dx, dy, L, l, b, r, b);             // SEN:668-671 edge order
-    m = fminf(m, seg_hit(px, py, dx, dy, L, r, t, r, b));
-    m = fminf(m, seg_hit(px, py, dx, dy, L, r, t, l, t));
-    m = fminf(m, seg_hit(px, py, dx, dy, L, l, b, l, t));
-    return m;
-}
-
-struct RayEnv {  // per-env inputs of the ray pass, loaded once
-    float px, py;
-    double dir;
-    int scenario, snap_pushes;
-};
-
-FTL_HD void ray_env_load(const DevState& s, int i, RayEnv& r) {
-    float2 p = s.pos[i];  // robot 0 = follower
-    r.px = p.x; r.py = p.y;
-    r.dir = s.rd[(size_t)RD_DIR * s.n + i];
-    r.scenario = s.gi[(size_t)GI_SCENARIO * s.n + i];
-    r.snap_pushes = s.gi[(size_t)GI_SNAP_PUSHES * s.n + i];
-}
-
-// One ray of one sensor of one env: writes H values (history rows, oldest first) into rows[].
-FTL_HD void cast_ray(const DevCfg& cfg, const DevState& s, const DevPool& pool, int i, const RayEnv& re,
-                     const FtlRaySensorConfig& sc, int k, float* rows) {
-    const FtlConfig& c = cfg.c;
-    const int H = sc.max_prev_obs;
-    const int NBr = s.n_bears;
-    const float L = (float)sc.laser_length;
-    double ang = (re.dir + sc.first_laser_angle_offset) + k * (360.0 / sc.lasers_count);
-    double sn, cs;
-    sincos_deg(ang, &sn, &cs);
-    const float dx = (float)(cs * sc.laser_length), dy = (float)(sn * sc.laser_length);
-    const float px = re.px, py = re.py;
-    const float lox = fminf(px, px + dx) - 1.f, hix = fmaxf(px, px + dx) + 1.f;
-    const float loy = fminf(py, py + dy) - 1.f, hiy = fmaxf(py, py + dy) + 1.f;
-
-    // history rows: row j has age H-1-j; valid once enough scans happened (SEN:964-968 seeds zeros)
-    int tail[FTL_MAX_HIST], head[FTL_MAX_HIST];
-    bool valid[FTL_MAX_HIST];
-    int min_tail = 0x7fffffff, max_head = -0x7fffffff;
-#pragma unroll
-    for (int j = 0; j < FTL_MAX_HIST; j++) {
-        rows[j] = kNoHit;
-        valid[j] = false;
-        tail[j] = head[j] = 0;
-        if (j < H) {
-            int age = H - 1 - j;
-            if (age < re.snap_pushes) {
-                int slot = (re.snap_pushes - 1 - age) % FTL_MAX_HIST;
-                int2 rg = s.snap_range[(size_t)slot * s.n + i];
-                tail[j] = rg.x; head[j] = rg.y;
-                valid[j] = true;
-                min_tail = rg.x < min_tail ? rg.x : min_tail;
-                max_head = rg.y > max_head ? rg.y : max_head;
-            }
-        }
-    }
-    const int mode = sc.react_to_obstacles;
-    // ---- static rectangles: once for all rows ------------------------------------------------------------
-    if (mode == FTL_REACT_ALL || mode == FTL_REACT_STATIC) {
-        const int4* statics = pool.static_rects + (size_t)re.scenario * c.static_cap;
-        const int n_static = pool.n_static[re.scenario];
-        float m = kNoHit;
-        for (int q = 0; q < n_static; q++) m = fminf(m, rect_hit(px, py, dx, dy, L, statics[q], lox, hix, loy, hiy));
-#pragma unroll
-        for (int j = 0; j < FTL_MAX_HIST; j++)
-            if (valid[j]) rows[j] = fminf(rows[j], m);
-    }
-    // ---- dynamic rectangles: per row (leader belongs to game_object_list: ALL and STATIC) -----------------
-#pragma unroll
-    for (int j = 0; j < FTL_MAX_HIST; j++) {
-        if (!valid[j]) continue;
-        int age = H - 1 - j;
-        int slot = (re.snap_pushes - 1 - age) % FTL_MAX_HIST;
-        const int4* sr = s.snap_rect + ((size_t)slot * (1 + NBr)) * s.n + i;
-        if (mode == FTL_REACT_ALL || mode == FTL_REACT_STATIC)
-            rows[j] = fminf(rows[j], rect_hit(px, py, dx, dy, L, sr[0], lox, hix, loy, hiy));
-        if (mode == FTL_REACT_ALL || mode == FTL_REACT_DYNAMIC)
-            for (int b = 0; b < NBr; b++)
-                rows[j] = fminf(rows[j], rect_hit(px, py, dx, dy, L, sr[(size_t)(1 + b) * s.n], lox, hix, loy, hiy));
-    }
-    // ---- corridor ring: every side segment once, merged into the rows whose range holds it ------------------
-    const float4* corr = s.corridor + (size_t)i * c.corridor_cap;
-    const int cmask = c.corridor_cap - 1;
-    if (sc.react_to_safe_corridor && max_head > min_tail) {
-        float4 a = corr[min_tail & cmask];
-        for (int q = min_tail; q < max_head - 1; q++) {
-            float4 b = corr[(q + 1) & cmask];
-            float m = kNoHit;
-            bool rbox = !(fmaxf(a.x, b.x) < lox || fminf(a.x, b.x) > hix || fmaxf(a.y, b.y) < loy || fminf(a.y, b.y) > hiy);
-            bool lbox = !(fmaxf(a.z, b.z) < lox || fminf(a.z, b.z) > hix || fmaxf(a.w, b.w) < loy || fminf(a.w, b.w) > hiy);
-            if (rbox) m = seg_hit(px, py, dx, dy, L, a.x, a.y, b.x, b.y);
-            if (lbox) m = fminf(m, seg_hit(px, py, dx, dy, L, a.z, a.w, b.z, b.w));
-            if (m < kNoHit) {
-#pragma unroll
-                for (int j = 0; j < FTL_MAX_HIST; j++)
-                    if (valid[j] && q >= tail[j] && q < head[j] - 1) rows[j] = fminf(rows[j], m);
-            }
-            a = b;
-        }
-    }
-    if (sc.react_to_green_zone) {  // end caps of each stored corridor, SEN:648-650
-#pragma unroll
-        for (int j = 0; j < FTL_MAX_HIST; j++) {
-            if (!valid[j]) continue;
-            float4 a = corr[tail[j] & cmask], b = corr[(head[j] - 1) & cmask];
-            rows[j] = fminf(rows[j], seg_hit(px, py, dx, dy, L, a.x, a.y, a.z, a.w));
-            rows[j] = fminf(rows[j], seg_hit(px, py, dx, dy, L, b.x, b.y, b.z, b.w));
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < FTL_MAX_HIST; j++)
-        if (rows[j] >= kNoHit) rows[j] = L;  // no hit: the laser end point, SEN:926-930
-}
-
-// where ray k of a sensor lands in the env's output vector; pad_sectors layout of SEN:932-953
-FTL_HD void store_ray_rows(const FtlRaySensorConfig& sc, float* dst, int k, const float* rows) {
-    const int R = sc.lasers_count, H = sc.max_prev_obs;
-    if (!sc.pad_sectors) {
-        for (int j = 0; j < H; j++) dst[(size_t)j * R + k] = rows[j];
-    } else {
-        double in_sector = R / 4.0;
-        int sector = (k < in_sector) ? 0 : (k < 2 * in_sector) ? 1 : (k < 3 * in_sector) ? 2 : 3;
-        for (int j = 0; j < H; j++)
-            for (int q = 0; q < 4; q++) dst[(size_t)j * 4 * R + (size_t)q * R + k] = (q == sector) ? rows[j] : 0.f;
-    }
-}
-
 FTL_HD int sensor_width(const FtlRaySensorConfig& sc) {
     return sc.max_prev_obs * (sc.pad_sectors ? 4 * sc.lasers_count : sc.lasers_count);
-}
-
-// flat ray index -> (sensor, ray, output offset)
-FTL_HD bool locate_ray(const FtlConfig& c, int flat, int* sensor, int* k, int* offset) {
-    int off = 0;
-    for (int sidx = 0; sidx < c.n_ray_sensors; sidx++) {
-        int R = c.ray[sidx].lasers_count;
-        if (flat < R) { *sensor = sidx; *k = flat; *offset = off; return true; }
-        flat -= R;
-        off += sensor_width(c.ray[sidx]);
-    }
-    return false;
 }
 
 FTL_HD int total_rays(const FtlConfig& c) {
     int n = 0;
     for (int sidx = 0; sidx < c.n_ray_sensors; sidx++) n += c.ray[sidx].lasers_count;
     return n;
+}
+
+FTL_HD int f2i_bits(float f) {
+#if defined(__CUDA_ARCH__)
+    return __float_as_int(f);
+#else
+    int i; memcpy(&i, &f, 4); return i;
+#endif
+}
+FTL_HD float i2f_bits(int i) {
+#if defined(__CUDA_ARCH__)
+    return __int_as_float(i);
+#else
+    float f; memcpy(&f, &i, 4); return f;
+#endif
+}
+
+// =====================================================================================================
+// Warp-cooperative ray pass (one warp per env).
+//
+// Written as "lane phases": every FTL_LANES(lane) block is executed by the 32 lanes of a warp on the
+// GPU and by a plain loop over lane = 0..31 in the host test build; phases only communicate through
+// the RayShared block (shared memory on the GPU), so the same source runs in both places.
+//
+//   setup   per-sensor table, ray direction table (one float64 sincos per sensor, rotated by a host-made
+//           table of cos/sin(k * 360/R)), result arrays
+//   A1      raw items (static rects, dynamic rect snapshots, corridor segments, end caps), one per lane:
+//           culled against the sensors' reach box; rectangles keep only their front-facing edges; survivors
+//           go to a compact edge list in shared memory
+//   A2      one edge per lane: the angular interval the edge subtends from the follower (polynomial atan2,
+//           widened) selects the few rays that can reach it -> compact (edge, ray) pair list
+//   B       one pair per lane: the exact segment test; results merged with integer atomicMin (non-negative
+//           floats order like ints) into res[age][ray] / res[static][ray]
+//   out     rows assembled (static minimum merged into every valid history row), written coalesced
+// =====================================================================================================
+#if defined(__CUDA_ARCH__)
+#define FTL_LANES(lane) for (int lane = (int)(threadIdx.x & 31), ftl_once_ = 1; ftl_once_; ftl_once_ = 0)
+#define FTL_WARP_SYNC() __syncwarp()
+FTL_HD int smem_atomic_add(int* p, int v) { return atomicAdd(p, v); }
+FTL_HD void smem_atomic_min(int* p, int v) { atomicMin(p, v); }
+#else
+#define FTL_LANES(lane) for (int lane = 0; lane < 32; ++lane)
+#define FTL_WARP_SYNC() ((void)0)
+FTL_HD int smem_atomic_add(int* p, int v) { int o = *p; *p = o + v; return o; }
+FTL_HD void smem_atomic_min(int* p, int v) { if (v < *p) *p = v; }
+#endif
+
+constexpr int kEdgeCap = 224;       // compact edge list per flush
+constexpr int kPairCap = 512;       // (edge, ray) pairs per flush
+constexpr int kCorridorChunk = 96;  // corridor ring entries per flush (2 edges each)
+constexpr int kStaticBit = 8;       // row-mask bit of the static minimum (merged into all valid rows)
+constexpr int kNoHitBits = 0x7f7fffff;
+enum EdgeClass { EC_STATIC = 0, EC_LEADER = 1, EC_BEAR = 2, EC_CORRIDOR = 3, EC_CAP = 4, EC_COUNT = 5 };
+
+struct RayEdge { float ax, ay, bx, by; int mask; };  // mask: bits 0..8 rows (ages / static), bits 16.. class
+
+struct RaySensorTab {
+    int base, R, H, cls_mask;      // cls_mask: which EdgeClass this sensor reacts to
+    float L, theta0, inv_period, eps;
+};
+
+struct RayShared {
+    float px, py;
+    int scenario, snap_pushes, n_valid, ne, np;
+    float reach[EC_COUNT];                         // largest laser_length among sensors reacting to the class
+    int tail[FTL_MAX_HIST], head[FTL_MAX_HIST];    // by age (0 = newest)
+    RaySensorTab sen[FTL_MAX_RAY_SENSORS];
+    RayEdge e[kEdgeCap];
+    int pair[kPairCap];                            // edge << 16 | flat ray
+    // arrays of length rays_total behind the struct: dx, dy, len (float), res[9] (int)
+};
+
+struct RayArrays { float *dx, *dy, *len; int* res; int rt; };
+
+FTL_HD size_t ray_shared_bytes(int rays_total) {
+    return sizeof(RayShared) + (size_t)rays_total * (3 * 4 + (FTL_MAX_HIST + 1) * 4);
+}
+FTL_HD RayArrays ray_arrays(RayShared* sh, int rt) {
+    RayArrays a;
+    float* base = (float*)(sh + 1);
+    a.dx = base; a.dy = base + rt; a.len = base + 2 * rt;
+    a.res = (int*)(base + 3 * rt);
+    a.rt = rt;
+    return a;
+}
+
+FTL_HD int sensor_class_mask(const FtlRaySensorConfig& sc) {
+    int m = 0, mode = sc.react_to_obstacles;
+    if (mode == FTL_REACT_ALL || mode == FTL_REACT_STATIC) m |= (1 << EC_STATIC) | (1 << EC_LEADER);  // game_object_list
+    if (mode == FTL_REACT_ALL || mode == FTL_REACT_DYNAMIC) m |= 1 << EC_BEAR;                        // game_dynamic_list
+    if (sc.react_to_safe_corridor) m |= 1 << EC_CORRIDOR;
+    if (sc.react_to_green_zone) m |= 1 << EC_CAP;
+    return m;
+}
+
+// atan2 in degrees, |error| < 1e-3 degrees (odd minimax polynomial on [0,1] + octant folding)
+FTL_HD float atan2_deg_approx(float y, float x) {
+    float ax = fabsf(x), ay = fabsf(y);
+    float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    float t = mn / fmaxf(mx, 1e-30f);
+    float t2 = t * t;
+    float p = fmaf(t2, -0.01172120f, 0.05265332f);
+    p = fmaf(t2, p, -0.11643287f);
+    p = fmaf(t2, p, 0.19354346f);
+    p = fmaf(t2, p, -0.33262347f);
+    p = fmaf(t2, p, 0.99997726f);
+    float r = p * t * 57.29577951308232f;
+    if (ay > ax) r = 90.f - r;
+    if (x < 0.f) r = 180.f - r;
+    return y < 0.f ? -r : r;
+}
+
+FTL_HD void edge_append(RayShared& sh, float ax, float ay, float bx, float by, int mask) {
+    int slot = smem_atomic_add(&sh.ne, 1);
+    if (slot < kEdgeCap) {
+        RayEdge ed = {ax, ay, bx, by, mask};
+        sh.e[slot] = ed;
+    }
+}
+
+// A1 for one rectangle: reach cull + front-facing edges (edge order/orientation of SEN:668-671).  A ray from
+// outside enters through a front-facing edge; the exit through a back-facing edge is farther and never the
+// minimum the reference reports.  (inside only happens after a crash: then every edge is kept.)
+FTL_HD void rect_append(RayShared& sh, int4 q, int cls, int rows) {
+    const float l = (float)q.x, t = (float)q.y, r = (float)(q.x + q.z), b = (float)(q.y + q.w);
+    const float px = sh.px, py = sh.py, reach = sh.reach[cls] + 1.f;
+    if (r < px - reach || l > px + reach || b < py - reach || t > py + reach) return;
+    const int mask = rows | (1 << (16 + cls));
+    const bool inside = px >= l && px <= r && py >= t && py <= b;
+    if (inside || py > b) edge_append(sh, l, b, r, b, mask);
+    if (inside || px > r) edge_append(sh, r, t, r, b, mask);
+    if (inside || py < t) edge_append(sh, r, t, l, t, mask);
+    if (inside || px < l) edge_append(sh, l, b, l, t, mask);
+}
+FTL_HD void seg_append(RayShared& sh, float ax, float ay, float bx, float by, int cls, int rows) {
+    const float px = sh.px, py = sh.py, reach = sh.reach[cls] + 1.f;
+    if (fmaxf(ax, bx) < px - reach || fminf(ax, bx) > px + reach || fmaxf(ay, by) < py - reach ||
+        fminf(ay, by) > py + reach)
+        return;
+    edge_append(sh, ax, ay, bx, by, rows | (1 << (16 + cls)));
+}
+
+FTL_HD void pair_apply(const RayShared& sh, const RayArrays& ra, int ei, int f, int rows) {
+    const RayEdge& ed = sh.e[ei];
+    float d = seg_hit(sh.px, sh.py, ra.dx[f], ra.dy[f], ra.len[f], ed.ax, ed.ay, ed.bx, ed.by);
+    if (d >= kNoHit) return;
+    int bits = f2i_bits(d);
+    for (int a = 0; a <= FTL_MAX_HIST; a++)
+        if (rows & (1 << a)) smem_atomic_min(&ra.res[a * ra.rt + f], bits);
+}
+
+// A2 + B over the current edge list, then empty it
+FTL_HD void ray_flush(RayShared& sh, const RayArrays& ra, int n_sensors) {
+    FTL_WARP_SYNC();
+    const int ne = sh.ne < kEdgeCap ? sh.ne : kEdgeCap;
+    // ---- A2: edges -> (edge, ray) pairs ----------------------------------------------------------------------
+    FTL_LANES(lane) {
+        for (int ei = lane; ei < ne; ei += 32) {
+            const RayEdge ed = sh.e[ei];
+            const int cls_bit = ed.mask >> 16;
+            const float ba = atan2_deg_approx(ed.ay - sh.py, ed.ax - sh.px);
+            const float bb = atan2_deg_approx(ed.by - sh.py, ed.bx - sh.px);
+            for (int sidx = 0; sidx < n_sensors; sidx++) {
+                const RaySensorTab& st = sh.sen[sidx];
+                if (!(st.cls_mask & cls_bit)) continue;
+                int rows = ed.mask & 0x1ff;
+                if (!(rows & (1 << kStaticBit))) rows &= (1 << st.H) - 1;   // rows this sensor keeps
+                if (!rows) continue;
+                // reach of THIS sensor (the list was culled with the class maximum)
+                const float reach = st.L + 1.f;
+                if (fmaxf(ed.ax, ed.bx) < sh.px - reach || fminf(ed.ax, ed.bx) > sh.px + reach ||
+                    fmaxf(ed.ay, ed.by) < sh.py - reach || fminf(ed.ay, ed.by) > sh.py + reach)
+                    continue;
+                const float Rf = (float)st.R;
+                float ka = (ba - st.theta0) * st.inv_period;
+                float d = (bb - ba) * st.inv_period;
+                d = d - Rf * rintf(d / Rf);                    // short way round, (-R/2, R/2]
+                int klo = (int)ceilf(fminf(ka, ka + d) - st.eps), khi = (int)floorf(fmaxf(ka, ka + d) + st.eps);
+                int cnt = khi - klo + 1;
+                if (cnt <= 0) continue;
+                if (cnt >= st.R) { klo = 0; cnt = st.R; }
+                int slot = smem_atomic_add(&sh.np, cnt);
+                for (int k = 0; k < cnt; k++) {
+                    int kk = (klo + k) % st.R;
+                    if (kk < 0) kk += st.R;
+                    if (slot + k < kPairCap)
+                        sh.pair[slot + k] = (ei << 16) | (st.base + kk);
+                    else
+                        pair_apply(sh, ra, ei, st.base + kk, rows);   // list full: do it in place
+                }
+            }
+        }
+    }
+    FTL_WARP_SYNC();
+    // ---- B: uniform pair tests ----------------------------------------------------------------------------------
+    const int np = sh.np < kPairCap ? sh.np : kPairCap;
+    FTL_LANES(lane) {
+        for (int t = lane; t < np; t += 32) {
+            int pr = sh.pair[t], ei = pr >> 16, f = pr & 0xffff;
+            int rows = sh.e[ei].mask & 0x1ff;
+            // the row restriction of the ray's sensor
+            int sidx = 0;
+            while (sidx + 1 < n_sensors && f >= sh.sen[sidx + 1].base) sidx++;
+            if (!(rows & (1 << kStaticBit))) rows &= (1 << sh.sen[sidx].H) - 1;
+            pair_apply(sh, ra, ei, f, rows);
+        }
+    }
+    FTL_WARP_SYNC();
+    FTL_LANES(lane) { if (lane == 0) { sh.ne = 0; sh.np = 0; } }
+    FTL_WARP_SYNC();
+}
+
+// the whole ray pass of env i.  rot: [rays_total] (cos, sin)(k * 360/R) per flat ray, made on the host.
+FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool, const double2* rot, int i,
+                      RayShared& sh, float* rays_out) {
+    const FtlConfig& c = cfg.c;
+    const int rt = cfg.rays_total;
+    const RayArrays ra = ray_arrays(&sh, rt);
+    const int NBr = s.n_bears, ns = c.n_ray_sensors;
+    const double dir = s.rd[(size_t)RD_DIR * s.n + i];
+    // ---- setup ------------------------------------------------------------------------------------------
+    FTL_LANES(lane) {
+        if (lane == 0) {
+            float2 p = s.pos[i];
+            sh.px = p.x; sh.py = p.y;
+            sh.scenario = s.gi[(size_t)GI_SCENARIO * s.n + i];
+            int pushes = s.gi[(size_t)GI_SNAP_PUSHES * s.n + i];
+            sh.snap_pushes = pushes;
+            sh.n_valid = pushes < FTL_MAX_HIST ? pushes : FTL_MAX_HIST;
+            sh.ne = 0; sh.np = 0;
+            for (int k = 0; k < EC_COUNT; k++) sh.reach[k] = -1e30f;
+            int base = 0;
+            for (int sidx = 0; sidx < ns; sidx++) {
+                const FtlRaySensorConfig& sc = c.ray[sidx];
+                RaySensorTab st;
+                st.base = base; st.R = sc.lasers_count; st.H = sc.max_prev_obs;
+                st.cls_mask = sensor_class_mask(sc);
+                st.L = (float)sc.laser_length;
+                st.theta0 = (float)(dir + sc.first_laser_angle_offset);
+                st.inv_period = (float)sc.lasers_count / 360.f;
+                st.eps = 0.02f + 5e-5f * (float)sc.lasers_count;
+                sh.sen[sidx] = st;
+                for (int k = 0; k < EC_COUNT; k++)
+                    if (st.cls_mask & (1 << k)) sh.reach[k] = fmaxf(sh.reach[k], st.L);
+                base += sc.lasers_count;
+            }
+        }
+        if (lane < FTL_MAX_HIST) {
+            int pushes = s.gi[(size_t)GI_SNAP_PUSHES * s.n + i];
+            int2 rg = make_int2(0, 0);
+            if (lane < pushes) rg = s.snap_range[(size_t)((pushes - 1 - lane) % FTL_MAX_HIST) * s.n + i];
+            sh.tail[lane] = rg.x; sh.head[lane] = rg.y;
+        }
+    }
+    FTL_WARP_SYNC();
+    FTL_LANES(lane) {
+        int sidx = 0;
+        double sn0 = 0, cs0 = 1;
+        int cur = -1;
+        for (int f = lane; f < rt; f += 32) {
+            while (sidx + 1 < ns && f >= sh.sen[sidx + 1].base) sidx++;
+            const FtlRaySensorConfig& sc = c.ray[sidx];
+            if (cur != sidx) { sincos_deg(dir + sc.first_laser_angle_offset, &sn0, &cs0); cur = sidx; }
+            double2 r = rot[f];   // (cos, sin) of k * period
+            ra.dx[f] = (float)((cs0 * r.x - sn0 * r.y) * sc.laser_length);
+            ra.dy[f] = (float)((sn0 * r.x + cs0 * r.y) * sc.laser_length);
+            ra.len[f] = (float)sc.laser_length;
+            for (int a = 0; a <= FTL_MAX_HIST; a++) ra.res[a * rt + f] = kNoHitBits;
+        }
+    }
+    FTL_WARP_SYNC();
+    const int n_valid = sh.n_valid;
+    if (n_valid > 0) {
+        // ---- A1: rectangles -----------------------------------------------------------------------------
+        const int4* statics = pool.static_rects + (size_t)sh.scenario * c.static_cap;
+        const int n_static = pool.n_static[sh.scenario];
+        const int n_dyn = n_valid * (1 + NBr);
+        FTL_LANES(lane) {
+            if (sh.reach[EC_STATIC] > 0.f)
+                for (int q = lane; q < n_static; q += 32) rect_append(sh, statics[q], EC_STATIC, 1 << kStaticBit);
+            for (int q = lane; q < n_dyn; q += 32) {
+                int age = q / (1 + NBr), k = q % (1 + NBr);
+                int cls = k == 0 ? EC_LEADER : EC_BEAR;
+                if (sh.reach[cls] > 0.f) {
+                    int slot = (sh.snap_pushes - 1 - age) % FTL_MAX_HIST;
+                    rect_append(sh, s.snap_rect[((size_t)slot * (1 + NBr) + k) * s.n + i], cls, 1 << age);
+                }
+            }
+        }
+        ray_flush(sh, ra, ns);
+        // ---- A1: corridor sides (union of the stored ranges) and end caps --------------------------------------
+        const float4* corr = s.corridor + (size_t)i * c.corridor_cap;
+        const int cmask = c.corridor_cap - 1;
+        if (sh.reach[EC_CORRIDOR] > 0.f) {
+            int min_tail = sh.tail[0], max_head = sh.head[0];
+            for (int a = 1; a < n_valid; a++) {
+                min_tail = sh.tail[a] < min_tail ? sh.tail[a] : min_tail;
+                max_head = sh.head[a] > max_head ? sh.head[a] : max_head;
+            }
+            for (int q0 = min_tail; q0 < max_head - 1; q0 += kCorridorChunk) {
+                FTL_LANES(lane) {
+                    int q1 = q0 + kCorridorChunk < max_head - 1 ? q0 + kCorridorChunk : max_head - 1;
+                    for (int q = q0 + lane; q < q1; q += 32) {
+                        int rows = 0;
+                        for (int a = 0; a < n_valid; a++)
+                            if (q >= sh.tail[a] && q < sh.head[a] - 1) rows |= 1 << a;
+                        if (rows) {
+                            float4 a4 = corr[q & cmask], b4 = corr[(q + 1) & cmask];
+                            seg_append(sh, a4.x, a4.y, b4.x, b4.y, EC_CORRIDOR, rows);
+                            seg_append(sh, a4.z, a4.w, b4.z, b4.w, EC_CORRIDOR, rows);
+                        }
+                    }
+                }
+                ray_flush(sh, ra, ns);
+            }
+        }
+        if (sh.reach[EC_CAP] > 0.f) {
+            FTL_LANES(lane) {
+                if (lane < 2 * n_valid) {   // SEN:648-650
+                    int age = lane >> 1;
+                    int idx = (lane & 1) ? sh.head[age] - 1 : sh.tail[age];
+                    float4 a4 = corr[idx & cmask];
+                    seg_append(sh, a4.x, a4.y, a4.z, a4.w, EC_CAP, 1 << age);
+                }
+            }
+            ray_flush(sh, ra, ns);
+        }
+    }
+    // ---- out: assemble rows and write ------------------------------------------------------------------------
+    FTL_LANES(lane) {
+        int off = 0;
+        for (int sidx = 0; sidx < ns; sidx++) {
+            const FtlRaySensorConfig& sc = c.ray[sidx];
+            const int R = sc.lasers_count, H = sc.max_prev_obs, base = sh.sen[sidx].base;
+            const float L = (float)sc.laser_length;
+            float* dst = rays_out + (size_t)i * cfg.rays_per_env + off;
+            const int width = sc.pad_sectors ? 4 * R : R;
+            const double in_sector = R / 4.0;
+            for (int e = lane; e < H * width; e += 32) {
+                int j = e / width, rem = e - j * width, sec = rem / R, k = rem - sec * R, age = H - 1 - j;
+                float v = L;
+                if (age < n_valid) {
+                    int bits = ra.res[age * rt + base + k], sb = ra.res[kStaticBit * rt + base + k];
+                    bits = sb < bits ? sb : bits;
+                    if (bits != kNoHitBits) v = i2f_bits(bits);
+                }
+                if (sc.pad_sectors) {   // SEN:932-953: four sector-masked copies side by side
+                    int ksec = (k < in_sector) ? 0 : (k < 2 * in_sector) ? 1 : (k < 3 * in_sector) ? 2 : 3;
+                    if (sec != ksec) v = 0.f;
+                }
+                dst[e] = v;
+            }
+            off += sensor_width(sc);
+        }
+    }
+    FTL_WARP_SYNC();
 }
 
 }  // namespace ftl

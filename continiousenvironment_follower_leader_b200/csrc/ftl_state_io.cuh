@@ -91,8 +91,14 @@ FTL_HD void unpack_env(const DevCfg& cfg, const DevState& s, int i, const FtlEnv
               (o.leader_status << FL_LEADER_SHIFT);
     episode_store(s, i, e);
     Tracker t = {o.saving_counter, o.ring_tail, o.ring_head, o.hist_f64_end};
-    GreenCache gc;  // derived: rebuild from the (already uploaded) trail
-    green_cache_invalidate(cfg, s.trail + (size_t)i * cfg.c.trail_cap, o.trail_len, gc);
+    GreenCache gc;  // derived data: rebuild from the (already uploaded) trail
+    {
+        float2* trail = s.trail + (size_t)i * cfg.c.trail_cap;
+        float* trail_d = s.trail_d + (size_t)i * cfg.c.trail_cap;
+        double* trail_s = s.trail_s + (size_t)i * cfg.c.trail_cap;
+        for (int k = 0; k < o.trail_len; k++) trail_push(trail, trail_d, trail_s, k, trail[k].x, trail[k].y);
+        green_cache_invalidate(cfg, trail_d, o.trail_len, gc);
+    }
     int pushes = o.snap_pushes;
     cache_store(s, i, gc, t, pushes);
     for (int j2 = 0; j2 < FTL_MAX_HIST; j2++) {

@@ -51,10 +51,16 @@ FTL_HD void cache_load(const DevState& s, int i, GreenCache& gc, Tracker& t, int
     const int* g = s.gi + i;
     size_t n = s.n;
     gc.g_lo = g[GI_G_LO * n];
+    gc.g_unc = g[GI_G_UNC * n];
     gc.a_star = g[GI_A_STAR * n];
     gc.b_star = g[GI_B_STAR * n];
+    gc.nice_from = g[GI_NICE_FROM * n];
     gc.lb_g = s.gf[GF_LB_GREEN * n + i];
     gc.lb_all = s.gf[GF_LB_ALL * n + i];
+    gc.sgx = s.gf[GF_SCAN_GX * n + i];
+    gc.sgy = s.gf[GF_SCAN_GY * n + i];
+    gc.sax = s.gf[GF_SCAN_AX * n + i];
+    gc.say = s.gf[GF_SCAN_AY * n + i];
     t.saving_counter = g[GI_SAVING_COUNTER * n];
     t.ring_tail = g[GI_RING_TAIL * n];
     t.ring_head = g[GI_RING_HEAD * n];
@@ -65,10 +71,16 @@ FTL_HD void cache_store(const DevState& s, int i, const GreenCache& gc, const Tr
     int* g = s.gi + i;
     size_t n = s.n;
     g[GI_G_LO * n] = gc.g_lo;
+    g[GI_G_UNC * n] = gc.g_unc;
     g[GI_A_STAR * n] = gc.a_star;
     g[GI_B_STAR * n] = gc.b_star;
+    g[GI_NICE_FROM * n] = gc.nice_from;
     s.gf[GF_LB_GREEN * n + i] = gc.lb_g;
     s.gf[GF_LB_ALL * n + i] = gc.lb_all;
+    s.gf[GF_SCAN_GX * n + i] = gc.sgx;
+    s.gf[GF_SCAN_GY * n + i] = gc.sgy;
+    s.gf[GF_SCAN_AX * n + i] = gc.sax;
+    s.gf[GF_SCAN_AY * n + i] = gc.say;
     g[GI_SAVING_COUNTER * n] = t.saving_counter;
     g[GI_RING_TAIL * n] = t.ring_tail;
     g[GI_RING_HEAD * n] = t.ring_head;
@@ -139,6 +151,7 @@ template <int NB>
 FTL_HD void write_outputs(const DevCfg& cfg, const DevPool& pool, const DevOutputs& out, int i, const World<NB>& w,
                           const Episode& e, bool obs_only) {
     const FtlConfig& c = cfg.c;
+    if (i >= out.n) return;  // filler env of the last warp
     if (out.numerical_features) {  // ENV:1793-1802
         float* nf = out.numerical_features + (size_t)i * 10;
         nf[0] = w.leader.px; nf[1] = w.leader.py;
@@ -197,6 +210,8 @@ FTL_HD void env_reset(const DevCfg& cfg, const DevState& s, const DevPool& pool,
     e.lead_acc = e.lead_cum = 0.0;
     // seed the trail, ENV:533-539 (float32 linspace follower -> leader)
     float2* trail = s.trail + (size_t)i * c.trail_cap;
+    float* trail_d = s.trail_d + (size_t)i * c.trail_cap;
+    double* trail_s = s.trail_s + (size_t)i * c.trail_cap;
     float q = sqrtf(d2_f32(fp.x, fp.y, lp.x, lp.y)) / cfg.trail_seed_denom_f32;
     int m = (int)q;
     if (m > c.trail_cap) { m = c.trail_cap; e.overflow |= 1; }
@@ -205,13 +220,13 @@ FTL_HD void env_reset(const DevCfg& cfg, const DevState& s, const DevPool& pool,
         float stepx = m > 1 ? dx / (float)(m - 1) : 0.f, stepy = m > 1 ? dy / (float)(m - 1) : 0.f;
         for (int k = 0; k < m; k++) {
             float tx = (float)k * stepx, ty = (float)k * stepy;
-            trail[k] = make_float2(tx + fp.x, ty + fp.y);
+            if (k == m - 1 && m > 1) trail_push(trail, trail_d, trail_s, k, lp.x, lp.y);
+            else trail_push(trail, trail_d, trail_s, k, tx + fp.x, ty + fp.y);
         }
-        if (m > 1) trail[m - 1] = lp;
     }
     e.trail_len = m;
     GreenCache gc;
-    green_cache_invalidate(cfg, trail, m, gc);
+    green_cache_invalidate(cfg, trail_d, m, gc);
     Tracker t = {0, 0, 0, 0};
     // ring indices restart at 0; old snapshots are dropped by zeroing the push counter
     int snap_pushes = 0;
@@ -229,6 +244,8 @@ FTL_HD void env_step(const DevCfg& cfg, const DevState& s, const DevPool& pool, 
     int snap_pushes;
     cache_load(s, i, gc, t, &snap_pushes);
     float2* trail = s.trail + (size_t)i * c.trail_cap;
+    float* trail_d = s.trail_d + (size_t)i * c.trail_cap;
+    double* trail_s = s.trail_s + (size_t)i * c.trail_cap;
     const int4* statics = pool.static_rects + (size_t)e.scenario * c.static_cap;
     const int n_static = pool.n_static[e.scenario];
     const int n_route = pool.n_route[e.scenario];
@@ -245,7 +262,6 @@ FTL_HD void env_step(const DevCfg& cfg, const DevState& s, const DevPool& pool, 
         int mission = FTL_MISSION_IN_PROGRESS, agent = FTL_AGENT_MOVING, leader_st = FTL_LEADER_MOVING;
         // (1) follower, ENV:957-964
         robot_move(w.follower, c.follower);
-        green_cache_moved(gc, (float)fabs(w.follower.speed) + 2e-4f);
         if (!c.ignore_follower_collisions) {
             bool hit = robots_collide(w.follower, w.leader) || collide_static_masked(w.follower, statics, fmask) ||
                        out_of_bounds(c, w.follower);
@@ -259,7 +275,7 @@ FTL_HD void env_step(const DevCfg& cfg, const DevState& s, const DevPool& pool, 
         }
         // (2) green zone + flags, ENV:966-973
         bool in_box, on_trace;
-        green_flags(cfg, trail, e.trail_len, w.follower.px, w.follower.py, gc, &in_box, &on_trace);
+        green_flags(cfg, trail, trail_d, e.trail_len, w.follower.px, w.follower.py, gc, &in_box, &on_trace);
         bool too_close = d2_f32(w.leader.px, w.leader.py, w.follower.px, w.follower.py) <= cfg.min_dist2_f32;
         // (3) waypoint advance, ENV:978-983
         {
@@ -296,9 +312,9 @@ FTL_HD void env_step(const DevCfg& cfg, const DevState& s, const DevPool& pool, 
         // (6) trail append on the virtual clock, ENV:1074-1075
         if (e.step_count % c.trajectory_saving_period == 0) {
             if (e.trail_len < c.trail_cap) {
-                trail[e.trail_len] = make_float2(w.leader.px, w.leader.py);
+                trail_push(trail, trail_d, trail_s, e.trail_len, w.leader.px, w.leader.py);
                 e.trail_len++;
-                green_cache_appended(cfg, trail, e.trail_len, w.follower.px, w.follower.py, gc);
+                green_cache_appended(cfg, trail, trail_d, trail_s, e.trail_len, gc);
             } else {
                 e.overflow |= 1;
             }
@@ -350,7 +366,8 @@ FTL_HD void env_step(const DevCfg& cfg, const DevState& s, const DevPool& pool, 
 }
 
 // ---- action decode, ENV:918-925 -------------------------------------------------------------------------------
-FTL_HD void decode_action(const FtlConfig& c, const void* actions, int i, double* a0, double* a1) {
+FTL_HD void decode_action(const FtlConfig& c, const void* actions, int i, int n_real, double* a0, double* a1) {
+    if (i >= n_real) { *a0 = 0.0; *a1 = 0.0; return; }  // filler envs idle
     if (c.action_mode == FTL_ACTION_DISCRETE) {
         int a = ((const int32_t*)actions)[i];
         a = a < 0 ? 0 : a > 4 ? 4 : a;

@@ -30,11 +30,11 @@ k_step(const __grid_constant__ DevCfg cfg, const DevState s, const DevPool pool,
     episode_load(s, i, e);
     const bool was_done = (e.flags & FL_DONE) != 0;
     double a0, a1;
-    decode_action(cfg.c, actions, i, &a0, &a1);
+    decode_action(cfg.c, actions, i, s.n_real, &a0, &a1);
     env_step<NB>(cfg, s, pool, i, a0, a1, w, e);
     write_outputs<NB>(cfg, pool, out, i, w, e, false);
     const bool done = (e.flags & FL_DONE) != 0;
-    if (done && !was_done) {  // episode statistics (reduced across ranks with NCCL by the host)
+    if (done && !was_done && i < s.n_real) {  // episode statistics (reduced across ranks with NCCL by the host)
         add_stat(stats, FTL_STAT_EPISODES, 1.0);
         add_stat(stats, FTL_STAT_RETURN_SUM, e.overall);
         add_stat(stats, FTL_STAT_LENGTH_SUM, (double)e.step_count);
@@ -45,7 +45,7 @@ k_step(const __grid_constant__ DevCfg cfg, const DevState s, const DevPool pool,
         if (leader_st == FTL_LEADER_CRASH) add_stat(stats, FTL_STAT_LEADER_CRASH, 1.0);
         if (e.overflow) add_stat(stats, FTL_STAT_OVERFLOW, 1.0);
     }
-    if (cfg.c.auto_reset && done) {
+    if ((cfg.c.auto_reset || i >= s.n_real) && done) {
         // reward/done/status of the finished episode stay in `out`; the observation becomes the first
         // one of the next episode (vector-env convention)
         int scen = next_scenario(cfg, pool.n_scenarios, i, e.episode);
@@ -59,14 +59,14 @@ k_step(const __grid_constant__ DevCfg cfg, const DevState s, const DevPool pool,
 template <int NB>
 __global__ void __launch_bounds__(128)
 k_reset(const __grid_constant__ DevCfg cfg, const DevState s, const DevPool pool, const uint8_t* __restrict__ mask,
-        const int* __restrict__ scenario_ids, const DevOutputs out) {
+        const int* __restrict__ scenario_ids, const DevOutputs out, int reset_filler) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= s.n) return;
-    if (mask && !mask[i]) return;
+    if (i < s.n_real ? (mask && !mask[i]) : !reset_filler) return;
     World<NB> w;
     Episode e;
     int episodes = s.gi[(size_t)GI_EPISODE * s.n + i];
-    int scen = scenario_ids ? scenario_ids[i] : next_scenario(cfg, pool.n_scenarios, i, episodes);
+    int scen = (scenario_ids && i < s.n_real) ? scenario_ids[i] : next_scenario(cfg, pool.n_scenarios, i, episodes);
     scen = scen < 0 ? 0 : scen >= pool.n_scenarios ? pool.n_scenarios - 1 : scen;
     env_reset<NB>(cfg, s, pool, i, scen, w, e);
     write_outputs<NB>(cfg, pool, out, i, w, e, false);
@@ -80,11 +80,12 @@ k_reset(const __grid_constant__ DevCfg cfg, const DevState s, const DevPool pool
 
 void FTL_CAT(ftl_launch_step_nb, FTL_NB)(const DevCfg& cfg, const DevState& s, const DevPool& pool, const void* actions,
                                           const DevOutputs& out, double* stats, cudaStream_t st) {
-    int threads = 128, blocks = (s.n + threads - 1) / threads;
+    // 64-thread blocks: 65536 envs are only ~14 warps per SM, small blocks spread them evenly over the 148 SMs
+    int threads = 64, blocks = (s.n + threads - 1) / threads;
     k_step<FTL_NB><<<blocks, threads, 0, st>>>(cfg, s, pool, actions, out, stats);
 }
 void FTL_CAT(ftl_launch_reset_nb, FTL_NB)(const DevCfg& cfg, const DevState& s, const DevPool& pool, const uint8_t* mask,
-                                           const int* ids, const DevOutputs& out, cudaStream_t st) {
+                                           const int* ids, const DevOutputs& out, int reset_filler, cudaStream_t st) {
     int threads = 128, blocks = (s.n + threads - 1) / threads;
-    k_reset<FTL_NB><<<blocks, threads, 0, st>>>(cfg, s, pool, mask, ids, out);
+    k_reset<FTL_NB><<<blocks, threads, 0, st>>>(cfg, s, pool, mask, ids, out, reset_filler);
 }

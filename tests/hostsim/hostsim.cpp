@@ -28,6 +28,7 @@ struct FtlHandle_ {
     std::vector<void*> allocs, pool_allocs;
     bool have_pool = false;
     int rays_total = 0;
+    std::vector<double2> rot;
 };
 
 template <typename T>
@@ -57,7 +58,7 @@ static void step_all(FtlHandle_* h, const void* actions, const DevOutputs& out) 
         world_load<NB>(h->st, i, w);
         episode_load(h->st, i, e);
         double a0, a1;
-        decode_action(h->cfg.c, actions, i, &a0, &a1);
+        decode_action(h->cfg.c, actions, i, h->n, &a0, &a1);
         env_step<NB>(h->cfg, h->st, h->pool, i, a0, a1, w, e);
         write_outputs<NB>(h->cfg, h->pool, out, i, w, e, false);
         if (h->cfg.c.auto_reset && (e.flags & FL_DONE)) {
@@ -85,20 +86,14 @@ static void reset_all(FtlHandle_* h, const uint8_t* mask, const int* ids, const 
 }
 static void rays_all(FtlHandle_* h, float* rays) {
     if (!rays || !h->rays_total) return;
-    for (int i = 0; i < h->n; i++)
-        for (int f = 0; f < h->rays_total; f++) {
-            int sensor, k, offset;
-            if (!locate_ray(h->cfg.c, f, &sensor, &k, &offset)) continue;
-            RayEnv re;
-            ray_env_load(h->st, i, re);
-            float rows[FTL_MAX_HIST];
-            cast_ray(h->cfg, h->st, h->pool, i, re, h->cfg.c.ray[sensor], k, rows);
-            store_ray_rows(h->cfg.c.ray[sensor], rays + (size_t)i * h->cfg.rays_per_env + offset, k, rows);
-        }
+    std::vector<unsigned char> buf(ray_shared_bytes(h->rays_total) + 16);
+    RayShared& sh = *reinterpret_cast<RayShared*>(buf.data());
+    for (int i = 0; i < h->n; i++) rays_warp(h->cfg, h->st, h->pool, h->rot.data(), i, sh, rays);
 }
 
 static DevOutputs dev_out(const FtlOutputs* o) {
     DevOutputs d{};
+    d.n = 1 << 30;
     if (o) {
         d.numerical_features = o->numerical_features; d.leader_target = o->leader_target; d.rays = o->rays;
         d.reward = o->reward; d.done = o->done; d.status = o->status;
@@ -121,6 +116,14 @@ int ftl_create(const FtlConfig* cfg, int32_t n_envs, int32_t device, int64_t env
     d.env_id_base = env_id_base;
     for (int s = 0; s < c.n_ray_sensors; s++) d.rays_per_env += sensor_width(c.ray[s]);
     h->rays_total = total_rays(c);
+    d.rays_total = h->rays_total;
+    for (int s = 0; s < c.n_ray_sensors; s++)
+        for (int k = 0; k < c.ray[s].lasers_count; k++) {
+            double th = (k * (360.0 / c.ray[s].lasers_count)) * kDeg2Rad;
+            h->rot.push_back(make_double2(std::cos(th), std::sin(th)));
+        }
+    d.eps_f32 = (float)c.leader_pos_epsilon;
+    d.dev_f32 = (float)c.max_dev;
     d.eps2_f32 = sq_threshold(c.leader_pos_epsilon);
     d.dev2_f32 = sq_threshold(c.max_dev);
     d.min_dist2_f32 = sq_threshold(c.min_distance);
@@ -138,7 +141,7 @@ int ftl_create(const FtlConfig* cfg, int32_t n_envs, int32_t device, int64_t env
     size_t n = n_envs;
     int nb = c.n_bears, nr = 2 + nb;
     DevState& s = h->st;
-    s.n = n_envs; s.n_bears = nb;
+    s.n = n_envs; s.n_real = n_envs; s.n_bears = nb;
     s.gd = zalloc<double>(h->allocs, GD_COUNT * n);
     s.rd = zalloc<double>(h->allocs, (size_t)nr * RD_COUNT * n);
     s.bear_tgt = zalloc<double>(h->allocs, (size_t)nb * 2 * n);
@@ -149,6 +152,8 @@ int ftl_create(const FtlConfig* cfg, int32_t n_envs, int32_t device, int64_t env
     s.pos = zalloc<float2>(h->allocs, (size_t)nr * n);
     s.rect = zalloc<int4>(h->allocs, (size_t)nr * n);
     s.trail = zalloc<float2>(h->allocs, n * c.trail_cap);
+    s.trail_d = zalloc<float>(h->allocs, n * c.trail_cap);
+    s.trail_s = zalloc<double>(h->allocs, n * c.trail_cap);
     s.hist = zalloc<double2>(h->allocs, n * c.corridor_cap);
     s.corridor = zalloc<float4>(h->allocs, n * c.corridor_cap);
     s.snap_range = zalloc<int2>(h->allocs, (size_t)FTL_MAX_HIST * n);
