@@ -120,6 +120,7 @@ struct RayEdge { float ax, ay, bx, by; int mask; };  // mask: bits 0..8 rows (ag
 struct RaySensorTab {
     int base, R, H, cls_mask;      // cls_mask: which EdgeClass this sensor reacts to
     float L, theta0, inv_period, eps;
+    double cs0, sn0;               // cos/sin of the direction of ray 0
 };
 
 struct RayShared {
@@ -243,9 +244,9 @@ FTL_HD void ray_flush(RayShared& sh, const RayArrays& ra, int n_sensors) {
                 if (cnt <= 0) continue;
                 if (cnt >= st.R) { klo = 0; cnt = st.R; }
                 int slot = smem_atomic_add(&sh.np, cnt);
-                for (int k = 0; k < cnt; k++) {
-                    int kk = (klo + k) % st.R;
-                    if (kk < 0) kk += st.R;
+                int kk = klo % st.R;
+                if (kk < 0) kk += st.R;
+                for (int k = 0; k < cnt; k++, kk = (kk + 1 == st.R) ? 0 : kk + 1) {
                     if (slot + k < kPairCap)
                         sh.pair[slot + k] = (ei << 16) | (st.base + kk);
                     else
@@ -317,13 +318,15 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
     }
     FTL_WARP_SYNC();
     FTL_LANES(lane) {
+        if (lane < ns) sincos_deg(dir + c.ray[lane].first_laser_angle_offset, &sh.sen[lane].sn0, &sh.sen[lane].cs0);
+    }
+    FTL_WARP_SYNC();
+    FTL_LANES(lane) {
         int sidx = 0;
-        double sn0 = 0, cs0 = 1;
-        int cur = -1;
         for (int f = lane; f < rt; f += 32) {
             while (sidx + 1 < ns && f >= sh.sen[sidx + 1].base) sidx++;
             const FtlRaySensorConfig& sc = c.ray[sidx];
-            if (cur != sidx) { sincos_deg(dir + sc.first_laser_angle_offset, &sn0, &cs0); cur = sidx; }
+            const double cs0 = sh.sen[sidx].cs0, sn0 = sh.sen[sidx].sn0;
             double2 r = rot[f];   // (cos, sin) of k * period
             ra.dx[f] = (float)((cs0 * r.x - sn0 * r.y) * sc.laser_length);
             ra.dy[f] = (float)((sn0 * r.x + cs0 * r.y) * sc.laser_length);
@@ -350,8 +353,8 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
                 }
             }
         }
-        ray_flush(sh, ra, ns);
-        // ---- A1: corridor sides (union of the stored ranges) and end caps --------------------------------------
+        // ---- A1: corridor sides (union of the stored ranges) and end caps; the list is only flushed when the next
+        //      batch might not fit ----------------------------------------------------------------------------------
         const float4* corr = s.corridor + (size_t)i * c.corridor_cap;
         const int cmask = c.corridor_cap - 1;
         if (sh.reach[EC_CORRIDOR] > 0.f) {
@@ -361,6 +364,8 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
                 max_head = sh.head[a] > max_head ? sh.head[a] : max_head;
             }
             for (int q0 = min_tail; q0 < max_head - 1; q0 += kCorridorChunk) {
+                FTL_WARP_SYNC();
+                if (sh.ne + 2 * kCorridorChunk > kEdgeCap) ray_flush(sh, ra, ns);
                 FTL_LANES(lane) {
                     int q1 = q0 + kCorridorChunk < max_head - 1 ? q0 + kCorridorChunk : max_head - 1;
                     for (int q = q0 + lane; q < q1; q += 32) {
@@ -374,10 +379,11 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
                         }
                     }
                 }
-                ray_flush(sh, ra, ns);
             }
         }
         if (sh.reach[EC_CAP] > 0.f) {
+            FTL_WARP_SYNC();
+            if (sh.ne + 2 * FTL_MAX_HIST > kEdgeCap) ray_flush(sh, ra, ns);
             FTL_LANES(lane) {
                 if (lane < 2 * n_valid) {   // SEN:648-650
                     int age = lane >> 1;
@@ -386,10 +392,10 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
                     seg_append(sh, a4.x, a4.y, a4.z, a4.w, EC_CAP, 1 << age);
                 }
             }
-            ray_flush(sh, ra, ns);
         }
+        ray_flush(sh, ra, ns);
     }
-    // ---- out: assemble rows and write ------------------------------------------------------------------------
+    // ---- out: assemble rows and write (row-major per sensor; consecutive lanes write consecutive floats) ------
     FTL_LANES(lane) {
         int off = 0;
         for (int sidx = 0; sidx < ns; sidx++) {
@@ -397,21 +403,26 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
             const int R = sc.lasers_count, H = sc.max_prev_obs, base = sh.sen[sidx].base;
             const float L = (float)sc.laser_length;
             float* dst = rays_out + (size_t)i * cfg.rays_per_env + off;
-            const int width = sc.pad_sectors ? 4 * R : R;
+            const int nsec = sc.pad_sectors ? 4 : 1;
             const double in_sector = R / 4.0;
-            for (int e = lane; e < H * width; e += 32) {
-                int j = e / width, rem = e - j * width, sec = rem / R, k = rem - sec * R, age = H - 1 - j;
-                float v = L;
-                if (age < n_valid) {
-                    int bits = ra.res[age * rt + base + k], sb = ra.res[kStaticBit * rt + base + k];
-                    bits = sb < bits ? sb : bits;
-                    if (bits != kNoHitBits) v = i2f_bits(bits);
+            for (int j = 0; j < H; j++) {
+                const int age = H - 1 - j;
+                const int* row = ra.res + age * rt + base;
+                const int* srow = ra.res + kStaticBit * rt + base;
+                for (int k = lane; k < R; k += 32) {
+                    float v = L;
+                    if (age < n_valid) {
+                        int bits = row[k], sb = srow[k];
+                        bits = sb < bits ? sb : bits;
+                        if (bits != kNoHitBits) v = i2f_bits(bits);
+                    }
+                    if (nsec == 1) {
+                        dst[j * R + k] = v;
+                    } else {   // SEN:932-953: four sector-masked copies side by side
+                        int ksec = (k < in_sector) ? 0 : (k < 2 * in_sector) ? 1 : (k < 3 * in_sector) ? 2 : 3;
+                        for (int sec = 0; sec < 4; sec++) dst[(j * 4 + sec) * R + k] = sec == ksec ? v : 0.f;
+                    }
                 }
-                if (sc.pad_sectors) {   // SEN:932-953: four sector-masked copies side by side
-                    int ksec = (k < in_sector) ? 0 : (k < 2 * in_sector) ? 1 : (k < 3 * in_sector) ? 2 : 3;
-                    if (sec != ksec) v = 0.f;
-                }
-                dst[e] = v;
             }
             off += sensor_width(sc);
         }
