@@ -108,9 +108,15 @@ FTL_HD int smem_atomic_add(int* p, int v) { int o = *p; *p = o + v; return o; }
 FTL_HD void smem_atomic_min(int* p, int v) { if (v < *p) *p = v; }
 #endif
 
-constexpr int kEdgeCap = 224;       // compact edge list per flush
-constexpr int kPairCap = 512;       // (edge, ray) pairs per flush
-constexpr int kCorridorChunk = 96;  // corridor ring entries per flush (2 edges each)
+#ifndef FTL_EDGE_CAP
+#define FTL_EDGE_CAP 160
+#endif
+#ifndef FTL_PAIR_CAP
+#define FTL_PAIR_CAP 320
+#endif
+constexpr int kEdgeCap = FTL_EDGE_CAP;  // compact edge list per flush (overridable: tests build with tiny lists)
+constexpr int kPairCap = FTL_PAIR_CAP;  // (edge, ray) pairs per flush
+constexpr int kCorridorChunk = 64;  // corridor ring entries per batch (2 edges each)
 constexpr int kStaticBit = 8;       // row-mask bit of the static minimum (merged into all valid rows)
 constexpr int kNoHitBits = 0x7f7fffff;
 enum EdgeClass { EC_STATIC = 0, EC_LEADER = 1, EC_BEAR = 2, EC_CORRIDOR = 3, EC_CAP = 4, EC_COUNT = 5 };
@@ -125,7 +131,7 @@ struct RaySensorTab {
 
 struct RayShared {
     float px, py;
-    int scenario, snap_pushes, n_valid, ne, np;
+    int scenario, snap_pushes, n_valid, ne, np, rt, ns;
     float reach[EC_COUNT];                         // largest laser_length among sensors reacting to the class
     int tail[FTL_MAX_HIST], head[FTL_MAX_HIST];    // by age (0 = newest)
     RaySensorTab sen[FTL_MAX_RAY_SENSORS];
@@ -174,12 +180,34 @@ FTL_HD float atan2_deg_approx(float y, float x) {
     return y < 0.f ? -r : r;
 }
 
+// all candidate rays of one edge, tested in place (only used when the shared lists are full)
+FTL_HD_NOINLINE void edge_inline(RayShared& sh, int rt, const RayEdge ed, int n_sensors) {
+    const RayArrays ra = ray_arrays(&sh, rt);
+    const int cls_bit = ed.mask >> 16;
+    for (int sidx = 0; sidx < n_sensors; sidx++) {
+        const RaySensorTab& st = sh.sen[sidx];
+        if (!(st.cls_mask & cls_bit)) continue;
+        int rows = ed.mask & 0x1ff;
+        if (!(rows & (1 << kStaticBit))) rows &= (1 << st.H) - 1;
+        if (!rows) continue;
+        for (int k = 0; k < st.R; k++) {
+            int f = st.base + k;
+            float d = seg_hit(sh.px, sh.py, ra.dx[f], ra.dy[f], ra.len[f], ed.ax, ed.ay, ed.bx, ed.by);
+            if (d >= kNoHit) continue;
+            int bits = f2i_bits(d);
+            for (int a = 0; a <= FTL_MAX_HIST; a++)
+                if (rows & (1 << a)) smem_atomic_min(&ra.res[a * rt + f], bits);
+        }
+    }
+}
+
 FTL_HD void edge_append(RayShared& sh, float ax, float ay, float bx, float by, int mask) {
     int slot = smem_atomic_add(&sh.ne, 1);
-    if (slot < kEdgeCap) {
-        RayEdge ed = {ax, ay, bx, by, mask};
+    RayEdge ed = {ax, ay, bx, by, mask};
+    if (slot < kEdgeCap)
         sh.e[slot] = ed;
-    }
+    else
+        edge_inline(sh, sh.rt, ed, sh.ns);
 }
 
 // A1 for one rectangle: reach cull + front-facing edges (edge order/orientation of SEN:668-671).  A ray from
@@ -291,7 +319,7 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
             int pushes = s.gi[(size_t)GI_SNAP_PUSHES * s.n + i];
             sh.snap_pushes = pushes;
             sh.n_valid = pushes < FTL_MAX_HIST ? pushes : FTL_MAX_HIST;
-            sh.ne = 0; sh.np = 0;
+            sh.ne = 0; sh.np = 0; sh.rt = rt; sh.ns = ns;
             for (int k = 0; k < EC_COUNT; k++) sh.reach[k] = -1e30f;
             int base = 0;
             for (int sidx = 0; sidx < ns; sidx++) {
@@ -341,15 +369,27 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
         const int4* statics = pool.static_rects + (size_t)sh.scenario * c.static_cap;
         const int n_static = pool.n_static[sh.scenario];
         const int n_dyn = n_valid * (1 + NBr);
-        FTL_LANES(lane) {
-            if (sh.reach[EC_STATIC] > 0.f)
-                for (int q = lane; q < n_static; q += 32) rect_append(sh, statics[q], EC_STATIC, 1 << kStaticBit);
-            for (int q = lane; q < n_dyn; q += 32) {
-                int age = q / (1 + NBr), k = q % (1 + NBr);
-                int cls = k == 0 ? EC_LEADER : EC_BEAR;
-                if (sh.reach[cls] > 0.f) {
-                    int slot = (sh.snap_pushes - 1 - age) % FTL_MAX_HIST;
-                    rect_append(sh, s.snap_rect[((size_t)slot * (1 + NBr) + k) * s.n + i], cls, 1 << age);
+        if (sh.reach[EC_STATIC] > 0.f) {
+            for (int q0 = 0; q0 < n_static; q0 += 32) {
+                FTL_WARP_SYNC();
+                if (sh.ne + 4 * 32 > kEdgeCap) ray_flush(sh, ra, ns);   // a round adds at most 4 edges per lane
+                FTL_LANES(lane) {
+                    if (q0 + lane < n_static) rect_append(sh, statics[q0 + lane], EC_STATIC, 1 << kStaticBit);
+                }
+            }
+        }
+        for (int q0 = 0; q0 < n_dyn; q0 += 32) {
+            FTL_WARP_SYNC();
+            if (sh.ne + 4 * 32 > kEdgeCap) ray_flush(sh, ra, ns);
+            FTL_LANES(lane) {
+                int q = q0 + lane;
+                if (q < n_dyn) {
+                    int age = q / (1 + NBr), k = q - age * (1 + NBr);
+                    int cls = k == 0 ? EC_LEADER : EC_BEAR;
+                    if (sh.reach[cls] > 0.f) {
+                        int slot = (sh.snap_pushes - 1 - age) % FTL_MAX_HIST;
+                        rect_append(sh, s.snap_rect[((size_t)slot * (1 + NBr) + k) * s.n + i], cls, 1 << age);
+                    }
                 }
             }
         }
@@ -405,23 +445,23 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
             float* dst = rays_out + (size_t)i * cfg.rays_per_env + off;
             const int nsec = sc.pad_sectors ? 4 : 1;
             const double in_sector = R / 4.0;
-            for (int j = 0; j < H; j++) {
+            const float inv_R = 1.0f / (float)R;
+            const int* srow = ra.res + kStaticBit * rt + base;
+            for (int e = lane; e < H * R; e += 32) {
+                int j = (int)(((float)e + 0.5f) * inv_R);      // e / R without an integer division (H*R < 2^20)
+                int k = e - j * R;
                 const int age = H - 1 - j;
-                const int* row = ra.res + age * rt + base;
-                const int* srow = ra.res + kStaticBit * rt + base;
-                for (int k = lane; k < R; k += 32) {
-                    float v = L;
-                    if (age < n_valid) {
-                        int bits = row[k], sb = srow[k];
-                        bits = sb < bits ? sb : bits;
-                        if (bits != kNoHitBits) v = i2f_bits(bits);
-                    }
-                    if (nsec == 1) {
-                        dst[j * R + k] = v;
-                    } else {   // SEN:932-953: four sector-masked copies side by side
-                        int ksec = (k < in_sector) ? 0 : (k < 2 * in_sector) ? 1 : (k < 3 * in_sector) ? 2 : 3;
-                        for (int sec = 0; sec < 4; sec++) dst[(j * 4 + sec) * R + k] = sec == ksec ? v : 0.f;
-                    }
+                float v = L;
+                if (age < n_valid) {
+                    int bits = ra.res[age * rt + base + k], sb = srow[k];
+                    bits = sb < bits ? sb : bits;
+                    if (bits != kNoHitBits) v = i2f_bits(bits);
+                }
+                if (nsec == 1) {
+                    dst[e] = v;
+                } else {   // SEN:932-953: four sector-masked copies side by side
+                    int ksec = (k < in_sector) ? 0 : (k < 2 * in_sector) ? 1 : (k < 3 * in_sector) ? 2 : 3;
+                    for (int sec = 0; sec < 4; sec++) dst[(j * 4 + sec) * R + k] = sec == ksec ? v : 0.f;
                 }
             }
             off += sensor_width(sc);

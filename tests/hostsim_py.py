@@ -8,9 +8,9 @@ from continiousenvironment_follower_leader_b200 import capi
 _DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim")
 
 
-def lib():
-    subprocess.check_call(["make", "-C", _DIR, "-s", "libftl_hostsim.so"])
-    return capi.load(os.path.join(_DIR, "libftl_hostsim.so"))
+def lib(name="libftl_hostsim.so"):
+    subprocess.check_call(["make", "-C", _DIR, "-s", name])
+    return capi.load(os.path.join(_DIR, name))
 
 
 def make_env(gc, n, **kw):

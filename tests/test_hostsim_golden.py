@@ -24,3 +24,14 @@ def test_device_functions_reproduce_reference_trace(path):
     assert T == meta["n_env_steps"]
     parity.check_final_arrays(env.get_state(), d, gc)
     assert int(env.get_state().env[0]["overflow"]) == 0
+
+
+def test_ray_pass_overflow_paths_give_the_same_rays():
+    """Tiny shared-memory lists (6 edges, 5 pairs) force every overflow branch of the ray pass."""
+    from hostsim_py import lib
+    from continiousenvironment_follower_leader_b200 import capi
+    d, meta = parity.load_trace(parity.GOLDEN_DIR + "/cfg3_seed23_follow_then_random.npz")
+    gc = parity.config_for(meta, _route_len=len(d["scen_route"]), _n_static=len(d["scen_static_rects"]))
+    env = capi.HostEnv(gc, 1, lib=lib("libftl_hostsim_smallcaps.so"))
+    env.upload_scenarios(parity.pool_for(d, gc))
+    parity.replay(env, d, gc, float_rtol=0.0, ray_rtol=parity.RTOL, ray_outlier_budget=0, max_steps=120)
