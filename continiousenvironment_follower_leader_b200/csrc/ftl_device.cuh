@@ -367,6 +367,9 @@ struct GreenCache {
     float lb_all;  // lower bound of the distance from (sax, say) to every trail point
     float sgx, sgy, sax, say;  // follower positions at the last full scans
     int nice_from;  // all trail_d[k], k >= nice_from, are multiples of 2^-15 (exact float32 sums)
+    // register copies, not persisted: coordinates of the two witnesses and the newest trail point / length
+    float2 a_pt, b_pt, last_pt;
+    double last_s;
 };
 
 constexpr float kBoundSlack = 2e-3f;  // covers float32 rounding of positions/distances up to ~4000 px
@@ -392,11 +395,10 @@ FTL_HD int green_lo_exact(const float* trail_d, int n, float max_distance_f32) {
 // Such points (the leader covers 1.25 px per saved point and max_distance is 160 of those, so near-ties are the
 // rule on straight stretches) are kept as "uncertain" and only resolved with the exact walk if the flags ever
 // depend on them.  The window start only moves forward (float addition is monotone).
-FTL_HD void green_window_update(const double* trail_s, int n, float max_distance_f32, int nice_from, int* g_lo,
-                                int* g_unc) {
+FTL_HD void green_window_update(const double* trail_s, int n, double total, float max_distance_f32, int nice_from,
+                                int* g_lo, int* g_unc) {   // total = trail_s[n-1]
     if (n < 2) { *g_lo = n - 1; *g_unc = 0; return; }
     const double maxd = (double)max_distance_f32;
-    const double total = trail_s[n - 1];
     int lo = *g_lo - *g_unc;
     if (lo < 0) lo = 0;
     int first_unc = -1;
@@ -495,12 +497,12 @@ FTL_HD void green_flags(const DevCfg& cfg, const float2* trail, const float* tra
     int le_eps = 0, le_dev = 0;
     bool need = false;
     if (have_green) {
-        if (gc.a_star < gc.g_lo) gc.a_star = gc.g_lo;  // the witness left the window: its oldest certain point is the next guess
-        float ub2 = 3.0e38f;
-        if (gc.a_star <= hi) {
-            float2 p = trail[gc.a_star];
-            ub2 = d2_f32(p.x, p.y, fx, fy);
+        if (gc.a_star < gc.g_lo) {  // the witness left the window: its oldest certain point is the next guess
+            gc.a_star = gc.g_lo;
+            gc.a_pt = trail[gc.a_star];
         }
+        float ub2 = 3.0e38f;
+        if (gc.a_star <= hi) ub2 = d2_f32(gc.a_pt.x, gc.a_pt.y, fx, fy);
         float disp2 = d2_f32(fx, fy, gc.sgx, gc.sgy);
         le_eps = bound_decide(ub2, gc.lb_g, disp2, cfg.eps_f32, cfg.eps2_f32);
         le_dev = le_eps == 1 ? 1 : bound_decide(ub2, gc.lb_g, disp2, cfg.dev_f32, cfg.dev2_f32);
@@ -526,6 +528,7 @@ FTL_HD void green_flags(const DevCfg& cfg, const float2* trail, const float* tra
                 m_low = m;
             }
             gc.a_star = arg;
+            gc.a_pt = trail[arg];
             gc.lb_g = sqrtf(m_low) - kBoundSlack;
             gc.sgx = fx; gc.sgy = fy;
             le_eps = m <= cfg.eps2_f32;
@@ -538,10 +541,7 @@ FTL_HD void green_flags(const DevCfg& cfg, const float2* trail, const float* tra
     need = false;
     if (fallback) {
         float ub2a = 3.0e38f;
-        if (gc.b_star >= 0 && gc.b_star < n) {
-            float2 p = trail[gc.b_star];
-            ub2a = d2_f32(p.x, p.y, fx, fy);
-        }
+        if (gc.b_star >= 0 && gc.b_star < n) ub2a = d2_f32(gc.b_pt.x, gc.b_pt.y, fx, fy);
         float disp2a = d2_f32(fx, fy, gc.sax, gc.say);
         le = bound_decide(ub2a, gc.lb_all, disp2a, cfg.eps_f32, cfg.eps2_f32);
         FTL_COUNT(4, 1);
@@ -554,6 +554,7 @@ FTL_HD void green_flags(const DevCfg& cfg, const float2* trail, const float* tra
             FTL_COUNT(5, 1);
             FTL_COUNT(6, n);
             gc.b_star = arg;
+            gc.b_pt = trail[arg];
             gc.lb_all = sqrtf(m) - kBoundSlack;
             gc.sax = fx; gc.say = fy;
             le = m <= cfg.eps2_f32;
@@ -565,18 +566,15 @@ FTL_HD void green_flags(const DevCfg& cfg, const float2* trail, const float* tra
 
 // the trail grew: trail[n-1] is new (n = new length); trail[n-2] enters the green set.  New points are folded
 // into the bounds as distances from the respective scan positions.
-FTL_HD void green_cache_appended(const DevCfg& cfg, const float2* trail, const float* trail_d, const double* trail_s,
-                                 int n, GreenCache& gc) {
-    {
-        float d = trail_d[n - 1];
-        if (d * 32768.f != rintf(d * 32768.f)) gc.nice_from = n;  // term n-1 is not on the 2^-15 grid
-    }
-    green_window_update(trail_s, n, cfg.max_distance_f32, gc.nice_from, &gc.g_lo, &gc.g_unc);
-    float2 p = trail[n - 1];
+// the trail grew: `p` was appended at index n-1 (n = new length), the previous newest point `q` (index n-2)
+// enters the green set.  New points are folded into the bounds as distances from the respective scan positions.
+FTL_HD void green_cache_appended(const DevCfg& cfg, const double* trail_s, int n, float2 p, float2 q, float d_new,
+                                 GreenCache& gc) {
+    if (d_new * 32768.f != rintf(d_new * 32768.f)) gc.nice_from = n;  // term n-1 is not on the 2^-15 grid
+    green_window_update(trail_s, n, gc.last_s, cfg.max_distance_f32, gc.nice_from, &gc.g_lo, &gc.g_unc);
     float d = sqrtf(d2_f32(p.x, p.y, gc.sax, gc.say)) - kBoundSlack;
     if (d < gc.lb_all) gc.lb_all = d;
     if (n >= 2) {
-        float2 q = trail[n - 2];
         float dq = sqrtf(d2_f32(q.x, q.y, gc.sgx, gc.sgy)) - kBoundSlack;
         if (dq < gc.lb_g) gc.lb_g = dq;
     }
@@ -590,6 +588,15 @@ FTL_HD void green_cache_invalidate(const DevCfg& cfg, const float* trail_d, int 
     gc.lb_g = -1.f;
     gc.lb_all = -1.f;
     gc.sgx = gc.sgy = gc.sax = gc.say = 0.f;
+    gc.a_pt = gc.b_pt = make_float2(0.f, 0.f);
+}
+
+// register copies of the witnesses and of the trail tail (after a cache_load)
+FTL_HD void green_cache_hydrate(const float2* trail, const double* trail_s, int n, GreenCache& gc) {
+    gc.a_pt = (gc.a_star >= 0 && gc.a_star < n) ? trail[gc.a_star] : make_float2(0.f, 0.f);
+    gc.b_pt = (gc.b_star >= 0 && gc.b_star < n) ? trail[gc.b_star] : make_float2(0.f, 0.f);
+    gc.last_pt = n > 0 ? trail[n - 1] : make_float2(0.f, 0.f);
+    gc.last_s = n > 0 ? trail_s[n - 1] : 0.0;
 }
 
 // append one point to the trail and its derived arrays

@@ -246,6 +246,7 @@ FTL_HD void env_step(const DevCfg& cfg, const DevState& s, const DevPool& pool, 
     float2* trail = s.trail + (size_t)i * c.trail_cap;
     float* trail_d = s.trail_d + (size_t)i * c.trail_cap;
     double* trail_s = s.trail_s + (size_t)i * c.trail_cap;
+    green_cache_hydrate(trail, trail_s, e.trail_len, gc);
     const int4* statics = pool.static_rects + (size_t)e.scenario * c.static_cap;
     const int n_static = pool.n_static[e.scenario];
     const int n_route = pool.n_route[e.scenario];
@@ -254,6 +255,9 @@ FTL_HD void env_step(const DevCfg& cfg, const DevState& s, const DevPool& pool, 
     if (a1 < 0) command_turn(w.follower, c.follower, fabs(a1), -1);
     else if (a1 > 0) command_turn(w.follower, c.follower, a1, 1);
     else command_turn(w.follower, c.follower, 0, 0);
+
+    // the leader's current target lives in registers; it is re-read only when the waypoint index advances
+    int2 target = route_point(pool, c, e.scenario, e.cur_target_id < n_route ? e.cur_target_id : n_route - 1);
 
     const uint64_t fmask = near_static_mask(statics, n_static, w.follower.px, w.follower.py, cfg.static_inflate[0]);
     const uint64_t lmask = near_static_mask(statics, n_static, w.leader.px, w.leader.py, cfg.static_inflate[1]);
@@ -278,13 +282,11 @@ FTL_HD void env_step(const DevCfg& cfg, const DevState& s, const DevPool& pool, 
         green_flags(cfg, trail, trail_d, e.trail_len, w.follower.px, w.follower.py, gc, &in_box, &on_trace);
         bool too_close = d2_f32(w.leader.px, w.leader.py, w.follower.px, w.follower.py) <= cfg.min_dist2_f32;
         // (3) waypoint advance, ENV:978-983
-        {
-            int tid = e.cur_target_id < n_route ? e.cur_target_id : n_route - 1;
-            int2 p = route_point(pool, c, e.scenario, tid);
-            if (dist_f64((double)w.leader.px, (double)w.leader.py, (double)p.x, (double)p.y) < c.leader_pos_epsilon) {
-                e.cur_target_id += 1;
-                if (e.cur_target_id >= n_route) e.flags |= FL_LEADER_FINISHED;
-            }
+        if (dist_f64((double)w.leader.px, (double)w.leader.py, (double)target.x, (double)target.y) <
+            c.leader_pos_epsilon) {
+            e.cur_target_id += 1;
+            if (e.cur_target_id >= n_route) e.flags |= FL_LEADER_FINISHED;   // cur_target_point keeps its last value
+            else target = route_point(pool, c, e.scenario, e.cur_target_id);
         }
         // (4) bears, ENV:987-995
 #pragma unroll
@@ -296,8 +298,7 @@ FTL_HD void env_step(const DevCfg& cfg, const DevState& s, const DevPool& pool, 
         if (!(e.flags & FL_LEADER_FINISHED)) {
             double speed = c.n_speed_regime > 0 ? leader_speed(cfg, e, i) : c.leader.max_speed;
             double accel = c.n_accel_regime > 0 ? leader_accel(cfg, e) / c.frames_per_step : 0.0;
-            int2 p = route_point(pool, c, e.scenario, e.cur_target_id);
-            move_to_the_point(w.leader, c.leader, (double)p.x, (double)p.y, true, speed + accel);
+            move_to_the_point(w.leader, c.leader, (double)target.x, (double)target.y, true, speed + accel);
         } else {
             command_forward(w.leader, c.leader, 0);
             command_turn(w.leader, c.leader, 0, 0);
@@ -312,9 +313,22 @@ FTL_HD void env_step(const DevCfg& cfg, const DevState& s, const DevPool& pool, 
         // (6) trail append on the virtual clock, ENV:1074-1075
         if (e.step_count % c.trajectory_saving_period == 0) {
             if (e.trail_len < c.trail_cap) {
-                trail_push(trail, trail_d, trail_s, e.trail_len, w.leader.px, w.leader.py);
+                // trail_push with the previous tail in registers
+                const int k = e.trail_len;
+                const float2 p = make_float2(w.leader.px, w.leader.py), q = gc.last_pt;
+                float dk = 0.f;
+                trail[k] = p;
+                if (k > 0) {
+                    dk = sqrtf(d2_f32(p.x, p.y, q.x, q.y));   // euclidean(newer, older) in float32, ENV:1838
+                    gc.last_s = gc.last_s + (double)dk;
+                } else {
+                    gc.last_s = 0.0;
+                }
+                trail_d[k] = dk;
+                trail_s[k] = gc.last_s;
+                gc.last_pt = p;
                 e.trail_len++;
-                green_cache_appended(cfg, trail, trail_d, trail_s, e.trail_len, gc);
+                green_cache_appended(cfg, trail_s, e.trail_len, p, q, dk, gc);
             } else {
                 e.overflow |= 1;
             }

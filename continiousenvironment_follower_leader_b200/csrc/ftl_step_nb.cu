@@ -18,6 +18,20 @@ using namespace ftl;
 
 __device__ __forceinline__ void add_stat(double* stats, int which, double v) { atomicAdd(stats + which, v); }
 
+// The in-step auto-reset is a cold path: kept out of line with its own registers so that it neither grows the
+// hot loop nor forces the step's state through local memory.
+template <int NB>
+__device__ __noinline__ void reset_in_place(const DevCfg& cfg, const DevState& s, const DevPool& pool,
+                                            const DevOutputs& out, int i, int episode) {
+    World<NB> w;
+    Episode e;
+    int scen = next_scenario(cfg, pool.n_scenarios, i, episode);
+    env_reset<NB>(cfg, s, pool, i, scen, w, e);
+    write_outputs<NB>(cfg, pool, out, i, w, e, true);
+    world_store<NB>(s, i, w);
+    episode_store(s, i, e);
+}
+
 template <int NB>
 __global__ void __launch_bounds__(128)
 k_step(const __grid_constant__ DevCfg cfg, const DevState s, const DevPool pool, const void* __restrict__ actions,
@@ -47,13 +61,15 @@ k_step(const __grid_constant__ DevCfg cfg, const DevState s, const DevPool pool,
     }
     if ((cfg.c.auto_reset || i >= s.n_real) && done) {
         // reward/done/status of the finished episode stay in `out`; the observation becomes the first
-        // one of the next episode (vector-env convention)
-        int scen = next_scenario(cfg, pool.n_scenarios, i, e.episode);
-        env_reset<NB>(cfg, s, pool, i, scen, w, e);
-        write_outputs<NB>(cfg, pool, out, i, w, e, true);
+        // one of the next episode (vector-env convention).  accel_consumed / episode are read back from the
+        // arrays by env_reset, so store them first.
+        s.gi[(size_t)GI_ACCEL_CONSUMED * s.n + i] = e.accel_consumed;
+        s.gi[(size_t)GI_EPISODE * s.n + i] = e.episode;
+        reset_in_place<NB>(cfg, s, pool, out, i, e.episode);
+    } else {
+        world_store<NB>(s, i, w);
+        episode_store(s, i, e);
     }
-    world_store<NB>(s, i, w);
-    episode_store(s, i, e);
 }
 
 template <int NB>
