@@ -32,7 +32,7 @@ _LIBS = {}
 
 def load(path=None):
     """dlopen a library exporting the include/ftl.h entry points and declare their signatures."""
-    path = os.path.abspath(path or DEFAULT_LIB)
+    path = os.path.abspath(path or os.environ.get("FTL_LIB") or DEFAULT_LIB)
     if path in _LIBS:
         return _LIBS[path]
     if not os.path.exists(path):

@@ -173,7 +173,7 @@ class GameConfig:
             corridor_cap = 64
             if c.tracker_enabled:
                 per_save = max(lead_v * c.frames_per_step * c.saving_period / max(c.tracker_scans_per_step, 1), 1e-6)
-                corridor_cap = _pow2_at_least(int(1.5 * c.corridor_length / per_save) + 32)
+                corridor_cap = min(_pow2_at_least(int(1.5 * c.corridor_length / per_save) + 32), 512)
         if corridor_cap & (corridor_cap - 1) or corridor_cap > 512:
             raise ValueError("corridor_cap must be a power of two <= 512")
         c.corridor_cap = int(corridor_cap)

@@ -150,6 +150,24 @@ FTL_HD double angle_to_point(double cx, double cy, double tx, double ty) {  // M
     return angle_correction(res);
 }
 
+// int(angle_to_point(...)) as move_to_the_point uses it (CLS:192): only the integer part of the bearing reaches
+// the state, so it is taken from a float32 evaluation whenever that is at least 2e-3 degrees away from an integer
+// (float32 atan + scaling is good to ~1e-4 degrees), and from the float64 formula otherwise.  Same result as the
+// float64 formula in every case, ~5x fewer instructions on the common path.
+FTL_HD int bearing_int(double cx, double cy, double tx, double ty) {
+    const double rxd = tx - cx, ryd = ty - cy;
+    const float rx = (float)rxd, ry = (float)ryd;
+    if (fabsf(rx) > 1e-3f) {
+        float a = atanf(ry / rx) * 57.29577951308232f;
+        if (rx < 0.f) a += 180.f;
+        if (a < 0.f) a += 360.f;          // angle_correction; a in (-90, 270) here
+        float fl = floorf(a);
+        float frac = a - fl;
+        if (frac > 2e-3f && frac < 1.f - 2e-3f && a > 2e-3f && a < 360.f - 2e-3f) return (int)fl;
+    }
+    return (int)angle_to_point(cx, cy, tx, ty);
+}
+
 FTL_HD float d2_f32(float ax, float ay, float bx, float by) {  // float32 (a-b)^2 summed, numpy order
     float dx = ax - bx, dy = ay - by;
     float sx = dx * dx, sy = dy * dy;
@@ -226,6 +244,22 @@ FTL_HD void rotated_size(int w, int h, double angle_py, int* ow, int* oh) {
         if (turns & 1) { *ow = h; *oh = w; } else { *ow = w; *oh = h; }
         return;
     }
+    {   // float32 evaluation decides unless a bound is within 1e-3 of an integer (sizes are < 100 px: float32 error ~1e-5)
+        float snf, csf;
+#if defined(__CUDA_ARCH__)
+        sincosf(angle * 0.017453292519943295f, &snf, &csf);
+#else
+        snf = sinf(angle * 0.017453292519943295f); csf = cosf(angle * 0.017453292519943295f);
+#endif
+        float cxf = fabsf(csf) * (float)w, cyf = fabsf(csf) * (float)h, sxf = fabsf(snf) * (float)w, syf = fabsf(snf) * (float)h;
+        float mxf = cxf + syf, myf = sxf + cyf;   // max |cx +- sy| = |cx| + |sy|, same for the other axis
+        float fx = mxf - floorf(mxf), fy = myf - floorf(myf);
+        if (fx > 1e-3f && fx < 1.f - 1e-3f && fy > 1e-3f && fy < 1.f - 1e-3f) {
+            *ow = (int)mxf;
+            *oh = (int)myf;
+            return;
+        }
+    }
     double rad = angle * .01745329251994329, sn, cs;
 #if defined(__CUDA_ARCH__)
     sincos(rad, &sn, &cs);
@@ -291,7 +325,7 @@ FTL_HD void robot_move(Robot& r, const FtlRobotConfig& c) {  // CLS:129-182
 FTL_HD void move_to_the_point(Robot& r, const FtlRobotConfig& c, double tx, double ty, bool has_speed,
                               double speed) {  // CLS:184-215
     double new_speed = has_speed ? speed : dist_f64((double)r.px, (double)r.py, tx, ty);
-    int desirable_angle = (int)angle_to_point((double)r.px, (double)r.py, tx, ty);
+    int desirable_angle = bearing_int((double)r.px, (double)r.py, tx, ty);
     int cur = (int)r.dir;
     int delta, nrd;
     if (desirable_angle - cur > 0) {
@@ -304,6 +338,31 @@ FTL_HD void move_to_the_point(Robot& r, const FtlRobotConfig& c, double tx, doub
     command_turn(r, c, (double)delta, nrd);
     command_forward(r, c, new_speed);
     robot_move(r, c);
+}
+
+// Out-of-line versions for the step kernel: the robot code (two float64 sincos, one atan, the rotated bounding box)
+// is ~1.5k instructions; inlined at every call site the frame loop overflows the instruction caches.  Robots
+// travel by value (registers), so nothing is forced into local memory.
+FTL_HD_NOINLINE Robot robot_move_nv(Robot r, const FtlRobotConfig* c) {
+    robot_move(r, *c);
+    return r;
+}
+FTL_HD_NOINLINE Robot move_to_the_point_nv(Robot r, const FtlRobotConfig* c, double tx, double ty, int has_speed,
+                                           double speed) {
+    double new_speed = has_speed ? speed : dist_f64((double)r.px, (double)r.py, tx, ty);
+    int desirable_angle = bearing_int((double)r.px, (double)r.py, tx, ty);
+    int cur = (int)r.dir;
+    int delta, nrd;
+    if (desirable_angle - cur > 0) {
+        if (desirable_angle - cur > 180) { delta = cur + (360 - desirable_angle); nrd = -1; }
+        else { delta = desirable_angle - cur; nrd = 1; }
+    } else {
+        if (cur - desirable_angle > 180) { nrd = 1; delta = (360 - cur) + desirable_angle; }
+        else { nrd = -1; delta = cur - desirable_angle; }
+    }
+    command_turn(r, *c, (double)delta, nrd);
+    command_forward(r, *c, new_speed);
+    return robot_move_nv(r, c);
 }
 
 // ---- collisions -----------------------------------------------------------------------------------------

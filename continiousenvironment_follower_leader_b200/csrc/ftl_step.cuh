@@ -265,7 +265,7 @@ FTL_HD void env_step(const DevCfg& cfg, const DevState& s, const DevPool& pool, 
     for (int f = 0; f < c.frames_per_step; f++) {
         int mission = FTL_MISSION_IN_PROGRESS, agent = FTL_AGENT_MOVING, leader_st = FTL_LEADER_MOVING;
         // (1) follower, ENV:957-964
-        robot_move(w.follower, c.follower);
+        w.follower = robot_move_nv(w.follower, &c.follower);
         if (!c.ignore_follower_collisions) {
             bool hit = robots_collide(w.follower, w.leader) || collide_static_masked(w.follower, statics, fmask) ||
                        out_of_bounds(c, w.follower);
@@ -292,13 +292,13 @@ FTL_HD void env_step(const DevCfg& cfg, const DevState& s, const DevPool& pool, 
 #pragma unroll
         for (int b = 0; b < NB; b++) {
             bear_target(c, b, w.bear[b], w.leader, &w.btx[b], &w.bty[b], &w.bidx[b]);
-            move_to_the_point(w.bear[b], c.bear, w.btx[b], w.bty[b], false, 0.0);
+            w.bear[b] = move_to_the_point_nv(w.bear[b], &c.bear, w.btx[b], w.bty[b], 0, 0.0);
         }
         // (5) leader, ENV:1048-1072
         if (!(e.flags & FL_LEADER_FINISHED)) {
             double speed = c.n_speed_regime > 0 ? leader_speed(cfg, e, i) : c.leader.max_speed;
             double accel = c.n_accel_regime > 0 ? leader_accel(cfg, e) / c.frames_per_step : 0.0;
-            move_to_the_point(w.leader, c.leader, (double)target.x, (double)target.y, true, speed + accel);
+            w.leader = move_to_the_point_nv(w.leader, &c.leader, (double)target.x, (double)target.y, 1, speed + accel);
         } else {
             command_forward(w.leader, c.leader, 0);
             command_turn(w.leader, c.leader, 0, 0);

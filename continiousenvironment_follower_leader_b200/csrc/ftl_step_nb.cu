@@ -32,8 +32,14 @@ __device__ __noinline__ void reset_in_place(const DevCfg& cfg, const DevState& s
     episode_store(s, i, e);
 }
 
+#ifndef FTL_STEP_THREADS
+#define FTL_STEP_THREADS 64   // 65536 envs are only ~14 warps per SM: small blocks spread them evenly over the 148 SMs
+#endif
+#ifndef FTL_STEP_MINBLOCKS
+#define FTL_STEP_MINBLOCKS 1
+#endif
 template <int NB>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(FTL_STEP_THREADS, FTL_STEP_MINBLOCKS)
 k_step(const __grid_constant__ DevCfg cfg, const DevState s, const DevPool pool, const void* __restrict__ actions,
        const DevOutputs out, double* __restrict__ stats) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -96,8 +102,7 @@ k_reset(const __grid_constant__ DevCfg cfg, const DevState s, const DevPool pool
 
 void FTL_CAT(ftl_launch_step_nb, FTL_NB)(const DevCfg& cfg, const DevState& s, const DevPool& pool, const void* actions,
                                           const DevOutputs& out, double* stats, cudaStream_t st) {
-    // 64-thread blocks: 65536 envs are only ~14 warps per SM, small blocks spread them evenly over the 148 SMs
-    int threads = 64, blocks = (s.n + threads - 1) / threads;
+    int threads = FTL_STEP_THREADS, blocks = (s.n + threads - 1) / threads;
     k_step<FTL_NB><<<blocks, threads, 0, st>>>(cfg, s, pool, actions, out, stats);
 }
 void FTL_CAT(ftl_launch_reset_nb, FTL_NB)(const DevCfg& cfg, const DevState& s, const DevPool& pool, const uint8_t* mask,
