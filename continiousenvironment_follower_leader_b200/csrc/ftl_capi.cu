@@ -28,11 +28,11 @@ using namespace ftl;
 // =================================================================================================
 __global__ void __launch_bounds__(128)
 k_rays(const __grid_constant__ DevCfg cfg, const DevState s, const DevPool pool, const double2* __restrict__ rot,
-       float* __restrict__ rays_out, int smem_per_warp) {
+       float* __restrict__ rays_out, int smem_per_warp, int first_env, int end_env) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5;
-    const int i = blockIdx.x * (blockDim.x >> 5) + warp;  // one warp per env
-    if (i >= s.n_real) return;
+    const int i = first_env + blockIdx.x * (blockDim.x >> 5) + warp;  // one warp per env
+    if (i >= end_env) return;
     RayShared& sh = *reinterpret_cast<RayShared*>(smem + (size_t)warp * smem_per_warp);
     rays_warp(cfg, s, pool, rot, i, sh, rays_out);
 }
@@ -86,6 +86,8 @@ struct FtlHandle_ {
     int rays_total = 0;
     bool rays_smem_opted = false;
     double2* d_rot = nullptr;   // (cos, sin)(k * 360/R) per flat ray
+    cudaStream_t copy_stream = nullptr;   // host path: D2H copies overlap the ray kernel chunk by chunk
+    cudaEvent_t chunk_ev[8] = {};
     // optional per-kernel timing (ftl_profile): three events per step on the launching stream
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;
@@ -179,8 +181,10 @@ static DevOutputs to_dev_outputs(const FtlOutputs* o, int n_real) {
     return d;
 }
 
-static int launch_rays(ftl_handle h, float* rays, cudaStream_t st) {
+static int launch_rays(ftl_handle h, float* rays, cudaStream_t st, int first_env = 0, int end_env = -1) {
     if (!rays || h->rays_total == 0) return FTL_OK;
+    if (end_env < 0) end_env = h->n;
+    if (end_env <= first_env) return FTL_OK;
     const int warps = 4, threads = warps * 32;
     const int per_warp = (int)((ray_shared_bytes(h->rays_total) + 15) & ~(size_t)15);
     const int smem = per_warp * warps;
@@ -188,8 +192,8 @@ static int launch_rays(ftl_handle h, float* rays, cudaStream_t st) {
         CUDA_TRY(cudaFuncSetAttribute(k_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         h->rays_smem_opted = true;
     }
-    int blocks = (h->n + warps - 1) / warps;
-    k_rays<<<blocks, threads, smem, st>>>(h->cfg, h->st, h->pool, h->d_rot, rays, per_warp);
+    int blocks = (end_env - first_env + warps - 1) / warps;
+    k_rays<<<blocks, threads, smem, st>>>(h->cfg, h->st, h->pool, h->d_rot, rays, per_warp, first_env, end_env);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return FTL_OK;
@@ -333,6 +337,8 @@ int ftl_destroy(ftl_handle h) {
     for (void* p : h->pool_allocs) cudaFree(p);
     if (h->d_state_stage) cudaFree(h->d_state_stage);
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->chunk_ev) if (e) cudaEventDestroy(e);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     delete h;
     return FTL_OK;
 }
@@ -428,15 +434,54 @@ int ftl_step(ftl_handle h, const void* actions_dev, const FtlOutputs* out_dev, v
 
 int ftl_step_host(ftl_handle h, const void* actions_host, const FtlOutputs* out_host, void* cuda_stream) {
     if (!h || !actions_host) return fail(FTL_ERR_INVALID, "NULL argument");
+    if (!h->was_reset) return fail(FTL_ERR_STATE, "ftl_reset must be called before ftl_step");
     CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    size_t action_bytes = (h->cfg.c.action_mode == FTL_ACTION_CONTINUOUS ? 8 : 4) * (size_t)h->n;
+    const size_t n = h->n;
+    if (!h->copy_stream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        for (auto& e : h->chunk_ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    cudaStream_t cs = h->copy_stream;
+    size_t action_bytes = (h->cfg.c.action_mode == FTL_ACTION_CONTINUOUS ? 8 : 4) * n;
     CUDA_TRY(cudaMemcpyAsync(h->d_actions, actions_host, action_bytes, cudaMemcpyHostToDevice, st));
     FtlOutputs o = staged_outputs(h, out_host);
-    int rc = ftl_step(h, h->d_actions, &o, cuda_stream);
+    // fused step kernel, everything except the rays
+    FtlOutputs no_rays = o;
+    no_rays.rays = nullptr;
+    int rc = ftl_step(h, h->d_actions, &no_rays, cuda_stream);
     if (rc) return rc;
-    if (!out_host) { CUDA_TRY(cudaStreamSynchronize(st)); return FTL_OK; }
-    return copy_outputs_to_host(h, out_host, st);
+    if (!out_host) {
+        rc = launch_rays(h, h->d_out.rays, st);
+        if (rc) return rc;
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return FTL_OK;
+    }
+    const DevOutputs& d = h->d_out;
+    CUDA_TRY(cudaEventRecord(h->chunk_ev[0], st));
+    CUDA_TRY(cudaStreamWaitEvent(cs, h->chunk_ev[0], 0));
+    if (out_host->numerical_features) CUDA_TRY(cudaMemcpyAsync(out_host->numerical_features, d.numerical_features, 40 * n, cudaMemcpyDeviceToHost, cs));
+    if (out_host->leader_target) CUDA_TRY(cudaMemcpyAsync(out_host->leader_target, d.leader_target, 8 * n, cudaMemcpyDeviceToHost, cs));
+    if (out_host->reward) CUDA_TRY(cudaMemcpyAsync(out_host->reward, d.reward, 4 * n, cudaMemcpyDeviceToHost, cs));
+    if (out_host->done) CUDA_TRY(cudaMemcpyAsync(out_host->done, d.done, n, cudaMemcpyDeviceToHost, cs));
+    if (out_host->status) CUDA_TRY(cudaMemcpyAsync(out_host->status, d.status, 4 * n, cudaMemcpyDeviceToHost, cs));
+    // ray kernel in chunks of envs: the D2H copy of chunk c runs while chunk c+1 is being cast
+    if (out_host->rays && h->cfg.rays_per_env) {
+        const int chunks = h->n >= 8192 ? 6 : 1;
+        const size_t row = sizeof(float) * (size_t)h->cfg.rays_per_env;
+        for (int c = 0; c < chunks; c++) {
+            int first = (int)((long long)h->n * c / chunks), end = (int)((long long)h->n * (c + 1) / chunks);
+            rc = launch_rays(h, h->d_out.rays, st, first, end);
+            if (rc) return rc;
+            CUDA_TRY(cudaEventRecord(h->chunk_ev[1 + c], st));
+            CUDA_TRY(cudaStreamWaitEvent(cs, h->chunk_ev[1 + c], 0));
+            CUDA_TRY(cudaMemcpyAsync((char*)out_host->rays + row * first, (const char*)d.rays + row * first,
+                                     row * (size_t)(end - first), cudaMemcpyDeviceToHost, cs));
+        }
+    }
+    CUDA_TRY(cudaStreamSynchronize(cs));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return FTL_OK;
 }
 
 int ftl_reset_host(ftl_handle h, const uint8_t* mask_host, const int32_t* scenario_ids_host, const FtlOutputs* out_host,

@@ -11,7 +11,7 @@ import pytest
 
 import parity
 from continiousenvironment_follower_leader_b200 import abi, capi
-from continiousenvironment_follower_leader_b200.config import GameConfig, cfg3_sensors
+from continiousenvironment_follower_leader_b200.config import GameConfig, cfg3_sensors, TEST_GAME_MANUAL_GAZEBO_KWARGS
 from continiousenvironment_follower_leader_b200.scenario import synthetic_pool
 
 pytestmark = pytest.mark.gpu
@@ -74,6 +74,8 @@ def _ray_outliers(got, want, rtol=parity.RTOL):
                   follower_sensors={"LeaderPositionsTracker_v2": cfg3_sensors()["LeaderPositionsTracker_v2"]}), 4096, 40),
     ("cfg3", dict(bear_number=1, follower_sensors=cfg3_sensors()), 2048, 60),
     ("cfg3_3bears_discrete", dict(bear_number=3, discrete_action_space=True, follower_sensors=cfg3_sensors(24, 20, 3)), 512, 40),
+    ("cfg4_gazebo_hardcore", dict(TEST_GAME_MANUAL_GAZEBO_KWARGS, max_steps=900, auto_reset=True), 1024, 120),
+    ("cfg5_rays_360", dict(bear_number=2, frames_per_step=3, follower_sensors=cfg3_sensors(72, 360, 4)), 256, 30),
 ])
 def test_cuda_matches_oracle_on_seeded_batch(name, kwargs, n, steps):
     from oracle_py import OracleEnv

@@ -17,6 +17,9 @@ CASES = [
     ("cfg3_3bears_discrete", dict(bear_number=3, discrete_action_space=True, follower_sensors=cfg3_sensors(24, 20, 3)), 48, 50),
     ("cfg3_autoreset", dict(bear_number=1, follower_sensors=cfg3_sensors(), max_steps=200, auto_reset=True), 64, 70),
     ("gazebo_ranges", dict(TEST_GAME_MANUAL_GAZEBO_KWARGS, max_steps=600, auto_reset=True), 48, 150),
+    # BASELINE.json configs[4]: ray-count sweep up to 360 lasers (the reference only accepts 12/20/24/36, SEN:761)
+    ("rays_360", dict(bear_number=2, frames_per_step=3, follower_sensors=cfg3_sensors(72, 360, 4)), 24, 40),
+    ("rays_120_f1", dict(bear_number=1, frames_per_step=2, follower_sensors=cfg3_sensors(20, 120, 8)), 24, 60),
 ]
 
 
