@@ -26,7 +26,7 @@ using namespace ftl;
 // =================================================================================================
 // kernels
 // =================================================================================================
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 8)   // <= 64 registers: 8 blocks (32 warps) per SM with 7 KB of shared memory per warp
 k_rays(const __grid_constant__ DevCfg cfg, const DevState s, const DevPool pool, const double2* __restrict__ rot,
        float* __restrict__ rays_out, int smem_per_warp, int first_env, int end_env) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -35,6 +35,14 @@ k_rays(const __grid_constant__ DevCfg cfg, const DevState s, const DevPool pool,
     if (i >= end_env) return;
     RayShared& sh = *reinterpret_cast<RayShared*>(smem + (size_t)warp * smem_per_warp);
     rays_warp(cfg, s, pool, rot, i, sh, rays_out);
+}
+
+__global__ void __launch_bounds__(128)
+k_rays_exact(const __grid_constant__ DevCfg cfg, const DevState s, const DevPool pool, float* __restrict__ rays_out,
+             int first_env, int end_env) {
+    const int i = first_env + blockIdx.x * blockDim.x + threadIdx.x;   // one thread per env, idle unless a pair was inconclusive
+    if (i >= end_env) return;
+    rays_exact_env(cfg, s, pool, i, rays_out);
 }
 
 // ---- state exchange: SoA <-> FtlEnvState (AoS) ----------------------------------------------------
@@ -194,7 +202,8 @@ static int launch_rays(ftl_handle h, float* rays, cudaStream_t st, int first_env
     }
     int blocks = (end_env - first_env + warps - 1) / warps;
     k_rays<<<blocks, threads, smem, st>>>(h->cfg, h->st, h->pool, h->d_rot, rays, per_warp, first_env, end_env);
-    h->launches++;
+    k_rays_exact<<<(end_env - first_env + 127) / 128, 128, 0, st>>>(h->cfg, h->st, h->pool, rays, first_env, end_env);
+    h->launches += 2;
     CUDA_TRY(cudaGetLastError());
     return FTL_OK;
 }
@@ -303,6 +312,8 @@ int ftl_create(const FtlConfig* cfg, int32_t n_envs, int32_t device, int64_t env
     ok(dalloc(h, &s.corridor, n * c.corridor_cap));
     ok(dalloc(h, &s.snap_range, (size_t)FTL_MAX_HIST * n));
     ok(dalloc(h, &s.snap_rect, (size_t)FTL_MAX_HIST * (1 + nb) * n));
+    ok(dalloc(h, &s.unc_rec, n * kUncPerEnv));
+    ok(dalloc(h, &s.unc_count, n));
     ok(dalloc(h, &h->d_stats, (size_t)FTL_STAT_COUNT));
     ok(dalloc(h, &h->d_rot, (size_t)h->rays_total));
     if (e == cudaSuccess && h->rays_total > 0) {

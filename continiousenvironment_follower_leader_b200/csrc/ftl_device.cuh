@@ -70,6 +70,8 @@ enum {
     FL_MISSION_SHIFT = 8, FL_AGENT_SHIFT = 10, FL_LEADER_SHIFT = 13
 };
 
+struct UncRec { float ax, ay, bx, by; int f; int rows; };  // an (edge, ray) pair left to the exact ray pass
+
 struct DevState {
     int n;             // padded to a multiple of 32 (array stride and grid size); envs >= n_real are filler
     int n_real;        // environments the caller sees
@@ -90,6 +92,8 @@ struct DevState {
     float4* corridor;  // [n][corridor_cap]   (right.x, right.y, left.x, left.y)
     int2* snap_range;  // [FTL_MAX_HIST][n]   ring slot = push index % FTL_MAX_HIST
     int4* snap_rect;   // [FTL_MAX_HIST][1+n_bears][n]
+    UncRec* unc_rec;   // [n][kUncPerEnv]  scratch of the ray pass
+    int* unc_count;    // [n]
 };
 
 struct DevPool {  // scenario pool in device (or host, for hostsim) memory

@@ -33,24 +33,60 @@ FTL_HD float diff_of_products(float a, float b, float c, float d) {
 
 // distance along the ray (origin P, vector D of length L) to segment AB, or kNoHit.
 // Mirrors intersect()/seg_intersect(): strict ccw tests, t = num/denom, value = t * L.
-FTL_HD float seg_hit(float px, float py, float dx, float dy, float L, float ax, float ay, float bx, float by) {
+// *uncertain is set when one of the three predicates that involve the ray end point is closer to zero than the
+// float32 evaluation can resolve against the reference's float64 one (the ray grazes a vertex or ends on the
+// edge's line within ~1e-4 px); the caller then repeats the test with the reference's float64 arithmetic.
+FTL_HD float seg_hit(float px, float py, float dx, float dy, float L, float ax, float ay, float bx, float by,
+                     bool* uncertain) {
     float uax = px - ax, uay = py - ay;  // C - A, float32 like the reference
     float ubx = px - bx, uby = py - by;  // C - B
     // ccw(A,C,D) != ccw(B,C,D): A and B on different sides of the ray's line
     float ca = diff_of_products(uax, dy, uay, dx);
     float cb = diff_of_products(ubx, dy, uby, dx);
-    if ((ca > 0.f) == (cb > 0.f)) return kNoHit;
+    // one bound for all three predicates.  Edges are culled to |C-A|_1, |C-B|_1 <= 2(L+1), so the rounding of the
+    // float32 evaluation against the reference's float64 one stays below M(L+M)*2.5e-7 <= 1.5e-6 L^2: a ray that
+    // passes a vertex (or ends at the edge's line) closer than ~3e-4 px is re-done in float64.
+    const float bound = L * L * 1.5e-6f;
+    bool unc = fminf(fabsf(ca), fabsf(cb)) <= bound;
+    if (!unc && (ca > 0.f) == (cb > 0.f)) { *uncertain = false; return kNoHit; }
     float ex = bx - ax, ey = by - ay;
     float p3 = uay * ex, q3 = ey * uax;  // ccw(A,B,C): float32 products compared, exactly the reference's
     bool c3 = p3 > q3;
     float s1 = diff_of_products(uay, ex, ey, uax);
     float s2 = diff_of_products(ex, dy, ey, dx);   // = dap . db, the reference's denominator
-    bool c4 = (s1 + s2) > 0.f;                       // ccw(A,B,D)
+    float s12 = s1 + s2;
+    unc = unc || fabsf(s12) <= 2.f * bound;
+    *uncertain = unc;
+    if (unc) return kNoHit;
+    bool c4 = s12 > 0.f;                             // ccw(A,B,D)
     if (c3 == c4) return kNoHit;
     float m0 = (-ey) * (-uax), m1 = ex * (-uay);    // np.multiply(dap, dp) in float32
     float num = m0 + m1;
     float t = num / s2;
     return fabsf(t) * L;
+}
+
+// The same test with the reference's arithmetic (SEN:608-640 on the arrays SEN:903-906 builds): float32 edge and
+// follower position, float64 ray end point.  Returns the float32 value the reference stores, or kNoHit.
+FTL_HD_NOINLINE float seg_hit_exact(float px, float py, double ex, double ey, float ax, float ay, float bx, float by) {
+    float uax = px - ax, uay = py - ay, ubx = px - bx, uby = py - by;
+    bool cA = (ey - (double)ay) * (double)uax > (double)uay * (ex - (double)ax);   // ccw(A, C, D)
+    bool cB = (ey - (double)by) * (double)ubx > (double)uby * (ex - (double)bx);   // ccw(B, C, D)
+    if (cA == cB) return kNoHit;
+    float edx = bx - ax, edy = by - ay;
+    float p3 = uay * edx, q3 = edy * uax;
+    bool c3 = p3 > q3;                                                             // ccw(A, B, C), float32
+    bool c4 = (ey - (double)ay) * (double)edx > (double)edy * (ex - (double)ax);   // ccw(A, B, D)
+    if (c3 == c4) return kNoHit;
+    double dbx = ex - (double)px, dby = ey - (double)py;
+    float dpx = ax - px, dpy = ay - py, dapx = -edy, dapy = edx;
+    double denom = fma((double)dapx, dbx, (double)dapy * dby);
+    float m0 = dapx * dpx, m1 = dapy * dpy;
+    float num = m0 + m1;
+    double t = (double)num / denom;
+    double xx = t * dbx + (double)px, xy = t * dby + (double)py;
+    double ddx = xx - (double)px, ddy = xy - (double)py;
+    return (float)sqrt(fma(ddy, ddy, ddx * ddx));
 }
 
 FTL_HD int sensor_width(const FtlRaySensorConfig& sc) {
@@ -123,20 +159,29 @@ enum EdgeClass { EC_STATIC = 0, EC_LEADER = 1, EC_BEAR = 2, EC_CORRIDOR = 3, EC_
 
 struct RayEdge { float ax, ay, bx, by; int mask; };  // mask: bits 0..8 rows (ages / static), bits 16.. class
 
+#ifndef FTL_UNC_PER_ENV
+#define FTL_UNC_PER_ENV 16
+#endif
+constexpr int kUncPerEnv = FTL_UNC_PER_ENV;  // records per env for the exact pass; more -> the env is recast exactly
+
 struct RaySensorTab {
     int base, R, H, cls_mask;      // cls_mask: which EdgeClass this sensor reacts to
     float L, theta0, inv_period, eps;
     double cs0, sn0;               // cos/sin of the direction of ray 0
+    double offset, Ld;             // first_laser_angle_offset, laser_length (float64, for the exact fallback)
 };
 
 struct RayShared {
     float px, py;
+    double dir;                                    // follower heading (float64, for the exact fallback)
     int scenario, snap_pushes, n_valid, ne, np, rt, ns;
     float reach[EC_COUNT];                         // largest laser_length among sensors reacting to the class
     int tail[FTL_MAX_HIST], head[FTL_MAX_HIST];    // by age (0 = newest)
     RaySensorTab sen[FTL_MAX_RAY_SENSORS];
     RayEdge e[kEdgeCap];
     int pair[kPairCap];                            // edge << 16 | flat ray
+    int nu;                                        // (edge, ray) pairs of this env whose float32 predicates were inconclusive
+    UncRec* unc;                                   // this env's slice of DevState.unc_rec
     // arrays of length rays_total behind the struct: dx, dy, len (float), res[9] (int)
 };
 
@@ -180,6 +225,30 @@ FTL_HD float atan2_deg_approx(float y, float x) {
     return y < 0.f ? -r : r;
 }
 
+// hot paths only RECORD an inconclusive pair; k_rays_exact (one thread per env, almost always idle) redoes it in
+// float64.  No float64 code and no calls in the ray kernel's loops.
+FTL_HD void unc_push(RayShared& sh, float ax, float ay, float bx, float by, int f, int rows) {
+    int slot = smem_atomic_add(&sh.nu, 1);
+    if (slot < kUncPerEnv) {
+        UncRec r = {ax, ay, bx, by, f, rows};
+        sh.unc[slot] = r;
+    }
+}
+
+FTL_HD void hit_merge(const RayArrays& ra, int f, int rows, float d) {
+    if (d >= kNoHit) return;
+    int bits = f2i_bits(d);
+    for (int a = 0; a <= FTL_MAX_HIST; a++)
+        if (rows & (1 << a)) smem_atomic_min(&ra.res[a * ra.rt + f], bits);
+}
+
+FTL_HD void edge_ray_test(RayShared& sh, const RayArrays& ra, int f, int rows, float ax, float ay, float bx, float by) {
+    bool uncertain;
+    float d = seg_hit(sh.px, sh.py, ra.dx[f], ra.dy[f], ra.len[f], ax, ay, bx, by, &uncertain);
+    if (uncertain) unc_push(sh, ax, ay, bx, by, f, rows);
+    else hit_merge(ra, f, rows, d);
+}
+
 // all candidate rays of one edge, tested in place (only used when the shared lists are full)
 FTL_HD_NOINLINE void edge_inline(RayShared& sh, int rt, const RayEdge ed, int n_sensors) {
     const RayArrays ra = ray_arrays(&sh, rt);
@@ -190,14 +259,7 @@ FTL_HD_NOINLINE void edge_inline(RayShared& sh, int rt, const RayEdge ed, int n_
         int rows = ed.mask & 0x1ff;
         if (!(rows & (1 << kStaticBit))) rows &= (1 << st.H) - 1;
         if (!rows) continue;
-        for (int k = 0; k < st.R; k++) {
-            int f = st.base + k;
-            float d = seg_hit(sh.px, sh.py, ra.dx[f], ra.dy[f], ra.len[f], ed.ax, ed.ay, ed.bx, ed.by);
-            if (d >= kNoHit) continue;
-            int bits = f2i_bits(d);
-            for (int a = 0; a <= FTL_MAX_HIST; a++)
-                if (rows & (1 << a)) smem_atomic_min(&ra.res[a * rt + f], bits);
-        }
+        for (int k = 0; k < st.R; k++) edge_ray_test(sh, ra, st.base + k, rows, ed.ax, ed.ay, ed.bx, ed.by);
     }
 }
 
@@ -232,13 +294,12 @@ FTL_HD void seg_append(RayShared& sh, float ax, float ay, float bx, float by, in
     edge_append(sh, ax, ay, bx, by, rows | (1 << (16 + cls)));
 }
 
-FTL_HD void pair_apply(const RayShared& sh, const RayArrays& ra, int ei, int f, int rows) {
-    const RayEdge& ed = sh.e[ei];
-    float d = seg_hit(sh.px, sh.py, ra.dx[f], ra.dy[f], ra.len[f], ed.ax, ed.ay, ed.bx, ed.by);
-    if (d >= kNoHit) return;
-    int bits = f2i_bits(d);
-    for (int a = 0; a <= FTL_MAX_HIST; a++)
-        if (rows & (1 << a)) smem_atomic_min(&ra.res[a * ra.rt + f], bits);
+FTL_HD int pair_rows(const RayShared& sh, int ei, int f, int n_sensors) {
+    int rows = sh.e[ei].mask & 0x1ff;
+    int sidx = 0;
+    while (sidx + 1 < n_sensors && f >= sh.sen[sidx + 1].base) sidx++;
+    if (!(rows & (1 << kStaticBit))) rows &= (1 << sh.sen[sidx].H) - 1;   // the row restriction of the ray's sensor
+    return rows;
 }
 
 // A2 + B over the current edge list, then empty it
@@ -269,8 +330,13 @@ FTL_HD void ray_flush(RayShared& sh, const RayArrays& ra, int n_sensors) {
                 d = d - Rf * rintf(d / Rf);                    // short way round, (-R/2, R/2]
                 int klo = (int)ceilf(fminf(ka, ka + d) - st.eps), khi = (int)floorf(fmaxf(ka, ka + d) + st.eps);
                 int cnt = khi - klo + 1;
-                if (cnt <= 0) continue;
-                if (cnt >= st.R) { klo = 0; cnt = st.R; }
+                // the follower (almost) on the edge's line between its end points, or on an end point: the edge
+                // subtends ~180 degrees and "the short way round" is ambiguous -> every ray is a candidate
+                const bool degenerate = fabsf(d) > 0.49f * Rf ||
+                                        fabsf(ed.ax - sh.px) + fabsf(ed.ay - sh.py) < 1e-3f ||
+                                        fabsf(ed.bx - sh.px) + fabsf(ed.by - sh.py) < 1e-3f;
+                if (cnt <= 0 && !degenerate) continue;
+                if (cnt >= st.R || degenerate) { klo = 0; cnt = st.R; }
                 int slot = smem_atomic_add(&sh.np, cnt);
                 int kk = klo % st.R;
                 if (kk < 0) kk += st.R;
@@ -278,7 +344,7 @@ FTL_HD void ray_flush(RayShared& sh, const RayArrays& ra, int n_sensors) {
                     if (slot + k < kPairCap)
                         sh.pair[slot + k] = (ei << 16) | (st.base + kk);
                     else
-                        pair_apply(sh, ra, ei, st.base + kk, rows);   // list full: do it in place
+                        edge_ray_test(sh, ra, st.base + kk, rows, ed.ax, ed.ay, ed.bx, ed.by);   // list full: in place
                 }
             }
         }
@@ -289,12 +355,8 @@ FTL_HD void ray_flush(RayShared& sh, const RayArrays& ra, int n_sensors) {
     FTL_LANES(lane) {
         for (int t = lane; t < np; t += 32) {
             int pr = sh.pair[t], ei = pr >> 16, f = pr & 0xffff;
-            int rows = sh.e[ei].mask & 0x1ff;
-            // the row restriction of the ray's sensor
-            int sidx = 0;
-            while (sidx + 1 < n_sensors && f >= sh.sen[sidx + 1].base) sidx++;
-            if (!(rows & (1 << kStaticBit))) rows &= (1 << sh.sen[sidx].H) - 1;
-            pair_apply(sh, ra, ei, f, rows);
+            const RayEdge ed = sh.e[ei];
+            edge_ray_test(sh, ra, f, pair_rows(sh, ei, f, n_sensors), ed.ax, ed.ay, ed.bx, ed.by);
         }
     }
     FTL_WARP_SYNC();
@@ -315,11 +377,13 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
         if (lane == 0) {
             float2 p = s.pos[i];
             sh.px = p.x; sh.py = p.y;
+            sh.dir = dir;
             sh.scenario = s.gi[(size_t)GI_SCENARIO * s.n + i];
             int pushes = s.gi[(size_t)GI_SNAP_PUSHES * s.n + i];
             sh.snap_pushes = pushes;
             sh.n_valid = pushes < FTL_MAX_HIST ? pushes : FTL_MAX_HIST;
-            sh.ne = 0; sh.np = 0; sh.rt = rt; sh.ns = ns;
+            sh.ne = 0; sh.np = 0; sh.nu = 0; sh.rt = rt; sh.ns = ns;
+            sh.unc = s.unc_rec + (size_t)i * kUncPerEnv;
             for (int k = 0; k < EC_COUNT; k++) sh.reach[k] = -1e30f;
             int base = 0;
             for (int sidx = 0; sidx < ns; sidx++) {
@@ -331,6 +395,8 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
                 st.theta0 = (float)(dir + sc.first_laser_angle_offset);
                 st.inv_period = (float)sc.lasers_count / 360.f;
                 st.eps = 0.02f + 5e-5f * (float)sc.lasers_count;
+                st.offset = sc.first_laser_angle_offset;
+                st.Ld = sc.laser_length;
                 sh.sen[sidx] = st;
                 for (int k = 0; k < EC_COUNT; k++)
                     if (st.cls_mask & (1 << k)) sh.reach[k] = fmaxf(sh.reach[k], st.L);
@@ -466,8 +532,132 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
             }
             off += sensor_width(sc);
         }
+        if (lane == 0) s.unc_count[i] = sh.nu;   // 0 almost always; > kUncPerEnv: recast the env exactly
     }
     FTL_WARP_SYNC();
+}
+
+// =====================================================================================================
+// Exact pass (one thread per env): pairs whose float32 predicates were inconclusive are redone with the
+// reference's float64 arithmetic and merged into the already written rows; an env with more such pairs than
+// fit its record slice is recast from scratch, edge list by edge list, like the reference does.
+// =====================================================================================================
+struct ExactEnv {
+    float px, py;
+    double dir;
+    int n_valid, pushes, scenario;
+};
+
+FTL_HD void exact_ray_end(const FtlRaySensorConfig& sc, const ExactEnv& ee, int k, double* ex, double* ey) {
+    double ang = (ee.dir + sc.first_laser_angle_offset) + k * (360.0 / sc.lasers_count);   // SEN:888-891
+    double sn, cs;
+    sincos_deg(ang, &sn, &cs);
+    *ex = (double)ee.px + cs * sc.laser_length;
+    *ey = (double)ee.py + sn * sc.laser_length;
+}
+
+// index of (row j, ray k) in the sensor's output block; pad_sectors layout of SEN:932-953
+FTL_HD int ray_out_index(const FtlRaySensorConfig& sc, int j, int k) {
+    const int R = sc.lasers_count;
+    if (!sc.pad_sectors) return j * R + k;
+    double in_sector = R / 4.0;
+    int ksec = (k < in_sector) ? 0 : (k < 2 * in_sector) ? 1 : (k < 3 * in_sector) ? 2 : 3;
+    return (j * 4 + ksec) * R + k;
+}
+
+FTL_HD float exact_rect_min(const ExactEnv& ee, double ex, double ey, int4 q) {
+    float l = (float)q.x, t = (float)q.y, r = (float)(q.x + q.z), b = (float)(q.y + q.w);
+    float m = seg_hit_exact(ee.px, ee.py, ex, ey, l, b, r, b);
+    m = fminf(m, seg_hit_exact(ee.px, ee.py, ex, ey, r, t, r, b));
+    m = fminf(m, seg_hit_exact(ee.px, ee.py, ex, ey, r, t, l, t));
+    return fminf(m, seg_hit_exact(ee.px, ee.py, ex, ey, l, b, l, t));
+}
+
+FTL_HD_NOINLINE void rays_exact_recast(const DevCfg& cfg, const DevState& s, const DevPool& pool, int i,
+                                       const ExactEnv& ee, float* rays_out) {
+    const FtlConfig& c = cfg.c;
+    const int NBr = s.n_bears, cmask = c.corridor_cap - 1;
+    const float4* corr = s.corridor + (size_t)i * c.corridor_cap;
+    const int4* statics = pool.static_rects + (size_t)ee.scenario * c.static_cap;
+    const int n_static = pool.n_static[ee.scenario];
+    int off = 0;
+    for (int sidx = 0; sidx < c.n_ray_sensors; sidx++) {
+        const FtlRaySensorConfig& sc = c.ray[sidx];
+        const int cls = sensor_class_mask(sc);
+        float* dst = rays_out + (size_t)i * cfg.rays_per_env + off;
+        for (int k = 0; k < sc.lasers_count; k++) {
+            double ex, ey;
+            exact_ray_end(sc, ee, k, &ex, &ey);
+            float m_static = kNoHit;
+            if (cls & (1 << EC_STATIC))
+                for (int q = 0; q < n_static; q++) m_static = fminf(m_static, exact_rect_min(ee, ex, ey, statics[q]));
+            for (int j = 0; j < sc.max_prev_obs; j++) {
+                const int age = sc.max_prev_obs - 1 - j;
+                float m = kNoHit;
+                if (age < ee.n_valid) {
+                    m = m_static;
+                    const int slot = (ee.pushes - 1 - age) % FTL_MAX_HIST;
+                    const int2 rg = s.snap_range[(size_t)slot * s.n + i];
+                    for (int r = 0; r < 1 + NBr; r++)
+                        if (cls & (1 << (r == 0 ? EC_LEADER : EC_BEAR)))
+                            m = fminf(m, exact_rect_min(ee, ex, ey, s.snap_rect[((size_t)slot * (1 + NBr) + r) * s.n + i]));
+                    if (cls & (1 << EC_CORRIDOR))
+                        for (int q = rg.x; q < rg.y - 1; q++) {
+                            float4 a4 = corr[q & cmask], b4 = corr[(q + 1) & cmask];
+                            m = fminf(m, seg_hit_exact(ee.px, ee.py, ex, ey, a4.x, a4.y, b4.x, b4.y));
+                            m = fminf(m, seg_hit_exact(ee.px, ee.py, ex, ey, a4.z, a4.w, b4.z, b4.w));
+                        }
+                    if (cls & (1 << EC_CAP)) {
+                        float4 a4 = corr[rg.x & cmask], b4 = corr[(rg.y - 1) & cmask];
+                        m = fminf(m, seg_hit_exact(ee.px, ee.py, ex, ey, a4.x, a4.y, a4.z, a4.w));
+                        m = fminf(m, seg_hit_exact(ee.px, ee.py, ex, ey, b4.x, b4.y, b4.z, b4.w));
+                    }
+                }
+                dst[ray_out_index(sc, j, k)] = m >= kNoHit ? (float)sc.laser_length : m;
+            }
+        }
+        off += sensor_width(sc);
+    }
+}
+
+FTL_HD void rays_exact_env(const DevCfg& cfg, const DevState& s, const DevPool& pool, int i, float* rays_out) {
+    const int count = s.unc_count[i];
+    if (count == 0) return;
+    const FtlConfig& c = cfg.c;
+    ExactEnv ee;
+    float2 p = s.pos[i];
+    ee.px = p.x; ee.py = p.y;
+    ee.dir = s.rd[(size_t)RD_DIR * s.n + i];
+    ee.pushes = s.gi[(size_t)GI_SNAP_PUSHES * s.n + i];
+    ee.n_valid = ee.pushes < FTL_MAX_HIST ? ee.pushes : FTL_MAX_HIST;
+    ee.scenario = s.gi[(size_t)GI_SCENARIO * s.n + i];
+    if (count > kUncPerEnv) {
+        rays_exact_recast(cfg, s, pool, i, ee, rays_out);
+        return;
+    }
+    const UncRec* rec = s.unc_rec + (size_t)i * kUncPerEnv;
+    for (int t = 0; t < count; t++) {
+        const UncRec r = rec[t];
+        int sidx = 0, base = 0, off = 0;
+        while (sidx + 1 < c.n_ray_sensors && r.f >= base + c.ray[sidx].lasers_count) {
+            base += c.ray[sidx].lasers_count;
+            off += sensor_width(c.ray[sidx]);
+            sidx++;
+        }
+        const FtlRaySensorConfig& sc = c.ray[sidx];
+        double ex, ey;
+        exact_ray_end(sc, ee, r.f - base, &ex, &ey);
+        float d = seg_hit_exact(ee.px, ee.py, ex, ey, r.ax, r.ay, r.bx, r.by);
+        if (d >= kNoHit) continue;
+        float* dst = rays_out + (size_t)i * cfg.rays_per_env + off;
+        for (int j = 0; j < sc.max_prev_obs; j++) {
+            const int age = sc.max_prev_obs - 1 - j;
+            if (age >= ee.n_valid) continue;
+            if (!((r.rows >> age) & 1) && !((r.rows >> kStaticBit) & 1)) continue;
+            float* cell = dst + ray_out_index(sc, j, r.f - base);
+            if (d < *cell) *cell = d;
+        }
+    }
 }
 
 }  // namespace ftl

@@ -89,6 +89,7 @@ static void rays_all(FtlHandle_* h, float* rays) {
     std::vector<unsigned char> buf(ray_shared_bytes(h->rays_total) + 16);
     RayShared& sh = *reinterpret_cast<RayShared*>(buf.data());
     for (int i = 0; i < h->n; i++) rays_warp(h->cfg, h->st, h->pool, h->rot.data(), i, sh, rays);
+    for (int i = 0; i < h->n; i++) rays_exact_env(h->cfg, h->st, h->pool, i, rays);
 }
 
 static DevOutputs dev_out(const FtlOutputs* o) {
@@ -158,6 +159,8 @@ int ftl_create(const FtlConfig* cfg, int32_t n_envs, int32_t device, int64_t env
     s.corridor = zalloc<float4>(h->allocs, n * c.corridor_cap);
     s.snap_range = zalloc<int2>(h->allocs, (size_t)FTL_MAX_HIST * n);
     s.snap_rect = zalloc<int4>(h->allocs, (size_t)FTL_MAX_HIST * (1 + nb) * n);
+    s.unc_rec = zalloc<UncRec>(h->allocs, n * kUncPerEnv);
+    s.unc_count = zalloc<int>(h->allocs, n);
     *out = h;
     return FTL_OK;
 }

@@ -55,3 +55,39 @@ def test_hostsim_matches_oracle(name, kwargs, n, steps):
         _compare_states(sim.get_state(), orc.get_state(), gc, n, 0.0)
     assert bad == 0, "%d of %d ray values outside tolerance" % (bad, total)
     assert int(sim.get_state().env["overflow"].max()) == 0
+
+
+@pytest.mark.parametrize("libname", ["libftl_hostsim.so", "libftl_hostsim_smallcaps.so"])
+def test_grazing_rays_resolve_like_the_reference(libname):
+    """Follower parked on integer coordinates with an axis-aligned heading: rays run exactly through rectangle
+    corners and along edges, where the float32 predicates are inconclusive and the float64 fallback must
+    reproduce the reference's strict ccw decisions."""
+    gc = GameConfig(bear_number=1, follower_sensors=cfg3_sensors(12, 36, 5))
+    pool = synthetic_pool(gc, 8, seed=2)
+    n = 64
+    from hostsim_py import lib
+    from continiousenvironment_follower_leader_b200 import capi
+    # the second library has 2 exact-pass records per env: most of these envs overflow and are recast exactly
+    sim, orc = capi.HostEnv(gc, n, lib=lib(libname)), OracleEnv(gc, n)
+    sim.upload_scenarios(pool)
+    orc.upload_scenarios(pool)
+    ids = (np.arange(n) % pool.n).astype(np.int32)
+    sim.reset(scenario_ids=ids)
+    orc.reset(scenario_ids=ids)
+    st = orc.get_state()
+    rng = np.random.RandomState(3)
+    for i in range(n):   # park next to a rock: corner-aligned, edge-aligned or 25 px off, heading a multiple of 45 degrees
+        rects = pool.static_rects[ids[i], 2:pool.n_static[ids[i]]]
+        x, y, w, h = rects[rng.randint(len(rects))]
+        dx, dy = [(-60, 0), (-60, 25), (-60, h), (w + 40, -30), (w // 2, -50), (-40, -40)][i % 6]
+        st.env["follower"]["pos"][i] = (x + dx, y + dy)
+        st.env["follower"]["dir"][i] = 45.0 * (i % 8)
+        st.env["follower"]["speed"][i] = 0.0
+        st.env["follower"]["rot_speed"][i] = 0.0
+    orc.set_state(st)
+    sim.set_state(st)
+    zero = np.zeros((n, 2), np.float32)
+    for t in range(6):
+        a, b = sim.step(zero), orc.step(zero)
+        assert np.array_equal(a.numerical_features, b.numerical_features)
+        assert _ray_outliers(a.rays, b.rays, rtol=1e-5) == 0
