@@ -29,8 +29,7 @@ def test_cuda_reproduces_reference_trace(path):
     gc = parity.config_for(meta, _route_len=len(d["scen_route"]), _n_static=len(d["scen_static_rects"]))
     env = _cuda_env(gc, 33)   # 33 copies: more than a warp, all must agree
     env.upload_scenarios(parity.pool_for(d, gc))
-    n_vals = max(1, meta["n_env_steps"] * gc.rays_per_env)
-    budget = max(2, int(1e-4 * n_vals))
+    budget = 0     # hit / no-hit decisions are the reference's by construction (float64 fallback), values within 1e-4
     for idx in (0, 32):
         T, outliers = parity.replay(env, d, gc, env_index=idx, float_rtol=parity.RTOL, ray_rtol=parity.RTOL,
                                     ray_outlier_budget=budget)
@@ -106,7 +105,7 @@ def test_cuda_matches_oracle_on_seeded_batch(name, kwargs, n, steps):
         if t % 10 == 9 or t == steps - 1:
             _compare_states(cuda.get_state(), orc.get_state(), gc, n, parity.RTOL)
     if total_rays:
-        assert bad_rays <= max(2, 1e-4 * total_rays), "%d of %d ray values outside tolerance" % (bad_rays, total_rays)
+        assert bad_rays <= 2, "%d of %d ray values outside tolerance" % (bad_rays, total_rays)
 
 
 def test_auto_reset_matches_oracle():
@@ -218,3 +217,35 @@ def test_device_and_host_entry_points_agree():
         assert np.array_equal(dev.rays.cpu().numpy(), oh.rays)
         assert np.array_equal(rew.cpu().numpy(), oh.reward)
     assert dev.launch_count >= 24
+
+
+def test_grazing_rays_resolve_like_the_reference_on_the_gpu():
+    """Followers parked on integer coordinates with axis-aligned headings: many rays run exactly through corners and
+    along edges.  k_rays records those pairs, k_rays_exact must reproduce the reference's strict ccw decisions."""
+    from oracle_py import OracleEnv
+    gc = GameConfig(bear_number=1, follower_sensors=cfg3_sensors(12, 36, 5))
+    pool = synthetic_pool(gc, 8, seed=2)
+    n = 256
+    cuda, orc = _cuda_env(gc, n), OracleEnv(gc, n, n_threads=8)
+    cuda.upload_scenarios(pool)
+    orc.upload_scenarios(pool)
+    ids = (np.arange(n) % pool.n).astype(np.int32)
+    cuda.reset(scenario_ids=ids)
+    orc.reset(scenario_ids=ids)
+    st = orc.get_state()
+    rng = np.random.RandomState(3)
+    for i in range(n):
+        rects = pool.static_rects[ids[i], 2:pool.n_static[ids[i]]]
+        x, y, w, h = rects[rng.randint(len(rects))]
+        dx, dy = [(-60, 0), (-60, 25), (-60, h), (w + 40, -30), (w // 2, -50), (-40, -40)][i % 6]
+        st.env["follower"]["pos"][i] = (x + dx, y + dy)
+        st.env["follower"]["dir"][i] = 45.0 * (i % 8)
+        st.env["follower"]["speed"][i] = 0.0
+        st.env["follower"]["rot_speed"][i] = 0.0
+    orc.set_state(st)
+    cuda.set_state(st)
+    zero = np.zeros((n, 2), np.float32)
+    for t in range(4):
+        a, b = cuda.step(zero), orc.step(zero)
+        assert np.array_equal(a.numerical_features, b.numerical_features)
+        assert _ray_outliers(a.rays, b.rays, rtol=1e-5) == 0

@@ -6,9 +6,13 @@ from continiousenvironment_follower_leader_b200.batch_env import FtlBatchEnv
 from continiousenvironment_follower_leader_b200.config import GameConfig, cfg3_sensors
 from continiousenvironment_follower_leader_b200.scenario import synthetic_pool
 
-def run(n, F, rays=(12, 36), steps=120, warm=40, auto_reset=True, max_steps=5000):
+def run(n, F, rays=(12, 36), steps=200, warm=100, auto_reset=True, max_steps=5000, ref_pool=False):
     gc = GameConfig(bear_number=1, follower_sensors=cfg3_sensors(rays[0], rays[1]), frames_per_step=F, auto_reset=auto_reset, max_steps=max_steps)
     pool = synthetic_pool(gc, 256, seed=0)
+    if ref_pool:
+        import numpy as np
+        from continiousenvironment_follower_leader_b200.scenario import ScenarioPool
+        pool = ScenarioPool.from_arrays(np.load('continiousenvironment_follower_leader_b200/data/pool_cfg3_reference.npz'))
     env = FtlBatchEnv(n, game_config=gc, scenario_pool=pool)
     env.reset()
     g = torch.Generator(device="cuda").manual_seed(1)
