@@ -249,3 +249,31 @@ def test_grazing_rays_resolve_like_the_reference_on_the_gpu():
         a, b = cuda.step(zero), orc.step(zero)
         assert np.array_equal(a.numerical_features, b.numerical_features)
         assert _ray_outliers(a.rays, b.rays, rtol=1e-5) == 0
+
+
+def test_gym_surface_on_the_gpu_replays_a_reference_trace():
+    """gym_surface.Game (single-env view, batch of one) through libftl.so: reset on the exported scenario, 4-tuple
+    steps, numerical features bit-equal to the reference trace, rays within 1e-4, same reward/done/info."""
+    from continiousenvironment_follower_leader_b200 import gym_surface as gs, scenario_gen, wrappers
+    d, meta = parity.load_trace(parity.GOLDEN_DIR + "/cfg3_seed5_follow.npz")
+    env = gs.make("Test-Cont-Env-Auto-v0", **meta["kwargs"])
+    wrapped = wrappers.ContinuousObserveModifier_sensorPrev(env, max_prev_obs=5)
+    sc = scenario_gen.Scenario()
+    sc.static_rects = [tuple(r) for r in d["scen_static_rects"]]
+    sc.route = [tuple(p) for p in d["scen_route"]]
+    sc.leader_pos, sc.leader_dir = d["scen_leader_pos"], float(d["scen_leader_dir"])
+    sc.follower_pos, sc.follower_dir = d["scen_follower_pos"], float(d["scen_follower_dir"])
+    sc.found_target_point = True
+    obs = env.reset(scenario=sc)
+    assert np.allclose(obs["numerical_features"], d["t_nf"][0], rtol=parity.RTOL)
+    for t, a in enumerate(d["actions"][:260]):
+        obs, reward, done, info = env.step(a)
+        ints = d["t_ints"][t + 1]
+        assert np.allclose(obs["numerical_features"], d["t_nf"][t + 1], rtol=parity.RTOL, atol=1e-4)
+        assert abs(reward - d["t_floats"][t + 1][0]) < 1e-6 and done == bool(ints[4])
+        assert info["mission_status"] == abi.MISSION_STATUS[ints[10]] and info["agent_status"] == abi.AGENT_STATUS[ints[11]]
+        got = np.concatenate([obs[n].reshape(-1) for n in meta["ray_names"]])
+        assert np.allclose(got, d["t_rays"][t + 1], rtol=parity.RTOL)
+        feats = wrapped.observation(obs)
+        assert feats.shape == (5, 48) and feats.min() >= 0 and feats.max() <= 1
+    assert env.step_count == 2600

@@ -26,11 +26,16 @@ def run(n, F, rays=(12, 36), steps=200, warm=100, auto_reset=True, max_steps=500
     return a / c, b / c
 
 if __name__ == "__main__":
-    for F in (2, 5, 10, 20):
-        a, b = run(65536, F)
-        print("N=65536 F=%2d  k_step %.4f ms  k_rays %.4f ms" % (F, a, b), flush=True)
-    for n in (16384, 32768, 131072, 262144):
-        a, b = run(n, 10)
-        print("N=%6d F=10  k_step %.4f ms  k_rays %.4f ms  -> %.1f M env-steps/s" % (n, a, b, n / (a + b) / 1e3), flush=True)
-    a, b = run(65536, 10, auto_reset=False)
-    print("no auto reset: k_step %.4f k_rays %.4f" % (a, b))
+    # BASELINE.json configs[4]: frames_per_step sweep and ray-count sweep (single GPU; 262144 envs over 8 GPUs = 32768 per GPU)
+    print("== frames_per_step sweep, 32768 envs, cfg3 sensors")
+    for F in (2, 3, 5, 8, 10):
+        a, b = run(32768, F, ref_pool=True)
+        print("F=%2d  k_step %.4f ms  k_rays %.4f ms  -> %.1f M env-steps/s" % (F, a, b, 32768 / (a + b) / 1e3), flush=True)
+    print("== obstacle-sensor ray-count sweep, 32768 envs, F=10")
+    for R in (12, 24, 36, 72, 120, 180, 360):
+        a, b = run(32768, 10, rays=(12, R), ref_pool=True)
+        print("R=%3d  k_step %.4f ms  k_rays %.4f ms  -> %.1f M env-steps/s" % (R, a, b, 32768 / (a + b) / 1e3), flush=True)
+    print("== env-count sweep, F=10, cfg3")
+    for n in (4096, 16384, 65536, 131072, 262144):
+        a, b = run(n, 10, ref_pool=True)
+        print("N=%6d  k_step %.4f ms  k_rays %.4f ms  -> %.1f M env-steps/s" % (n, a, b, n / (a + b) / 1e3), flush=True)
