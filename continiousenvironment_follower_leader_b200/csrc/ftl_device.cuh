@@ -183,6 +183,19 @@ FTL_HD double dist_f64(double ax, double ay, double bx, double by) {
     return sqrt(sx + sy);
 }
 
+// One shared copy of the float64 sincos / distance code for the hot loop of the step kernel: its frame loop is
+// bound by instruction fetch (ncu: no_instruction stalls), so every inlined copy of these ~200-instruction
+// sequences costs more than the call.
+struct SinCos { double s, c; };
+FTL_HD void sincos_deg(double deg, double* s, double* c);
+FTL_HD_NOINLINE SinCos sincos_deg_nv(double deg) {
+    SinCos r;
+    sincos_deg(deg, &r.s, &r.c);
+    return r;
+}
+FTL_HD double dist_f64(double ax, double ay, double bx, double by);
+FTL_HD_NOINLINE double dist_f64_nv(double ax, double ay, double bx, double by) { return dist_f64(ax, ay, bx, by); }
+
 FTL_HD void sincos_deg(double deg, double* s, double* c) {
     double th = deg * kDeg2Rad;
 #if defined(__CUDA_ARCH__)
@@ -315,8 +328,8 @@ FTL_HD void robot_move(Robot& r, const FtlRobotConfig& c) {  // CLS:129-182
         r.rx = cx - (nw >> 1);
         r.ry = cy - (nh >> 1);
     }
-    double sn, cs;
-    sincos_deg(r.dir, &sn, &cs);
+    const SinCos sc_ = sincos_deg_nv(r.dir);
+    const double sn = sc_.s, cs = sc_.c;
     float mx = (float)(cs * r.speed), my = (float)(sn * r.speed);
     r.px = r.px + mx;
     r.py = r.py + my;
@@ -328,7 +341,7 @@ FTL_HD void robot_move(Robot& r, const FtlRobotConfig& c) {  // CLS:129-182
 
 FTL_HD void move_to_the_point(Robot& r, const FtlRobotConfig& c, double tx, double ty, bool has_speed,
                               double speed) {  // CLS:184-215
-    double new_speed = has_speed ? speed : dist_f64((double)r.px, (double)r.py, tx, ty);
+    double new_speed = has_speed ? speed : dist_f64_nv((double)r.px, (double)r.py, tx, ty);
     int desirable_angle = bearing_int((double)r.px, (double)r.py, tx, ty);
     int cur = (int)r.dir;
     int delta, nrd;
@@ -353,7 +366,7 @@ FTL_HD_NOINLINE Robot robot_move_nv(Robot r, const FtlRobotConfig* c) {
 }
 FTL_HD_NOINLINE Robot move_to_the_point_nv(Robot r, const FtlRobotConfig* c, double tx, double ty, int has_speed,
                                            double speed) {
-    double new_speed = has_speed ? speed : dist_f64((double)r.px, (double)r.py, tx, ty);
+    double new_speed = has_speed ? speed : dist_f64_nv((double)r.px, (double)r.py, tx, ty);
     int desirable_angle = bearing_int((double)r.px, (double)r.py, tx, ty);
     int cur = (int)r.dir;
     int delta, nrd;
@@ -745,7 +758,7 @@ FTL_HD double leader_accel(const DevCfg& cfg, Episode& e) {  // ENV:1159-1174
 // bear target, ENV:722-758 and 819-837
 FTL_HD void bear_target(const FtlConfig& c, int idx, const Robot& bear, const Robot& leader, double* tx, double* ty,
                         int* index) {
-    double d = dist_f64((double)bear.px, (double)bear.py, *tx, *ty);
+    double d = dist_f64_nv((double)bear.px, (double)bear.py, *tx, *ty);
     double radius, ang;
     if (c.move_bear_v4 && (idx & 1)) {
         if (d < c.leader_pos_epsilon) *index += 1;
@@ -764,10 +777,9 @@ FTL_HD void bear_target(const FtlConfig& c, int idx, const Robot& bear, const Ro
         radius = 100.0 * (idx + 1);
         ang = *index == 0 ? leader.dir - 130 : leader.dir + 130;
     }
-    double sn, cs;
-    sincos_deg(ang, &sn, &cs);
-    *tx = (double)leader.px + cs * radius;
-    *ty = (double)leader.py + sn * radius;
+    const SinCos sc_ = sincos_deg_nv(ang);
+    *tx = (double)leader.px + sc_.c * radius;
+    *ty = (double)leader.py + sc_.s * radius;
 }
 
 // ---- tracker (LeaderPositionsTracker_v2.scan, SEN:243-327) ---------------------------------------------------

@@ -282,7 +282,7 @@ FTL_HD void env_step(const DevCfg& cfg, const DevState& s, const DevPool& pool, 
         green_flags(cfg, trail, trail_d, e.trail_len, w.follower.px, w.follower.py, gc, &in_box, &on_trace);
         bool too_close = d2_f32(w.leader.px, w.leader.py, w.follower.px, w.follower.py) <= cfg.min_dist2_f32;
         // (3) waypoint advance, ENV:978-983
-        if (dist_f64((double)w.leader.px, (double)w.leader.py, (double)target.x, (double)target.y) <
+        if (dist_f64_nv((double)w.leader.px, (double)w.leader.py, (double)target.x, (double)target.y) <
             c.leader_pos_epsilon) {
             e.cur_target_id += 1;
             if (e.cur_target_id >= n_route) e.flags |= FL_LEADER_FINISHED;   // cur_target_point keeps its last value
