@@ -398,15 +398,22 @@ FTL_HD bool out_of_bounds(const FtlConfig& c, const Robot& r) {  // ENV:1182-118
 // `inflate` (half the largest hit-box diagonal + the distance covered in F frames + slack), contains
 // the robot's position at the start of the step.  Exact: the per-frame test still uses the integer
 // rectangles, the mask only skips rectangles that are provably out of reach.
-FTL_HD uint64_t near_static_mask(const int4* rects, int n_static, float px, float py, float inflate) {
-    uint64_t m = 0;
+FTL_HD bool near_rect(int4 q, float px, float py, float inflate) {
+    return px >= (float)q.x - inflate && px <= (float)(q.x + q.z) + inflate && py >= (float)q.y - inflate &&
+           py <= (float)(q.y + q.w) + inflate;
+}
+// one pass over the scenario's rectangles for both robots (the table is read once per step)
+FTL_HD void near_static_masks(const int4* rects, int n_static, float2 p0, float inflate0, float2 p1, float inflate1,
+                              uint64_t* m0, uint64_t* m1) {
+    uint64_t a = 0, b = 0;
+#pragma unroll 4
     for (int k = 0; k < n_static; k++) {
         int4 q = rects[k];
-        if (px >= (float)q.x - inflate && px <= (float)(q.x + q.z) + inflate && py >= (float)q.y - inflate &&
-            py <= (float)(q.y + q.w) + inflate)
-            m |= (uint64_t)1 << k;
+        if (near_rect(q, p0.x, p0.y, inflate0)) a |= (uint64_t)1 << k;
+        if (near_rect(q, p1.x, p1.y, inflate1)) b |= (uint64_t)1 << k;
     }
-    return m;
+    *m0 = a;
+    *m1 = b;
 }
 FTL_HD bool collide_static_masked(const Robot& r, const int4* rects, uint64_t mask) {
     while (mask) {
@@ -456,12 +463,21 @@ FTL_HD int green_lo_exact(const float* trail_d, int n, float max_distance_f32) {
     int lo = n - 1;  // empty
     float acc = 0.f;
     FTL_COUNT(2, 1);
-    for (int i = n - 2; i >= 0; i--) {
-        acc = acc + trail_d[i + 1];
-        if (acc <= max_distance_f32)
-            lo = i;
-        else
-            break;
+    // same additions in the same order; the loads are issued eight at a time so that the walk is not one
+    // memory round trip per point
+    for (int i = n - 2; i >= 0; i -= 8) {
+        float d[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) d[j] = trail_d[i + 1 - j > 1 ? i + 1 - j : 1];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (j > i) return lo;
+            acc = acc + d[j];
+            if (acc <= max_distance_f32)
+                lo = i - j;
+            else
+                return lo;
+        }
     }
     return lo;
 }

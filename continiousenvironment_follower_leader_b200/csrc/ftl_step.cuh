@@ -259,8 +259,9 @@ FTL_HD void env_step(const DevCfg& cfg, const DevState& s, const DevPool& pool, 
     // the leader's current target lives in registers; it is re-read only when the waypoint index advances
     int2 target = route_point(pool, c, e.scenario, e.cur_target_id < n_route ? e.cur_target_id : n_route - 1);
 
-    const uint64_t fmask = near_static_mask(statics, n_static, w.follower.px, w.follower.py, cfg.static_inflate[0]);
-    const uint64_t lmask = near_static_mask(statics, n_static, w.leader.px, w.leader.py, cfg.static_inflate[1]);
+    uint64_t fmask, lmask;
+    near_static_masks(statics, n_static, make_float2(w.follower.px, w.follower.py), cfg.static_inflate[0],
+                      make_float2(w.leader.px, w.leader.py), cfg.static_inflate[1], &fmask, &lmask);
 
     for (int f = 0; f < c.frames_per_step; f++) {
         int mission = FTL_MISSION_IN_PROGRESS, agent = FTL_AGENT_MOVING, leader_st = FTL_LEADER_MOVING;

@@ -40,8 +40,8 @@ __device__ __noinline__ void reset_in_place(const DevCfg& cfg, const DevState& s
 #endif                            // (measured: 128 regs 0.276 ms, 168 regs 0.31 ms, 210 regs 0.325 ms, 96 regs 0.29 ms per step)
 template <int NB>
 __global__ void __launch_bounds__(FTL_STEP_THREADS, FTL_STEP_MINBLOCKS)
-k_step(const __grid_constant__ DevCfg cfg, const DevState s, const DevPool pool, const void* __restrict__ actions,
-       const DevOutputs out, double* __restrict__ stats) {
+k_step(const __grid_constant__ DevCfg cfg, const __grid_constant__ DevState s, const __grid_constant__ DevPool pool,
+       const void* __restrict__ actions, const __grid_constant__ DevOutputs out, double* __restrict__ stats) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= s.n) return;
     World<NB> w;
