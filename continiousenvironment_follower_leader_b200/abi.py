@@ -7,11 +7,12 @@ import ctypes as C
 
 import numpy as np
 
-FTL_ABI_VERSION = 1
+FTL_ABI_VERSION = 2
 FTL_MAX_BEARS = 4
 FTL_MAX_RAY_SENSORS = 4
 FTL_MAX_REGIME = 16
 FTL_MAX_HIST = 8
+FTL_MAX_CUSTOM_ANGLES = 8
 
 FTL_OK = 0
 FTL_ERR_INVALID, FTL_ERR_CUDA, FTL_ERR_STATE, FTL_ERR_NOMEM = -1, -2, -3, -4
@@ -40,7 +41,9 @@ class FtlRaySensorConfig(C.Structure):
     _fields_ = [("lasers_count", C.c_int32), ("max_prev_obs", C.c_int32), ("pad_sectors", C.c_int32),
                 ("react_to_safe_corridor", C.c_int32), ("react_to_green_zone", C.c_int32),
                 ("react_to_obstacles", C.c_int32), ("laser_length", C.c_double),
-                ("first_laser_angle_offset", C.c_double)]
+                ("first_laser_angle_offset", C.c_double),
+                ("n_custom_angles", C.c_int32), ("pad_", C.c_int32),
+                ("custom_angle", C.c_double * FTL_MAX_CUSTOM_ANGLES)]
 
 
 class FtlConfig(C.Structure):
@@ -75,7 +78,9 @@ class FtlConfig(C.Structure):
         ("ray", FtlRaySensorConfig * FTL_MAX_RAY_SENSORS),
         ("trail_cap", C.c_int32), ("corridor_cap", C.c_int32), ("route_cap", C.c_int32),
         ("static_cap", C.c_int32), ("auto_reset", C.c_int32),
-        ("reserved", C.c_int32 * 7),
+        ("fused_sensor_prev", C.c_int32),
+        ("track_vector_len", C.c_int32), ("track_vector_mode", C.c_int32),
+        ("reserved", C.c_int32 * 4),
     ]
 
 
@@ -129,7 +134,8 @@ class FtlStateBuffers(C.Structure):
 
 class FtlOutputs(C.Structure):
     _fields_ = [("numerical_features", C.c_void_p), ("leader_target", C.c_void_p), ("rays", C.c_void_p),
-                ("reward", C.c_void_p), ("done", C.c_void_p), ("status", C.c_void_p)]
+                ("reward", C.c_void_p), ("done", C.c_void_p), ("status", C.c_void_p),
+                ("follower_info", C.c_void_p), ("track_vectors", C.c_void_p)]
 
 
 ENV_STATE_DTYPE = np.dtype(FtlEnvState)

@@ -8,6 +8,11 @@ action spaces), the return value is ``(obs, reward, done, info)`` with CUDA tens
     obs["numerical_features"]  float32 [N, 10]                      ENV:1793-1802
     obs["leader_target_point"] int32   [N, 2]                       ENV:1803-1806
     obs[<ray sensor name>]     float32 [N, H, R] (or [N, H, 4R])    SEN:883-962
+    obs[<flat ray sensor>]     float32 [N, R]                       LeaderCorridor_lasers(_v2), SEN:571-807
+    obs[<FollowerInfo>]        float32 [N, 2]                       SEN:834-842
+    obs[<LeaderTrackDetector_vector>] float32 [N, P, 2]            SEN:365-380
+    obs["sensor_prev"]         float32 [N, H, sum of widths]        WRP:203-221, instead of the sensor entries when the
+                                                                    config was built with fused_sensor_prev=True
     reward float32 [N], done bool [N]
     info["status"] uint8 [N, 4] = (mission_status, agent_status, leader_status, crash) codes, see abi.py
 """
@@ -40,9 +45,16 @@ class FtlBatchEnv:
         self.reward = torch.zeros(n, dtype=torch.float32, device=dev)
         self.done = torch.zeros(n, dtype=torch.uint8, device=dev)
         self.status = torch.zeros((n, 4), dtype=torch.uint8, device=dev)
+        # optional sensors: FollowerInfo [N, 2], LeaderTrackDetector_vector [N, P, 2]
+        self.follower_info = torch.zeros((n, 2), dtype=torch.float32, device=dev) \
+            if self.gc.follower_info_name is not None else None
+        self.track_vectors = torch.zeros((n, self.cfg.track_vector_len, 2), dtype=torch.float32, device=dev) \
+            if self.cfg.track_vector_len else None
         self._out = abi.FtlOutputs(self.numerical_features.data_ptr(), self.leader_target.data_ptr(),
                                    self.rays.data_ptr() if rpe else None, self.reward.data_ptr(),
-                                   self.done.data_ptr(), self.status.data_ptr())
+                                   self.done.data_ptr(), self.status.data_ptr(),
+                                   None if self.follower_info is None else self.follower_info.data_ptr(),
+                                   None if self.track_vectors is None else self.track_vectors.data_ptr())
         self._stats = torch.zeros(abi.STAT_COUNT, dtype=torch.float64, device=dev)
         self._ray_layout = self.gc.ray_layout()
         self._pool = None
@@ -73,9 +85,25 @@ class FtlBatchEnv:
     # ---- gym-like surface ----------------------------------------------------------------------------
     def _obs(self):
         obs = {"numerical_features": self.numerical_features, "leader_target_point": self.leader_target}
-        for name, off, h, w in self._ray_layout:
-            obs[name] = self.rays[:, off:off + h * w].view(self.n, h, w)
+        if self.follower_info is not None:
+            obs[self.gc.follower_info_name] = self.follower_info
+        if self.track_vectors is not None:
+            obs[self.gc.track_vector_name] = self.track_vectors
+        if self.cfg.fused_sensor_prev:   # one [N, H, sum of widths] matrix, already clip(v / laser_length, 0, 1)
+            obs["sensor_prev"] = self.sensor_prev()
+            return obs
+        for k, (name, off, h, w) in enumerate(self._ray_layout):
+            block = self.rays[:, off:off + h * w]
+            obs[name] = block if self.gc.ray_sensor_flat[k] else block.view(self.n, h, w)
         return obs
+
+    def sensor_prev(self):
+        """What ContinuousObserveModifier_sensorPrev.observation returns (WRP:203-221), batched: [N, H, sum W]."""
+        if not self.cfg.fused_sensor_prev:
+            from .wrappers import sensor_prev_observation
+            return sensor_prev_observation(self)
+        h = self._ray_layout[0][2]
+        return self.rays.view(self.n, h, self.gc.rays_per_env // h)
 
     def reset(self, mask=None, scenario_ids=None):
         m = None if mask is None else mask.to(device=self.device, dtype=torch.uint8).contiguous()

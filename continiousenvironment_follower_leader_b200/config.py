@@ -39,6 +39,8 @@ GAME_DEFAULTS = OrderedDict(  # ENV:45-105
 
 TRACKER_CLASSES = ("LeaderPositionsTracker_v2",)
 RAY_CLASSES = ("LeaderCorridor_Prev_lasers_v2", "LaserPrevSensor")
+# sensors without history on the same ray engine (max_prev_obs = 1, output of shape (R,)): SEN:571-807
+FLAT_RAY_CLASSES = ("LeaderCorridor_lasers", "LeaderCorridor_lasers_v2")
 # Every class name the reference registry knows (SEN:1291-1307); anything else is "undefined".
 KNOWN_SENSOR_CLASSES = (
     "LaserSensor", "LeaderPositionsTracker", "LeaderPositionsTracker_v2", "LeaderTrackDetector_vector",
@@ -61,7 +63,7 @@ class GameConfig:
     """Parsed constructor arguments; ``.c`` is the ``FtlConfig`` struct handed to libftl."""
 
     def __init__(self, trail_cap=None, corridor_cap=None, route_cap=None, static_cap=None, auto_reset=False,
-                 strict_lasers_count=False, **kwargs):
+                 strict_lasers_count=False, fused_sensor_prev=False, **kwargs):
         kw = OrderedDict(GAME_DEFAULTS)
         extra = {k: v for k, v in kwargs.items() if k not in kw}
         kw.update({k: v for k, v in kwargs.items() if k in kw})
@@ -92,6 +94,8 @@ class GameConfig:
 
         c = abi.FtlConfig()
         c.abi_version = abi.FTL_ABI_VERSION
+        # library option: `rays` carries ContinuousObserveModifier_sensorPrev's output (WRP:203-221) directly
+        c.fused_sensor_prev = int(bool(fused_sensor_prev))
         c.game_width, c.game_height = int(g["game_width"]), int(g["game_height"])
         c.frames_per_step = int(g["frames_per_step"])
         c.max_steps, c.warm_start = int(g["max_steps"]), int(g["warm_start"])
@@ -223,6 +227,15 @@ class GameConfig:
         c.tracker_enabled = 0
         c.tracker_scans_per_step = 2  # CLS:263-286: the v2 tracker is scanned twice per use_sensors
         c.n_ray_sensors = 0
+        c.track_vector_len = 0
+        self.ray_sensor_flat = []          # True: the sensor returns (R,), not (H, R)
+        self.follower_info_name = None     # dict key of the FollowerInfo sensor, if any
+        self.track_vector_name = None      # dict key of the LeaderTrackDetector_vector sensor, if any
+        for k in (sensors or {}):          # CLS:240-244
+            if k in ("LeaderTrackDetector_vector", "LeaderTrackDetector_radar") and \
+                    "LeaderPositionsTracker" not in sensors and "LeaderPositionsTracker_v2" not in sensors:
+                raise ValueError(
+                    "Sensor {} requires sensor LeaderPositionsTracker for tracking leader movement.".format(k))
         for name, sc in (sensors or {}).items():
             cls = sc.get("sensor_class", name)
             if cls not in KNOWN_SENSOR_CLASSES:  # CLS:244-249
@@ -266,13 +279,65 @@ class GameConfig:
                                      "react_to_obstacles equal to one of the values: True, 'all', 'dynamic', 'static'")
                 r.react_to_obstacles = _REACT[rto]
                 r.first_laser_angle_offset = float(args.get("first_laser_angle_offset", 0 if legacy else -45))
+                r.n_custom_angles = 0
                 self.ray_sensor_names.append(name)
+                self.ray_sensor_flat.append(False)
                 c.n_ray_sensors += 1
+            elif cls in FLAT_RAY_CLASSES:
+                if c.n_ray_sensors >= abi.FTL_MAX_RAY_SENSORS:
+                    raise ValueError("at most %d ray sensors" % abi.FTL_MAX_RAY_SENSORS)
+                r = c.ray[c.n_ray_sensors]
+                if cls == "LeaderCorridor_lasers":   # SEN:577-606, 675-700: a fixed fan
+                    front, back = int(args.get("front_lasers_count", 3)), int(args.get("back_lasers_count", 0))
+                    assert front in [3, 5]           # SEN:597-598
+                    assert back in [0, 2]
+                    angles = [-40.0, 0.0, 40.0] + ([-90.0, 90.0] if front == 5 else []) + \
+                             ([-150.0, 150.0] if back == 2 else [])
+                    r.lasers_count = r.n_custom_angles = len(angles)
+                    for k, a in enumerate(angles):
+                        r.custom_angle[k] = a
+                else:                                # SEN:742-769
+                    r.lasers_count = int(args.get("lasers_count", 12))
+                    if self.strict_lasers_count and r.lasers_count not in [12, 24, 20, 36]:
+                        raise ValueError("Invalid number of laser beams, should be 12,24,20 or 36")
+                    if r.lasers_count < 1:
+                        raise ValueError("lasers_count must be positive")
+                    r.n_custom_angles = 0
+                r.laser_length = float(args.get("laser_length", 100))
+                r.max_prev_obs, r.pad_sectors = 1, 0
+                r.react_to_safe_corridor = int(bool(args.get("react_to_safe_corridor", True)))
+                r.react_to_green_zone = int(bool(args.get("react_to_green_zone", False)))
+                rto = args.get("react_to_obstacles", False)
+                if rto not in _REACT:
+                    raise ValueError("You need to specify which obstacles the sensor should respond to. Set "
+                                     "react_to_obstacles equal to one of the values: True, 'all', 'dynamic', 'static'")
+                r.react_to_obstacles = _REACT[rto]
+                r.first_laser_angle_offset = 0.0
+                self.ray_sensor_names.append(name)
+                self.ray_sensor_flat.append(True)
+                c.n_ray_sensors += 1
+            elif cls == "FollowerInfo":              # SEN:822-842
+                if int(args.get("speed_direction_param", 2)) != 2:
+                    raise NotImplementedError("FollowerInfo: only speed_direction_param=2 (the default) is supported")
+                if self.follower_info_name is not None:
+                    raise NotImplementedError("one FollowerInfo sensor at most")
+                self.follower_info_name = name
+            elif cls == "LeaderTrackDetector_vector":  # SEN:349-380
+                if self.track_vector_name is not None:
+                    raise NotImplementedError("one LeaderTrackDetector_vector sensor at most")
+                mode = args.get("detectable_positions", "new")
+                if mode not in ("new", "old"):
+                    raise ValueError("detectable_positions must be 'new' or 'old'")
+                c.track_vector_len = int(args.get("position_sequence_length", 100))
+                if c.track_vector_len < 1:
+                    raise ValueError("position_sequence_length must be positive")
+                c.track_vector_mode = 0 if mode == "new" else 1
+                self.track_vector_name = name
             else:
                 raise NotImplementedError(
                     "sensor class %s is outside the accelerated path (SURVEY.md section 8(f)3)" % cls)
-        if c.n_ray_sensors and not c.tracker_enabled:
-            raise ValueError("ray sensors need the LeaderPositionsTracker_v2 corridor (CLS:263-280)")
+        if (c.n_ray_sensors or c.track_vector_len) and not c.tracker_enabled:
+            raise ValueError("ray sensors and track detectors need the LeaderPositionsTracker_v2 corridor (CLS:263-280)")
 
     # ---- spaces (ENV:360-378, 1812-1824) -----------------------------------------------------------
     def action_bounds(self):

@@ -52,6 +52,12 @@ __global__ void k_pack_state(const DevState s, int first, int count, FtlEnvState
     pack_env(s, first + j, dst[j]);
 }
 
+// FollowerInfo / LeaderTrackDetector_vector outputs from the stored state (launched only when requested)
+__global__ void k_optional_sensors(const __grid_constant__ DevCfg cfg, const DevState s, const DevOutputs out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < out.n) write_optional_sensors(cfg.c, s, out, i);
+}
+
 __global__ void k_unpack_state(const __grid_constant__ DevCfg cfg, const DevState s, int first, int count,
                                const FtlEnvState* __restrict__ src) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -117,7 +123,7 @@ static std::vector<double2> ray_rotation_table(const FtlConfig& c) {
     std::vector<double2> rot;
     for (int s = 0; s < c.n_ray_sensors; s++)
         for (int k = 0; k < c.ray[s].lasers_count; k++) {
-            double th = (k * (360.0 / c.ray[s].lasers_count)) * kDeg2Rad;
+            double th = ray_angle(c.ray[s], k) * kDeg2Rad;
             rot.push_back(make_double2(std::cos(th), std::sin(th)));
         }
     return rot;
@@ -173,9 +179,15 @@ static int validate(const FtlConfig* c, int n_envs) {
         if (r.lasers_count < 1) return fail(FTL_ERR_INVALID, "lasers_count must be positive (SEN:761)");
         if (r.max_prev_obs < 1 || r.max_prev_obs > FTL_MAX_HIST)
             return fail(FTL_ERR_INVALID, "max_prev_obs must be in [1, FTL_MAX_HIST] (SEN:876)");
+        if (c->fused_sensor_prev && r.max_prev_obs != c->ray[0].max_prev_obs)
+            return fail(FTL_ERR_INVALID, "fused_sensor_prev needs the same max_prev_obs on every sensor (WRP:209-210)");
+        if (r.n_custom_angles != 0 && (r.n_custom_angles != r.lasers_count || r.n_custom_angles > FTL_MAX_CUSTOM_ANGLES))
+            return fail(FTL_ERR_INVALID, "n_custom_angles must be 0 or lasers_count (<= FTL_MAX_CUSTOM_ANGLES)");
         if (r.react_to_obstacles < 0 || r.react_to_obstacles > 3)
             return fail(FTL_ERR_INVALID, "react_to_obstacles must be True/'all'/'static'/'dynamic'/False (SEN:650-661)");
     }
+    if (c->track_vector_len < 0 || (c->track_vector_len > 0 && !c->tracker_enabled))
+        return fail(FTL_ERR_INVALID, "LeaderTrackDetector_vector needs LeaderPositionsTracker_v2 (CLS:240-244)");
     return FTL_OK;
 }
 
@@ -185,8 +197,17 @@ static DevOutputs to_dev_outputs(const FtlOutputs* o, int n_real) {
     if (o) {
         d.numerical_features = o->numerical_features; d.leader_target = o->leader_target; d.rays = o->rays;
         d.reward = o->reward; d.done = o->done; d.status = o->status;
+        d.follower_info = o->follower_info; d.track_vectors = o->track_vectors;
     }
     return d;
+}
+
+static int launch_optional_sensors(ftl_handle h, const DevOutputs& o, cudaStream_t st) {
+    if (!o.follower_info && !(o.track_vectors && h->cfg.c.track_vector_len > 0)) return FTL_OK;
+    k_optional_sensors<<<(h->n + 127) / 128, 128, 0, st>>>(h->cfg, h->st, o);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return FTL_OK;
 }
 
 static int launch_rays(ftl_handle h, float* rays, cudaStream_t st, int first_env = 0, int end_env = -1) {
@@ -217,6 +238,9 @@ static int copy_outputs_to_host(ftl_handle h, const FtlOutputs* o, cudaStream_t 
     if (o->reward) CUDA_TRY(cudaMemcpyAsync(o->reward, d.reward, 4 * n, cudaMemcpyDeviceToHost, st));
     if (o->done) CUDA_TRY(cudaMemcpyAsync(o->done, d.done, n, cudaMemcpyDeviceToHost, st));
     if (o->status) CUDA_TRY(cudaMemcpyAsync(o->status, d.status, 4 * n, cudaMemcpyDeviceToHost, st));
+    if (o->follower_info) CUDA_TRY(cudaMemcpyAsync(o->follower_info, d.follower_info, 8 * n, cudaMemcpyDeviceToHost, st));
+    if (o->track_vectors && h->cfg.c.track_vector_len)
+        CUDA_TRY(cudaMemcpyAsync(o->track_vectors, d.track_vectors, 8 * n * h->cfg.c.track_vector_len, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return FTL_OK;
 }
@@ -232,6 +256,8 @@ static FtlOutputs staged_outputs(ftl_handle h, const FtlOutputs* want) {
         if (want->reward) o.reward = d.reward;
         if (want->done) o.done = d.done;
         if (want->status) o.status = d.status;
+        if (want->follower_info) o.follower_info = d.follower_info;
+        if (want->track_vectors && h->cfg.c.track_vector_len) o.track_vectors = d.track_vectors;
     }
     return o;
 }
@@ -267,6 +293,7 @@ int ftl_create(const FtlConfig* cfg, int32_t n_envs, int32_t device, int64_t env
     d.env_id_base = env_id_base;
     d.rays_per_env = 0;
     for (int s = 0; s < c.n_ray_sensors; s++) d.rays_per_env += sensor_width(c.ray[s]);
+    ray_out_layout(d);
     h->rays_total = total_rays(c);
     d.rays_total = h->rays_total;
     d.eps_f32 = (float)c.leader_pos_epsilon;
@@ -331,6 +358,8 @@ int ftl_create(const FtlConfig* cfg, int32_t n_envs, int32_t device, int64_t env
     ok(dalloc(h, &h->d_out.reward, n));
     ok(dalloc(h, &h->d_out.done, n));
     ok(dalloc(h, &h->d_out.status, 4 * n));
+    ok(dalloc(h, &h->d_out.follower_info, 2 * n));
+    ok(dalloc(h, &h->d_out.track_vectors, (size_t)(c.track_vector_len > 0 ? c.track_vector_len : 1) * 2 * n));
     if (e != cudaSuccess) {
         for (void* p : h->allocs) cudaFree(p);
         delete h;
@@ -418,6 +447,8 @@ int ftl_reset(ftl_handle h, const uint8_t* mask_dev, const int32_t* scenario_ids
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     h->was_reset = true;
+    int rc = launch_optional_sensors(h, o, st);
+    if (rc) return rc;
     return launch_rays(h, o.rays, st);
 }
 
@@ -437,8 +468,10 @@ int ftl_step(ftl_handle h, const void* actions_dev, const FtlOutputs* out_dev, v
     }
     h->launches++;
     CUDA_TRY(cudaGetLastError());
+    int rc = launch_optional_sensors(h, o, st);
+    if (rc) return rc;
     if (h->profiling) prof_event(h, st);
-    int rc = launch_rays(h, o.rays, st);
+    rc = launch_rays(h, o.rays, st);
     if (h->profiling) prof_event(h, st);
     return rc;
 }
@@ -476,6 +509,9 @@ int ftl_step_host(ftl_handle h, const void* actions_host, const FtlOutputs* out_
     if (out_host->reward) CUDA_TRY(cudaMemcpyAsync(out_host->reward, d.reward, 4 * n, cudaMemcpyDeviceToHost, cs));
     if (out_host->done) CUDA_TRY(cudaMemcpyAsync(out_host->done, d.done, n, cudaMemcpyDeviceToHost, cs));
     if (out_host->status) CUDA_TRY(cudaMemcpyAsync(out_host->status, d.status, 4 * n, cudaMemcpyDeviceToHost, cs));
+    if (out_host->follower_info) CUDA_TRY(cudaMemcpyAsync(out_host->follower_info, d.follower_info, 8 * n, cudaMemcpyDeviceToHost, cs));
+    if (out_host->track_vectors && h->cfg.c.track_vector_len)
+        CUDA_TRY(cudaMemcpyAsync(out_host->track_vectors, d.track_vectors, 8 * n * h->cfg.c.track_vector_len, cudaMemcpyDeviceToHost, cs));
     // ray kernel in chunks of envs: the D2H copy of chunk c runs while chunk c+1 is being cast
     if (out_host->rays && h->cfg.rays_per_env) {
         const int chunks = h->n >= 8192 ? 6 : 1;

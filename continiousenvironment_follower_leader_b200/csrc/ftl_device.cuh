@@ -116,6 +116,8 @@ struct DevOutputs {
     float* reward;
     uint8_t* done;
     uint8_t* status;
+    float* follower_info;   // [N][2] or NULL
+    float* track_vectors;   // [N][track_vector_len][2] or NULL
 };
 
 // Configuration as the kernels want it: the user's FtlConfig plus values derived once on the host.
@@ -134,6 +136,8 @@ struct DevCfg {
     float corridor_length_f32;
     float corridor_width_f32;
     float static_inflate[2];     // pre-filter margin for follower / leader static collisions
+    // where sensor s writes inside an env's block of `rays`: cell (row j, column q) = base + j * stride + q
+    int ray_out_base[FTL_MAX_RAY_SENSORS], ray_out_stride[FTL_MAX_RAY_SENSORS];
 };
 
 // ---- tiny helpers -----------------------------------------------------------------------------------

@@ -20,6 +20,13 @@
 #include "ftl_device.cuh"
 
 namespace ftl {
+// what lands in `rays`: the distance, or the wrapper's clip(v / laser_length, 0, 1) (float32 division, WRP:211)
+FTL_HD float ray_out_value(const FtlConfig& c, float L, float v) {
+    if (!c.fused_sensor_prev) return v;
+    v = v / L;
+    return v < 0.f ? 0.f : v > 1.f ? 1.f : v;
+}
+
 
 constexpr float kNoHit = 3.0e38f;
 
@@ -91,6 +98,28 @@ FTL_HD_NOINLINE float seg_hit_exact(float px, float py, double ex, double ey, fl
 
 FTL_HD int sensor_width(const FtlRaySensorConfig& sc) {
     return sc.max_prev_obs * (sc.pad_sectors ? 4 * sc.lasers_count : sc.lasers_count);
+}
+
+// direction of ray k relative to (heading + first_laser_angle_offset), degrees: SEN:888-891, or the fixed fan of
+// LeaderCorridor_lasers (SEN:678-700)
+FTL_HD double ray_angle(const FtlRaySensorConfig& sc, int k) {
+    return sc.n_custom_angles ? sc.custom_angle[k] : k * (360.0 / sc.lasers_count);
+}
+
+FTL_HD int sensor_row_width(const FtlRaySensorConfig& sc) { return sc.pad_sectors ? 4 * sc.lasers_count : sc.lasers_count; }
+
+// raw: sensor blocks one after the other, each [H][W]; fused (WRP:203-221): one [H][sum W] matrix
+inline void ray_out_layout(DevCfg& d) {
+    const FtlConfig& c = d.c;
+    int sum_w = 0, off = 0, col = 0;
+    for (int s = 0; s < c.n_ray_sensors; s++) sum_w += sensor_row_width(c.ray[s]);
+    for (int s = 0; s < c.n_ray_sensors; s++) {
+        const int w = sensor_row_width(c.ray[s]);
+        d.ray_out_base[s] = c.fused_sensor_prev ? col : off;
+        d.ray_out_stride[s] = c.fused_sensor_prev ? sum_w : w;
+        col += w;
+        off += w * c.ray[s].max_prev_obs;
+    }
 }
 
 FTL_HD int total_rays(const FtlConfig& c) {
@@ -365,6 +394,39 @@ FTL_HD void ray_flush(RayShared& sh, const RayArrays& ra, int n_sensors) {
 }
 
 // the whole ray pass of env i.  rot: [rays_total] (cos, sin)(k * 360/R) per flat ray, made on the host.
+// The same rows written as ContinuousObserveModifier_sensorPrev's matrix (WRP:203-221): [H][sum of widths], values
+// clip(v / laser_length, 0, 1).  Out of line so that the default path's instruction footprint does not grow.
+FTL_HD_NOINLINE void ray_rows_write_fused(const DevCfg& cfg, const RayShared& sh, const RayArrays& ra, int i, int lane,
+                                          float* rays_out) {
+    const FtlConfig& c = cfg.c;
+    const int rt = sh.rt, n_valid = sh.n_valid;
+    for (int sidx = 0; sidx < sh.ns; sidx++) {
+        const FtlRaySensorConfig& sc = c.ray[sidx];
+        const int R = sc.lasers_count, H = sc.max_prev_obs, base = sh.sen[sidx].base;
+        const float L = (float)sc.laser_length;
+        float* dst = rays_out + (size_t)i * cfg.rays_per_env + cfg.ray_out_base[sidx];
+        const int stride = cfg.ray_out_stride[sidx];
+        const double in_sector = R / 4.0;
+        const int* srow = ra.res + kStaticBit * rt + base;
+        for (int e = lane; e < H * R; e += 32) {
+            const int j = e / R, k = e - j * R, age = H - 1 - j;
+            float v = L;
+            if (age < n_valid) {
+                int bits = ra.res[age * rt + base + k], sb = srow[k];
+                bits = sb < bits ? sb : bits;
+                if (bits != kNoHitBits) v = i2f_bits(bits);
+            }
+            v = ray_out_value(c, L, v);
+            if (!sc.pad_sectors) {
+                dst[j * stride + k] = v;
+            } else {   // SEN:932-953
+                int ksec = (k < in_sector) ? 0 : (k < 2 * in_sector) ? 1 : (k < 3 * in_sector) ? 2 : 3;
+                for (int sec = 0; sec < 4; sec++) dst[j * stride + sec * R + k] = sec == ksec ? v : 0.f;
+            }
+        }
+    }
+}
+
 FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool, const double2* rot, int i,
                       RayShared& sh, float* rays_out) {
     const FtlConfig& c = cfg.c;
@@ -394,7 +456,9 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
                 st.L = (float)sc.laser_length;
                 st.theta0 = (float)(dir + sc.first_laser_angle_offset);
                 st.inv_period = (float)sc.lasers_count / 360.f;
-                st.eps = 0.02f + 5e-5f * (float)sc.lasers_count;
+                // rays that are not evenly spaced (custom angles) cannot be binned by angle: a huge margin makes every
+                // edge a candidate for every ray of the sensor (cnt >= R below)
+                st.eps = sc.n_custom_angles ? 1e6f : 0.02f + 5e-5f * (float)sc.lasers_count;
                 st.offset = sc.first_laser_angle_offset;
                 st.Ld = sc.laser_length;
                 sh.sen[sidx] = st;
@@ -503,34 +567,41 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
     }
     // ---- out: assemble rows and write (row-major per sensor; consecutive lanes write consecutive floats) ------
     FTL_LANES(lane) {
-        int off = 0;
-        for (int sidx = 0; sidx < ns; sidx++) {
-            const FtlRaySensorConfig& sc = c.ray[sidx];
-            const int R = sc.lasers_count, H = sc.max_prev_obs, base = sh.sen[sidx].base;
-            const float L = (float)sc.laser_length;
-            float* dst = rays_out + (size_t)i * cfg.rays_per_env + off;
-            const int nsec = sc.pad_sectors ? 4 : 1;
-            const double in_sector = R / 4.0;
-            const float inv_R = 1.0f / (float)R;
-            const int* srow = ra.res + kStaticBit * rt + base;
-            for (int e = lane; e < H * R; e += 32) {
-                int j = (int)(((float)e + 0.5f) * inv_R);      // e / R without an integer division (H*R < 2^20)
-                int k = e - j * R;
-                const int age = H - 1 - j;
-                float v = L;
-                if (age < n_valid) {
-                    int bits = ra.res[age * rt + base + k], sb = srow[k];
-                    bits = sb < bits ? sb : bits;
-                    if (bits != kNoHitBits) v = i2f_bits(bits);
+#ifndef FTL_NO_FUSED
+        if (c.fused_sensor_prev) {
+            ray_rows_write_fused(cfg, sh, ra, i, lane, rays_out);
+        } else
+#endif
+        {
+            int off = 0;
+            for (int sidx = 0; sidx < ns; sidx++) {
+                const FtlRaySensorConfig& sc = c.ray[sidx];
+                const int R = sc.lasers_count, H = sc.max_prev_obs, base = sh.sen[sidx].base;
+                const float L = (float)sc.laser_length;
+                float* dst = rays_out + (size_t)i * cfg.rays_per_env + off;
+                const int nsec = sc.pad_sectors ? 4 : 1;
+                const double in_sector = R / 4.0;
+                const float inv_R = 1.0f / (float)R;
+                const int* srow = ra.res + kStaticBit * rt + base;
+                for (int e = lane; e < H * R; e += 32) {
+                    int j = (int)(((float)e + 0.5f) * inv_R);      // e / R without an integer division (H*R < 2^20)
+                    int k = e - j * R;
+                    const int age = H - 1 - j;
+                    float v = L;
+                    if (age < n_valid) {
+                        int bits = ra.res[age * rt + base + k], sb = srow[k];
+                        bits = sb < bits ? sb : bits;
+                        if (bits != kNoHitBits) v = i2f_bits(bits);
+                    }
+                    if (nsec == 1) {
+                        dst[e] = v;
+                    } else {   // SEN:932-953: four sector-masked copies side by side
+                        int ksec = (k < in_sector) ? 0 : (k < 2 * in_sector) ? 1 : (k < 3 * in_sector) ? 2 : 3;
+                        for (int sec = 0; sec < 4; sec++) dst[(j * 4 + sec) * R + k] = sec == ksec ? v : 0.f;
+                    }
                 }
-                if (nsec == 1) {
-                    dst[e] = v;
-                } else {   // SEN:932-953: four sector-masked copies side by side
-                    int ksec = (k < in_sector) ? 0 : (k < 2 * in_sector) ? 1 : (k < 3 * in_sector) ? 2 : 3;
-                    for (int sec = 0; sec < 4; sec++) dst[(j * 4 + sec) * R + k] = sec == ksec ? v : 0.f;
-                }
+                off += sensor_width(sc);
             }
-            off += sensor_width(sc);
         }
         if (lane == 0) s.unc_count[i] = sh.nu;   // 0 almost always; > kUncPerEnv: recast the env exactly
     }
@@ -549,20 +620,20 @@ struct ExactEnv {
 };
 
 FTL_HD void exact_ray_end(const FtlRaySensorConfig& sc, const ExactEnv& ee, int k, double* ex, double* ey) {
-    double ang = (ee.dir + sc.first_laser_angle_offset) + k * (360.0 / sc.lasers_count);   // SEN:888-891
+    double ang = (ee.dir + sc.first_laser_angle_offset) + ray_angle(sc, k);   // SEN:888-891
     double sn, cs;
     sincos_deg(ang, &sn, &cs);
     *ex = (double)ee.px + cs * sc.laser_length;
     *ey = (double)ee.py + sn * sc.laser_length;
 }
 
-// index of (row j, ray k) in the sensor's output block; pad_sectors layout of SEN:932-953
-FTL_HD int ray_out_index(const FtlRaySensorConfig& sc, int j, int k) {
+// index of (row j, ray k) relative to the sensor's output base; pad_sectors layout of SEN:932-953
+FTL_HD int ray_out_index(const FtlRaySensorConfig& sc, int stride, int j, int k) {
     const int R = sc.lasers_count;
-    if (!sc.pad_sectors) return j * R + k;
+    if (!sc.pad_sectors) return j * stride + k;
     double in_sector = R / 4.0;
     int ksec = (k < in_sector) ? 0 : (k < 2 * in_sector) ? 1 : (k < 3 * in_sector) ? 2 : 3;
-    return (j * 4 + ksec) * R + k;
+    return j * stride + ksec * R + k;
 }
 
 FTL_HD float exact_rect_min(const ExactEnv& ee, double ex, double ey, int4 q) {
@@ -580,11 +651,11 @@ FTL_HD_NOINLINE void rays_exact_recast(const DevCfg& cfg, const DevState& s, con
     const float4* corr = s.corridor + (size_t)i * c.corridor_cap;
     const int4* statics = pool.static_rects + (size_t)ee.scenario * c.static_cap;
     const int n_static = pool.n_static[ee.scenario];
-    int off = 0;
     for (int sidx = 0; sidx < c.n_ray_sensors; sidx++) {
         const FtlRaySensorConfig& sc = c.ray[sidx];
         const int cls = sensor_class_mask(sc);
-        float* dst = rays_out + (size_t)i * cfg.rays_per_env + off;
+        const int stride = cfg.ray_out_stride[sidx];
+        float* dst = rays_out + (size_t)i * cfg.rays_per_env + cfg.ray_out_base[sidx];
         for (int k = 0; k < sc.lasers_count; k++) {
             double ex, ey;
             exact_ray_end(sc, ee, k, &ex, &ey);
@@ -613,10 +684,10 @@ FTL_HD_NOINLINE void rays_exact_recast(const DevCfg& cfg, const DevState& s, con
                         m = fminf(m, seg_hit_exact(ee.px, ee.py, ex, ey, b4.x, b4.y, b4.z, b4.w));
                     }
                 }
-                dst[ray_out_index(sc, j, k)] = m >= kNoHit ? (float)sc.laser_length : m;
+                dst[ray_out_index(sc, stride, j, k)] =
+                    ray_out_value(c, (float)sc.laser_length, m >= kNoHit ? (float)sc.laser_length : m);
             }
         }
-        off += sensor_width(sc);
     }
 }
 
@@ -638,10 +709,9 @@ FTL_HD void rays_exact_env(const DevCfg& cfg, const DevState& s, const DevPool& 
     const UncRec* rec = s.unc_rec + (size_t)i * kUncPerEnv;
     for (int t = 0; t < count; t++) {
         const UncRec r = rec[t];
-        int sidx = 0, base = 0, off = 0;
+        int sidx = 0, base = 0;
         while (sidx + 1 < c.n_ray_sensors && r.f >= base + c.ray[sidx].lasers_count) {
             base += c.ray[sidx].lasers_count;
-            off += sensor_width(c.ray[sidx]);
             sidx++;
         }
         const FtlRaySensorConfig& sc = c.ray[sidx];
@@ -649,12 +719,13 @@ FTL_HD void rays_exact_env(const DevCfg& cfg, const DevState& s, const DevPool& 
         exact_ray_end(sc, ee, r.f - base, &ex, &ey);
         float d = seg_hit_exact(ee.px, ee.py, ex, ey, r.ax, r.ay, r.bx, r.by);
         if (d >= kNoHit) continue;
-        float* dst = rays_out + (size_t)i * cfg.rays_per_env + off;
+        d = ray_out_value(c, (float)sc.laser_length, d);   // monotone, so the minimum can be taken on the written scale
+        float* dst = rays_out + (size_t)i * cfg.rays_per_env + cfg.ray_out_base[sidx];
         for (int j = 0; j < sc.max_prev_obs; j++) {
             const int age = sc.max_prev_obs - 1 - j;
             if (age >= ee.n_valid) continue;
             if (!((r.rows >> age) & 1) && !((r.rows >> kStaticBit) & 1)) continue;
-            float* cell = dst + ray_out_index(sc, j, r.f - base);
+            float* cell = dst + ray_out_index(sc, cfg.ray_out_stride[sidx], j, r.f - base);
             if (d < *cell) *cell = d;
         }
     }

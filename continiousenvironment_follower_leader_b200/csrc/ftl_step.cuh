@@ -147,6 +147,35 @@ FTL_HD void sense_serial(const DevCfg& cfg, const DevState& s, int i, const Worl
     }
 }
 
+// FollowerInfo.scan (SEN:834-842: float64 quotients stored as float32) and LeaderTrackDetector_vector.scan
+// (SEN:365-380) on the tracker ring as the step left it: np.array(slice) - position with a float32 position, cast
+// into the float32 buffer.  Reads the stored state after the step / reset kernel (its own small kernel, launched
+// only when one of these outputs is requested: the step kernel of the BASELINE.json configurations is untouched).
+FTL_HD void write_optional_sensors(const FtlConfig& c, const DevState& s, const DevOutputs& out, int i) {
+    const float2 fp = s.pos[i];   // robot 0 = follower
+    if (out.follower_info) {
+        const double fspeed = s.rd[(size_t)RD_SPEED * s.n + i], fdir = s.rd[(size_t)RD_DIR * s.n + i];
+        out.follower_info[2 * (size_t)i] = (float)(fspeed / c.follower.max_speed);
+        out.follower_info[2 * (size_t)i + 1] = (float)(fdir / 360);
+    }
+    if (!out.track_vectors || c.track_vector_len <= 0) return;
+    const int P = c.track_vector_len, mask = c.corridor_cap - 1;
+    const int tail = s.gi[(size_t)GI_RING_TAIL * s.n + i], head = s.gi[(size_t)GI_RING_HEAD * s.n + i];
+    const double2* hist = s.hist + (size_t)i * c.corridor_cap;
+    float* v = out.track_vectors + (size_t)i * P * 2;
+    const int len = head - tail, cnt = len < P ? len : P;
+    const int first = c.track_vector_mode == 0 ? head - cnt : tail;   // "new": the last P points, "old": the first P
+    for (int k = 0; k < P; k++) {
+        float2 o = make_float2(0.f, 0.f);
+        if (k < cnt) {
+            const double2 p = hist[(first + k) & mask];
+            o = make_float2((float)(p.x - (double)fp.x), (float)(p.y - (double)fp.y));
+        }
+        v[2 * k] = o.x;
+        v[2 * k + 1] = o.y;
+    }
+}
+
 template <int NB>
 FTL_HD void write_outputs(const DevCfg& cfg, const DevPool& pool, const DevOutputs& out, int i, const World<NB>& w,
                           const Episode& e, bool obs_only) {

@@ -242,8 +242,14 @@ class Game(Env):
                "leader_target_point": (int(out.leader_target[0, 0]), int(out.leader_target[0, 1]))}
         if self.gc.c.tracker_enabled:
             obs["LeaderPositionsTracker_v2"] = self._tracker_obs()   # CLS:263-286 puts the tracker's tuple in the dict
-        for name, off, h, w in self.gc.ray_layout():
-            obs[name] = out.rays[0, off:off + h * w].reshape(h, w).copy()
+        for k, (name, off, h, w) in enumerate(self.gc.ray_layout()):
+            block = out.rays[0, off:off + h * w]
+            # the sensors without history return (R,) (SEN:724-726, 805-807), the history sensors (H, R)
+            obs[name] = block.copy() if self.gc.ray_sensor_flat[k] else block.reshape(h, w).copy()
+        if self.gc.follower_info_name is not None:   # SEN:834-842
+            obs[self.gc.follower_info_name] = out.follower_info[0].copy()
+        if self.gc.track_vector_name is not None:    # SEN:365-380
+            obs[self.gc.track_vector_name] = out.track_vectors[0].copy()
         return obs
 
     def _tracker_obs(self):

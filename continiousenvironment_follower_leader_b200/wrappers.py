@@ -127,9 +127,13 @@ class MyFrameStack(ObservationWrapper):
 def sensor_prev_observation(batch_env):
     """Batched ContinuousObserveModifier_sensorPrev.observation on device tensors: [N, H, sum of widths]."""
     import torch
+    if batch_env.cfg.fused_sensor_prev:   # the ray kernel already wrote this matrix
+        return batch_env.sensor_prev()
     feats = []
     layout = batch_env.gc.ray_layout()
     for i, (name, off, h, w) in enumerate(layout):
         L = batch_env.gc.c.ray[i].laser_length
-        feats.append(torch.clamp(batch_env.rays[:, off:off + h * w].view(batch_env.n, h, w) / L, 0, 1))
+        # a tensor divisor: torch turns division by a python scalar into a multiplication by 1/L (1 ulp off numpy's)
+        div = torch.tensor(L, dtype=torch.float32, device=batch_env.rays.device)
+        feats.append(torch.clamp(batch_env.rays[:, off:off + h * w].view(batch_env.n, h, w) / div, 0, 1))
     return torch.cat(feats, dim=2)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FTL_ABI_VERSION 1
+#define FTL_ABI_VERSION 2
 
 #define FTL_MAX_BEARS 4
 #define FTL_MAX_RAY_SENSORS 4
@@ -70,7 +70,11 @@ typedef struct FtlRobotConfig {
 } FtlRobotConfig;
 
 /* One history ray sensor = LeaderCorridor_Prev_lasers_v2 (SEN:867-968); the retired class name
- * LaserPrevSensor maps onto it with corridor/green-zone off and offset 0 (SEN:847-851). */
+ * LaserPrevSensor maps onto it with corridor/green-zone off and offset 0 (SEN:847-851).
+ * The sensors without history run on the same engine with max_prev_obs = 1 and offset 0:
+ * LeaderCorridor_lasers_v2 (SEN:736-807, rays at k*360/R) and LeaderCorridor_lasers (SEN:571-726, the fixed fan
+ * -40, 0, +40 [, -90, +90] [, -150, +150] degrees, given here as custom angles). */
+#define FTL_MAX_CUSTOM_ANGLES 8
 typedef struct FtlRaySensorConfig {
     int32_t lasers_count;
     int32_t max_prev_obs;            /* H */
@@ -80,6 +84,9 @@ typedef struct FtlRaySensorConfig {
     int32_t react_to_obstacles;      /* FTL_REACT_* */
     double laser_length;
     double first_laser_angle_offset; /* SEN:873, default -45 */
+    int32_t n_custom_angles;         /* 0: ray k points at offset + k*360/R; else == lasers_count and ray k points at */
+    int32_t pad_;                    /*    offset + custom_angle[k] (degrees, relative to the follower's heading)     */
+    double custom_angle[FTL_MAX_CUSTOM_ANGLES];
 } FtlRaySensorConfig;
 
 typedef struct FtlConfig {
@@ -129,7 +136,15 @@ typedef struct FtlConfig {
     int32_t route_cap;     /* waypoints per scenario */
     int32_t static_cap;    /* static rectangles per scenario (2 bridge walls + rocks) */
     int32_t auto_reset;    /* 1: envs that finished are re-initialised at the end of the step */
-    int32_t reserved[7];
+    /* 1: `rays` holds what ContinuousObserveModifier_sensorPrev.observation (WRP:203-221) returns instead of
+     * the raw sensor blocks: [H][sum of sensor widths], every value clip(v / laser_length, 0, 1); needs the same
+     * max_prev_obs on every sensor (the wrapper asserts it, WRP:209-210).  Same number of floats per env. */
+    int32_t fused_sensor_prev;
+    /* LeaderTrackDetector_vector (SEN:342-391): vectors from the follower to the newest (mode 0, "new") or oldest
+     * (mode 1, "old") track_vector_len points of the tracker's history; 0 = sensor absent */
+    int32_t track_vector_len;
+    int32_t track_vector_mode;
+    int32_t reserved[4];
 } FtlConfig;
 
 /* Scenario pool = what Game.reset() builds (ENV:434-543) before the first sensor scan, as data.
@@ -206,6 +221,8 @@ typedef struct FtlOutputs {
     float* reward;             /* [N] */
     uint8_t* done;             /* [N] */
     uint8_t* status;           /* [N][4]  mission, agent, leader, crash */
+    float* follower_info;      /* [N][2]   FollowerInfo.scan: speed / max_speed, direction / 360 (SEN:834-842); may be NULL */
+    float* track_vectors;      /* [N][track_vector_len][2]  LeaderTrackDetector_vector.scan (SEN:365-380); may be NULL */
 } FtlOutputs;
 
 /* Episode statistics accumulated on the device (summed over envs), the vector reduced with NCCL. */

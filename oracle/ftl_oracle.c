@@ -813,7 +813,9 @@ static void ray_sensor_scan(const FtlOracle* o, int env_index, int sensor, float
         float* row = out + (size_t)j * width;
         for (int k = 0; k < width; k++) row[k] = 0.f;
         for (int i = 0; i < R; i++) {
-            double ang = (e->follower.dir + sc->first_laser_angle_offset) + i * period;
+            /* SEN:888-891; the fan of LeaderCorridor_lasers (SEN:678-700) comes in as custom angles */
+            double ang = (e->follower.dir + sc->first_laser_angle_offset) +
+                         (sc->n_custom_angles ? sc->custom_angle[i] : i * period);
             double th = ang * DEG2RAD;
             double ex = (double)px + cos(th) * L, ey = (double)py + sin(th) * L; /* laser end, float64 */
             double best = -1, bx_ = 0, by_ = 0;
@@ -892,6 +894,23 @@ static void use_sensors(FtlOracle* o, int i, const FtlOutputs* out) { /* CLS:255
     FtlEnvState* e = &o->env[i];
     if (cfg->tracker_enabled)
         for (int k = 0; k < cfg->tracker_scans_per_step; k++) tracker_scan(o, i);
+    if (out && out->follower_info) { /* FollowerInfo.scan, SEN:834-842: float64 quotients stored as float32 */
+        out->follower_info[2 * i] = (float)(e->follower.speed / cfg->follower.max_speed);
+        out->follower_info[2 * i + 1] = (float)(e->follower.dir / 360);
+    }
+    if (out && out->track_vectors && cfg->track_vector_len > 0) { /* LeaderTrackDetector_vector.scan, SEN:365-380 */
+        const int P = cfg->track_vector_len, cap = cfg->corridor_cap;
+        const double* hist = o->hist + (size_t)i * cap * 2;
+        float* v = out->track_vectors + (size_t)i * P * 2;
+        int len = e->ring_head - e->ring_tail;
+        int cnt = len < P ? len : P;
+        int first = cfg->track_vector_mode == 0 ? e->ring_head - cnt : e->ring_tail; /* "new": the last P, "old": the first P */
+        for (int k = 0; k < 2 * P; k++) v[k] = 0.f;
+        for (int k = 0; k < cnt; k++) { /* np.array(slice) - position (float32), cast into the float32 buffer */
+            v[2 * k] = (float)(hist[2 * RING(first + k)] - (double)e->follower.pos[0]);
+            v[2 * k + 1] = (float)(hist[2 * RING(first + k) + 1] - (double)e->follower.pos[1]);
+        }
+    }
     if (cfg->n_ray_sensors > 0) {
         /* history_obstacles_list.pop(0); append(current), SEN:894-895 (one shared ring: every sensor
          * snapshots the same world at the same instants) */

@@ -74,7 +74,7 @@ def _robot(r):
             [int(r.rotation_direction), int(r.desirable_rotation_direction), rect.x, rect.y, rect.w, rect.h])
 
 
-def capture(env, obs, reward, done, info, ray_names, n_bears):
+def capture(env, obs, reward, done, info, ray_names, n_bears, gc=None):
     rec = {}
     robots = [env.follower, env.leader] + list(env.game_dynamic_list)[:n_bears]
     rf, ri = zip(*[_robot(r) for r in robots])
@@ -106,6 +106,10 @@ def capture(env, obs, reward, done, info, ray_names, n_bears):
         rec["corr_first"] = np.array([corr[0][0], corr[0][1]], np.float64).reshape(4)
     if ray_names:
         rec["rays"] = np.concatenate([np.asarray(obs[n], np.float32).reshape(-1) for n in ray_names])
+    if gc is not None and gc.follower_info_name is not None:
+        rec["follower_info"] = np.asarray(obs[gc.follower_info_name], np.float32)
+    if gc is not None and gc.track_vector_name is not None:
+        rec["track_vectors"] = np.asarray(obs[gc.track_vector_name], np.float32)
     return rec
 
 
@@ -144,7 +148,7 @@ def run_trace(name, env_id, kwargs, seed, policy, max_env_steps, action_seed=0, 
     rng = np.random.RandomState(action_seed)
     scen = extract_scenario(env)
     info0 = {"mission_status": "in_progress", "agent_status": "moving", "leader_status": "moving"}
-    recs = [capture(env, obs, 0.0, False, info0, ray_names, n_bears)]
+    recs = [capture(env, obs, 0.0, False, info0, ray_names, n_bears, gc)]
     actions = []
     pol = POLICIES[policy]
     for t in range(max_env_steps):
@@ -153,7 +157,7 @@ def run_trace(name, env_id, kwargs, seed, policy, max_env_steps, action_seed=0, 
         a = pol(rng, env, lo, hi)
         obs, reward, done, info = rh.step(env, a)
         actions.append(a)
-        recs.append(capture(env, obs, reward, done, info, ray_names, n_bears))
+        recs.append(capture(env, obs, reward, done, info, ray_names, n_bears, gc))
         if until_done and done:
             break
     out = {"actions": np.array(actions, np.float32)}
@@ -226,6 +230,31 @@ TRACES = [
          kwargs=dict(TEST_GAME_MANUAL_GAZEBO_KWARGS, leader_speed_regime={0: 1}, leader_acceleration_regime=None,
                      early_stopping={"max_distance_coef": 1.5, "low_reward": -40}),
          seed=4, policy="random", max_env_steps=400, until_done=True),
+    # the sensors without history on the same ray engine (LeaderCorridor_lasers_v2 = rays at k*360/R,
+    # LeaderCorridor_lasers = the fixed 7-ray fan), FollowerInfo and LeaderTrackDetector_vector ("new")
+    dict(name="flat_sensors_seed9", env_id="Test-Cont-Env-Auto-v0",
+         kwargs=dict(bear_number=2, follower_sensors={
+             "LeaderPositionsTracker_v2": cfg3_sensors()["LeaderPositionsTracker_v2"],
+             "LeaderCorridor_lasers_v2": dict(sensor_class="LeaderCorridor_lasers_v2", react_to_safe_corridor=True,
+                                              react_to_obstacles=True, react_to_green_zone=True, lasers_count=24,
+                                              laser_length=180),
+             "LeaderCorridor_lasers": dict(sensor_class="LeaderCorridor_lasers", react_to_safe_corridor=True,
+                                           react_to_obstacles="dynamic", front_lasers_count=5, back_lasers_count=2,
+                                           laser_length=120),
+             "FollowerInfo": dict(sensor_class="FollowerInfo"),
+             "LeaderTrackDetector_vector": dict(sensor_class="LeaderTrackDetector_vector", position_sequence_length=12,
+                                                detectable_positions="new")}),
+         seed=9, policy="follow", max_env_steps=220, switch=(160, "random")),
+    # the "old" end of the history, a history sensor next to a flat one, 3-ray fan
+    dict(name="flat_sensors_old_seed13", env_id="Test-Cont-Env-Auto-v0",
+         kwargs=dict(bear_number=1, frames_per_step=5, follower_sensors={
+             "LeaderPositionsTracker_v2": cfg3_sensors()["LeaderPositionsTracker_v2"],
+             "LeaderCorridor_Prev_lasers_v2": cfg3_sensors()["LeaderCorridor_Prev_lasers_v2"],
+             "fan": dict(sensor_class="LeaderCorridor_lasers", react_to_safe_corridor=True, react_to_obstacles=True,
+                         laser_length=100),
+             "LeaderTrackDetector_vector": dict(sensor_class="LeaderTrackDetector_vector", position_sequence_length=50,
+                                                detectable_positions="old")}),
+         seed=13, policy="follow", max_env_steps=200),
 ]
 
 

@@ -54,7 +54,9 @@ class OracleEnv:
         self._h = self._L.ftl_oracle_create(C.byref(self.cfg), n_envs, env_id_base, n_threads)
         if not self._h:
             raise ValueError("oracle rejected the configuration")
-        self.out = HostOutputs(n_envs, abi.rays_per_env(self.cfg))
+        self.out = HostOutputs(n_envs, abi.rays_per_env(self.cfg),
+                               follower_info=getattr(game_config, "follower_info_name", None) is not None,
+                               track_vector_len=self.cfg.track_vector_len)
 
     def close(self):
         if self._h:

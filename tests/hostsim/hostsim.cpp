@@ -84,6 +84,10 @@ static void reset_all(FtlHandle_* h, const uint8_t* mask, const int* ids, const 
         episode_store(h->st, i, e);
     }
 }
+static void optional_all(FtlHandle_* h, const DevOutputs& out) {
+    if (!out.follower_info && !out.track_vectors) return;
+    for (int i = 0; i < h->n; i++) write_optional_sensors(h->cfg.c, h->st, out, i);
+}
 static void rays_all(FtlHandle_* h, float* rays) {
     if (!rays || !h->rays_total) return;
     std::vector<unsigned char> buf(ray_shared_bytes(h->rays_total) + 16);
@@ -98,6 +102,7 @@ static DevOutputs dev_out(const FtlOutputs* o) {
     if (o) {
         d.numerical_features = o->numerical_features; d.leader_target = o->leader_target; d.rays = o->rays;
         d.reward = o->reward; d.done = o->done; d.status = o->status;
+        d.follower_info = o->follower_info; d.track_vectors = o->track_vectors;
     }
     return d;
 }
@@ -116,11 +121,12 @@ int ftl_create(const FtlConfig* cfg, int32_t n_envs, int32_t device, int64_t env
     d.c = c;
     d.env_id_base = env_id_base;
     for (int s = 0; s < c.n_ray_sensors; s++) d.rays_per_env += sensor_width(c.ray[s]);
+    ray_out_layout(d);
     h->rays_total = total_rays(c);
     d.rays_total = h->rays_total;
     for (int s = 0; s < c.n_ray_sensors; s++)
         for (int k = 0; k < c.ray[s].lasers_count; k++) {
-            double th = (k * (360.0 / c.ray[s].lasers_count)) * kDeg2Rad;
+            double th = ray_angle(c.ray[s], k) * kDeg2Rad;
             h->rot.push_back(make_double2(std::cos(th), std::sin(th)));
         }
     d.eps_f32 = (float)c.leader_pos_epsilon;
@@ -205,6 +211,7 @@ int ftl_reset_host(ftl_handle h, const uint8_t* mask, const int32_t* ids, const 
         case 3: reset_all<3>(h, mask, ids, o); break;
         default: reset_all<4>(h, mask, ids, o); break;
     }
+    optional_all(h, o);
     rays_all(h, o.rays);
     return FTL_OK;
 }
@@ -217,6 +224,7 @@ int ftl_step_host(ftl_handle h, const void* actions, const FtlOutputs* out, void
         case 3: step_all<3>(h, actions, o); break;
         default: step_all<4>(h, actions, o); break;
     }
+    optional_all(h, o);
     rays_all(h, o.rays);
     return FTL_OK;
 }

@@ -148,6 +148,20 @@ def check_record(t, d, gc, out, st, env_index=0, float_rtol=0.0, ray_rtol=RTOL, 
         _equal(st.hist[env_index, tail % cap], d["t_hist_first"][t], "hist[0]", t)
         _equal(st.corridor[env_index, (h - 1) % cap], d["t_corr_last"][t].astype(np.float32), "corridor[-1] (f32)", t)
         _equal(st.corridor[env_index, tail % cap], d["t_corr_first"][t].astype(np.float32), "corridor[0] (f32)", t)
+    # ---- FollowerInfo / LeaderTrackDetector_vector (SEN:834-842, 365-380) -------------------------
+    if "t_follower_info" in d:
+        if float_rtol == 0.0:
+            _equal(out.follower_info[env_index], d["t_follower_info"][t], "FollowerInfo", t)
+        else:
+            _close(out.follower_info[env_index], d["t_follower_info"][t], float_rtol, "FollowerInfo", t)
+    if "t_track_vectors" in d:
+        want = d["t_track_vectors"][t]
+        if float_rtol == 0.0:
+            _equal(out.track_vectors[env_index], want, "LeaderTrackDetector_vector", t)
+        else:   # differences of positions: absolute tolerance on the scale of the positions themselves
+            err = np.abs(out.track_vectors[env_index].astype(np.float64) - want)
+            if np.any(err > float_rtol * 1500.0):
+                raise Mismatch("step %d: LeaderTrackDetector_vector differs by %g" % (t, err.max()))
     # ---- rays -----------------------------------------------------------------------------------
     bad = 0
     if c.n_ray_sensors:
@@ -195,3 +209,14 @@ def check_final_arrays(st, d, gc, env_index=0):
         idx = [(i % cap) for i in range(int(e["ring_tail"]), int(e["ring_head"]))]
         _equal(st.hist[env_index, idx], d["final_hist"], "whole tracker history", -1)
         _equal(st.corridor[env_index, idx], d["final_corridor"].astype(np.float32), "whole corridor (f32)", -1)
+
+
+def sensor_prev_expected(gc, rays):
+    """ContinuousObserveModifier_sensorPrev.observation (WRP:203-221) applied with numpy to raw sensor blocks
+    [N, rays_per_env]: clip(block / laser_length, 0, 1) per sensor, concatenated along the ray axis -> [N, H, sum W]."""
+    feats = []
+    for i, (_name, off, h, w) in enumerate(gc.ray_layout()):
+        L = gc.c.ray[i].laser_length
+        block = rays[:, off:off + h * w].reshape(rays.shape[0], h, w)   # float32 / python float -> float32 (NEP 50)
+        feats.append(np.clip(block / L, 0, 1))
+    return np.concatenate(feats, axis=2)

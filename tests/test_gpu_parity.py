@@ -277,3 +277,97 @@ def test_gym_surface_on_the_gpu_replays_a_reference_trace():
         feats = wrapped.observation(obs)
         assert feats.shape == (5, 48) and feats.min() >= 0 and feats.max() <= 1
     assert env.step_count == 2600
+
+
+@pytest.mark.gpu
+def test_fused_sensor_prev_output_on_the_gpu():
+    """fused_sensor_prev=True on the device (both entry points) against the wrapper's arithmetic applied to the
+    oracle's raw sensor output (WRP:203-221); the exact pass patches cells on the normalised scale."""
+    from oracle_py import OracleEnv
+    kwargs = dict(bear_number=1, follower_sensors=cfg3_sensors())
+    n, steps = 2048, 40
+    gc, gc_raw = GameConfig(fused_sensor_prev=True, **kwargs), GameConfig(**kwargs)
+    pool = synthetic_pool(gc, 64, seed=1)
+    cuda, orc = _cuda_env(gc, n), OracleEnv(gc_raw, n, n_threads=8)
+    cuda.upload_scenarios(pool)
+    orc.upload_scenarios(pool)
+    ids = (np.arange(n) % pool.n).astype(np.int32)
+    oc, oo = cuda.reset(scenario_ids=ids), orc.reset(scenario_ids=ids)
+    rng = np.random.RandomState(7)
+    bounds = gc.action_bounds()
+    bad = 0
+    for t in range(steps):
+        want = parity.sensor_prev_expected(gc_raw, oo.rays)
+        got = oc.rays.reshape(want.shape)
+        bad += int(np.sum(np.abs(got - want) > parity.RTOL))
+        a = rng.uniform(bounds[0], bounds[1], size=(n, 2)).astype(np.float32)
+        oc, oo = cuda.step(a), orc.step(a)
+    assert bad <= 2, "%d fused cells differ" % bad
+
+    import torch
+    from continiousenvironment_follower_leader_b200.batch_env import FtlBatchEnv
+    from continiousenvironment_follower_leader_b200.wrappers import sensor_prev_observation
+    fused, raw = FtlBatchEnv(512, game_config=gc, scenario_pool=pool), FtlBatchEnv(512, game_config=gc_raw, scenario_pool=pool)
+    ids_t = torch.arange(512, dtype=torch.int32, device="cuda") % pool.n
+    fused.reset(scenario_ids=ids_t)
+    raw.reset(scenario_ids=ids_t)
+    for t in range(10):
+        a = torch.from_numpy(rng.uniform(bounds[0], bounds[1], size=(512, 2)).astype(np.float32)).cuda()
+        obs_f, *_ = fused.step(a)
+        raw.step(a)
+        assert torch.equal(obs_f["sensor_prev"], sensor_prev_observation(raw))
+
+
+def _scenario_of(d):
+    from continiousenvironment_follower_leader_b200 import scenario_gen
+    sc = scenario_gen.Scenario()
+    sc.static_rects = [tuple(r) for r in d["scen_static_rects"]]
+    sc.route = [tuple(p) for p in d["scen_route"]]
+    sc.leader_pos, sc.leader_dir = d["scen_leader_pos"], float(d["scen_leader_dir"])
+    sc.follower_pos, sc.follower_dir = d["scen_follower_pos"], float(d["scen_follower_dir"])
+    sc.found_target_point = True
+    return sc
+
+
+@pytest.mark.gpu
+def test_gym_surface_returns_the_flat_sensors_like_the_reference():
+    """LeaderCorridor_lasers_v2 / LeaderCorridor_lasers / FollowerInfo / LeaderTrackDetector_vector through the
+    single-env view: same dict keys and shapes as the reference's use_sensors (CLS:255-288), values of the trace."""
+    from continiousenvironment_follower_leader_b200 import gym_surface as gs
+    d, meta = parity.load_trace(parity.GOLDEN_DIR + "/flat_sensors_seed9.npz")
+    env = gs.make("Test-Cont-Env-Auto-v0", **meta["kwargs"])
+    obs = env.reset(scenario=_scenario_of(d))
+    for t, a in enumerate(d["actions"][:120]):
+        obs, reward, done, info = env.step(a)
+        assert obs["LeaderCorridor_lasers_v2"].shape == (24,) and obs["LeaderCorridor_lasers"].shape == (7,)
+        assert obs["FollowerInfo"].shape == (2,) and obs["LeaderTrackDetector_vector"].shape == (12, 2)
+        got = np.concatenate([obs[n].reshape(-1) for n in meta["ray_names"]])
+        assert np.allclose(got, d["t_rays"][t + 1], rtol=parity.RTOL)
+        assert np.allclose(obs["FollowerInfo"], d["t_follower_info"][t + 1], rtol=parity.RTOL, atol=1e-6)
+        assert np.allclose(obs["LeaderTrackDetector_vector"], d["t_track_vectors"][t + 1], atol=0.15 * parity.RTOL * 1500)
+
+
+@pytest.mark.gpu
+def test_flat_sensors_match_the_oracle_on_a_batch():
+    from oracle_py import OracleEnv
+    d, meta = parity.load_trace(parity.GOLDEN_DIR + "/flat_sensors_old_seed13.npz")
+    kwargs = dict(meta["kwargs"], auto_reset=True, max_steps=400)
+    n, steps = 1024, 90
+    gc = GameConfig(**kwargs)
+    pool = synthetic_pool(gc, 64, seed=5)
+    cuda, orc = _cuda_env(gc, n), OracleEnv(gc, n, n_threads=8)
+    cuda.upload_scenarios(pool)
+    orc.upload_scenarios(pool)
+    ids = (np.arange(n) % pool.n).astype(np.int32)
+    oc, oo = cuda.reset(scenario_ids=ids), orc.reset(scenario_ids=ids)
+    rng = np.random.RandomState(3)
+    bounds = gc.action_bounds()
+    bad = 0
+    for t in range(steps):
+        assert np.allclose(oc.track_vectors, oo.track_vectors, atol=0.15), "track vectors differ at step %d" % t
+        bad += _ray_outliers(oc.rays, oo.rays)
+        a = rng.uniform(bounds[0], bounds[1], size=(n, 2)).astype(np.float32)
+        a[: n // 2, 0], a[: n // 2, 1] = bounds[1][0], 0.0
+        oc, oo = cuda.step(a), orc.step(a)
+        assert np.array_equal(oc.done, oo.done) and np.array_equal(oc.status, oo.status)
+    assert bad <= 2

@@ -10,6 +10,8 @@ from hostsim_py import make_env
 from oracle_py import OracleEnv
 from test_gpu_parity import _compare_states, _ray_outliers
 
+FLAT_SENSOR_KWARGS = parity.load_trace(parity.GOLDEN_DIR + "/flat_sensors_seed9.npz")[1]["kwargs"]
+
 CASES = [
     ("cfg2", dict(add_obstacles=False, add_bear=False,
                   follower_sensors={"LeaderPositionsTracker_v2": cfg3_sensors()["LeaderPositionsTracker_v2"]}), 96, 60),
@@ -20,6 +22,8 @@ CASES = [
     # BASELINE.json configs[4]: ray-count sweep up to 360 lasers (the reference only accepts 12/20/24/36, SEN:761)
     ("rays_360", dict(bear_number=2, frames_per_step=3, follower_sensors=cfg3_sensors(72, 360, 4)), 24, 40),
     ("rays_120_f1", dict(bear_number=1, frames_per_step=2, follower_sensors=cfg3_sensors(20, 120, 8)), 24, 60),
+    # sensors without history, FollowerInfo, LeaderTrackDetector_vector (kwargs of the golden trace)
+    ("flat_sensors", dict(FLAT_SENSOR_KWARGS, auto_reset=True, max_steps=300), 48, 80),
 ]
 
 
@@ -52,6 +56,10 @@ def test_hostsim_matches_oracle(name, kwargs, n, steps):
         if gc.rays_per_env:
             bad += _ray_outliers(os_.rays, oo.rays)
             total += os_.rays.size
+        if os_.follower_info is not None:
+            assert np.array_equal(os_.follower_info, oo.follower_info)
+        if os_.track_vectors is not None:
+            assert np.array_equal(os_.track_vectors, oo.track_vectors)
         _compare_states(sim.get_state(), orc.get_state(), gc, n, 0.0)
     assert bad == 0, "%d of %d ray values outside tolerance" % (bad, total)
     assert int(sim.get_state().env["overflow"].max()) == 0
@@ -91,3 +99,36 @@ def test_grazing_rays_resolve_like_the_reference(libname):
         a, b = sim.step(zero), orc.step(zero)
         assert np.array_equal(a.numerical_features, b.numerical_features)
         assert _ray_outliers(a.rays, b.rays, rtol=1e-5) == 0
+
+
+@pytest.mark.parametrize("pad", [False, True], ids=["plain", "pad_sectors"])
+def test_fused_sensor_prev_output_is_the_wrapper_applied_to_the_oracle(pad):
+    """fused_sensor_prev=True: the ray kernel writes ContinuousObserveModifier_sensorPrev's matrix (WRP:203-221);
+    checked bit for bit against the wrapper's arithmetic applied to the same build's raw sensor output, and within
+    the ray tolerance against the wrapper applied to the oracle's."""
+    sensors = cfg3_sensors(12, 24, 4)
+    for name in sensors:
+        if "pad_sectors" in sensors[name]:
+            sensors[name]["pad_sectors"] = pad
+    kwargs = dict(bear_number=1, follower_sensors=sensors)
+    n, steps = 48, 40
+    gc, gc_raw = GameConfig(fused_sensor_prev=True, **kwargs), GameConfig(**kwargs)
+    assert gc.rays_per_env == gc_raw.rays_per_env
+    pool = synthetic_pool(gc, 16, seed=3)
+    sim, sim_raw, orc = make_env(gc, n), make_env(gc_raw, n), OracleEnv(gc_raw, n, n_threads=4)
+    for e in (sim, sim_raw, orc):
+        e.upload_scenarios(pool)
+    ids = (np.arange(n) % pool.n).astype(np.int32)
+    o_s, o_r, o_o = sim.reset(scenario_ids=ids), sim_raw.reset(scenario_ids=ids), orc.reset(scenario_ids=ids)
+    rng = np.random.RandomState(11)
+    bounds = gc.action_bounds()
+    for t in range(steps):
+        same_build = parity.sensor_prev_expected(gc_raw, o_r.rays)
+        want = parity.sensor_prev_expected(gc_raw, o_o.rays)
+        got = o_s.rays.reshape(want.shape)
+        assert same_build.dtype == np.float32 and np.array_equal(got, same_build), "fused output differs at step %d" % t
+        assert np.all(np.abs(got - want) <= parity.RTOL), "fused output differs from the oracle's at step %d" % t
+        assert got.min() >= 0.0 and got.max() <= 1.0
+        a = rng.uniform(bounds[0], bounds[1], size=(n, 2)).astype(np.float32)
+        a[: n // 2, 0], a[: n // 2, 1] = bounds[1][0], 0.0
+        o_s, o_r, o_o = sim.step(a), sim_raw.step(a), orc.step(a)
