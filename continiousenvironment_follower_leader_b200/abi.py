@@ -95,6 +95,17 @@ class FtlScenarioPool(C.Structure):
     ]
 
 
+class FtlScenarioGenConfig(C.Structure):
+    _fields_ = [("game_width", C.c_int32), ("game_height", C.c_int32),
+                ("min_distance", C.c_double), ("max_distance", C.c_double), ("leader_pos_epsilon", C.c_double),
+                ("leader_width", C.c_int32), ("leader_height", C.c_int32),
+                ("follower_width", C.c_int32), ("follower_height", C.c_int32),
+                ("leader_width_f", C.c_double), ("leader_height_f", C.c_double),
+                ("add_obstacles", C.c_int32), ("obstacle_number", C.c_int32), ("step_grid", C.c_int32),
+                ("bridge_size", C.c_int32 * 2), ("leader_margin", C.c_double),
+                ("path_finding", C.c_int32), ("pad_", C.c_int32)]
+
+
 class FtlRobotState(C.Structure):
     _fields_ = [("pos", C.c_float * 2), ("rect", C.c_int32 * 4), ("dir", C.c_double),
                 ("speed", C.c_double), ("rot_speed", C.c_double),

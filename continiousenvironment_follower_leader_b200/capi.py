@@ -51,6 +51,7 @@ def load(path=None):
     L.ftl_step_host.argtypes = [vp, vp, C.POINTER(abi.FtlOutputs), vp]
     L.ftl_get_state.argtypes = [vp, i32, i32, C.POINTER(abi.FtlStateBuffers)]
     L.ftl_set_state.argtypes = [vp, i32, i32, C.POINTER(abi.FtlStateBuffers)]
+    L.ftl_generate_scenarios.argtypes = [C.POINTER(abi.FtlScenarioGenConfig), vp, i32, C.POINTER(abi.FtlScenarioPool), i32]
     for name, argtypes, restype in (
             ("ftl_reset", [vp, vp, vp, C.POINTER(abi.FtlOutputs), vp], C.c_int),
             ("ftl_step", [vp, vp, C.POINTER(abi.FtlOutputs), vp], C.c_int),

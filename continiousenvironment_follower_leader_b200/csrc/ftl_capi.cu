@@ -69,6 +69,7 @@ __global__ void k_unpack_state(const __grid_constant__ DevCfg cfg, const DevStat
 // host side: handle, C-ABI
 // =================================================================================================
 static thread_local std::string g_err;
+void ftl_set_error_message(const char* msg) { g_err = msg; }   // for ftl_scenario_gen.cpp
 static int fail(int code, const std::string& msg) {
     g_err = msg;
     return code;

@@ -143,6 +143,43 @@ def generate(gc, trajectory=None):
     return sc
 
 
+def gen_config(gc):
+    """GameConfig -> the FtlScenarioGenConfig of include/ftl.h (what ftl_generate_scenarios needs)."""
+    from . import abi
+    g, c = gc.kwargs, gc.c
+    if g["multiple_end_points"]:
+        raise NotImplementedError("multiple_end_points (three chained D* runs, ENV:1549-1612) is not supported")
+    if g["trajectory"] is not None:
+        raise ValueError("an explicit trajectory= needs no generated route: use generate()")
+    s = abi.FtlScenarioGenConfig()
+    s.game_width, s.game_height = c.game_width, c.game_height
+    s.min_distance, s.max_distance, s.leader_pos_epsilon = c.min_distance, c.max_distance, c.leader_pos_epsilon
+    s.leader_width, s.leader_height = c.leader.width, c.leader.height
+    s.follower_width, s.follower_height = c.follower.width, c.follower.height
+    s.leader_width_f = g["leader_size"][0] * g["pixels_to_meter"]
+    s.leader_height_f = g["leader_size"][1] * g["pixels_to_meter"]
+    s.add_obstacles, s.obstacle_number, s.step_grid = int(bool(g["add_obstacles"])), int(g["obstacle_number"]), int(g["step_grid"])
+    s.bridge_size[0], s.bridge_size[1] = int(g["bridge_size"][0]), int(g["bridge_size"][1])
+    s.leader_margin = float(g["leader_margin"])
+    s.path_finding = 0 if g["path_finding_algorythm"] == "dstar" else 1
+    return s
+
+
+def generate_pool_native(gc, seeds, n_threads=0, lib_path=None):
+    """Scenario pool for ``seeds`` through the C++ generator (ftl_generate_scenarios in libftl.so, all host cores):
+    the same layouts and routes as ``random.seed(s); generate(gc)`` per seed, without the Python loop."""
+    import ctypes as C
+    from . import capi
+    from .scenario import ScenarioPool
+    L = capi.load(lib_path)
+    seeds = np.ascontiguousarray(seeds, dtype=np.int64)
+    pool = ScenarioPool(len(seeds), gc.c.static_cap, gc.c.route_cap)
+    st, cfg = pool.c_struct(), gen_config(gc)
+    capi.check(L, L.ftl_generate_scenarios(C.byref(cfg), seeds.ctypes.data, len(seeds), C.byref(st), int(n_threads)),
+               "ftl_generate_scenarios")
+    return pool
+
+
 def _shortest_path(blocked, nx, ny, start, goal, max_iter=None):
     """8-connected Dijkstra with euclidean step costs (the metric of dstar.State.cost / astar)."""
     if not (0 <= start[0] < nx and 0 <= start[1] < ny and 0 <= goal[0] < nx and 0 <= goal[1] < ny):

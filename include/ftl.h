@@ -164,6 +164,22 @@ typedef struct FtlScenarioPool {
     const uint8_t* found_target_point; /* [S] what SkipBadSeeds looks at, WRP:823; may be NULL */
 } FtlScenarioPool;
 
+/* What Game.reset() needs to draw a scenario (ENV:434-543): the constructor arguments that shape the layout, already
+ * converted to pixels like FtlConfig.  Host-only; see ftl_generate_scenarios. */
+typedef struct FtlScenarioGenConfig {
+    int32_t game_width, game_height;
+    double min_distance, max_distance;        /* pixels, ENV:283-284 */
+    double leader_pos_epsilon;
+    int32_t leader_width, leader_height;      /* integer sprites, CLS:42 */
+    int32_t follower_width, follower_height;
+    double leader_width_f, leader_height_f;   /* leader_size * pixels_to_meter as floats (ENV:634-640, 1496) */
+    int32_t add_obstacles, obstacle_number, step_grid;
+    int32_t bridge_size[2];                   /* ENV:617 */
+    double leader_margin;
+    int32_t path_finding;                     /* 0: the D* grid (ENV:1493-1507), 1: the A* grid (ENV:1632-1712) */
+    int32_t pad_;
+} FtlScenarioGenConfig;
+
 /* ---- canonical per-env state record used by get/set_state and by the oracle ----------------- */
 typedef struct FtlRobotState {
     float pos[2];          /* np.float32 position, CLS:47 */
@@ -274,6 +290,15 @@ int64_t ftl_launch_count(ftl_handle h);
  * step kernel and of the ray kernel over `steps` steps, then clears the accumulation. */
 int ftl_profile(ftl_handle h, int32_t enable);
 int ftl_profile_read(ftl_handle h, double* step_kernel_ms, double* ray_kernel_ms, int64_t* steps);
+
+/* Replaces the scenario-building part of Game.reset() (ENV:434-543: _create_robots, _create_obstacles,
+ * generate_finish_point, trajectory planning, _pos_follower_behind_leader) after env.seed(seeds[i]) (ENV:429-432),
+ * for n seeds on n_threads host threads (0 = all cores).  Fills the first n scenarios of `out`, whose arrays are
+ * HOST memory allocated by the caller with out->static_cap / out->route_cap.  The layout of seed s is the one the
+ * reference draws (same MT19937 stream and call order as python's `random`); routes are shortest paths on the
+ * reference's grid (its D* tie-breaking depends on object addresses and cannot be matched).  No GPU needed. */
+int ftl_generate_scenarios(const FtlScenarioGenConfig* cfg, const int64_t* seeds, int32_t n, const FtlScenarioPool* out,
+                           int32_t n_threads);
 
 #ifdef __cplusplus
 }

@@ -19,6 +19,7 @@
 using namespace ftl;
 
 static std::string g_err;
+void ftl_set_error_message(const char* msg) { g_err = msg; }   // for ftl_scenario_gen.cpp
 
 struct FtlHandle_ {
     DevCfg cfg;
