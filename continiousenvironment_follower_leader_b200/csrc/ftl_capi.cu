@@ -26,7 +26,10 @@ using namespace ftl;
 // =================================================================================================
 // kernels
 // =================================================================================================
-__global__ void __launch_bounds__(128, 8)   // <= 64 registers: 8 blocks (32 warps) per SM with 7 KB of shared memory per warp
+#ifndef FTL_RAYS_MINB
+#define FTL_RAYS_MINB 7   // shared memory (7.2 KB per warp) allows 7 blocks per SM anyway: 72 registers, no spills
+#endif
+__global__ void __launch_bounds__(128, FTL_RAYS_MINB)
 k_rays(const __grid_constant__ DevCfg cfg, const DevState s, const DevPool pool, const double2* __restrict__ rot,
        float* __restrict__ rays_out, int smem_per_warp, int first_env, int end_env) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -216,7 +219,7 @@ static int launch_rays(ftl_handle h, float* rays, cudaStream_t st, int first_env
     if (end_env < 0) end_env = h->n;
     if (end_env <= first_env) return FTL_OK;
     const int warps = 4, threads = warps * 32;
-    const int per_warp = (int)((ray_shared_bytes(h->rays_total) + 15) & ~(size_t)15);
+    const int per_warp = (int)((ray_shared_bytes(h->rays_total, h->cfg.ray_hmax) + 15) & ~(size_t)15);
     const int smem = per_warp * warps;
     if (smem > 48 * 1024 && !h->rays_smem_opted) {
         CUDA_TRY(cudaFuncSetAttribute(k_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -295,6 +298,7 @@ int ftl_create(const FtlConfig* cfg, int32_t n_envs, int32_t device, int64_t env
     d.rays_per_env = 0;
     for (int s = 0; s < c.n_ray_sensors; s++) d.rays_per_env += sensor_width(c.ray[s]);
     ray_out_layout(d);
+    d.ray_hmax = ray_hmax(c);
     h->rays_total = total_rays(c);
     d.rays_total = h->rays_total;
     d.eps_f32 = (float)c.leader_pos_epsilon;

@@ -126,6 +126,7 @@ struct DevCfg {
     int64_t env_id_base;
     int rays_per_env;
     int rays_total;              // number of rays over all sensors
+    int ray_hmax;                // largest max_prev_obs over the ray sensors (rows of minima the ray pass keeps)
     // float32 thresholds on SQUARED distances, exactly equivalent to the reference's comparisons of
     // float32 square roots (largest x with sqrtf(x) <= (float)limit)
     float eps2_f32, dev2_f32, min_dist2_f32;

@@ -203,7 +203,7 @@ struct RaySensorTab {
 struct RayShared {
     float px, py;
     double dir;                                    // follower heading (float64, for the exact fallback)
-    int scenario, snap_pushes, n_valid, ne, np, rt, ns;
+    int scenario, snap_pushes, n_valid, ne, np, rt, ns, hmax;
     float reach[EC_COUNT];                         // largest laser_length among sensors reacting to the class
     int tail[FTL_MAX_HIST], head[FTL_MAX_HIST];    // by age (0 = newest)
     RaySensorTab sen[FTL_MAX_RAY_SENSORS];
@@ -211,20 +211,27 @@ struct RayShared {
     int pair[kPairCap];                            // edge << 16 | flat ray
     int nu;                                        // (edge, ray) pairs of this env whose float32 predicates were inconclusive
     UncRec* unc;                                   // this env's slice of DevState.unc_rec
-    // arrays of length rays_total behind the struct: dx, dy, len (float), res[9] (int)
+    // arrays of length rays_total behind the struct: dx, dy, len (float), res[hmax + 1] (int): one row of minima per
+    // history age in use plus the row of the static minimum
 };
 
-struct RayArrays { float *dx, *dy, *len; int* res; int rt; };
+struct RayArrays { float *dx, *dy, *len; int* res; int rt, hmax; };   // hmax: largest max_prev_obs = index of the static row
 
-FTL_HD size_t ray_shared_bytes(int rays_total) {
-    return sizeof(RayShared) + (size_t)rays_total * (3 * 4 + (FTL_MAX_HIST + 1) * 4);
+FTL_HD int ray_hmax(const FtlConfig& c) {
+    int h = 1;
+    for (int sidx = 0; sidx < c.n_ray_sensors; sidx++) h = c.ray[sidx].max_prev_obs > h ? c.ray[sidx].max_prev_obs : h;
+    return h;
 }
-FTL_HD RayArrays ray_arrays(RayShared* sh, int rt) {
+FTL_HD size_t ray_shared_bytes(int rays_total, int hmax) {
+    return sizeof(RayShared) + (size_t)rays_total * (3 * 4 + (hmax + 1) * 4);
+}
+FTL_HD RayArrays ray_arrays(RayShared* sh, int rt, int hmax) {
     RayArrays a;
     float* base = (float*)(sh + 1);
     a.dx = base; a.dy = base + rt; a.len = base + 2 * rt;
     a.res = (int*)(base + 3 * rt);
     a.rt = rt;
+    a.hmax = hmax;
     return a;
 }
 
@@ -267,8 +274,10 @@ FTL_HD void unc_push(RayShared& sh, float ax, float ay, float bx, float by, int 
 FTL_HD void hit_merge(const RayArrays& ra, int f, int rows, float d) {
     if (d >= kNoHit) return;
     int bits = f2i_bits(d);
-    for (int a = 0; a <= FTL_MAX_HIST; a++)
+    // constant trip count (unrolled, predicated): bits at or above hmax are never set, so no row beyond hmax is touched
+    for (int a = 0; a < FTL_MAX_HIST; a++)
         if (rows & (1 << a)) smem_atomic_min(&ra.res[a * ra.rt + f], bits);
+    if (rows & (1 << kStaticBit)) smem_atomic_min(&ra.res[ra.hmax * ra.rt + f], bits);
 }
 
 FTL_HD void edge_ray_test(RayShared& sh, const RayArrays& ra, int f, int rows, float ax, float ay, float bx, float by) {
@@ -280,7 +289,7 @@ FTL_HD void edge_ray_test(RayShared& sh, const RayArrays& ra, int f, int rows, f
 
 // all candidate rays of one edge, tested in place (only used when the shared lists are full)
 FTL_HD_NOINLINE void edge_inline(RayShared& sh, int rt, const RayEdge ed, int n_sensors) {
-    const RayArrays ra = ray_arrays(&sh, rt);
+    const RayArrays ra = ray_arrays(&sh, rt, sh.hmax);
     const int cls_bit = ed.mask >> 16;
     for (int sidx = 0; sidx < n_sensors; sidx++) {
         const RaySensorTab& st = sh.sen[sidx];
@@ -407,7 +416,7 @@ FTL_HD_NOINLINE void ray_rows_write_fused(const DevCfg& cfg, const RayShared& sh
         float* dst = rays_out + (size_t)i * cfg.rays_per_env + cfg.ray_out_base[sidx];
         const int stride = cfg.ray_out_stride[sidx];
         const double in_sector = R / 4.0;
-        const int* srow = ra.res + kStaticBit * rt + base;
+        const int* srow = ra.res + ra.hmax * rt + base;
         for (int e = lane; e < H * R; e += 32) {
             const int j = e / R, k = e - j * R, age = H - 1 - j;
             float v = L;
@@ -431,7 +440,7 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
                       RayShared& sh, float* rays_out) {
     const FtlConfig& c = cfg.c;
     const int rt = cfg.rays_total;
-    const RayArrays ra = ray_arrays(&sh, rt);
+    const RayArrays ra = ray_arrays(&sh, rt, cfg.ray_hmax);
     const int NBr = s.n_bears, ns = c.n_ray_sensors;
     const double dir = s.rd[(size_t)RD_DIR * s.n + i];
     // ---- setup ------------------------------------------------------------------------------------------
@@ -444,7 +453,7 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
             int pushes = s.gi[(size_t)GI_SNAP_PUSHES * s.n + i];
             sh.snap_pushes = pushes;
             sh.n_valid = pushes < FTL_MAX_HIST ? pushes : FTL_MAX_HIST;
-            sh.ne = 0; sh.np = 0; sh.nu = 0; sh.rt = rt; sh.ns = ns;
+            sh.ne = 0; sh.np = 0; sh.nu = 0; sh.rt = rt; sh.ns = ns; sh.hmax = cfg.ray_hmax;
             sh.unc = s.unc_rec + (size_t)i * kUncPerEnv;
             for (int k = 0; k < EC_COUNT; k++) sh.reach[k] = -1e30f;
             int base = 0;
@@ -489,7 +498,7 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
             ra.dx[f] = (float)((cs0 * r.x - sn0 * r.y) * sc.laser_length);
             ra.dy[f] = (float)((sn0 * r.x + cs0 * r.y) * sc.laser_length);
             ra.len[f] = (float)sc.laser_length;
-            for (int a = 0; a <= FTL_MAX_HIST; a++) ra.res[a * rt + f] = kNoHitBits;
+            for (int a = 0; a <= ra.hmax; a++) ra.res[a * rt + f] = kNoHitBits;
         }
     }
     FTL_WARP_SYNC();
@@ -582,7 +591,7 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
                 const int nsec = sc.pad_sectors ? 4 : 1;
                 const double in_sector = R / 4.0;
                 const float inv_R = 1.0f / (float)R;
-                const int* srow = ra.res + kStaticBit * rt + base;
+                const int* srow = ra.res + ra.hmax * rt + base;
                 for (int e = lane; e < H * R; e += 32) {
                     int j = (int)(((float)e + 0.5f) * inv_R);      // e / R without an integer division (H*R < 2^20)
                     int k = e - j * R;

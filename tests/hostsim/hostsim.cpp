@@ -91,7 +91,7 @@ static void optional_all(FtlHandle_* h, const DevOutputs& out) {
 }
 static void rays_all(FtlHandle_* h, float* rays) {
     if (!rays || !h->rays_total) return;
-    std::vector<unsigned char> buf(ray_shared_bytes(h->rays_total) + 16);
+    std::vector<unsigned char> buf(ray_shared_bytes(h->rays_total, h->cfg.ray_hmax) + 16);
     RayShared& sh = *reinterpret_cast<RayShared*>(buf.data());
     for (int i = 0; i < h->n; i++) rays_warp(h->cfg, h->st, h->pool, h->rot.data(), i, sh, rays);
     for (int i = 0; i < h->n; i++) rays_exact_env(h->cfg, h->st, h->pool, i, rays);
@@ -123,6 +123,7 @@ int ftl_create(const FtlConfig* cfg, int32_t n_envs, int32_t device, int64_t env
     d.env_id_base = env_id_base;
     for (int s = 0; s < c.n_ray_sensors; s++) d.rays_per_env += sensor_width(c.ray[s]);
     ray_out_layout(d);
+    d.ray_hmax = ray_hmax(c);
     h->rays_total = total_rays(c);
     d.rays_total = h->rays_total;
     for (int s = 0; s < c.n_ray_sensors; s++)
