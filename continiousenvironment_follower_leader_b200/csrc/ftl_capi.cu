@@ -299,6 +299,7 @@ int ftl_create(const FtlConfig* cfg, int32_t n_envs, int32_t device, int64_t env
     for (int s = 0; s < c.n_ray_sensors; s++) d.rays_per_env += sensor_width(c.ray[s]);
     ray_out_layout(d);
     d.ray_hmax = ray_hmax(c);
+    ray_static_tables(d);
     h->rays_total = total_rays(c);
     d.rays_total = h->rays_total;
     d.eps_f32 = (float)c.leader_pos_epsilon;

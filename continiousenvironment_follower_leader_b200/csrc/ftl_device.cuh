@@ -120,6 +120,12 @@ struct DevOutputs {
     float* track_vectors;   // [N][track_vector_len][2] or NULL
 };
 
+// per-sensor constants of the ray pass that do not depend on the env (filled by ray_static_tables, ftl_rays.cuh)
+struct RaySensorStatic {
+    int base, R, H, cls_mask;      // first flat ray, rays, history rows, EdgeClass bits the sensor reacts to
+    float L, inv_period, eps, pad_;
+};
+
 // Configuration as the kernels want it: the user's FtlConfig plus values derived once on the host.
 struct DevCfg {
     FtlConfig c;
@@ -127,6 +133,8 @@ struct DevCfg {
     int rays_per_env;
     int rays_total;              // number of rays over all sensors
     int ray_hmax;                // largest max_prev_obs over the ray sensors (rows of minima the ray pass keeps)
+    RaySensorStatic ray_static[FTL_MAX_RAY_SENSORS];
+    float ray_reach[8];          // per EdgeClass: largest laser_length among the sensors reacting to it (or < 0)
     // float32 thresholds on SQUARED distances, exactly equivalent to the reference's comparisons of
     // float32 square roots (largest x with sqrtf(x) <= (float)limit)
     float eps2_f32, dev2_f32, min_dist2_f32;

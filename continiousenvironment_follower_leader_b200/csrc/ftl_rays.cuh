@@ -197,7 +197,6 @@ struct RaySensorTab {
     int base, R, H, cls_mask;      // cls_mask: which EdgeClass this sensor reacts to
     float L, theta0, inv_period, eps;
     double cs0, sn0;               // cos/sin of the direction of ray 0
-    double offset, Ld;             // first_laser_angle_offset, laser_length (float64, for the exact fallback)
 };
 
 struct RayShared {
@@ -245,6 +244,28 @@ FTL_HD int sensor_class_mask(const FtlRaySensorConfig& sc) {
 }
 
 // atan2 in degrees, |error| < 1e-3 degrees (odd minimax polynomial on [0,1] + octant folding)
+// env-independent part of the per-sensor tables, computed once at ftl_create
+inline void ray_static_tables(DevCfg& d) {
+    const FtlConfig& c = d.c;
+    for (int k = 0; k < 8; k++) d.ray_reach[k] = -1e30f;
+    int base = 0;
+    for (int sidx = 0; sidx < c.n_ray_sensors; sidx++) {
+        const FtlRaySensorConfig& sc = c.ray[sidx];
+        RaySensorStatic& st = d.ray_static[sidx];
+        st.base = base; st.R = sc.lasers_count; st.H = sc.max_prev_obs;
+        st.cls_mask = sensor_class_mask(sc);
+        st.L = (float)sc.laser_length;
+        st.inv_period = (float)sc.lasers_count / 360.f;
+        // rays that are not evenly spaced (custom angles) cannot be binned by angle: a huge margin makes every
+        // edge a candidate for every ray of the sensor (cnt >= R in ray_flush)
+        st.eps = sc.n_custom_angles ? 1e6f : 0.02f + 5e-5f * (float)sc.lasers_count;
+        st.pad_ = 0.f;
+        for (int k = 0; k < EC_COUNT; k++)
+            if (st.cls_mask & (1 << k)) d.ray_reach[k] = fmaxf(d.ray_reach[k], st.L);
+        base += sc.lasers_count;
+    }
+}
+
 FTL_HD float atan2_deg_approx(float y, float x) {
     float ax = fabsf(x), ay = fabsf(y);
     float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
@@ -443,49 +464,37 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
     const RayArrays ra = ray_arrays(&sh, rt, cfg.ray_hmax);
     const int NBr = s.n_bears, ns = c.n_ray_sensors;
     const double dir = s.rd[(size_t)RD_DIR * s.n + i];
-    // ---- setup ------------------------------------------------------------------------------------------
+    // ---- setup: lane 0 the scalars, lanes < ns the sensor tables (static part from DevCfg), lanes 8.. the class
+    //      reaches, lanes 16.. the stored corridor ranges -------------------------------------------------------
     FTL_LANES(lane) {
+        const int pushes = s.gi[(size_t)GI_SNAP_PUSHES * s.n + i];
         if (lane == 0) {
             float2 p = s.pos[i];
             sh.px = p.x; sh.py = p.y;
             sh.dir = dir;
             sh.scenario = s.gi[(size_t)GI_SCENARIO * s.n + i];
-            int pushes = s.gi[(size_t)GI_SNAP_PUSHES * s.n + i];
             sh.snap_pushes = pushes;
             sh.n_valid = pushes < FTL_MAX_HIST ? pushes : FTL_MAX_HIST;
             sh.ne = 0; sh.np = 0; sh.nu = 0; sh.rt = rt; sh.ns = ns; sh.hmax = cfg.ray_hmax;
             sh.unc = s.unc_rec + (size_t)i * kUncPerEnv;
-            for (int k = 0; k < EC_COUNT; k++) sh.reach[k] = -1e30f;
-            int base = 0;
-            for (int sidx = 0; sidx < ns; sidx++) {
-                const FtlRaySensorConfig& sc = c.ray[sidx];
-                RaySensorTab st;
-                st.base = base; st.R = sc.lasers_count; st.H = sc.max_prev_obs;
-                st.cls_mask = sensor_class_mask(sc);
-                st.L = (float)sc.laser_length;
-                st.theta0 = (float)(dir + sc.first_laser_angle_offset);
-                st.inv_period = (float)sc.lasers_count / 360.f;
-                // rays that are not evenly spaced (custom angles) cannot be binned by angle: a huge margin makes every
-                // edge a candidate for every ray of the sensor (cnt >= R below)
-                st.eps = sc.n_custom_angles ? 1e6f : 0.02f + 5e-5f * (float)sc.lasers_count;
-                st.offset = sc.first_laser_angle_offset;
-                st.Ld = sc.laser_length;
-                sh.sen[sidx] = st;
-                for (int k = 0; k < EC_COUNT; k++)
-                    if (st.cls_mask & (1 << k)) sh.reach[k] = fmaxf(sh.reach[k], st.L);
-                base += sc.lasers_count;
-            }
         }
-        if (lane < FTL_MAX_HIST) {
-            int pushes = s.gi[(size_t)GI_SNAP_PUSHES * s.n + i];
+        if (lane < ns) {
+            const RaySensorStatic& ss = cfg.ray_static[lane];
+            RaySensorTab st;
+            st.base = ss.base; st.R = ss.R; st.H = ss.H; st.cls_mask = ss.cls_mask;
+            st.L = ss.L; st.inv_period = ss.inv_period; st.eps = ss.eps;
+            const double a0 = dir + c.ray[lane].first_laser_angle_offset;
+            st.theta0 = (float)a0;
+            sincos_deg(a0, &st.sn0, &st.cs0);
+            sh.sen[lane] = st;
+        }
+        if (lane >= 8 && lane < 8 + EC_COUNT) sh.reach[lane - 8] = cfg.ray_reach[lane - 8];
+        if (lane >= 16 && lane < 16 + FTL_MAX_HIST) {
+            const int age = lane - 16;
             int2 rg = make_int2(0, 0);
-            if (lane < pushes) rg = s.snap_range[(size_t)((pushes - 1 - lane) % FTL_MAX_HIST) * s.n + i];
-            sh.tail[lane] = rg.x; sh.head[lane] = rg.y;
+            if (age < pushes) rg = s.snap_range[(size_t)((pushes - 1 - age) % FTL_MAX_HIST) * s.n + i];
+            sh.tail[age] = rg.x; sh.head[age] = rg.y;
         }
-    }
-    FTL_WARP_SYNC();
-    FTL_LANES(lane) {
-        if (lane < ns) sincos_deg(dir + c.ray[lane].first_laser_angle_offset, &sh.sen[lane].sn0, &sh.sen[lane].cs0);
     }
     FTL_WARP_SYNC();
     FTL_LANES(lane) {
