@@ -123,7 +123,7 @@ struct DevOutputs {
 // per-sensor constants of the ray pass that do not depend on the env (filled by ray_static_tables, ftl_rays.cuh)
 struct RaySensorStatic {
     int base, R, H, cls_mask;      // first flat ray, rays, history rows, EdgeClass bits the sensor reacts to
-    float L, inv_period, eps, pad_;
+    float L, inv_period, eps, inv_R;
 };
 
 // Configuration as the kernels want it: the user's FtlConfig plus values derived once on the host.

@@ -195,7 +195,7 @@ constexpr int kUncPerEnv = FTL_UNC_PER_ENV;  // records per env for the exact pa
 
 struct RaySensorTab {
     int base, R, H, cls_mask;      // cls_mask: which EdgeClass this sensor reacts to
-    float L, theta0, inv_period, eps;
+    float L, theta0, inv_period, eps, inv_R, pad_;
     double cs0, sn0;               // cos/sin of the direction of ray 0
 };
 
@@ -259,7 +259,7 @@ inline void ray_static_tables(DevCfg& d) {
         // rays that are not evenly spaced (custom angles) cannot be binned by angle: a huge margin makes every
         // edge a candidate for every ray of the sensor (cnt >= R in ray_flush)
         st.eps = sc.n_custom_angles ? 1e6f : 0.02f + 5e-5f * (float)sc.lasers_count;
-        st.pad_ = 0.f;
+        st.inv_R = 1.f / (float)sc.lasers_count;
         for (int k = 0; k < EC_COUNT; k++)
             if (st.cls_mask & (1 << k)) d.ray_reach[k] = fmaxf(d.ray_reach[k], st.L);
         base += sc.lasers_count;
@@ -269,7 +269,11 @@ inline void ray_static_tables(DevCfg& d) {
 FTL_HD float atan2_deg_approx(float y, float x) {
     float ax = fabsf(x), ay = fabsf(y);
     float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+#if defined(__CUDA_ARCH__)
+    float t = __fdividef(mn, fmaxf(mx, 1e-30f));   // candidates only need to be a superset: 2 ulp are inside the margin
+#else
     float t = mn / fmaxf(mx, 1e-30f);
+#endif
     float t2 = t * t;
     float p = fmaf(t2, -0.01172120f, 0.05265332f);
     p = fmaf(t2, p, -0.11643287f);
@@ -372,6 +376,11 @@ FTL_HD void ray_flush(RayShared& sh, const RayArrays& ra, int n_sensors) {
             const int cls_bit = ed.mask >> 16;
             const float ba = atan2_deg_approx(ed.ay - sh.py, ed.ax - sh.px);
             const float bb = atan2_deg_approx(ed.by - sh.py, ed.bx - sh.px);
+            // the follower on an end point of the edge: its bearing is meaningless -> every ray is a candidate
+            const bool on_end = fabsf(ed.ax - sh.px) + fabsf(ed.ay - sh.py) < 1e-3f ||
+                                fabsf(ed.bx - sh.px) + fabsf(ed.by - sh.py) < 1e-3f;
+            const float exlo = fminf(ed.ax, ed.bx), exhi = fmaxf(ed.ax, ed.bx);
+            const float eylo = fminf(ed.ay, ed.by), eyhi = fmaxf(ed.ay, ed.by);
             for (int sidx = 0; sidx < n_sensors; sidx++) {
                 const RaySensorTab& st = sh.sen[sidx];
                 if (!(st.cls_mask & cls_bit)) continue;
@@ -380,25 +389,22 @@ FTL_HD void ray_flush(RayShared& sh, const RayArrays& ra, int n_sensors) {
                 if (!rows) continue;
                 // reach of THIS sensor (the list was culled with the class maximum)
                 const float reach = st.L + 1.f;
-                if (fmaxf(ed.ax, ed.bx) < sh.px - reach || fminf(ed.ax, ed.bx) > sh.px + reach ||
-                    fmaxf(ed.ay, ed.by) < sh.py - reach || fminf(ed.ay, ed.by) > sh.py + reach)
-                    continue;
+                if (exhi < sh.px - reach || exlo > sh.px + reach || eyhi < sh.py - reach || eylo > sh.py + reach) continue;
                 const float Rf = (float)st.R;
                 float ka = (ba - st.theta0) * st.inv_period;
                 float d = (bb - ba) * st.inv_period;
-                d = d - Rf * rintf(d / Rf);                    // short way round, (-R/2, R/2]
+                d = d - Rf * rintf(d * st.inv_R);              // short way round, about (-R/2, R/2]
                 int klo = (int)ceilf(fminf(ka, ka + d) - st.eps), khi = (int)floorf(fmaxf(ka, ka + d) + st.eps);
                 int cnt = khi - klo + 1;
-                // the follower (almost) on the edge's line between its end points, or on an end point: the edge
-                // subtends ~180 degrees and "the short way round" is ambiguous -> every ray is a candidate
-                const bool degenerate = fabsf(d) > 0.49f * Rf ||
-                                        fabsf(ed.ax - sh.px) + fabsf(ed.ay - sh.py) < 1e-3f ||
-                                        fabsf(ed.bx - sh.px) + fabsf(ed.by - sh.py) < 1e-3f;
+                // the follower (almost) on the edge's line between its end points: the edge subtends ~180 degrees and
+                // "the short way round" is ambiguous -> every ray is a candidate
+                const bool degenerate = on_end || fabsf(d) > 0.49f * Rf;
                 if (cnt <= 0 && !degenerate) continue;
                 if (cnt >= st.R || degenerate) { klo = 0; cnt = st.R; }
                 int slot = smem_atomic_add(&sh.np, cnt);
-                int kk = klo % st.R;
-                if (kk < 0) kk += st.R;
+                int kk = klo;                                  // klo mod R; |klo| < 3R (bearings and theta0 are bounded)
+                while (kk < 0) kk += st.R;
+                while (kk >= st.R) kk -= st.R;
                 for (int k = 0; k < cnt; k++, kk = (kk + 1 == st.R) ? 0 : kk + 1) {
                     if (slot + k < kPairCap)
                         sh.pair[slot + k] = (ei << 16) | (st.base + kk);
@@ -482,7 +488,7 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
             const RaySensorStatic& ss = cfg.ray_static[lane];
             RaySensorTab st;
             st.base = ss.base; st.R = ss.R; st.H = ss.H; st.cls_mask = ss.cls_mask;
-            st.L = ss.L; st.inv_period = ss.inv_period; st.eps = ss.eps;
+            st.L = ss.L; st.inv_period = ss.inv_period; st.eps = ss.eps; st.inv_R = ss.inv_R; st.pad_ = 0.f;
             const double a0 = dir + c.ray[lane].first_laser_angle_offset;
             st.theta0 = (float)a0;
             sincos_deg(a0, &st.sn0, &st.cs0);
