@@ -348,7 +348,7 @@ def main():
             "kernels_ms_per_step": k_ms,
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_kind,
-                         "note": "k_rays is issue-bound (57% of issue slots busy, ncu), not HBM-bound: traffic is 1 KB/env-step",
+                         "note": "k_rays is issue-bound (62% of issue slots busy, ncu), not HBM-bound: measured DRAM traffic is 1.3 KB/env-step",
                          "algorithmic_bytes_per_env_step": BYTES_STEP_KERNEL if dominant == "k_step" else BYTES_RAY_KERNEL,
                          "fp32_alu": {"flop_per_env_step": FLOP_PER_ENV_STEP,
                                       "achieved_tflops": FLOP_PER_ENV_STEP * n * args.steps / (ms * 1e-3) / 1e12,
