@@ -89,6 +89,7 @@ struct FtlHandle_ {
     int n = 0, n_pad = 0, device = 0;
     int n_robots = 2;
     DevState st{};
+    DevState image{};   // env s = scenario s right after reset (built by ftl_upload_scenarios); the in-step auto-reset copies from it
     DevPool pool{};
     bool have_pool = false, was_reset = false;
     std::vector<void*> allocs, pool_allocs;
@@ -159,6 +160,35 @@ static cudaError_t dalloc(FtlHandle_* h, T** p, size_t count, std::vector<void*>
     return cudaSuccess;
 }
 
+// the per-env arrays of a DevState whose n / n_real / n_bears are set (the env batch, and the per-scenario reset image)
+static cudaError_t alloc_state(FtlHandle_* h, DevState& s, const FtlConfig& c, std::vector<void*>* list) {
+    const size_t n = s.n;
+    const int nb = s.n_bears, nr = 2 + nb;
+    cudaError_t e = cudaSuccess;
+    auto ok = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
+    ok(dalloc(h, &s.gd, GD_COUNT * n, list));
+    ok(dalloc(h, &s.rd, (size_t)nr * RD_COUNT * n, list));
+    ok(dalloc(h, &s.bear_tgt, (size_t)nb * 2 * n, list));
+    ok(dalloc(h, &s.gi, GI_COUNT * n, list));
+    ok(dalloc(h, &s.ri, (size_t)nr * n, list));
+    ok(dalloc(h, &s.bear_idx, (size_t)nb * n, list));
+    ok(dalloc(h, &s.gf, GF_COUNT * n, list));
+    ok(dalloc(h, &s.pos, (size_t)nr * n, list));
+    ok(dalloc(h, &s.rect, (size_t)nr * n, list));
+    ok(dalloc(h, &s.trail, n * c.trail_cap, list));
+    ok(dalloc(h, &s.trail_d, n * c.trail_cap, list));
+    ok(dalloc(h, &s.trail_s, n * c.trail_cap, list));
+    ok(dalloc(h, &s.hist, n * c.corridor_cap, list));
+    ok(dalloc(h, &s.corridor, n * c.corridor_cap, list));
+    ok(dalloc(h, &s.seg_d, n * c.corridor_cap, list));
+    ok(dalloc(h, &s.seg_f, n * c.corridor_cap, list));
+    ok(dalloc(h, &s.snap_range, (size_t)FTL_MAX_HIST * n, list));
+    ok(dalloc(h, &s.snap_rect, (size_t)FTL_MAX_HIST * (1 + nb) * n, list));
+    ok(dalloc(h, &s.unc_rec, n * kUncPerEnv, list));
+    ok(dalloc(h, &s.unc_count, n, list));
+    return e;
+}
+
 static int validate(const FtlConfig* c, int n_envs) {
     if (!c) return fail(FTL_ERR_INVALID, "config is NULL");
     if (c->abi_version != FTL_ABI_VERSION) return fail(FTL_ERR_INVALID, "FtlConfig.abi_version mismatch");
@@ -204,6 +234,17 @@ static DevOutputs to_dev_outputs(const FtlOutputs* o, int n_real) {
         d.follower_info = o->follower_info; d.track_vectors = o->track_vectors;
     }
     return d;
+}
+
+static void launch_reset(FtlHandle_* h, const DevState& s, const uint8_t* mask, const int* ids, const DevOutputs& o,
+                         int reset_filler, cudaStream_t st) {
+    switch (h->cfg.c.n_bears) {
+        case 0: ftl_launch_reset_nb0(h->cfg, s, h->pool, mask, ids, o, reset_filler, st); break;
+        case 1: ftl_launch_reset_nb1(h->cfg, s, h->pool, mask, ids, o, reset_filler, st); break;
+        case 2: ftl_launch_reset_nb2(h->cfg, s, h->pool, mask, ids, o, reset_filler, st); break;
+        case 3: ftl_launch_reset_nb3(h->cfg, s, h->pool, mask, ids, o, reset_filler, st); break;
+        default: ftl_launch_reset_nb4(h->cfg, s, h->pool, mask, ids, o, reset_filler, st); break;
+    }
 }
 
 static int launch_optional_sensors(ftl_handle h, const DevOutputs& o, cudaStream_t st) {
@@ -329,24 +370,7 @@ int ftl_create(const FtlConfig* cfg, int32_t n_envs, int32_t device, int64_t env
     s.n_bears = nb;
     cudaError_t e = cudaSuccess;
     auto ok = [&](cudaError_t x) { if (e == cudaSuccess) e = x; };
-    ok(dalloc(h, &s.gd, GD_COUNT * n));
-    ok(dalloc(h, &s.rd, (size_t)nr * RD_COUNT * n));
-    ok(dalloc(h, &s.bear_tgt, (size_t)nb * 2 * n));
-    ok(dalloc(h, &s.gi, GI_COUNT * n));
-    ok(dalloc(h, &s.ri, (size_t)nr * n));
-    ok(dalloc(h, &s.bear_idx, (size_t)nb * n));
-    ok(dalloc(h, &s.gf, GF_COUNT * n));
-    ok(dalloc(h, &s.pos, (size_t)nr * n));
-    ok(dalloc(h, &s.rect, (size_t)nr * n));
-    ok(dalloc(h, &s.trail, n * c.trail_cap));
-    ok(dalloc(h, &s.trail_d, n * c.trail_cap));
-    ok(dalloc(h, &s.trail_s, n * c.trail_cap));
-    ok(dalloc(h, &s.hist, n * c.corridor_cap));
-    ok(dalloc(h, &s.corridor, n * c.corridor_cap));
-    ok(dalloc(h, &s.snap_range, (size_t)FTL_MAX_HIST * n));
-    ok(dalloc(h, &s.snap_rect, (size_t)FTL_MAX_HIST * (1 + nb) * n));
-    ok(dalloc(h, &s.unc_rec, n * kUncPerEnv));
-    ok(dalloc(h, &s.unc_count, n));
+    ok(alloc_state(h, s, c, nullptr));
     ok(dalloc(h, &h->d_stats, (size_t)FTL_STAT_COUNT));
     ok(dalloc(h, &h->d_rot, (size_t)h->rays_total));
     if (e == cudaSuccess && h->rays_total > 0) {
@@ -431,6 +455,28 @@ int ftl_upload_scenarios(ftl_handle h, const FtlScenarioPool* p) {
     CUDA_TRY(cudaMemcpy(fd, p->follower_dir, S * sizeof(double), cudaMemcpyHostToDevice));
     d.static_rects = sr; d.n_static = dns; d.route = rt; d.n_route = dnr;
     d.leader_pos = lp; d.leader_dir = ld; d.follower_pos = fp; d.follower_dir = fd;
+    // the reset image: one k_reset over a DevState with one env per scenario
+    DevState& im = h->image;
+    im = DevState{};
+    im.n = (p->n_scenarios + 31) & ~31;
+    im.n_real = p->n_scenarios;
+    im.n_bears = c.n_bears;
+    {
+        cudaError_t e = alloc_state(h, im, c, &h->pool_allocs);
+        if (e != cudaSuccess)
+            return fail(e == cudaErrorMemoryAllocation ? FTL_ERR_NOMEM : FTL_ERR_CUDA,
+                        std::string("reset image allocation failed: ") + cudaGetErrorString(e));
+    }
+    int* ids;
+    CUDA_TRY(dalloc(h, &ids, (size_t)im.n, &h->pool_allocs));
+    std::vector<int> iota(im.n);
+    for (int k = 0; k < im.n; k++) iota[k] = k < p->n_scenarios ? k : 0;
+    CUDA_TRY(cudaMemcpy(ids, iota.data(), sizeof(int) * iota.size(), cudaMemcpyHostToDevice));
+    DevOutputs none{};
+    launch_reset(h, im, nullptr, ids, none, 1, nullptr);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaDeviceSynchronize());
     h->have_pool = true;
     return FTL_OK;
 }
@@ -443,13 +489,7 @@ int ftl_reset(ftl_handle h, const uint8_t* mask_dev, const int32_t* scenario_ids
     cudaStream_t st = (cudaStream_t)cuda_stream;
     DevOutputs o = to_dev_outputs(out_dev, h->n);
     const int reset_filler = (!mask_dev || !h->was_reset) ? 1 : 0;
-    switch (h->cfg.c.n_bears) {
-        case 0: ftl_launch_reset_nb0(h->cfg, h->st, h->pool, mask_dev, scenario_ids_dev, o, reset_filler, st); break;
-        case 1: ftl_launch_reset_nb1(h->cfg, h->st, h->pool, mask_dev, scenario_ids_dev, o, reset_filler, st); break;
-        case 2: ftl_launch_reset_nb2(h->cfg, h->st, h->pool, mask_dev, scenario_ids_dev, o, reset_filler, st); break;
-        case 3: ftl_launch_reset_nb3(h->cfg, h->st, h->pool, mask_dev, scenario_ids_dev, o, reset_filler, st); break;
-        default: ftl_launch_reset_nb4(h->cfg, h->st, h->pool, mask_dev, scenario_ids_dev, o, reset_filler, st); break;
-    }
+    launch_reset(h, h->st, mask_dev, scenario_ids_dev, o, reset_filler, st);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     h->was_reset = true;
@@ -466,11 +506,11 @@ int ftl_step(ftl_handle h, const void* actions_dev, const FtlOutputs* out_dev, v
     DevOutputs o = to_dev_outputs(out_dev, h->n);
     if (h->profiling) prof_event(h, st);
     switch (h->cfg.c.n_bears) {
-        case 0: ftl_launch_step_nb0(h->cfg, h->st, h->pool, actions_dev, o, h->d_stats, st); break;
-        case 1: ftl_launch_step_nb1(h->cfg, h->st, h->pool, actions_dev, o, h->d_stats, st); break;
-        case 2: ftl_launch_step_nb2(h->cfg, h->st, h->pool, actions_dev, o, h->d_stats, st); break;
-        case 3: ftl_launch_step_nb3(h->cfg, h->st, h->pool, actions_dev, o, h->d_stats, st); break;
-        default: ftl_launch_step_nb4(h->cfg, h->st, h->pool, actions_dev, o, h->d_stats, st); break;
+        case 0: ftl_launch_step_nb0(h->cfg, h->st, h->pool, h->image, actions_dev, o, h->d_stats, st); break;
+        case 1: ftl_launch_step_nb1(h->cfg, h->st, h->pool, h->image, actions_dev, o, h->d_stats, st); break;
+        case 2: ftl_launch_step_nb2(h->cfg, h->st, h->pool, h->image, actions_dev, o, h->d_stats, st); break;
+        case 3: ftl_launch_step_nb3(h->cfg, h->st, h->pool, h->image, actions_dev, o, h->d_stats, st); break;
+        default: ftl_launch_step_nb4(h->cfg, h->st, h->pool, h->image, actions_dev, o, h->d_stats, st); break;
     }
     h->launches++;
     CUDA_TRY(cudaGetLastError());

@@ -90,6 +90,8 @@ struct DevState {
     double* trail_s;   // [n][trail_cap]  cumulative arc length in float64 (derived; decides the green window)
     double2* hist;     // [n][corridor_cap]
     float4* corridor;  // [n][corridor_cap]   (right.x, right.y, left.x, left.y)
+    double* seg_d;     // [n][corridor_cap]   |hist[k+1] - hist[k]| in float64 and ...
+    float* seg_f;      // [n][corridor_cap]   ... in float32 (derived: the tracker's length test sums them, SEN:283-287)
     int2* snap_range;  // [FTL_MAX_HIST][n]   ring slot = push index % FTL_MAX_HIST
     int4* snap_rect;   // [FTL_MAX_HIST][1+n_bears][n]
     UncRec* unc_rec;   // [n][kUncPerEnv]  scratch of the ray pass
@@ -849,21 +851,25 @@ FTL_HD T np_sum(int n, F f) {  // n <= 512 here (corridor_cap): at most two leve
     return a + b;
 }
 
-FTL_HD bool tracker_too_long(const DevCfg& cfg, const Tracker& t, const double2* hist, int cap) {  // SEN:283-287
+// The length test of SEN:283-287 re-measures every segment of the history on every save (and once more per dropped
+// point); a segment's length depends on its two end points only, so both forms the reference can ask for (float64
+// while a seeded float64 point is still in the list, float32 afterwards) are stored when the segment is created and
+// the test only sums them, in numpy's order.  Segment k joins ring entries k and k+1 and lives in slot k.
+FTL_HD void tracker_seg_store(const double2* hist, double* seg_d, float* seg_f, int mask, int k) {
+    const double2 a = hist[k & mask], b = hist[(k + 1) & mask];
+    seg_d[k & mask] = dist_f64(a.x, a.y, b.x, b.y);
+    seg_f[k & mask] = sqrtf(d2_f32((float)a.x, (float)a.y, (float)b.x, (float)b.y));
+}
+
+FTL_HD bool tracker_too_long(const DevCfg& cfg, const Tracker& t, const double* seg_d, const float* seg_f, int cap) {
     int n = t.ring_head - t.ring_tail;
     if (n < 2) return false;
     int mask = cap - 1, tail = t.ring_tail;
     if (tail < t.hist_f64_end) {
-        double len = np_sum<double>(n - 1, [&](int k) {
-            double2 a = hist[(tail + k) & mask], b = hist[(tail + k + 1) & mask];
-            return dist_f64(a.x, a.y, b.x, b.y);
-        });
+        double len = np_sum<double>(n - 1, [&](int k) { return seg_d[(tail + k) & mask]; });
         return len > cfg.c.corridor_length;
     } else {
-        float len = np_sum<float>(n - 1, [&](int k) {
-            double2 a = hist[(tail + k) & mask], b = hist[(tail + k + 1) & mask];
-            return sqrtf(d2_f32((float)a.x, (float)a.y, (float)b.x, (float)b.y));
-        });
+        float len = np_sum<float>(n - 1, [&](int k) { return seg_f[(tail + k) & mask]; });
         return len > cfg.corridor_length_f32;
     }
 }
@@ -902,8 +908,8 @@ struct TrackerInput {  // what the tracker reads from the robots, by value
     double fdir;
 };
 
-FTL_HD_NOINLINE void tracker_scan(const DevCfg& cfg, Tracker& t, double2* hist, float4* corr, TrackerInput in,
-                                  int* overflow) {
+FTL_HD_NOINLINE void tracker_scan(const DevCfg& cfg, Tracker& t, double2* hist, float4* corr, double* seg_d, float* seg_f,
+                                  TrackerInput in, int* overflow) {
     struct { float px, py; double dir; } follower = {in.fpx, in.fpy, in.fdir};
     struct { float px, py; } leader = {in.lpx, in.lpy};
     const FtlConfig& c = cfg.c;
@@ -944,13 +950,15 @@ FTL_HD_NOINLINE void tracker_scan(const DevCfg& cfg, Tracker& t, double2* hist, 
                 t.hist_f64_end = t.ring_tail;
             }
             if (m > 1) hist[(t.ring_head + m - 1) & mask] = make_double2(lx, ly);
+            for (int i = 0; i + 1 < m; i++) tracker_seg_store(hist, seg_d, seg_f, mask, t.ring_head + i);
             t.ring_head += m;
         } else {
             if (t.ring_head - t.ring_tail >= cap) { t.ring_tail++; *overflow |= 2; }
             hist[t.ring_head & mask] = make_double2((double)leader.px, (double)leader.py);
             t.ring_head++;
+            if (t.ring_head - t.ring_tail >= 2) tracker_seg_store(hist, seg_d, seg_f, mask, t.ring_head - 2);
         }
-        while (tracker_too_long(cfg, t, hist, cap)) t.ring_tail++;  // SEN:286-292
+        while (tracker_too_long(cfg, t, seg_d, seg_f, cap)) t.ring_tail++;  // SEN:286-292
         n = t.ring_head - t.ring_tail;
         if (n > 1) {
             if (t.saving_counter == 0) {  // SEN:300-308

@@ -99,6 +99,12 @@ FTL_HD void unpack_env(const DevCfg& cfg, const DevState& s, int i, const FtlEnv
         for (int k = 0; k < o.trail_len; k++) trail_push(trail, trail_d, trail_s, k, trail[k].x, trail[k].y);
         green_cache_invalidate(cfg, trail_d, o.trail_len, gc);
     }
+    {   // derived as well: the tracker's segment lengths, from the (already uploaded) history ring
+        const int cap = cfg.c.corridor_cap;
+        const double2* hist = s.hist + (size_t)i * cap;
+        for (int k = t.ring_tail; k + 1 < t.ring_head; k++)
+            tracker_seg_store(hist, s.seg_d + (size_t)i * cap, s.seg_f + (size_t)i * cap, cap - 1, k);
+    }
     int pushes = o.snap_pushes;
     cache_store(s, i, gc, t, pushes);
     for (int j2 = 0; j2 < FTL_MAX_HIST; j2++) {

@@ -5,6 +5,12 @@
 
 #include "ftl_device.cuh"
 
+// Hook at the top of every sub-frame: the step kernel may re-align the warps of a block there (instruction-cache
+// locality: the frame loop is larger than the SM's instruction cache); nothing elsewhere.
+#ifndef FTL_FRAME_SYNC
+#define FTL_FRAME_SYNC(f) ((void)0)
+#endif
+
 namespace ftl {
 
 FTL_HD void episode_load(const DevState& s, int i, Episode& e) {
@@ -133,8 +139,10 @@ FTL_HD void sense_serial(const DevCfg& cfg, const DevState& s, int i, const Worl
     if (!c.tracker_enabled) return;
     double2* hist = s.hist + (size_t)i * c.corridor_cap;
     float4* corr = s.corridor + (size_t)i * c.corridor_cap;
+    double* seg_d = s.seg_d + (size_t)i * c.corridor_cap;
+    float* seg_f = s.seg_f + (size_t)i * c.corridor_cap;
     TrackerInput in = {w.follower.px, w.follower.py, w.leader.px, w.leader.py, w.follower.dir};
-    for (int k = 0; k < c.tracker_scans_per_step; k++) tracker_scan(cfg, t, hist, corr, in, overflow);
+    for (int k = 0; k < c.tracker_scans_per_step; k++) tracker_scan(cfg, t, hist, corr, seg_d, seg_f, in, overflow);
     if (c.n_ray_sensors > 0 && t.ring_head - t.ring_tail > 1) {
         int slot = *snap_pushes % FTL_MAX_HIST;
         s.snap_range[(size_t)slot * s.n + i] = make_int2(t.ring_tail, t.ring_head);
@@ -293,6 +301,7 @@ FTL_HD void env_step(const DevCfg& cfg, const DevState& s, const DevPool& pool, 
                       make_float2(w.leader.px, w.leader.py), cfg.static_inflate[1], &fmask, &lmask);
 
     for (int f = 0; f < c.frames_per_step; f++) {
+        FTL_FRAME_SYNC(f);
         int mission = FTL_MISSION_IN_PROGRESS, agent = FTL_AGENT_MOVING, leader_st = FTL_LEADER_MOVING;
         // (1) follower, ENV:957-964
         w.follower = robot_move_nv(w.follower, &c.follower);

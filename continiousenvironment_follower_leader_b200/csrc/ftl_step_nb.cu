@@ -3,11 +3,24 @@
 //
 //   k_step<NB>   one thread per env: the F sub-frames fused in registers (robots, collisions, exact
 //                green-zone flags from cached bounds, reward/done bookkeeping), the two tracker scans,
-//                the history snapshot, non-ray outputs, episode statistics, optional in-place auto-reset
+//                the history snapshot, non-ray outputs, episode statistics, optional in-place auto-reset (a copy
+//                of the scenario's reset image)
 //   k_reset<NB>  masked re-initialisation from the scenario pool
 #include <cuda_runtime.h>
 
 #include "ftl_launch.h"
+
+#ifndef FTL_SYNC_EVERY
+#define FTL_SYNC_EVERY 0
+#endif
+#if FTL_SYNC_EVERY > 0
+__host__ __device__ static __forceinline__ void ftl_frame_sync(int f) {
+#if defined(__CUDA_ARCH__)
+    if (f % FTL_SYNC_EVERY == 0) __syncthreads();
+#endif
+}
+#define FTL_FRAME_SYNC(f) ftl_frame_sync(f)
+#endif
 #include "ftl_step.cuh"
 
 #ifndef FTL_NB
@@ -18,18 +31,50 @@ using namespace ftl;
 
 __device__ __forceinline__ void add_stat(double* stats, int which, double v) { atomicAdd(stats + which, v); }
 
-// The in-step auto-reset is a cold path: kept out of line with its own registers so that it neither grows the
-// hot loop nor forces the step's state through local memory.
+// In-step auto-reset.  What Game.reset() leaves behind depends on the scenario alone, so ftl_upload_scenarios runs
+// k_reset once per scenario into an "image" DevState (env s of the image = scenario s after reset) and the step kernel
+// only copies: the scalars by the lane that owns the env (same load/store helpers as the step itself), the rows
+// (trail seed, tracker ring, first history snapshot) by the whole warp, coalesced.  The serial reset in one lane used
+// to be the tail of the kernel: with random actions ~1 env in 130 finishes per step, i.e. every fifth warp.
 template <int NB>
-__device__ __noinline__ void reset_in_place(const DevCfg& cfg, const DevState& s, const DevPool& pool,
-                                            const DevOutputs& out, int i, int episode) {
-    World<NB> w;
-    Episode e;
-    int scen = next_scenario(cfg, pool.n_scenarios, i, episode);
-    env_reset<NB>(cfg, s, pool, i, scen, w, e);
+__device__ __forceinline__ void reset_scalars_from_image(const DevCfg& cfg, const DevState& s, const DevPool& pool,
+                                                         const DevState& img, const DevOutputs& out, int i, int scen,
+                                                         World<NB>& w, Episode& e, int* ring_head) {
+    const int accel_consumed = e.accel_consumed, episode = e.episode;
+    world_load<NB>(img, scen, w);
+    episode_load(img, scen, e);
+    e.accel_consumed = accel_consumed;   // never restored by the reference, ENV:1170
+    e.episode = episode + 1;
+    GreenCache gc;
+    Tracker t;
+    int snap_pushes;
+    cache_load(img, scen, gc, t, &snap_pushes);
+    cache_store(s, i, gc, t, snap_pushes);
+    if (snap_pushes > 0) {   // the reset's own sensor pass pushed history entry 0
+        s.snap_range[i] = img.snap_range[scen];
+#pragma unroll
+        for (int k = 0; k < 1 + NB; k++) s.snap_rect[(size_t)k * s.n + i] = img.snap_rect[(size_t)k * img.n + scen];
+    }
+    *ring_head = t.ring_head;
     write_outputs<NB>(cfg, pool, out, i, w, e, true);
-    world_store<NB>(s, i, w);
-    episode_store(s, i, e);
+}
+
+__device__ __forceinline__ void reset_rows_from_image(const FtlConfig& c, const DevState& s, const DevState& img, int env,
+                                                      int scen, int trail_len, int ring_head, int lane) {
+    const size_t to = (size_t)env * c.trail_cap, from = (size_t)scen * c.trail_cap;
+    for (int k = lane; k < trail_len; k += 32) {
+        s.trail[to + k] = img.trail[from + k];
+        s.trail_d[to + k] = img.trail_d[from + k];
+        s.trail_s[to + k] = img.trail_s[from + k];
+    }
+    const size_t rto = (size_t)env * c.corridor_cap, rfrom = (size_t)scen * c.corridor_cap;
+    const int nring = ring_head < c.corridor_cap ? ring_head : c.corridor_cap;
+    for (int k = lane; k < nring; k += 32) {
+        s.hist[rto + k] = img.hist[rfrom + k];
+        s.corridor[rto + k] = img.corridor[rfrom + k];
+        s.seg_d[rto + k] = img.seg_d[rfrom + k];
+        s.seg_f[rto + k] = img.seg_f[rfrom + k];
+    }
 }
 
 #ifndef FTL_STEP_THREADS
@@ -41,7 +86,8 @@ __device__ __noinline__ void reset_in_place(const DevCfg& cfg, const DevState& s
 template <int NB>
 __global__ void __launch_bounds__(FTL_STEP_THREADS, FTL_STEP_MINBLOCKS)
 k_step(const __grid_constant__ DevCfg cfg, const __grid_constant__ DevState s, const __grid_constant__ DevPool pool,
-       const void* __restrict__ actions, const __grid_constant__ DevOutputs out, double* __restrict__ stats) {
+       const __grid_constant__ DevState img, const void* __restrict__ actions, const __grid_constant__ DevOutputs out,
+       double* __restrict__ stats) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= s.n) return;
     World<NB> w;
@@ -65,16 +111,23 @@ k_step(const __grid_constant__ DevCfg cfg, const __grid_constant__ DevState s, c
         if (leader_st == FTL_LEADER_CRASH) add_stat(stats, FTL_STAT_LEADER_CRASH, 1.0);
         if (e.overflow) add_stat(stats, FTL_STAT_OVERFLOW, 1.0);
     }
-    if ((cfg.c.auto_reset || i >= s.n_real) && done) {
-        // reward/done/status of the finished episode stay in `out`; the observation becomes the first
-        // one of the next episode (vector-env convention).  accel_consumed / episode are read back from the
-        // arrays by env_reset, so store them first.
-        s.gi[(size_t)GI_ACCEL_CONSUMED * s.n + i] = e.accel_consumed;
-        s.gi[(size_t)GI_EPISODE * s.n + i] = e.episode;
-        reset_in_place<NB>(cfg, s, pool, out, i, e.episode);
-    } else {
-        world_store<NB>(s, i, w);
-        episode_store(s, i, e);
+    // reward/done/status of the finished episode stay in `out`; the observation becomes the first one of the next
+    // episode (vector-env convention)
+    const bool renew = (cfg.c.auto_reset || i >= s.n_real) && done;
+    int scen = 0, ring_head = 0;
+    if (renew) {
+        scen = next_scenario(cfg, pool.n_scenarios, i, e.episode);
+        reset_scalars_from_image<NB>(cfg, s, pool, img, out, i, scen, w, e, &ring_head);
+    }
+    world_store<NB>(s, i, w);
+    episode_store(s, i, e);
+    unsigned todo = __ballot_sync(0xffffffffu, renew);   // whole warps reach this point (n is padded to 32)
+    const int lane = threadIdx.x & 31;
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        reset_rows_from_image(cfg.c, s, img, __shfl_sync(0xffffffffu, i, src), __shfl_sync(0xffffffffu, scen, src),
+                              __shfl_sync(0xffffffffu, e.trail_len, src), __shfl_sync(0xffffffffu, ring_head, src), lane);
     }
 }
 
@@ -100,10 +153,15 @@ k_reset(const __grid_constant__ DevCfg cfg, const DevState s, const DevPool pool
 #define FTL_CAT2(a, b) a##b
 #define FTL_CAT(a, b) FTL_CAT2(a, b)
 
-void FTL_CAT(ftl_launch_step_nb, FTL_NB)(const DevCfg& cfg, const DevState& s, const DevPool& pool, const void* actions,
-                                          const DevOutputs& out, double* stats, cudaStream_t st) {
-    int threads = FTL_STEP_THREADS, blocks = (s.n + threads - 1) / threads;
-    k_step<FTL_NB><<<blocks, threads, 0, st>>>(cfg, s, pool, actions, out, stats);
+void FTL_CAT(ftl_launch_step_nb, FTL_NB)(const DevCfg& cfg, const DevState& s, const DevPool& pool, const DevState& img,
+                                          const void* actions, const DevOutputs& out, double* stats, cudaStream_t st) {
+#ifdef FTL_STEP_LAUNCH_THREADS
+    int threads = FTL_STEP_LAUNCH_THREADS;
+#else
+    int threads = FTL_STEP_THREADS;
+#endif
+    int blocks = (s.n + threads - 1) / threads;
+    k_step<FTL_NB><<<blocks, threads, 0, st>>>(cfg, s, pool, img, actions, out, stats);
 }
 void FTL_CAT(ftl_launch_reset_nb, FTL_NB)(const DevCfg& cfg, const DevState& s, const DevPool& pool, const uint8_t* mask,
                                            const int* ids, const DevOutputs& out, int reset_filler, cudaStream_t st) {

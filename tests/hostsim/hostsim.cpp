@@ -166,6 +166,8 @@ int ftl_create(const FtlConfig* cfg, int32_t n_envs, int32_t device, int64_t env
     s.trail_s = zalloc<double>(h->allocs, n * c.trail_cap);
     s.hist = zalloc<double2>(h->allocs, n * c.corridor_cap);
     s.corridor = zalloc<float4>(h->allocs, n * c.corridor_cap);
+    s.seg_d = zalloc<double>(h->allocs, n * c.corridor_cap);
+    s.seg_f = zalloc<float>(h->allocs, n * c.corridor_cap);
     s.snap_range = zalloc<int2>(h->allocs, (size_t)FTL_MAX_HIST * n);
     s.snap_rect = zalloc<int4>(h->allocs, (size_t)FTL_MAX_HIST * (1 + nb) * n);
     s.unc_rec = zalloc<UncRec>(h->allocs, n * kUncPerEnv);

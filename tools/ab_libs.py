@@ -1,8 +1,20 @@
-"""Time the two kernels for several builds of libftl.so (FTL_LIB override); diagnostic."""
+"""Time the two kernels for several builds of libftl.so (FTL_LIB override) on one box, with a checksum of the
+state after the run so that a variant that changes results is visible; diagnostic.
+
+    python tools/ab_libs.py [glob]         (default glob: tools/libftl_*.so)
+"""
 import glob, os, subprocess, sys
-libs = [None] + sorted(glob.glob("tools/libftl_*.so"))
-for lib in libs:
-    env = dict(os.environ)
-    if lib: env["FTL_LIB"] = os.path.abspath(lib)
-    out = subprocess.run([sys.executable, "-c", "import sys; sys.path.insert(0,'tools'); sys.path.insert(0,'.'); import sweep_f; a,b=sweep_f.run(65536,10,ref_pool=True); print('k_step %.4f k_rays %.4f'%(a,b))"], env=env, capture_output=True, text=True)
-    print(lib or "default", out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-300:], flush=True)
+pat = sys.argv[1] if len(sys.argv) > 1 else "tools/libftl_*.so"
+libs = [None] + sorted(glob.glob(pat))
+CODE = r'''
+import sys; sys.path.insert(0,'tools'); sys.path.insert(0,'.')
+import sweep_f, torch, hashlib
+a,b,h = sweep_f.run(65536,10,ref_pool=True,checksum=True)
+print('k_step %.4f k_rays %.4f sum %.4f  %s' % (a,b,a+b,h))
+'''
+for rep in range(int(os.environ.get("AB_REPS", "1"))):
+    for lib in libs:
+        env = dict(os.environ)
+        if lib: env["FTL_LIB"] = os.path.abspath(lib)
+        out = subprocess.run([sys.executable, "-c", CODE], env=env, capture_output=True, text=True)
+        print("%-28s" % (os.path.basename(lib) if lib else "default"), out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-600:], flush=True)

@@ -6,7 +6,7 @@ from continiousenvironment_follower_leader_b200.batch_env import FtlBatchEnv
 from continiousenvironment_follower_leader_b200.config import GameConfig, cfg3_sensors
 from continiousenvironment_follower_leader_b200.scenario import synthetic_pool
 
-def run(n, F, rays=(12, 36), steps=200, warm=100, auto_reset=True, max_steps=5000, ref_pool=False):
+def run(n, F, rays=(12, 36), steps=200, warm=100, auto_reset=True, max_steps=5000, ref_pool=False, checksum=False):
     gc = GameConfig(bear_number=1, follower_sensors=cfg3_sensors(rays[0], rays[1]), frames_per_step=F, auto_reset=auto_reset, max_steps=max_steps)
     pool = synthetic_pool(gc, 256, seed=0)
     if ref_pool:
@@ -22,8 +22,18 @@ def run(n, F, rays=(12, 36), steps=200, warm=100, auto_reset=True, max_steps=500
     env.profile(True)
     for k in range(steps): env.step_raw(acts[k % 8])
     a, b, c = env.profile_read()
+    h = None
+    if checksum:
+        import hashlib
+        st = env.get_state()
+        m = hashlib.sha1()
+        for f in ("step_count", "trail_len", "cur_target_id", "saving_counter"):
+            m.update(st.env[f].tobytes())
+        m.update(st.env["follower"]["rect"].tobytes())
+        m.update(env.rays.cpu().numpy().tobytes())
+        h = m.hexdigest()[:12]
     env.close()
-    return a / c, b / c
+    return (a / c, b / c, h) if checksum else (a / c, b / c)
 
 if __name__ == "__main__":
     # BASELINE.json configs[4]: frames_per_step sweep and ray-count sweep (single GPU; 262144 envs over 8 GPUs = 32768 per GPU)
