@@ -455,6 +455,36 @@ int ftl_upload_scenarios(ftl_handle h, const FtlScenarioPool* p) {
     CUDA_TRY(cudaMemcpy(fd, p->follower_dir, S * sizeof(double), cudaMemcpyHostToDevice));
     d.static_rects = sr; d.n_static = dns; d.route = rt; d.n_route = dnr;
     d.leader_pos = lp; d.leader_dir = ld; d.follower_pos = fp; d.follower_dir = fd;
+    {   // cell grid of nearby static rectangles (near_static_masks_grid): each rectangle marks the cells its grown box touches
+        const int gw = (c.game_width >> kNearGridShift) + 1, gh = (c.game_height >> kNearGridShift) + 1;
+        const float inf = std::fmax(h->cfg.static_inflate[0], h->cfg.static_inflate[1]) + 1.f;
+        const float cell = (float)(1 << kNearGridShift);
+        std::vector<uint64_t> grid(S * gw * gh, 0);
+        for (size_t sc = 0; sc < S; sc++) {
+            uint64_t* g = grid.data() + sc * gw * gh;
+            const int32_t* rects = p->static_rects + sc * c.static_cap * 4;   // x, y, w, h
+            for (int k = 0; k < ns[sc]; k++) {
+                const int32_t* q = rects + 4 * k;
+                const float lo_x = (float)q[0] - inf, hi_x = (float)(q[0] + q[2]) + inf;
+                const float lo_y = (float)q[1] - inf, hi_y = (float)(q[1] + q[3]) + inf;
+                int cx0 = (int)std::floor(lo_x / cell) - 1, cx1 = (int)std::floor(hi_x / cell) + 1;
+                int cy0 = (int)std::floor(lo_y / cell) - 1, cy1 = (int)std::floor(hi_y / cell) + 1;
+                cx0 = cx0 < 0 ? 0 : cx0; cy0 = cy0 < 0 ? 0 : cy0;
+                cx1 = cx1 >= gw ? gw - 1 : cx1; cy1 = cy1 >= gh ? gh - 1 : cy1;
+                for (int cy = cy0; cy <= cy1; cy++)
+                    for (int cx = cx0; cx <= cx1; cx++) {
+                        // closed cell [x0, x0 + cell] x [y0, y0 + cell] against the grown box
+                        const float x0 = cx * cell, y0 = cy * cell;
+                        if (x0 + cell >= lo_x && x0 <= hi_x && y0 + cell >= lo_y && y0 <= hi_y)
+                            g[cy * gw + cx] |= (uint64_t)1 << k;
+                    }
+            }
+        }
+        uint64_t* dg;
+        CUDA_TRY(dalloc(h, &dg, grid.size(), &h->pool_allocs));
+        CUDA_TRY(cudaMemcpy(dg, grid.data(), grid.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+        d.near_grid = dg; d.near_grid_w = gw; d.near_grid_h = gh;
+    }
     // the reset image: one k_reset over a DevState with one env per scenario
     DevState& im = h->image;
     im = DevState{};

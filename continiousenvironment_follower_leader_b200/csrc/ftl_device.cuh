@@ -108,7 +108,13 @@ struct DevPool {  // scenario pool in device (or host, for hostsim) memory
     const double* leader_dir;
     const float2* follower_pos;
     const double* follower_dir;
+    // optional (NULL: every rectangle is examined): per scenario a grid of 64-px cells over the field; bit k of a cell
+    // is set when static rectangle k, grown by near_grid_inflate, touches the cell -- a superset of the rectangles
+    // near_rect() can accept for any position inside the cell
+    const uint64_t* near_grid;   // [S][near_grid_h][near_grid_w]
+    int near_grid_w, near_grid_h;
 };
+constexpr int kNearGridShift = 6;
 
 struct DevOutputs {
     int n;  // number of real envs: rows >= n are never written
@@ -429,6 +435,48 @@ FTL_HD void near_static_masks(const int4* rects, int n_static, float2 p0, float 
     }
     *m0 = a;
     *m1 = b;
+}
+FTL_HD int first_bit64(uint64_t m) {
+#if defined(__CUDA_ARCH__)
+    return __ffsll((long long)m) - 1;
+#else
+    return __builtin_ctzll(m);
+#endif
+}
+// the same masks from the scenario's cell grid: only the few rectangles of the robot's cell are examined.  Positions
+// outside the field (possible after a crash without auto-reset) take the full pass.
+FTL_HD bool near_grid_cell(const DevPool& pool, float2 p, int* cell) {
+    if (!(p.x >= 0.f && p.y >= 0.f)) return false;
+    const int cx = (int)p.x >> kNearGridShift, cy = (int)p.y >> kNearGridShift;
+    if (cx >= pool.near_grid_w || cy >= pool.near_grid_h) return false;
+    *cell = cy * pool.near_grid_w + cx;
+    return true;
+}
+FTL_HD uint64_t near_refine(const int4* rects, uint64_t cand, float2 p, float inflate) {
+    uint64_t m = 0;
+    while (cand) {
+        const int k = first_bit64(cand);
+        cand &= cand - 1;
+        if (near_rect(rects[k], p.x, p.y, inflate)) m |= (uint64_t)1 << k;
+    }
+    return m;
+}
+FTL_HD void near_static_masks_grid(const DevPool& pool, int scenario, const int4* rects, int n_static, float2 p0,
+                                   float inflate0, float2 p1, float inflate1, uint64_t* m0, uint64_t* m1) {
+    int c0, c1;
+#ifdef FTL_NO_NEAR_GRID
+    if (false)
+#else
+    if (pool.near_grid && near_grid_cell(pool, p0, &c0) && near_grid_cell(pool, p1, &c1))
+#endif
+    {
+        const uint64_t* g = pool.near_grid + (size_t)scenario * pool.near_grid_w * pool.near_grid_h;
+        const uint64_t g0 = g[c0], g1 = g[c1];
+        *m0 = near_refine(rects, g0, p0, inflate0);
+        *m1 = near_refine(rects, g1, p1, inflate1);
+        return;
+    }
+    near_static_masks(rects, n_static, p0, inflate0, p1, inflate1, m0, m1);
 }
 FTL_HD bool collide_static_masked(const Robot& r, const int4* rects, uint64_t mask) {
     while (mask) {

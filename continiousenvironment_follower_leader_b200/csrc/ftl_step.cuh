@@ -297,8 +297,9 @@ FTL_HD void env_step(const DevCfg& cfg, const DevState& s, const DevPool& pool, 
     int2 target = route_point(pool, c, e.scenario, e.cur_target_id < n_route ? e.cur_target_id : n_route - 1);
 
     uint64_t fmask, lmask;
-    near_static_masks(statics, n_static, make_float2(w.follower.px, w.follower.py), cfg.static_inflate[0],
-                      make_float2(w.leader.px, w.leader.py), cfg.static_inflate[1], &fmask, &lmask);
+    near_static_masks_grid(pool, e.scenario, statics, n_static, make_float2(w.follower.px, w.follower.py),
+                           cfg.static_inflate[0], make_float2(w.leader.px, w.leader.py), cfg.static_inflate[1], &fmask,
+                           &lmask);
 
     for (int f = 0; f < c.frames_per_step; f++) {
         FTL_FRAME_SYNC(f);
