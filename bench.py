@@ -298,24 +298,63 @@ def main():
     value = world * n * args.steps / (ms_max * 1e-3)
 
     # ---- end to end through the host-buffer C-ABI (pinned host memory both ways) ---------------------
-    host = capi.HostEnv(gc, n, device=local_rank, env_id_base=rank * n, pinned=True)
-    host.upload_scenarios(pool)
-    host.reset()
+    # (1) one synchronous ftl_step_host per step over the whole batch; (2) the batch as two halves driven alternately
+    # with ftl_step_host_begin / _wait on handle-owned streams (what a double-buffered rollout loop does: while one
+    # half's observations cross PCIe -- and its policy would run -- the other half's kernels execute).  Every step of
+    # every env still pays its H2D action copy and the D2H copy of all outputs.  (2) is the headline e2e.
     host_actions = [actions[k].cpu().numpy() for k in range(4)]
-    for w in range(3):
-        host.step(host_actions[w % 4])
-    barrier()
-    t0 = time.perf_counter()
-    for k in range(args.e2e_steps):
-        host.step(host_actions[k % 4])
-    torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * n * args.e2e_steps / float(t.item())
-    h2d, d2h = host.h2d_bytes_per_step, host.d2h_bytes_per_step
-    host.close()
+
+    def all_max(seconds):
+        tt = torch.tensor([seconds], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    e2e_sync_value = None
+    if args.e2e_steps > 0:
+        host = capi.HostEnv(gc, n, device=local_rank, env_id_base=rank * n, pinned=True)
+        host.upload_scenarios(pool)
+        host.reset()
+        for w in range(3):
+            host.step(host_actions[w % 4])
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(args.e2e_steps):
+            host.step(host_actions[k % 4])
+        torch.cuda.synchronize(dev)
+        e2e_sync_value = world * n * args.e2e_steps / all_max(time.perf_counter() - t0)
+        host.close()
+
+    e2e_value, h2d, d2h = None, 0, 0
+    if args.e2e_steps > 0:
+        half = n // 2
+        parts = [capi.HostEnv(gc, m, device=local_rank, env_id_base=rank * n + first, pinned=True, own_stream=True)
+                 for first, m in ((0, half), (half, n - half))]
+        acts = [[a[:half] for a in host_actions], [a[half:] for a in host_actions]]
+        for hpart in parts:
+            hpart.upload_scenarios(pool)
+            hpart.reset()
+        A, B = parts
+
+        def run(steps):
+            A.step_begin(acts[0][0])
+            for k in range(steps):
+                B.step_begin(acts[1][k % 4])
+                A.step_wait()                      # A's observation of step k is in host memory here
+                if k + 1 < steps:
+                    A.step_begin(acts[0][(k + 1) % 4])
+                B.step_wait()
+
+        run(3)
+        barrier()
+        t0 = time.perf_counter()
+        run(args.e2e_steps)
+        torch.cuda.synchronize(dev)
+        e2e_value = world * n * args.e2e_steps / all_max(time.perf_counter() - t0)
+        h2d = sum(x.h2d_bytes_per_step for x in parts)
+        d2h = sum(x.d2h_bytes_per_step for x in parts)
+        for hpart in parts:
+            hpart.close()
 
     stats = env.stats_dict(reduce_across_ranks=world > 1)
     if rank == 0:
@@ -343,7 +382,11 @@ def main():
                        "stats_allreduce_every": stats_every if world > 1 else None},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": args.e2e_steps, "api": "capi.HostEnv.step -> ftl_step_host (pinned host buffers)"},
+                    "steps": args.e2e_steps,
+                    "api": "two capi.HostEnv halves, step_begin/step_wait alternating -> ftl_step_host_begin/_wait "
+                           "(pinned host buffers, handle-owned streams)",
+                    "synchronous_whole_batch": e2e_sync_value,
+                    "synchronous_api": "capi.HostEnv.step -> ftl_step_host, one call per step for all envs"},
             "gpu_launches": int(launches),
             "kernels_ms_per_step": k_ms,
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",

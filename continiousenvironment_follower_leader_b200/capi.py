@@ -49,6 +49,12 @@ def load(path=None):
     L.ftl_upload_scenarios.argtypes = [vp, C.POINTER(abi.FtlScenarioPool)]
     L.ftl_reset_host.argtypes = [vp, vp, vp, C.POINTER(abi.FtlOutputs), vp]
     L.ftl_step_host.argtypes = [vp, vp, C.POINTER(abi.FtlOutputs), vp]
+    for name, argtypes, restype in (("ftl_step_host_begin", [vp, vp, C.POINTER(abi.FtlOutputs), vp], C.c_int),
+                                    ("ftl_step_host_wait", [vp], C.c_int),
+                                    ("ftl_host_stream", [vp], vp)):
+        if hasattr(L, name):   # not in the host-compiled test harness
+            getattr(L, name).argtypes = argtypes
+            getattr(L, name).restype = restype
     L.ftl_get_state.argtypes = [vp, i32, i32, C.POINTER(abi.FtlStateBuffers)]
     L.ftl_set_state.argtypes = [vp, i32, i32, C.POINTER(abi.FtlStateBuffers)]
     L.ftl_generate_scenarios.argtypes = [C.POINTER(abi.FtlScenarioGenConfig), vp, i32, C.POINTER(abi.FtlScenarioPool), i32]
@@ -122,7 +128,10 @@ def pinned_alloc(shape, dtype):
 class HostEnv:
     """N environments behind host (numpy) buffers; mirrors Game.reset/Game.step for a batch."""
 
-    def __init__(self, game_config, n_envs, device=0, env_id_base=0, lib=None, pinned=False):
+    def __init__(self, game_config, n_envs, device=0, env_id_base=0, lib=None, pinned=False, own_stream=False):
+        """own_stream: run on a non-blocking stream owned by the handle (ftl_host_stream) instead of the legacy
+        default stream, so that several HostEnv objects -- halves of a batch, vector-env workers in threads -- overlap:
+        one's kernels run while another's results cross PCIe."""
         self.gc = game_config
         self.cfg = game_config.c
         self.n = int(n_envs)
@@ -148,6 +157,11 @@ class HostEnv:
             shape, dt = (self.n,), np.int32
         self._actions = alloc(shape, dt) if alloc else np.zeros(shape, dt)
         self._pool = None
+        self._stream = None
+        if own_stream:
+            self._stream = self._L.ftl_host_stream(self._h)
+            if not self._stream:
+                raise FtlError("ftl_host_stream failed")
 
     def close(self):
         if getattr(self, "_h", None):
@@ -168,12 +182,24 @@ class HostEnv:
     def reset(self, mask=None, scenario_ids=None):
         m = None if mask is None else np.ascontiguousarray(mask, np.uint8)
         s = None if scenario_ids is None else np.ascontiguousarray(scenario_ids, np.int32)
-        check(self._L, self._L.ftl_reset_host(self._h, abi.ptr(m), abi.ptr(s), C.byref(self.out.c), None), "ftl_reset_host")
+        check(self._L, self._L.ftl_reset_host(self._h, abi.ptr(m), abi.ptr(s), C.byref(self.out.c), self._stream),
+              "ftl_reset_host")
         return self.out
 
     def step(self, actions):
         np.copyto(self._actions, np.asarray(actions).reshape(self._actions.shape), casting="same_kind")
-        check(self._L, self._L.ftl_step_host(self._h, abi.ptr(self._actions), C.byref(self.out.c), None), "ftl_step_host")
+        check(self._L, self._L.ftl_step_host(self._h, abi.ptr(self._actions), C.byref(self.out.c), self._stream),
+              "ftl_step_host")
+        return self.out
+
+    def step_begin(self, actions):
+        """Enqueue one step (ftl_step_host_begin) and return at once; ``step_wait`` delivers the outputs."""
+        np.copyto(self._actions, np.asarray(actions).reshape(self._actions.shape), casting="same_kind")
+        check(self._L, self._L.ftl_step_host_begin(self._h, abi.ptr(self._actions), C.byref(self.out.c), self._stream),
+              "ftl_step_host_begin")
+
+    def step_wait(self):
+        check(self._L, self._L.ftl_step_host_wait(self._h), "ftl_step_host_wait")
         return self.out
 
     def get_state(self, first=0, n=None):

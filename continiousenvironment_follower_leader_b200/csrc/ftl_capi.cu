@@ -106,6 +106,9 @@ struct FtlHandle_ {
     bool rays_smem_opted = false;
     double2* d_rot = nullptr;   // (cos, sin)(k * 360/R) per flat ray
     cudaStream_t copy_stream = nullptr;   // host path: D2H copies overlap the ray kernel chunk by chunk
+    cudaStream_t own_stream = nullptr;    // ftl_host_stream
+    cudaStream_t pending_stream = nullptr;   // stream of an ftl_step_host_begin that has not been waited for
+    bool pending = false;
     cudaEvent_t chunk_ev[8] = {};
     // optional per-kernel timing (ftl_profile): three events per step on the launching stream
     bool profiling = false;
@@ -409,6 +412,7 @@ int ftl_destroy(ftl_handle h) {
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     for (cudaEvent_t e : h->chunk_ev) if (e) cudaEventDestroy(e);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return FTL_OK;
 }
@@ -552,9 +556,35 @@ int ftl_step(ftl_handle h, const void* actions_dev, const FtlOutputs* out_dev, v
     return rc;
 }
 
+void* ftl_host_stream(ftl_handle h) {
+    if (!h) return nullptr;
+    if (!h->own_stream) {
+        cudaSetDevice(h->device);
+        if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) h->own_stream = nullptr;
+    }
+    return (void*)h->own_stream;
+}
+
+int ftl_step_host_wait(ftl_handle h) {
+    if (!h) return fail(FTL_ERR_INVALID, "NULL handle");
+    if (!h->pending) return FTL_OK;
+    h->pending = false;
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (h->copy_stream) CUDA_TRY(cudaStreamSynchronize(h->copy_stream));
+    CUDA_TRY(cudaStreamSynchronize(h->pending_stream));
+    return FTL_OK;
+}
+
 int ftl_step_host(ftl_handle h, const void* actions_host, const FtlOutputs* out_host, void* cuda_stream) {
+    int rc = ftl_step_host_begin(h, actions_host, out_host, cuda_stream);
+    if (rc) return rc;
+    return ftl_step_host_wait(h);
+}
+
+int ftl_step_host_begin(ftl_handle h, const void* actions_host, const FtlOutputs* out_host, void* cuda_stream) {
     if (!h || !actions_host) return fail(FTL_ERR_INVALID, "NULL argument");
     if (!h->was_reset) return fail(FTL_ERR_STATE, "ftl_reset must be called before ftl_step");
+    if (h->pending) return fail(FTL_ERR_STATE, "ftl_step_host_begin: the previous step has not been waited for");
     CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const size_t n = h->n;
@@ -571,10 +601,11 @@ int ftl_step_host(ftl_handle h, const void* actions_host, const FtlOutputs* out_
     no_rays.rays = nullptr;
     int rc = ftl_step(h, h->d_actions, &no_rays, cuda_stream);
     if (rc) return rc;
+    h->pending_stream = st;
     if (!out_host) {
         rc = launch_rays(h, h->d_out.rays, st);
         if (rc) return rc;
-        CUDA_TRY(cudaStreamSynchronize(st));
+        h->pending = true;
         return FTL_OK;
     }
     const DevOutputs& d = h->d_out;
@@ -602,8 +633,7 @@ int ftl_step_host(ftl_handle h, const void* actions_host, const FtlOutputs* out_
                                      row * (size_t)(end - first), cudaMemcpyDeviceToHost, cs));
         }
     }
-    CUDA_TRY(cudaStreamSynchronize(cs));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    h->pending = true;
     return FTL_OK;
 }
 

@@ -365,8 +365,14 @@ FTL_HD int pair_rows(const RayShared& sh, int ei, int f, int n_sensors) {
     return rows;
 }
 
-// A2 + B over the current edge list, then empty it
-FTL_HD void ray_flush(RayShared& sh, const RayArrays& ra, int n_sensors) {
+// A2 + B over the current edge list, then empty it.  One out-of-line copy for the five places that may flush: the
+// kernel is bound by instruction fetch as much as by issue slots, and warps in different flushes share these lines.
+#ifdef FTL_INLINE_FLUSH
+FTL_HD void ray_flush(RayShared& sh, int n_sensors) {
+#else
+FTL_HD_NOINLINE void ray_flush(RayShared& sh, int n_sensors) {
+#endif
+    const RayArrays ra = ray_arrays(&sh, sh.rt, sh.hmax);
     FTL_WARP_SYNC();
     const int ne = sh.ne < kEdgeCap ? sh.ne : kEdgeCap;
     // ---- A2: edges -> (edge, ray) pairs ----------------------------------------------------------------------
@@ -526,7 +532,7 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
         if (sh.reach[EC_STATIC] > 0.f) {
             for (int q0 = 0; q0 < n_static; q0 += 32) {
                 FTL_WARP_SYNC();
-                if (sh.ne + 4 * 32 > kEdgeCap) ray_flush(sh, ra, ns);   // a round adds at most 4 edges per lane
+                if (sh.ne + 4 * 32 > kEdgeCap) ray_flush(sh, ns);   // a round adds at most 4 edges per lane
                 FTL_LANES(lane) {
                     if (q0 + lane < n_static) rect_append(sh, statics[q0 + lane], EC_STATIC, 1 << kStaticBit);
                 }
@@ -534,7 +540,7 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
         }
         for (int q0 = 0; q0 < n_dyn; q0 += 32) {
             FTL_WARP_SYNC();
-            if (sh.ne + 4 * 32 > kEdgeCap) ray_flush(sh, ra, ns);
+            if (sh.ne + 4 * 32 > kEdgeCap) ray_flush(sh, ns);
             FTL_LANES(lane) {
                 int q = q0 + lane;
                 if (q < n_dyn) {
@@ -559,7 +565,7 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
             }
             for (int q0 = min_tail; q0 < max_head - 1; q0 += kCorridorChunk) {
                 FTL_WARP_SYNC();
-                if (sh.ne + 2 * kCorridorChunk > kEdgeCap) ray_flush(sh, ra, ns);
+                if (sh.ne + 2 * kCorridorChunk > kEdgeCap) ray_flush(sh, ns);
                 FTL_LANES(lane) {
                     int q1 = q0 + kCorridorChunk < max_head - 1 ? q0 + kCorridorChunk : max_head - 1;
                     for (int q = q0 + lane; q < q1; q += 32) {
@@ -577,7 +583,7 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
         }
         if (sh.reach[EC_CAP] > 0.f) {
             FTL_WARP_SYNC();
-            if (sh.ne + 2 * FTL_MAX_HIST > kEdgeCap) ray_flush(sh, ra, ns);
+            if (sh.ne + 2 * FTL_MAX_HIST > kEdgeCap) ray_flush(sh, ns);
             FTL_LANES(lane) {
                 if (lane < 2 * n_valid) {   // SEN:648-650
                     int age = lane >> 1;
@@ -587,7 +593,7 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
                 }
             }
         }
-        ray_flush(sh, ra, ns);
+        ray_flush(sh, ns);
     }
     // ---- out: assemble rows and write (row-major per sensor; consecutive lanes write consecutive floats) ------
     FTL_LANES(lane) {

@@ -275,6 +275,15 @@ int ftl_step(ftl_handle h, const void* actions_dev, const FtlOutputs* out_dev, v
 int ftl_step_host(ftl_handle h, const void* actions_host, const FtlOutputs* out_host, void* cuda_stream);
 int ftl_reset_host(ftl_handle h, const uint8_t* mask_host, const int32_t* scenario_ids_host,
                    const FtlOutputs* out_host, void* cuda_stream);
+/* Pipelined form of ftl_step_host for callers that drive several handles (halves of a batch, vector-env workers):
+ * _begin enqueues the copies and kernels and returns, _wait blocks until this handle's outputs are in `out_host`.
+ * While one handle's results cross PCIe, another handle's kernels run.  out_host and actions_host must stay valid
+ * (and should be pinned) until _wait returns.  ftl_step_host == _begin + _wait. */
+int ftl_step_host_begin(ftl_handle h, const void* actions_host, const FtlOutputs* out_host, void* cuda_stream);
+int ftl_step_host_wait(ftl_handle h);
+/* A non-blocking CUDA stream owned by the handle (created on first use, destroyed with it), for callers without a
+ * CUDA runtime of their own who want their handles to run concurrently: pass it as `cuda_stream`. */
+void* ftl_host_stream(ftl_handle h);
 
 /* ---- state access: teacher forcing, snapshots, the attribute reads of WRP:180-212 ------------- */
 int ftl_get_state(ftl_handle h, int32_t first_env, int32_t n, const FtlStateBuffers* host_out);

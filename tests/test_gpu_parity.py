@@ -219,6 +219,40 @@ def test_device_and_host_entry_points_agree():
     assert dev.launch_count >= 24
 
 
+def test_pipelined_halves_equal_the_whole_batch():
+    """Two half-batch handles on their own streams, driven with step_begin / step_wait (ftl_step_host_begin/_wait),
+    must deliver exactly what one synchronous whole-batch handle delivers -- auto-reset included (env ids are global)."""
+    gc = GameConfig(bear_number=1, follower_sensors=cfg3_sensors(), auto_reset=True, max_steps=150)
+    pool = synthetic_pool(gc, 8, seed=5)
+    n, half = 9000, 4480   # large enough for the chunked ray launches of the host path (>= 8192 envs)
+    whole = _cuda_env(gc, n, pinned=True)
+    parts = [_cuda_env(gc, m, env_id_base=first, pinned=True, own_stream=True) for first, m in ((0, half), (half, n - half))]
+    for e in [whole] + parts:
+        e.upload_scenarios(pool)
+        e.reset()
+    rng = np.random.RandomState(3)
+    lo, hi = gc.action_bounds()
+    acts = [rng.uniform(lo, hi, size=(n, 2)).astype(np.float32) for _ in range(25)]
+    A, B = parts
+    A.step_begin(acts[0][:half])
+    with pytest.raises(capi.FtlError):
+        A.step_begin(acts[0][:half])           # one step in flight per handle
+    for t, a in enumerate(acts):
+        B.step_begin(a[half:])
+        oa = A.step_wait()
+        ow = whole.step(a)
+        for f in ("numerical_features", "leader_target", "rays", "reward", "done", "status"):
+            assert np.array_equal(getattr(oa, f), getattr(ow, f)[:half]), (f, t)
+        if t + 1 < len(acts):
+            A.step_begin(acts[t + 1][:half])
+        ob = B.step_wait()
+        for f in ("numerical_features", "leader_target", "rays", "reward", "done", "status"):
+            assert np.array_equal(getattr(ob, f), getattr(ow, f)[half:]), (f, t)
+    assert whole.out.done.sum() >= 0
+    for e in [whole] + parts:
+        e.close()
+
+
 def test_grazing_rays_resolve_like_the_reference_on_the_gpu():
     """Followers parked on integer coordinates with axis-aligned headings: many rays run exactly through corners and
     along edges.  k_rays records those pairs, k_rays_exact must reproduce the reference's strict ccw decisions."""
