@@ -319,11 +319,7 @@ FTL_HD void env_step(const DevCfg& cfg, const DevState& s, const DevPool& pool, 
         }
         // (2) green zone + flags, ENV:966-973
         bool in_box, on_trace;
-#ifdef FTL_EXPERIMENT_NO_GREEN   // timing experiment only (results differ): how much of the frame is the green-zone code?
-        in_box = on_trace = (f & 1) != 0;
-#else
         green_flags(cfg, trail, trail_d, e.trail_len, w.follower.px, w.follower.py, gc, &in_box, &on_trace);
-#endif
         bool too_close = d2_f32(w.leader.px, w.leader.py, w.follower.px, w.follower.py) <= cfg.min_dist2_f32;
         // (3) waypoint advance, ENV:978-983
         if (dist_f64_nv((double)w.leader.px, (double)w.leader.py, (double)target.x, (double)target.y) <
