@@ -7,7 +7,7 @@ import ctypes as C
 
 import numpy as np
 
-FTL_ABI_VERSION = 2
+FTL_ABI_VERSION = 3
 FTL_MAX_BEARS = 4
 FTL_MAX_RAY_SENSORS = 4
 FTL_MAX_REGIME = 16
@@ -80,7 +80,8 @@ class FtlConfig(C.Structure):
         ("static_cap", C.c_int32), ("auto_reset", C.c_int32),
         ("fused_sensor_prev", C.c_int32),
         ("track_vector_len", C.c_int32), ("track_vector_mode", C.c_int32),
-        ("reserved", C.c_int32 * 4),
+        ("radar_sectors", C.c_int32), ("radar_len", C.c_int32), ("radar_mode", C.c_int32),
+        ("reserved", C.c_int32 * 1),
     ]
 
 
@@ -146,7 +147,7 @@ class FtlStateBuffers(C.Structure):
 class FtlOutputs(C.Structure):
     _fields_ = [("numerical_features", C.c_void_p), ("leader_target", C.c_void_p), ("rays", C.c_void_p),
                 ("reward", C.c_void_p), ("done", C.c_void_p), ("status", C.c_void_p),
-                ("follower_info", C.c_void_p), ("track_vectors", C.c_void_p)]
+                ("follower_info", C.c_void_p), ("track_vectors", C.c_void_p), ("radar", C.c_void_p)]
 
 
 ENV_STATE_DTYPE = np.dtype(FtlEnvState)

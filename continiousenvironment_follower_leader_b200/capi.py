@@ -84,7 +84,7 @@ def check(L, rc, what):
 class HostOutputs:
     """numpy buffers laid out as FtlOutputs."""
 
-    def __init__(self, n, rays_per_env, alloc=None, follower_info=False, track_vector_len=0):
+    def __init__(self, n, rays_per_env, alloc=None, follower_info=False, track_vector_len=0, radar_sectors=0):
         alloc = alloc or (lambda shape, dtype: np.zeros(shape, dtype))
         self.numerical_features = alloc((n, 10), np.float32)
         self.leader_target = alloc((n, 2), np.int32)
@@ -95,14 +95,16 @@ class HostOutputs:
         # the optional sensors' outputs exist only when the configuration has them (NULL pointers otherwise)
         self.follower_info = alloc((n, 2), np.float32) if follower_info else None
         self.track_vectors = alloc((n, track_vector_len, 2), np.float32) if track_vector_len else None
+        self.radar = alloc((n, radar_sectors), np.float32) if radar_sectors else None
         self.c = abi.FtlOutputs(abi.ptr(self.numerical_features), abi.ptr(self.leader_target), abi.ptr(self.rays),
                                 abi.ptr(self.reward), abi.ptr(self.done), abi.ptr(self.status),
                                 None if self.follower_info is None else abi.ptr(self.follower_info),
-                                None if self.track_vectors is None else abi.ptr(self.track_vectors))
+                                None if self.track_vectors is None else abi.ptr(self.track_vectors),
+                                None if self.radar is None else abi.ptr(self.radar))
 
     def nbytes(self):
         return sum(a.nbytes for a in (self.numerical_features, self.leader_target, self.rays, self.reward, self.done,
-                                      self.status, self.follower_info, self.track_vectors) if a is not None)
+                                      self.status, self.follower_info, self.track_vectors, self.radar) if a is not None)
 
 
 class HostState:
@@ -148,7 +150,7 @@ class HostEnv:
                 return a
         self.out = HostOutputs(self.n, abi.rays_per_env(self.cfg), alloc,
                                follower_info=getattr(game_config, "follower_info_name", None) is not None,
-                               track_vector_len=self.cfg.track_vector_len)
+                               track_vector_len=self.cfg.track_vector_len, radar_sectors=self.cfg.radar_sectors)
         if self.cfg.action_mode == abi.ACTION_CONTINUOUS:
             shape, dt = (self.n, 2), np.float32
         elif self.cfg.action_mode == abi.ACTION_CONST_SPEED:

@@ -228,6 +228,8 @@ class GameConfig:
         c.tracker_scans_per_step = 2  # CLS:263-286: the v2 tracker is scanned twice per use_sensors
         c.n_ray_sensors = 0
         c.track_vector_len = 0
+        c.radar_sectors = 0
+        self.radar_name = None             # dict key of the LeaderTrackDetector_radar sensor, if any
         self.ray_sensor_flat = []          # True: the sensor returns (R,), not (H, R)
         self.follower_info_name = None     # dict key of the FollowerInfo sensor, if any
         self.track_vector_name = None      # dict key of the LeaderTrackDetector_vector sensor, if any
@@ -333,10 +335,22 @@ class GameConfig:
                     raise ValueError("position_sequence_length must be positive")
                 c.track_vector_mode = 0 if mode == "new" else 1
                 self.track_vector_name = name
+            elif cls == "LeaderTrackDetector_radar":   # SEN:394-461
+                if self.radar_name is not None:
+                    raise NotImplementedError("one LeaderTrackDetector_radar sensor at most")
+                mode = args.get("detectable_positions", "old")
+                if mode not in ("new", "old", "near"):
+                    raise ValueError("detectable_positions must be 'new', 'old' or 'near'")
+                c.radar_len = int(args.get("position_sequence_length", 100))
+                c.radar_sectors = int(args.get("radar_sectors_number", 180))
+                if c.radar_len < 1 or c.radar_sectors < 1:
+                    raise ValueError("position_sequence_length and radar_sectors_number must be positive")
+                c.radar_mode = {"new": 0, "old": 1, "near": 2}[mode]
+                self.radar_name = name
             else:
                 raise NotImplementedError(
                     "sensor class %s is outside the accelerated path (SURVEY.md section 8(f)3)" % cls)
-        if (c.n_ray_sensors or c.track_vector_len) and not c.tracker_enabled:
+        if (c.n_ray_sensors or c.track_vector_len or c.radar_sectors) and not c.tracker_enabled:
             raise ValueError("ray sensors and track detectors need the LeaderPositionsTracker_v2 corridor (CLS:263-280)")
 
     # ---- spaces (ENV:360-378, 1812-1824) -----------------------------------------------------------

@@ -225,6 +225,8 @@ static int validate(const FtlConfig* c, int n_envs) {
     }
     if (c->track_vector_len < 0 || (c->track_vector_len > 0 && !c->tracker_enabled))
         return fail(FTL_ERR_INVALID, "LeaderTrackDetector_vector needs LeaderPositionsTracker_v2 (CLS:240-244)");
+    if (c->radar_sectors < 0 || (c->radar_sectors > 0 && (!c->tracker_enabled || c->radar_len < 1 || c->radar_mode < 0 || c->radar_mode > 2)))
+        return fail(FTL_ERR_INVALID, "LeaderTrackDetector_radar needs LeaderPositionsTracker_v2, a positive length and mode 0..2 (CLS:240-244, SEN:402-421)");
     return FTL_OK;
 }
 
@@ -235,6 +237,7 @@ static DevOutputs to_dev_outputs(const FtlOutputs* o, int n_real) {
         d.numerical_features = o->numerical_features; d.leader_target = o->leader_target; d.rays = o->rays;
         d.reward = o->reward; d.done = o->done; d.status = o->status;
         d.follower_info = o->follower_info; d.track_vectors = o->track_vectors;
+        d.radar = o->radar;
     }
     return d;
 }
@@ -251,7 +254,9 @@ static void launch_reset(FtlHandle_* h, const DevState& s, const uint8_t* mask, 
 }
 
 static int launch_optional_sensors(ftl_handle h, const DevOutputs& o, cudaStream_t st) {
-    if (!o.follower_info && !(o.track_vectors && h->cfg.c.track_vector_len > 0)) return FTL_OK;
+    if (!o.follower_info && !(o.track_vectors && h->cfg.c.track_vector_len > 0) &&
+        !(o.radar && h->cfg.c.radar_sectors > 0))
+        return FTL_OK;
     k_optional_sensors<<<(h->n + 127) / 128, 128, 0, st>>>(h->cfg, h->st, o);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
@@ -289,6 +294,8 @@ static int copy_outputs_to_host(ftl_handle h, const FtlOutputs* o, cudaStream_t 
     if (o->follower_info) CUDA_TRY(cudaMemcpyAsync(o->follower_info, d.follower_info, 8 * n, cudaMemcpyDeviceToHost, st));
     if (o->track_vectors && h->cfg.c.track_vector_len)
         CUDA_TRY(cudaMemcpyAsync(o->track_vectors, d.track_vectors, 8 * n * h->cfg.c.track_vector_len, cudaMemcpyDeviceToHost, st));
+    if (o->radar && h->cfg.c.radar_sectors)
+        CUDA_TRY(cudaMemcpyAsync(o->radar, d.radar, 4 * n * h->cfg.c.radar_sectors, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return FTL_OK;
 }
@@ -306,6 +313,7 @@ static FtlOutputs staged_outputs(ftl_handle h, const FtlOutputs* want) {
         if (want->status) o.status = d.status;
         if (want->follower_info) o.follower_info = d.follower_info;
         if (want->track_vectors && h->cfg.c.track_vector_len) o.track_vectors = d.track_vectors;
+        if (want->radar && h->cfg.c.radar_sectors) o.radar = d.radar;
     }
     return o;
 }
@@ -393,6 +401,7 @@ int ftl_create(const FtlConfig* cfg, int32_t n_envs, int32_t device, int64_t env
     ok(dalloc(h, &h->d_out.status, 4 * n));
     ok(dalloc(h, &h->d_out.follower_info, 2 * n));
     ok(dalloc(h, &h->d_out.track_vectors, (size_t)(c.track_vector_len > 0 ? c.track_vector_len : 1) * 2 * n));
+    ok(dalloc(h, &h->d_out.radar, (size_t)(c.radar_sectors > 0 ? c.radar_sectors : 1) * n));
     if (e != cudaSuccess) {
         for (void* p : h->allocs) cudaFree(p);
         delete h;
@@ -619,6 +628,8 @@ int ftl_step_host_begin(ftl_handle h, const void* actions_host, const FtlOutputs
     if (out_host->follower_info) CUDA_TRY(cudaMemcpyAsync(out_host->follower_info, d.follower_info, 8 * n, cudaMemcpyDeviceToHost, cs));
     if (out_host->track_vectors && h->cfg.c.track_vector_len)
         CUDA_TRY(cudaMemcpyAsync(out_host->track_vectors, d.track_vectors, 8 * n * h->cfg.c.track_vector_len, cudaMemcpyDeviceToHost, cs));
+    if (out_host->radar && h->cfg.c.radar_sectors)
+        CUDA_TRY(cudaMemcpyAsync(out_host->radar, d.radar, 4 * n * h->cfg.c.radar_sectors, cudaMemcpyDeviceToHost, cs));
     // ray kernel in chunks of envs: the D2H copy of chunk c runs while chunk c+1 is being cast
     if (out_host->rays && h->cfg.rays_per_env) {
         const int chunks = h->n >= 8192 ? 6 : 1;

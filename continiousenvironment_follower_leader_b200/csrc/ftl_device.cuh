@@ -126,6 +126,7 @@ struct DevOutputs {
     uint8_t* status;
     float* follower_info;   // [N][2] or NULL
     float* track_vectors;   // [N][track_vector_len][2] or NULL
+    float* radar;           // [N][radar_sectors] or NULL
 };
 
 // per-sensor constants of the ray pass that do not depend on the env (filled by ray_static_tables, ftl_rays.cuh)

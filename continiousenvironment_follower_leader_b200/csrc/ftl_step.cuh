@@ -159,6 +159,55 @@ FTL_HD void sense_serial(const DevCfg& cfg, const DevState& s, int i, const Worl
 // (SEN:365-380) on the tracker ring as the step left it: np.array(slice) - position with a float32 position, cast
 // into the float32 buffer.  Reads the stored state after the step / reset kernel (its own small kernel, launched
 // only when one of these outputs is requested: the step kernel of the BASELINE.json configurations is untouched).
+// LeaderTrackDetector_radar.scan (SEN:425-461; rotateVector / calculateAngle MSC:47-62): for every chosen history
+// point the angle to the follower's right-hand vector, negated behind the follower, selects one of R sectors of the
+// front half plane; a sector reports the distance to its nearest point, 0 when empty.  The chosen points are a float64
+// array as soon as one of them is a float64 point the tracker seeded, float32 otherwise (numpy's np.array(list)), and
+// distances / vectors keep that type; dot products are float64 (fma form of the gemv numpy dispatches to).
+FTL_HD void radar_scan(const FtlConfig& c, const double2* hist, int mask, int tail, int head, int f64_end, float2 fp,
+                       double dir, float* radar) {
+    const int R = c.radar_sectors;
+    for (int k = 0; k < R; k++) radar[k] = 0.f;
+    const int n = head - tail;
+    if (n <= 0) return;
+    int cnt = n < c.radar_len ? n : c.radar_len, first = tail;
+    if (c.radar_mode == 0) first = head - cnt;      // "new"
+    else if (c.radar_mode == 2) cnt = n;            // "near": all points (the reference's sort does not change minima)
+    const bool is64 = first < f64_end;
+    double rdir = dir + 90;
+    if (rdir >= 360) rdir -= 360;
+    double wdx, wdy, wrx, wry;
+    sincos_deg(dir, &wdy, &wdx);
+    sincos_deg(rdir, &wry, &wrx);
+    const double nwd = sqrt(fma(wdy, wdy, wdx * wdx)), nwr = sqrt(fma(wry, wry, wrx * wrx));
+    const double pi = 3.141592653589793, sa = pi / R;
+    for (int k = 0; k < cnt; k++) {
+        const double2 h = hist[(first + k) & mask];
+        double vx, vy, dist;
+        if (is64) {
+            vx = h.x - (double)fp.x; vy = h.y - (double)fp.y;
+            const double sx = vx * vx, sy = vy * vy;
+            dist = sqrt(sx + sy);
+        } else {
+            const float fx = (float)h.x - fp.x, fy = (float)h.y - fp.y;
+            dist = (double)sqrtf(d2_f32((float)h.x, (float)h.y, fp.x, fp.y));
+            vx = fx; vy = fy;
+        }
+        const double ad = acos(fma(vx, wdx, vy * wdy) / (dist * nwd));
+        double ar = acos(fma(vx, wrx, vy * wry) / (dist * nwr));
+        if (ad > pi / 2) ar = -ar;
+        if (!(ar >= 0.0)) continue;                  // behind the follower, or NaN (the reference drops those too)
+        int q = (int)(ar / sa);                      // candidate sector; the reference's own comparisons decide
+        q = q < 1 ? 0 : q - 1;
+        for (int t = 0; t < 3 && q < R; t++, q++)
+            if (ar >= sa * q && ar < sa * (q + 1)) {
+                const float d32 = (float)dist;
+                if (radar[q] == 0.f || d32 < radar[q]) radar[q] = d32;
+                break;
+            }
+    }
+}
+
 FTL_HD void write_optional_sensors(const FtlConfig& c, const DevState& s, const DevOutputs& out, int i) {
     const float2 fp = s.pos[i];   // robot 0 = follower
     if (out.follower_info) {
@@ -166,10 +215,14 @@ FTL_HD void write_optional_sensors(const FtlConfig& c, const DevState& s, const 
         out.follower_info[2 * (size_t)i] = (float)(fspeed / c.follower.max_speed);
         out.follower_info[2 * (size_t)i + 1] = (float)(fdir / 360);
     }
-    if (!out.track_vectors || c.track_vector_len <= 0) return;
-    const int P = c.track_vector_len, mask = c.corridor_cap - 1;
+    const int mask = c.corridor_cap - 1;
     const int tail = s.gi[(size_t)GI_RING_TAIL * s.n + i], head = s.gi[(size_t)GI_RING_HEAD * s.n + i];
     const double2* hist = s.hist + (size_t)i * c.corridor_cap;
+    if (out.radar && c.radar_sectors > 0)
+        radar_scan(c, hist, mask, tail, head, s.gi[(size_t)GI_HIST_F64_END * s.n + i], fp,
+                   s.rd[(size_t)RD_DIR * s.n + i], out.radar + (size_t)i * c.radar_sectors);
+    if (!out.track_vectors || c.track_vector_len <= 0) return;
+    const int P = c.track_vector_len;
     float* v = out.track_vectors + (size_t)i * P * 2;
     const int len = head - tail, cnt = len < P ? len : P;
     const int first = c.track_vector_mode == 0 ? head - cnt : tail;   // "new": the last P points, "old": the first P

@@ -250,6 +250,8 @@ class Game(Env):
             obs[self.gc.follower_info_name] = out.follower_info[0].copy()
         if self.gc.track_vector_name is not None:    # SEN:365-380
             obs[self.gc.track_vector_name] = out.track_vectors[0].copy()
+        if self.gc.radar_name is not None:           # SEN:425-461
+            obs[self.gc.radar_name] = out.radar[0].copy()
         return obs
 
     def _tracker_obs(self):

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FTL_ABI_VERSION 2
+#define FTL_ABI_VERSION 3
 
 #define FTL_MAX_BEARS 4
 #define FTL_MAX_RAY_SENSORS 4
@@ -144,7 +144,13 @@ typedef struct FtlConfig {
      * (mode 1, "old") track_vector_len points of the tracker's history; 0 = sensor absent */
     int32_t track_vector_len;
     int32_t track_vector_mode;
-    int32_t reserved[4];
+    /* LeaderTrackDetector_radar (SEN:394-461): for each of radar_sectors sectors of the half plane in front of the
+     * follower, the distance to the nearest of the chosen history points (mode 0 "new": the last radar_len points,
+     * 1 "old": the first radar_len, 2 "near": all of them), 0 where a sector is empty; radar_sectors = 0: absent */
+    int32_t radar_sectors;
+    int32_t radar_len;
+    int32_t radar_mode;
+    int32_t reserved[1];
 } FtlConfig;
 
 /* Scenario pool = what Game.reset() builds (ENV:434-543) before the first sensor scan, as data.
@@ -239,6 +245,7 @@ typedef struct FtlOutputs {
     uint8_t* status;           /* [N][4]  mission, agent, leader, crash */
     float* follower_info;      /* [N][2]   FollowerInfo.scan: speed / max_speed, direction / 360 (SEN:834-842); may be NULL */
     float* track_vectors;      /* [N][track_vector_len][2]  LeaderTrackDetector_vector.scan (SEN:365-380); may be NULL */
+    float* radar;              /* [N][radar_sectors]  LeaderTrackDetector_radar.scan (SEN:425-461); may be NULL */
 } FtlOutputs;
 
 /* Episode statistics accumulated on the device (summed over envs), the vector reduced with NCCL. */

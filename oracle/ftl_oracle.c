@@ -889,6 +889,57 @@ static void write_outputs(FtlOracle* o, int i, const FtlOutputs* out) {
     }
 }
 
+/* LeaderTrackDetector_radar.scan, SEN:425-461, with rotateVector / calculateAngle of MSC:47-62.
+ * chosen_dots = np.array(slice of the history): float64 as soon as one chosen point is one of the float64 points
+ * the tracker seeded (SEN:257-272), float32 otherwise; everything derived from it (the vectors to the follower,
+ * np.linalg.norm(axis=1) = sqrt(x*x + y*y) without fusion) keeps that type.  v.dot(w) is a float64 gemv
+ * (fma(v0, w0, v1*w1), like the other (k,2).(2,) products of this file), np.linalg.norm(w) = sqrt(ddot) (fma form). */
+static void radar_scan(FtlOracle* o, int i, float* radar) {
+    const FtlConfig* cfg = &o->cfg;
+    const FtlEnvState* e = &o->env[i];
+    const int R = cfg->radar_sectors, cap = cfg->corridor_cap;
+    const double* hist = o->hist + (size_t)i * cap * 2;
+    for (int k = 0; k < R; k++) radar[k] = 0.f;
+    const int n = e->ring_head - e->ring_tail;
+    if (n <= 0) return;
+    int cnt = n < cfg->radar_len ? n : cfg->radar_len, first = e->ring_tail;
+    if (cfg->radar_mode == 0) first = e->ring_head - cnt;          /* "new": islice(len - P, len) */
+    else if (cfg->radar_mode == 2) cnt = n;                        /* "near": every point (the sort does not matter) */
+    const int is64 = first < e->hist_f64_end;
+    const double dir = e->follower.dir;
+    double rdir = dir + 90;
+    if (rdir >= 360) rdir -= 360;
+    const double th = dir * (M_PI / 180.0), thr = rdir * (M_PI / 180.0); /* np.radians */
+    const double wdx = cos(th), wdy = sin(th), wrx = cos(thr), wry = sin(thr); /* np.dot(rot, [1, 0]) */
+    const double nwd = sqrt(fma(wdy, wdy, wdx * wdx)), nwr = sqrt(fma(wry, wry, wrx * wrx));
+    const double sa = M_PI / R;
+    const float px = e->follower.pos[0], py = e->follower.pos[1];
+    for (int k = 0; k < cnt; k++) {
+        const double hx = hist[2 * RING(first + k)], hy = hist[2 * RING(first + k) + 1];
+        double vx, vy, dist;
+        if (is64) {
+            vx = hx - (double)px; vy = hy - (double)py;
+            const double sx = vx * vx, sy = vy * vy;
+            dist = sqrt(sx + sy);
+        } else {
+            const float fx = (float)hx - px, fy = (float)hy - py;
+            const float sx = fx * fx, sy = fy * fy;
+            const float s = sx + sy;
+            dist = (double)sqrtf(s);
+            vx = fx; vy = fy;
+        }
+        const double ad = acos(fma(vx, wdx, vy * wdy) / (dist * nwd));
+        double ar = acos(fma(vx, wrx, vy * wry) / (dist * nwr));
+        if (ad > M_PI / 2) ar = -ar;
+        for (int q = 0; q < R; q++) { /* SEN:454-459, literally */
+            if (ar >= sa * q && ar < sa * (q + 1)) {
+                const float d32 = (float)dist;
+                if (radar[q] == 0.f || d32 < radar[q]) radar[q] = d32;
+            }
+        }
+    }
+}
+
 static void use_sensors(FtlOracle* o, int i, const FtlOutputs* out) { /* CLS:255-288 */
     const FtlConfig* cfg = &o->cfg;
     FtlEnvState* e = &o->env[i];
@@ -911,6 +962,7 @@ static void use_sensors(FtlOracle* o, int i, const FtlOutputs* out) { /* CLS:255
             v[2 * k + 1] = (float)(hist[2 * RING(first + k) + 1] - (double)e->follower.pos[1]);
         }
     }
+    if (out && out->radar && cfg->radar_sectors > 0) radar_scan(o, i, out->radar + (size_t)i * cfg->radar_sectors);
     if (cfg->n_ray_sensors > 0) {
         /* history_obstacles_list.pop(0); append(current), SEN:894-895 (one shared ring: every sensor
          * snapshots the same world at the same instants) */

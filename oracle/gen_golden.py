@@ -110,6 +110,8 @@ def capture(env, obs, reward, done, info, ray_names, n_bears, gc=None):
         rec["follower_info"] = np.asarray(obs[gc.follower_info_name], np.float32)
     if gc is not None and gc.track_vector_name is not None:
         rec["track_vectors"] = np.asarray(obs[gc.track_vector_name], np.float32)
+    if gc is not None and getattr(gc, "radar_name", None) is not None:
+        rec["radar"] = np.asarray(obs[gc.radar_name], np.float32)
     return rec
 
 
@@ -255,6 +257,26 @@ TRACES = [
              "LeaderTrackDetector_vector": dict(sensor_class="LeaderTrackDetector_vector", position_sequence_length=50,
                                                 detectable_positions="old")}),
          seed=13, policy="follow", max_env_steps=200),
+    # LeaderTrackDetector_radar (SEN:394-461): the oldest 30 points in 12 sectors next to the history ray sensor ...
+    dict(name="radar_old_seed17", env_id="Test-Cont-Env-Auto-v0",
+         kwargs=dict(bear_number=1, follower_sensors={
+             "LeaderPositionsTracker_v2": cfg3_sensors()["LeaderPositionsTracker_v2"],
+             "LeaderCorridor_Prev_lasers_v2": cfg3_sensors()["LeaderCorridor_Prev_lasers_v2"],
+             "LeaderTrackDetector_radar": dict(sensor_class="LeaderTrackDetector_radar", position_sequence_length=30,
+                                               detectable_positions="old", radar_sectors_number=12)}),
+         seed=17, policy="follow", max_env_steps=260, switch=(180, "random")),
+    # ... and the newest 100 points in 180 sectors (the class defaults apart from "new"), random walk
+    dict(name="radar_new_seed19", env_id="Test-Cont-Env-Auto-v0",
+         kwargs=dict(add_bear=False, follower_sensors={
+             "LeaderPositionsTracker_v2": cfg3_sensors()["LeaderPositionsTracker_v2"],
+             "LeaderTrackDetector_radar": dict(sensor_class="LeaderTrackDetector_radar", detectable_positions="new")}),
+         seed=19, policy="random", max_env_steps=200),
+    # "near": all points, few wide sectors
+    dict(name="radar_near_seed21", env_id="Test-Cont-Env-Auto-v0",
+         kwargs=dict(add_bear=False, follower_sensors={
+             "LeaderPositionsTracker_v2": cfg3_sensors()["LeaderPositionsTracker_v2"],
+             "radar": dict(sensor_class="LeaderTrackDetector_radar", detectable_positions="near", radar_sectors_number=7)}),
+         seed=21, policy="follow", max_env_steps=150),
 ]
 
 

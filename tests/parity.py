@@ -162,6 +162,18 @@ def check_record(t, d, gc, out, st, env_index=0, float_rtol=0.0, ray_rtol=RTOL, 
             err = np.abs(out.track_vectors[env_index].astype(np.float64) - want)
             if np.any(err > float_rtol * 1500.0):
                 raise Mismatch("step %d: LeaderTrackDetector_vector differs by %g" % (t, err.max()))
+    # ---- LeaderTrackDetector_radar (SEN:425-461) ------------------------------------------------------
+    if "t_radar" in d:
+        want = d["t_radar"][t]
+        got = out.radar[env_index]
+        if float_rtol == 0.0:
+            _equal(got, want, "LeaderTrackDetector_radar", t)
+        else:
+            # a point on a sector boundary may land in the neighbouring sector (the boundary test is discontinuous):
+            # such sectors must stay rare
+            err = np.abs(got.astype(np.float64) - want) > float_rtol * np.maximum(1.0, np.abs(want))
+            if err.sum() > max(2, 0.02 * err.size):
+                raise Mismatch("step %d: LeaderTrackDetector_radar differs in %d of %d sectors" % (t, err.sum(), err.size))
     # ---- rays -----------------------------------------------------------------------------------
     bad = 0
     if c.n_ray_sensors:

@@ -405,3 +405,56 @@ def test_flat_sensors_match_the_oracle_on_a_batch():
         oc, oo = cuda.step(a), orc.step(a)
         assert np.array_equal(oc.done, oo.done) and np.array_equal(oc.status, oo.status)
     assert bad <= 2
+
+
+def _radar_outliers(got, want):
+    """Sectors whose value differs by more than 1e-4 relative: a history point within rounding of a sector boundary
+    may fall into the neighbouring sector (arccos of float64 quotients; CUDA's libm differs from glibc in the last bit)."""
+    return int(np.sum(np.abs(got.astype(np.float64) - want) > parity.RTOL * np.maximum(1.0, np.abs(want))))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("trace", ["radar_old_seed17", "radar_new_seed19", "radar_near_seed21"])
+def test_radar_matches_the_oracle_on_a_batch(trace):
+    """LeaderTrackDetector_radar (SEN:394-461) through the C-ABI against the oracle, which reproduces the reference's
+    radar bit for bit on the golden traces."""
+    from oracle_py import OracleEnv
+    d, meta = parity.load_trace(parity.GOLDEN_DIR + "/%s.npz" % trace)
+    kwargs = dict(meta["kwargs"], auto_reset=True, max_steps=400)
+    n, steps = 1024, 80
+    gc = GameConfig(**kwargs)
+    pool = synthetic_pool(gc, 64, seed=6)
+    cuda, orc = _cuda_env(gc, n), OracleEnv(gc, n, n_threads=8)
+    cuda.upload_scenarios(pool)
+    orc.upload_scenarios(pool)
+    ids = (np.arange(n) % pool.n).astype(np.int32)
+    oc, oo = cuda.reset(scenario_ids=ids), orc.reset(scenario_ids=ids)
+    rng = np.random.RandomState(4)
+    bounds = gc.action_bounds()
+    bad, total, seen = 0, 0, 0
+    for t in range(steps):
+        assert oc.radar.shape == (n, gc.c.radar_sectors)
+        bad += _radar_outliers(oc.radar, oo.radar)
+        total += oc.radar.size
+        seen += int((oo.radar > 0).sum())
+        a = rng.uniform(bounds[0], bounds[1], size=(n, 2)).astype(np.float32)
+        a[: n // 2, 0], a[: n // 2, 1] = bounds[1][0], 0.0
+        oc, oo = cuda.step(a), orc.step(a)
+        assert np.array_equal(oc.done, oo.done) and np.array_equal(oc.status, oo.status)
+    assert seen > 1000, "the radar never saw the trail: the test is vacuous"
+    assert bad <= max(4, 2e-5 * total), "%d of %d radar sectors outside tolerance" % (bad, total)
+
+
+@pytest.mark.gpu
+def test_gym_surface_returns_the_radar_like_the_reference():
+    from continiousenvironment_follower_leader_b200 import gym_surface as gs
+    d, meta = parity.load_trace(parity.GOLDEN_DIR + "/radar_old_seed17.npz")
+    env = gs.make("Test-Cont-Env-Auto-v0", **meta["kwargs"])
+    obs = env.reset(scenario=_scenario_of(d))
+    assert _radar_outliers(obs["LeaderTrackDetector_radar"], d["t_radar"][0]) == 0
+    bad = 0
+    for t, a in enumerate(d["actions"][:150]):
+        obs, reward, done, info = env.step(a)
+        assert obs["LeaderTrackDetector_radar"].shape == (12,)
+        bad += _radar_outliers(obs["LeaderTrackDetector_radar"], d["t_radar"][t + 1])
+    assert bad <= 1

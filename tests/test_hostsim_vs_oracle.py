@@ -24,6 +24,11 @@ CASES = [
     ("rays_120_f1", dict(bear_number=1, frames_per_step=2, follower_sensors=cfg3_sensors(20, 120, 8)), 24, 60),
     # sensors without history, FollowerInfo, LeaderTrackDetector_vector (kwargs of the golden trace)
     ("flat_sensors", dict(FLAT_SENSOR_KWARGS, auto_reset=True, max_steps=300), 48, 80),
+    # LeaderTrackDetector_radar in its three modes (SEN:394-461)
+    ("radar_old", dict(parity.load_trace(parity.GOLDEN_DIR + "/radar_old_seed17.npz")[1]["kwargs"], auto_reset=True,
+                       max_steps=300), 48, 70),
+    ("radar_new", dict(parity.load_trace(parity.GOLDEN_DIR + "/radar_new_seed19.npz")[1]["kwargs"]), 32, 60),
+    ("radar_near", dict(parity.load_trace(parity.GOLDEN_DIR + "/radar_near_seed21.npz")[1]["kwargs"]), 32, 60),
 ]
 
 
@@ -60,6 +65,8 @@ def test_hostsim_matches_oracle(name, kwargs, n, steps):
             assert np.array_equal(os_.follower_info, oo.follower_info)
         if os_.track_vectors is not None:
             assert np.array_equal(os_.track_vectors, oo.track_vectors)
+        if os_.radar is not None:
+            assert np.array_equal(os_.radar, oo.radar), "radar differs at step %d" % t
         _compare_states(sim.get_state(), orc.get_state(), gc, n, 0.0)
     assert bad == 0, "%d of %d ray values outside tolerance" % (bad, total)
     assert int(sim.get_state().env["overflow"].max()) == 0
