@@ -26,16 +26,34 @@ using namespace ftl;
 // =================================================================================================
 // kernels
 // =================================================================================================
+#ifndef FTL_NO_PDL
+#define FTL_NO_PDL 0   // 1: plain stream order between k_step and k_rays
+#endif
 #ifndef FTL_RAYS_MINB
 #define FTL_RAYS_MINB 7   // shared memory (7.2 KB per warp) allows 7 blocks per SM anyway: 72 registers, no spills
 #endif
 __global__ void __launch_bounds__(128, FTL_RAYS_MINB)
 k_rays(const __grid_constant__ DevCfg cfg, const DevState s, const DevPool pool, const double2* __restrict__ rot,
-       float* __restrict__ rays_out, int smem_per_warp, int first_env, int end_env) {
+       float* __restrict__ rays_out, int smem_per_warp, int first_env, int end_env, int wait_seq) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5;
     const int i = first_env + blockIdx.x * (blockDim.x >> 5) + warp;  // one warp per env
     if (i >= end_env) return;
+    if (wait_seq) {
+        // launched as a programmatic dependent of k_step (see there): wait until the warp of k_step that owns this
+        // env's group of 32 has published step `wait_seq`.  Bounded: a flag that never arrives is a bug, not a hang.
+        if ((threadIdx.x & 31) == 0) {
+            const int* flag = s.step_flag + (i >> 5);
+            int seen, spins = 0;
+            for (;;) {
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+                if (seen == wait_seq) break;
+                __nanosleep(200);
+                if (++spins > (1 << 24)) __trap();
+            }
+        }
+        __syncwarp();
+    }
     RayShared& sh = *reinterpret_cast<RayShared*>(smem + (size_t)warp * smem_per_warp);
     rays_warp(cfg, s, pool, rot, i, sh, rays_out);
 }
@@ -102,6 +120,7 @@ struct FtlHandle_ {
     FtlEnvState* d_state_stage = nullptr;
     int state_stage_cap = 0;
     int64_t launches = 0;
+    int step_seq = 0;          // sequence number of the last k_step launch (step_flag protocol)
     int rays_total = 0;
     bool rays_smem_opted = false;
     double2* d_rot = nullptr;   // (cos, sin)(k * 360/R) per flat ray
@@ -189,6 +208,7 @@ static cudaError_t alloc_state(FtlHandle_* h, DevState& s, const FtlConfig& c, s
     ok(dalloc(h, &s.snap_rect, (size_t)FTL_MAX_HIST * (1 + nb) * n, list));
     ok(dalloc(h, &s.unc_rec, n * kUncPerEnv, list));
     ok(dalloc(h, &s.unc_count, n, list));
+    ok(dalloc(h, &s.step_flag, n / 32 + 1, list));
     return e;
 }
 
@@ -263,7 +283,7 @@ static int launch_optional_sensors(ftl_handle h, const DevOutputs& o, cudaStream
     return FTL_OK;
 }
 
-static int launch_rays(ftl_handle h, float* rays, cudaStream_t st, int first_env = 0, int end_env = -1) {
+static int launch_rays(ftl_handle h, float* rays, cudaStream_t st, int first_env = 0, int end_env = -1, int wait_seq = 0) {
     if (!rays || h->rays_total == 0) return FTL_OK;
     if (end_env < 0) end_env = h->n;
     if (end_env <= first_env) return FTL_OK;
@@ -275,7 +295,19 @@ static int launch_rays(ftl_handle h, float* rays, cudaStream_t st, int first_env
         h->rays_smem_opted = true;
     }
     int blocks = (end_env - first_env + warps - 1) / warps;
-    k_rays<<<blocks, threads, smem, st>>>(h->cfg, h->st, h->pool, h->d_rot, rays, per_warp, first_env, end_env);
+    if (wait_seq) {
+        // programmatic dependent launch behind k_step: the blocks start while k_step's last warps are still running
+        cudaLaunchConfig_t lc{};
+        lc.gridDim = dim3(blocks); lc.blockDim = dim3(threads); lc.dynamicSmemBytes = smem; lc.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = at; lc.numAttrs = 1;
+        const double2* rot = h->d_rot;
+        CUDA_TRY(cudaLaunchKernelEx(&lc, k_rays, h->cfg, h->st, h->pool, rot, rays, per_warp, first_env, end_env, wait_seq));
+    } else {
+        k_rays<<<blocks, threads, smem, st>>>(h->cfg, h->st, h->pool, h->d_rot, rays, per_warp, first_env, end_env, 0);
+    }
     k_rays_exact<<<(end_env - first_env + 127) / 128, 128, 0, st>>>(h->cfg, h->st, h->pool, rays, first_env, end_env);
     h->launches += 2;
     CUDA_TRY(cudaGetLastError());
@@ -548,19 +580,25 @@ int ftl_step(ftl_handle h, const void* actions_dev, const FtlOutputs* out_dev, v
     cudaStream_t st = (cudaStream_t)cuda_stream;
     DevOutputs o = to_dev_outputs(out_dev, h->n);
     if (h->profiling) prof_event(h, st);
+    const int seq = h->step_seq = (h->step_seq % 0x3fffffff) + 1;   // never 0
     switch (h->cfg.c.n_bears) {
-        case 0: ftl_launch_step_nb0(h->cfg, h->st, h->pool, h->image, actions_dev, o, h->d_stats, st); break;
-        case 1: ftl_launch_step_nb1(h->cfg, h->st, h->pool, h->image, actions_dev, o, h->d_stats, st); break;
-        case 2: ftl_launch_step_nb2(h->cfg, h->st, h->pool, h->image, actions_dev, o, h->d_stats, st); break;
-        case 3: ftl_launch_step_nb3(h->cfg, h->st, h->pool, h->image, actions_dev, o, h->d_stats, st); break;
-        default: ftl_launch_step_nb4(h->cfg, h->st, h->pool, h->image, actions_dev, o, h->d_stats, st); break;
+        case 0: ftl_launch_step_nb0(h->cfg, h->st, h->pool, h->image, actions_dev, o, h->d_stats, seq, st); break;
+        case 1: ftl_launch_step_nb1(h->cfg, h->st, h->pool, h->image, actions_dev, o, h->d_stats, seq, st); break;
+        case 2: ftl_launch_step_nb2(h->cfg, h->st, h->pool, h->image, actions_dev, o, h->d_stats, seq, st); break;
+        case 3: ftl_launch_step_nb3(h->cfg, h->st, h->pool, h->image, actions_dev, o, h->d_stats, seq, st); break;
+        default: ftl_launch_step_nb4(h->cfg, h->st, h->pool, h->image, actions_dev, o, h->d_stats, seq, st); break;
     }
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     int rc = launch_optional_sensors(h, o, st);
     if (rc) return rc;
+    // The ray kernel overlaps the tail of k_step (programmatic dependent launch + per-group flags) unless something
+    // was launched in between or per-kernel timing is on.
+    const bool overlap = !h->profiling && !FTL_NO_PDL &&
+                         !(o.follower_info || (o.track_vectors && h->cfg.c.track_vector_len > 0) ||
+                           (o.radar && h->cfg.c.radar_sectors > 0));
     if (h->profiling) prof_event(h, st);
-    rc = launch_rays(h, o.rays, st);
+    rc = launch_rays(h, o.rays, st, 0, -1, overlap ? seq : 0);
     if (h->profiling) prof_event(h, st);
     return rc;
 }

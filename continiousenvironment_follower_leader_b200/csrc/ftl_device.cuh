@@ -96,6 +96,7 @@ struct DevState {
     int4* snap_rect;   // [FTL_MAX_HIST][1+n_bears][n]
     UncRec* unc_rec;   // [n][kUncPerEnv]  scratch of the ray pass
     int* unc_count;    // [n]
+    int* step_flag;    // [n / 32]  sequence number of the last step whose state the owning warp of k_step has published
 };
 
 struct DevPool {  // scenario pool in device (or host, for hostsim) memory

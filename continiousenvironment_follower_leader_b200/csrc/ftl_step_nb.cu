@@ -87,7 +87,12 @@ template <int NB>
 __global__ void __launch_bounds__(FTL_STEP_THREADS, FTL_STEP_MINBLOCKS)
 k_step(const __grid_constant__ DevCfg cfg, const __grid_constant__ DevState s, const __grid_constant__ DevPool pool,
        const __grid_constant__ DevState img, const void* __restrict__ actions, const __grid_constant__ DevOutputs out,
-       double* __restrict__ stats) {
+       double* __restrict__ stats, int seq) {
+    // The ray kernel is launched as a programmatic dependent of this one: its blocks may start as soon as every block
+    // of this grid is running, take the SM resources that finished blocks free, and wait per env group on step_flag.
+    // This kernel is one wave whose end is set by its slowest warps (exact green-zone scans, resets); the ray kernel
+    // fills that tail.
+    asm volatile("griddepcontrol.launch_dependents;");
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= s.n) return;
     World<NB> w;
@@ -129,6 +134,10 @@ k_step(const __grid_constant__ DevCfg cfg, const __grid_constant__ DevState s, c
         reset_rows_from_image(cfg.c, s, img, __shfl_sync(0xffffffffu, i, src), __shfl_sync(0xffffffffu, scen, src),
                               __shfl_sync(0xffffffffu, e.trail_len, src), __shfl_sync(0xffffffffu, ring_head, src), lane);
     }
+    // publish: every lane's stores, then the warp's flag (release); k_rays acquires it before reading this group's state
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(s.step_flag + (i >> 5)), "r"(seq) : "memory");
 }
 
 template <int NB>
@@ -154,14 +163,15 @@ k_reset(const __grid_constant__ DevCfg cfg, const DevState s, const DevPool pool
 #define FTL_CAT(a, b) FTL_CAT2(a, b)
 
 void FTL_CAT(ftl_launch_step_nb, FTL_NB)(const DevCfg& cfg, const DevState& s, const DevPool& pool, const DevState& img,
-                                          const void* actions, const DevOutputs& out, double* stats, cudaStream_t st) {
+                                          const void* actions, const DevOutputs& out, double* stats, int seq,
+                                          cudaStream_t st) {
 #ifdef FTL_STEP_LAUNCH_THREADS
     int threads = FTL_STEP_LAUNCH_THREADS;
 #else
     int threads = FTL_STEP_THREADS;
 #endif
     int blocks = (s.n + threads - 1) / threads;
-    k_step<FTL_NB><<<blocks, threads, 0, st>>>(cfg, s, pool, img, actions, out, stats);
+    k_step<FTL_NB><<<blocks, threads, 0, st>>>(cfg, s, pool, img, actions, out, stats, seq);
 }
 void FTL_CAT(ftl_launch_reset_nb, FTL_NB)(const DevCfg& cfg, const DevState& s, const DevPool& pool, const uint8_t* mask,
                                            const int* ids, const DevOutputs& out, int reset_filler, cudaStream_t st) {
