@@ -157,6 +157,7 @@ struct DevCfg {
     float static_inflate[2];     // pre-filter margin for follower / leader static collisions
     // where sensor s writes inside an env's block of `rays`: cell (row j, column q) = base + j * stride + q
     int ray_out_base[FTL_MAX_RAY_SENSORS], ray_out_stride[FTL_MAX_RAY_SENSORS];
+    int ray_out_vec4;            // every lasers_count is a multiple of 4 and the layout is the raw one: rows leave as float4
 };
 
 // ---- tiny helpers -----------------------------------------------------------------------------------

@@ -120,6 +120,9 @@ inline void ray_out_layout(DevCfg& d) {
         col += w;
         off += w * c.ray[s].max_prev_obs;
     }
+    d.ray_out_vec4 = c.n_ray_sensors > 0 && !c.fused_sensor_prev;
+    for (int s = 0; s < c.n_ray_sensors; s++)
+        if (c.ray[s].pad_sectors || c.ray[s].lasers_count % 4 != 0) d.ray_out_vec4 = 0;
 }
 
 FTL_HD int total_rays(const FtlConfig& c) {
@@ -199,7 +202,7 @@ struct RaySensorTab {
     double cs0, sn0;               // cos/sin of the direction of ray 0
 };
 
-struct RayShared {
+struct alignas(16) RayShared {   // 16-byte multiple: the arrays behind it are read as int4 for the float4 row output
     float px, py;
     double dir;                                    // follower heading (float64, for the exact fallback)
     int scenario, snap_pushes, n_valid, ne, np, rt, ns, hmax;
@@ -600,6 +603,38 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
 #ifndef FTL_NO_FUSED
         if (c.fused_sensor_prev) {
             ray_rows_write_fused(cfg, sh, ra, i, lane, rays_out);
+        } else
+#endif
+#ifndef FTL_NO_VEC4_OUT
+        if (cfg.ray_out_vec4 && (((size_t)rays_out) & 15) == 0) {
+            // four consecutive rays of one row per lane: two 16-byte shared loads, one 16-byte store
+            int off = 0;
+            for (int sidx = 0; sidx < ns; sidx++) {
+                const FtlRaySensorConfig& sc = c.ray[sidx];
+                const int R = sc.lasers_count, H = sc.max_prev_obs, base = sh.sen[sidx].base, Q = R >> 2;
+                const float L = (float)sc.laser_length;
+                float* dst = rays_out + (size_t)i * cfg.rays_per_env + off;
+                const float inv_Q = 1.0f / (float)Q;
+                const int* srow = ra.res + ra.hmax * rt + base;
+                for (int e = lane; e < H * Q; e += 32) {
+                    const int j = (int)(((float)e + 0.5f) * inv_Q);   // e / Q without an integer division
+                    const int k = (e - j * Q) << 2;
+                    const int age = H - 1 - j;
+                    float4 v = make_float4(L, L, L, L);
+                    if (age < n_valid) {
+                        const int4 a = *reinterpret_cast<const int4*>(ra.res + age * rt + base + k);
+                        const int4 sb = *reinterpret_cast<const int4*>(srow + k);
+                        const int b0 = sb.x < a.x ? sb.x : a.x, b1 = sb.y < a.y ? sb.y : a.y;
+                        const int b2 = sb.z < a.z ? sb.z : a.z, b3 = sb.w < a.w ? sb.w : a.w;
+                        if (b0 != kNoHitBits) v.x = i2f_bits(b0);
+                        if (b1 != kNoHitBits) v.y = i2f_bits(b1);
+                        if (b2 != kNoHitBits) v.z = i2f_bits(b2);
+                        if (b3 != kNoHitBits) v.w = i2f_bits(b3);
+                    }
+                    *reinterpret_cast<float4*>(dst + j * R + k) = v;
+                }
+                off += H * R;
+            }
         } else
 #endif
         {

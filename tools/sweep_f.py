@@ -49,12 +49,12 @@ if __name__ == "__main__":
     print("== frames_per_step sweep, 32768 envs, cfg3 sensors")
     for F in (2, 3, 5, 8, 10):
         a, b = run(32768, F, ref_pool=True)
-        print("F=%2d  k_step %.4f ms  k_rays %.4f ms  -> %.1f M env-steps/s" % (F, a, b, 32768 / (a + b) / 1e3), flush=True)
+        print("F=%2d  k_step %.4f ms  k_rays %.4f ms  step %.4f ms -> %.1f M env-steps/s" % (F, a, b, run.last_total_ms, 32768 / run.last_total_ms / 1e3), flush=True)
     print("== obstacle-sensor ray-count sweep, 32768 envs, F=10")
     for R in (12, 24, 36, 72, 120, 180, 360):
         a, b = run(32768, 10, rays=(12, R), ref_pool=True)
-        print("R=%3d  k_step %.4f ms  k_rays %.4f ms  -> %.1f M env-steps/s" % (R, a, b, 32768 / (a + b) / 1e3), flush=True)
+        print("R=%3d  k_step %.4f ms  k_rays %.4f ms  step %.4f ms -> %.1f M env-steps/s" % (R, a, b, run.last_total_ms, 32768 / run.last_total_ms / 1e3), flush=True)
     print("== env-count sweep, F=10, cfg3")
     for n in (4096, 16384, 65536, 131072, 262144):
         a, b = run(n, 10, ref_pool=True)
-        print("N=%6d  k_step %.4f ms  k_rays %.4f ms  -> %.1f M env-steps/s" % (n, a, b, n / (a + b) / 1e3), flush=True)
+        print("N=%6d  k_step %.4f ms  k_rays %.4f ms  step %.4f ms -> %.1f M env-steps/s" % (n, a, b, run.last_total_ms, n / run.last_total_ms / 1e3), flush=True)
