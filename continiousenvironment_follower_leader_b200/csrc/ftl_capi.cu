@@ -29,12 +29,18 @@ using namespace ftl;
 #ifndef FTL_NO_PDL
 #define FTL_NO_PDL 0   // 1: plain stream order between k_step and k_rays
 #endif
+#ifndef FTL_EXACT_PDL
+#define FTL_EXACT_PDL 1   // k_rays_exact as a programmatic dependent launch of k_rays (hides its launch latency)
+#endif
 #ifndef FTL_RAYS_MINB
 #define FTL_RAYS_MINB 7   // shared memory (7.2 KB per warp) allows 7 blocks per SM anyway: 72 registers, no spills
 #endif
 __global__ void __launch_bounds__(128, FTL_RAYS_MINB)
 k_rays(const __grid_constant__ DevCfg cfg, const DevState s, const DevPool pool, const double2* __restrict__ rot,
        float* __restrict__ rays_out, int smem_per_warp, int first_env, int end_env, int wait_seq) {
+#if FTL_EXACT_PDL
+    asm volatile("griddepcontrol.launch_dependents;");   // k_rays_exact may be scheduled behind the last wave of this grid
+#endif
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5;
     const int i = first_env + blockIdx.x * (blockDim.x >> 5) + warp;  // one warp per env
@@ -61,6 +67,9 @@ k_rays(const __grid_constant__ DevCfg cfg, const DevState s, const DevPool pool,
 __global__ void __launch_bounds__(128)
 k_rays_exact(const __grid_constant__ DevCfg cfg, const DevState s, const DevPool pool, float* __restrict__ rays_out,
              int first_env, int end_env) {
+#if FTL_EXACT_PDL
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // launched early (programmatic dependent of k_rays): wait for all of it
+#endif
     const int i = first_env + blockIdx.x * blockDim.x + threadIdx.x;   // one thread per env, idle unless a pair was inconclusive
     if (i >= end_env) return;
     rays_exact_env(cfg, s, pool, i, rays_out);
@@ -243,6 +252,11 @@ static int validate(const FtlConfig* c, int n_envs) {
         if (r.react_to_obstacles < 0 || r.react_to_obstacles > 3)
             return fail(FTL_ERR_INVALID, "react_to_obstacles must be True/'all'/'static'/'dynamic'/False (SEN:650-661)");
     }
+    {
+        int total = 0;
+        for (int s = 0; s < c->n_ray_sensors; s++) total += c->ray[s].lasers_count;
+        if (total >= kMaxTotalRays) return fail(FTL_ERR_INVALID, "more than 4095 rays over all sensors");
+    }
     if (c->track_vector_len < 0 || (c->track_vector_len > 0 && !c->tracker_enabled))
         return fail(FTL_ERR_INVALID, "LeaderTrackDetector_vector needs LeaderPositionsTracker_v2 (CLS:240-244)");
     if (c->radar_sectors < 0 || (c->radar_sectors > 0 && (!c->tracker_enabled || c->radar_len < 1 || c->radar_mode < 0 || c->radar_mode > 2)))
@@ -308,7 +322,19 @@ static int launch_rays(ftl_handle h, float* rays, cudaStream_t st, int first_env
     } else {
         k_rays<<<blocks, threads, smem, st>>>(h->cfg, h->st, h->pool, h->d_rot, rays, per_warp, first_env, end_env, 0);
     }
+#if FTL_EXACT_PDL
+    {   // its blocks are scheduled while the last ray blocks run; griddepcontrol.wait at its top keeps the order
+        cudaLaunchConfig_t lc{};
+        lc.gridDim = dim3((end_env - first_env + 127) / 128); lc.blockDim = dim3(128); lc.dynamicSmemBytes = 0; lc.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = at; lc.numAttrs = 1;
+        CUDA_TRY(cudaLaunchKernelEx(&lc, k_rays_exact, h->cfg, h->st, h->pool, rays, first_env, end_env));
+    }
+#else
     k_rays_exact<<<(end_env - first_env + 127) / 128, 128, 0, st>>>(h->cfg, h->st, h->pool, rays, first_env, end_env);
+#endif
     h->launches += 2;
     CUDA_TRY(cudaGetLastError());
     return FTL_OK;

@@ -187,6 +187,10 @@ constexpr int kPairCap = FTL_PAIR_CAP;  // (edge, ray) pairs per flush
 constexpr int kCorridorChunk = 64;  // corridor ring entries per batch (2 edges each)
 constexpr int kStaticBit = 8;       // row-mask bit of the static minimum (merged into all valid rows)
 constexpr int kNoHitBits = 0x7f7fffff;
+// a pair word: flat ray (12 bits), edge slot (8 bits), rows of the ray's sensor that the edge belongs to (9 bits)
+constexpr int kPairEdgeShift = 12, kPairRowsShift = 20;
+static_assert(kEdgeCap <= (1 << (kPairRowsShift - kPairEdgeShift)), "edge slot does not fit the pair word");
+constexpr int kMaxTotalRays = 1 << kPairEdgeShift;   // checked at ftl_create
 enum EdgeClass { EC_STATIC = 0, EC_LEADER = 1, EC_BEAR = 2, EC_CORRIDOR = 3, EC_CAP = 4, EC_COUNT = 5 };
 
 struct RayEdge { float ax, ay, bx, by; int mask; };  // mask: bits 0..8 rows (ages / static), bits 16.. class
@@ -210,7 +214,7 @@ struct alignas(16) RayShared {   // 16-byte multiple: the arrays behind it are r
     int tail[FTL_MAX_HIST], head[FTL_MAX_HIST];    // by age (0 = newest)
     RaySensorTab sen[FTL_MAX_RAY_SENSORS];
     RayEdge e[kEdgeCap];
-    int pair[kPairCap];                            // edge << 16 | flat ray
+    int pair[kPairCap];                            // rows << 20 | edge << 12 | flat ray
     int nu;                                        // (edge, ray) pairs of this env whose float32 predicates were inconclusive
     UncRec* unc;                                   // this env's slice of DevState.unc_rec
     // arrays of length rays_total behind the struct: dx, dy, len (float), res[hmax + 1] (int): one row of minima per
@@ -360,14 +364,6 @@ FTL_HD void seg_append(RayShared& sh, float ax, float ay, float bx, float by, in
     edge_append(sh, ax, ay, bx, by, rows | (1 << (16 + cls)));
 }
 
-FTL_HD int pair_rows(const RayShared& sh, int ei, int f, int n_sensors) {
-    int rows = sh.e[ei].mask & 0x1ff;
-    int sidx = 0;
-    while (sidx + 1 < n_sensors && f >= sh.sen[sidx + 1].base) sidx++;
-    if (!(rows & (1 << kStaticBit))) rows &= (1 << sh.sen[sidx].H) - 1;   // the row restriction of the ray's sensor
-    return rows;
-}
-
 // A2 + B over the current edge list, then empty it.  One out-of-line copy for the five places that may flush: the
 // kernel is bound by instruction fetch as much as by issue slots, and warps in different flushes share these lines.
 #ifdef FTL_INLINE_FLUSH
@@ -414,9 +410,10 @@ FTL_HD_NOINLINE void ray_flush(RayShared& sh, int n_sensors) {
                 int kk = klo;                                  // klo mod R; |klo| < 3R (bearings and theta0 are bounded)
                 while (kk < 0) kk += st.R;
                 while (kk >= st.R) kk -= st.R;
+                const int packed = (rows << kPairRowsShift) | (ei << kPairEdgeShift);
                 for (int k = 0; k < cnt; k++, kk = (kk + 1 == st.R) ? 0 : kk + 1) {
                     if (slot + k < kPairCap)
-                        sh.pair[slot + k] = (ei << 16) | (st.base + kk);
+                        sh.pair[slot + k] = packed | (st.base + kk);
                     else
                         edge_ray_test(sh, ra, st.base + kk, rows, ed.ax, ed.ay, ed.bx, ed.by);   // list full: in place
                 }
@@ -428,9 +425,10 @@ FTL_HD_NOINLINE void ray_flush(RayShared& sh, int n_sensors) {
     const int np = sh.np < kPairCap ? sh.np : kPairCap;
     FTL_LANES(lane) {
         for (int t = lane; t < np; t += 32) {
-            int pr = sh.pair[t], ei = pr >> 16, f = pr & 0xffff;
+            const int pr = sh.pair[t], ei = (pr >> kPairEdgeShift) & ((1 << (kPairRowsShift - kPairEdgeShift)) - 1);
+            const int f = pr & ((1 << kPairEdgeShift) - 1), rows = pr >> kPairRowsShift;
             const RayEdge ed = sh.e[ei];
-            edge_ray_test(sh, ra, f, pair_rows(sh, ei, f, n_sensors), ed.ax, ed.ay, ed.bx, ed.by);
+            edge_ray_test(sh, ra, f, rows, ed.ax, ed.ay, ed.bx, ed.by);
         }
     }
     FTL_WARP_SYNC();
