@@ -32,10 +32,13 @@ using namespace ftl;
 #ifndef FTL_EXACT_PDL
 #define FTL_EXACT_PDL 1   // k_rays_exact as a programmatic dependent launch of k_rays (hides its launch latency)
 #endif
+#ifndef FTL_RAYS_WARPS
+#define FTL_RAYS_WARPS 2   // envs per block.  A block lives as long as its slowest env: 2-warp blocks measured 2.3 % faster
+#endif                     // than 4-warp ones (and they fit sooner into what a finished k_step block frees, section 4.5)
 #ifndef FTL_RAYS_MINB
-#define FTL_RAYS_MINB 7   // shared memory (7.2 KB per warp) allows 7 blocks per SM anyway: 72 registers, no spills
+#define FTL_RAYS_MINB (28 / FTL_RAYS_WARPS)   // 28 warps per SM: 72 registers, no spills; shared memory (7.2 KB per warp) allows no more
 #endif
-__global__ void __launch_bounds__(128, FTL_RAYS_MINB)
+__global__ void __launch_bounds__(32 * FTL_RAYS_WARPS, FTL_RAYS_MINB)
 k_rays(const __grid_constant__ DevCfg cfg, const DevState s, const DevPool pool, const double2* __restrict__ rot,
        float* __restrict__ rays_out, int smem_per_warp, int first_env, int end_env, int wait_seq) {
 #if FTL_EXACT_PDL
@@ -301,7 +304,7 @@ static int launch_rays(ftl_handle h, float* rays, cudaStream_t st, int first_env
     if (!rays || h->rays_total == 0) return FTL_OK;
     if (end_env < 0) end_env = h->n;
     if (end_env <= first_env) return FTL_OK;
-    const int warps = 4, threads = warps * 32;
+    const int warps = FTL_RAYS_WARPS, threads = warps * 32;
     const int per_warp = (int)((ray_shared_bytes(h->rays_total, h->cfg.ray_hmax) + 15) & ~(size_t)15);
     const int smem = per_warp * warps;
     if (smem > 48 * 1024 && !h->rays_smem_opted) {
