@@ -98,6 +98,9 @@ FTL_HD int2 route_point(const DevPool& pool, const FtlConfig& c, int scenario, i
     return pool.route[(size_t)scenario * c.route_cap + k];
 }
 
+constexpr int kFrameChunk = 10;   // frames per pass (frames_per_step = 10 in one go)
+enum { REC_FOLLOWER_HIT = 1, REC_TOO_CLOSE = 2, REC_LEADER_HIT = 4, REC_LEADER_FINISHED = 8 };
+
 template <int NB>
 struct World {  // registers of one env during a step
     Robot follower, leader;
@@ -354,119 +357,152 @@ FTL_HD void env_step(const DevCfg& cfg, const DevState& s, const DevPool& pool, 
                            cfg.static_inflate[0], make_float2(w.leader.px, w.leader.py), cfg.static_inflate[1], &fmask,
                            &lmask);
 
-    for (int f = 0; f < c.frames_per_step; f++) {
-        FTL_FRAME_SYNC(f);
-        int mission = FTL_MISSION_IN_PROGRESS, agent = FTL_AGENT_MOVING, leader_st = FTL_LEADER_MOVING;
-        // (1) follower, ENV:957-964
-        w.follower = robot_move_nv(w.follower, &c.follower);
-        if (!c.ignore_follower_collisions) {
-            bool hit = robots_collide(w.follower, w.leader) || collide_static_masked(w.follower, statics, fmask) ||
-                       out_of_bounds(c, w.follower);
+    // The frames run in two passes over chunks of kFrameChunk frames.  Pass 1 is the kinematics: nothing in it depends on
+    // the green-zone flags, the reward or the counters (the reference's simulation goes on after a crash), so it only
+    // records, per frame, the two positions and four bits the bookkeeping needs.  Pass 2 replays the bookkeeping in
+    // order (ENV:960-1139).  The split keeps the robot code and the green-zone code out of each other's instruction
+    // footprint and gives pass 2 all follower positions of the chunk at once (batched exact scans).
+    float2 rec_f[kFrameChunk], rec_l[kFrameChunk];
+    unsigned char rec_bits[kFrameChunk];
+    bool lfin = (e.flags & FL_LEADER_FINISHED) != 0;
+    for (int f0 = 0; f0 < c.frames_per_step; f0 += kFrameChunk) {
+        const int nf = c.frames_per_step - f0 < kFrameChunk ? c.frames_per_step - f0 : kFrameChunk;
+        const int sc_base = e.step_count;
+        // ---- pass 1: robots -------------------------------------------------------------------------------------
+        for (int j = 0; j < nf; j++) {
+            FTL_FRAME_SYNC(f0 + j);
+            int bits = 0;
+            // (1) follower, ENV:957-964
+            w.follower = robot_move_nv(w.follower, &c.follower);
+            if (!c.ignore_follower_collisions) {
+                bool hit = robots_collide(w.follower, w.leader) || collide_static_masked(w.follower, statics, fmask) ||
+                           out_of_bounds(c, w.follower);
 #pragma unroll
-            for (int b = 0; b < NB; b++) hit = hit || robots_collide(w.follower, w.bear[b]);
-            if (hit) {
+                for (int b = 0; b < NB; b++) hit = hit || robots_collide(w.follower, w.bear[b]);
+                if (hit) bits |= REC_FOLLOWER_HIT;
+            }
+            // too_close uses the leader before its move, ENV:973
+            if (d2_f32(w.leader.px, w.leader.py, w.follower.px, w.follower.py) <= cfg.min_dist2_f32) bits |= REC_TOO_CLOSE;
+            // (3) waypoint advance, ENV:978-983
+            if (dist_f64_nv((double)w.leader.px, (double)w.leader.py, (double)target.x, (double)target.y) <
+                c.leader_pos_epsilon) {
+                e.cur_target_id += 1;
+                if (e.cur_target_id >= n_route) lfin = true;   // cur_target_point keeps its last value
+                else target = route_point(pool, c, e.scenario, e.cur_target_id);
+            }
+            // (4) bears, ENV:987-995
+#pragma unroll
+            for (int b = 0; b < NB; b++) {
+                bear_target(c, b, w.bear[b], w.leader, &w.btx[b], &w.bty[b], &w.bidx[b]);
+                w.bear[b] = move_to_the_point_nv(w.bear[b], &c.bear, w.btx[b], w.bty[b], 0, 0.0);
+            }
+            // (5) leader, ENV:1048-1072
+            if (!lfin) {
+                e.step_count = sc_base + j;   // the regimes are keyed by the frame counter
+                double speed = c.n_speed_regime > 0 ? leader_speed(cfg, e, i) : c.leader.max_speed;
+                double accel = c.n_accel_regime > 0 ? leader_accel(cfg, e) / c.frames_per_step : 0.0;
+                w.leader = move_to_the_point_nv(w.leader, &c.leader, (double)target.x, (double)target.y, 1, speed + accel);
+            } else {
+                command_forward(w.leader, c.leader, 0);
+                command_turn(w.leader, c.leader, 0, 0);
+                bits |= REC_LEADER_FINISHED;
+            }
+            if (robots_collide(w.leader, w.follower) || collide_static_masked(w.leader, statics, lmask) ||
+                out_of_bounds(c, w.leader))
+                bits |= REC_LEADER_HIT;
+            rec_f[j] = make_float2(w.follower.px, w.follower.py);
+            rec_l[j] = make_float2(w.leader.px, w.leader.py);
+            rec_bits[j] = (unsigned char)bits;
+        }
+        e.step_count = sc_base;
+        // ---- pass 2: flags, trail, timers, reward ------------------------------------------------------------------
+        for (int j = 0; j < nf; j++) {
+            const int bits = rec_bits[j];
+            const float2 fp = rec_f[j], lp = rec_l[j];
+            int mission = FTL_MISSION_IN_PROGRESS, agent = FTL_AGENT_MOVING, leader_st = FTL_LEADER_MOVING;
+            if (bits & REC_FOLLOWER_HIT) {   // ENV:960-964
                 e.flags |= FL_CRASH | FL_DONE;
                 mission = FTL_MISSION_FAIL;
                 agent = FTL_AGENT_CRASH;
             }
-        }
-        // (2) green zone + flags, ENV:966-973
-        bool in_box, on_trace;
-        green_flags(cfg, trail, trail_d, e.trail_len, w.follower.px, w.follower.py, gc, &in_box, &on_trace);
-        bool too_close = d2_f32(w.leader.px, w.leader.py, w.follower.px, w.follower.py) <= cfg.min_dist2_f32;
-        // (3) waypoint advance, ENV:978-983
-        if (dist_f64_nv((double)w.leader.px, (double)w.leader.py, (double)target.x, (double)target.y) <
-            c.leader_pos_epsilon) {
-            e.cur_target_id += 1;
-            if (e.cur_target_id >= n_route) e.flags |= FL_LEADER_FINISHED;   // cur_target_point keeps its last value
-            else target = route_point(pool, c, e.scenario, e.cur_target_id);
-        }
-        // (4) bears, ENV:987-995
-#pragma unroll
-        for (int b = 0; b < NB; b++) {
-            bear_target(c, b, w.bear[b], w.leader, &w.btx[b], &w.bty[b], &w.bidx[b]);
-            w.bear[b] = move_to_the_point_nv(w.bear[b], &c.bear, w.btx[b], w.bty[b], 0, 0.0);
-        }
-        // (5) leader, ENV:1048-1072
-        if (!(e.flags & FL_LEADER_FINISHED)) {
-            double speed = c.n_speed_regime > 0 ? leader_speed(cfg, e, i) : c.leader.max_speed;
-            double accel = c.n_accel_regime > 0 ? leader_accel(cfg, e) / c.frames_per_step : 0.0;
-            w.leader = move_to_the_point_nv(w.leader, &c.leader, (double)target.x, (double)target.y, 1, speed + accel);
-        } else {
-            command_forward(w.leader, c.leader, 0);
-            command_turn(w.leader, c.leader, 0, 0);
-            leader_st = FTL_LEADER_FINISHED;
-        }
-        if (robots_collide(w.leader, w.follower) || collide_static_masked(w.leader, statics, lmask) ||
-            out_of_bounds(c, w.leader)) {
-            e.flags |= FL_DONE;
-            mission = FTL_MISSION_FAIL;
-            leader_st = FTL_LEADER_CRASH;
-        }
-        // (6) trail append on the virtual clock, ENV:1074-1075
-        if (e.step_count % c.trajectory_saving_period == 0) {
-            if (e.trail_len < c.trail_cap) {
-                // trail_push with the previous tail in registers
-                const int k = e.trail_len;
-                const float2 p = make_float2(w.leader.px, w.leader.py), q = gc.last_pt;
-                float dk = 0.f;
-                trail[k] = p;
-                if (k > 0) {
-                    dk = sqrtf(d2_f32(p.x, p.y, q.x, q.y));   // euclidean(newer, older) in float32, ENV:1838
-                    gc.last_s = gc.last_s + (double)dk;
+            // (2) green zone + flags, ENV:966-973
+            bool in_box, on_trace;
+            green_flags(cfg, trail, trail_d, e.trail_len, fp.x, fp.y, gc, &in_box, &on_trace);
+            const bool too_close = (bits & REC_TOO_CLOSE) != 0;
+            if (bits & REC_LEADER_FINISHED) {
+                e.flags |= FL_LEADER_FINISHED;
+                leader_st = FTL_LEADER_FINISHED;
+            }
+            if (bits & REC_LEADER_HIT) {     // ENV:1068-1072
+                e.flags |= FL_DONE;
+                mission = FTL_MISSION_FAIL;
+                leader_st = FTL_LEADER_CRASH;
+            }
+            // (6) trail append on the virtual clock, ENV:1074-1075
+            if (e.step_count % c.trajectory_saving_period == 0) {
+                if (e.trail_len < c.trail_cap) {
+                    // trail_push with the previous tail in registers
+                    const int k = e.trail_len;
+                    const float2 p = lp, q = gc.last_pt;
+                    float dk = 0.f;
+                    trail[k] = p;
+                    if (k > 0) {
+                        dk = sqrtf(d2_f32(p.x, p.y, q.x, q.y));   // euclidean(newer, older) in float32, ENV:1838
+                        gc.last_s = gc.last_s + (double)dk;
+                    } else {
+                        gc.last_s = 0.0;
+                    }
+                    trail_d[k] = dk;
+                    trail_s[k] = gc.last_s;
+                    gc.last_pt = p;
+                    e.trail_len++;
+                    green_cache_appended(cfg, trail_s, e.trail_len, p, q, dk, gc);
                 } else {
-                    gc.last_s = 0.0;
-                }
-                trail_d[k] = dk;
-                trail_s[k] = gc.last_s;
-                gc.last_pt = p;
-                e.trail_len++;
-                green_cache_appended(cfg, trail_s, e.trail_len, p, q, dk, gc);
-            } else {
-                e.overflow |= 1;
-            }
-        }
-        // (7) finish timer, ENV:1077-1087
-        if ((e.flags & FL_LEADER_FINISHED) && in_box) {
-            if (e.finish_timer < 0) {
-                e.finish_timer = 0;
-            } else {
-                e.finish_timer += 1;
-                if (e.finish_timer > c.frames_per_step * 20) {
-                    mission = FTL_MISSION_SUCCESS;
-                    leader_st = FTL_LEADER_FINISHED;
-                    agent = FTL_AGENT_FINISHED;
-                    e.flags |= FL_DONE;
+                    e.overflow |= 1;
                 }
             }
-        }
-        // (8) early stopping, ENV:1088-1107
-        if (e.step_count > c.warm_start) {
-            if (c.es_has_low_reward && e.acc_penalty < c.es_low_reward) {
-                mission = FTL_MISSION_FAIL; leader_st = FTL_LEADER_MOVING; agent = FTL_AGENT_LOW_REWARD;
-                e.flags |= FL_CRASH | FL_DONE;
+            // (7) finish timer, ENV:1077-1087
+            if ((e.flags & FL_LEADER_FINISHED) && in_box) {
+                if (e.finish_timer < 0) {
+                    e.finish_timer = 0;
+                } else {
+                    e.finish_timer += 1;
+                    if (e.finish_timer > c.frames_per_step * 20) {
+                        mission = FTL_MISSION_SUCCESS;
+                        leader_st = FTL_LEADER_FINISHED;
+                        agent = FTL_AGENT_FINISHED;
+                        e.flags |= FL_DONE;
+                    }
+                }
             }
-            if (c.es_has_max_distance_coef) {
-                float d = sqrtf(d2_f32(w.follower.px, w.follower.py, w.leader.px, w.leader.py));
-                if (d > cfg.es_far_f32) {
-                    mission = FTL_MISSION_FAIL; leader_st = FTL_LEADER_MOVING; agent = FTL_AGENT_TOO_FAR;
+            // (8) early stopping, ENV:1088-1107
+            if (e.step_count > c.warm_start) {
+                if (c.es_has_low_reward && e.acc_penalty < c.es_low_reward) {
+                    mission = FTL_MISSION_FAIL; leader_st = FTL_LEADER_MOVING; agent = FTL_AGENT_LOW_REWARD;
                     e.flags |= FL_CRASH | FL_DONE;
                 }
+                if (c.es_has_max_distance_coef) {
+                    float d = sqrtf(d2_f32(fp.x, fp.y, lp.x, lp.y));
+                    if (d > cfg.es_far_f32) {
+                        mission = FTL_MISSION_FAIL; leader_st = FTL_LEADER_MOVING; agent = FTL_AGENT_TOO_FAR;
+                        e.flags |= FL_CRASH | FL_DONE;
+                    }
+                }
             }
+            // (9) reward + counters, ENV:1109-1139
+            double r = reward_of(c, e, too_close, in_box, on_trace);
+            if (r < 0) e.acc_penalty += r; else e.acc_penalty = 0;
+            e.overall += r;
+            e.step_count += 1;
+            if (e.step_count > c.max_steps) {
+                mission = FTL_MISSION_FINISHED_BY_TIME; leader_st = FTL_LEADER_MOVING; agent = FTL_AGENT_MOVING;
+                e.flags |= FL_DONE;
+            }
+            e.last_reward = c.aggregate_reward ? e.overall : r;
+            e.flags = (e.flags & (FL_DONE | FL_CRASH | FL_LEADER_FINISHED)) | (in_box ? FL_IN_BOX : 0) |
+                      (on_trace ? FL_ON_TRACE : 0) | (too_close ? FL_TOO_CLOSE : 0) | (mission << FL_MISSION_SHIFT) |
+                      (agent << FL_AGENT_SHIFT) | (leader_st << FL_LEADER_SHIFT);
         }
-        // (9) reward + counters, ENV:1109-1139
-        double r = reward_of(c, e, too_close, in_box, on_trace);
-        if (r < 0) e.acc_penalty += r; else e.acc_penalty = 0;
-        e.overall += r;
-        e.step_count += 1;
-        if (e.step_count > c.max_steps) {
-            mission = FTL_MISSION_FINISHED_BY_TIME; leader_st = FTL_LEADER_MOVING; agent = FTL_AGENT_MOVING;
-            e.flags |= FL_DONE;
-        }
-        e.last_reward = c.aggregate_reward ? e.overall : r;
-        e.flags = (e.flags & (FL_DONE | FL_CRASH | FL_LEADER_FINISHED)) | (in_box ? FL_IN_BOX : 0) |
-                  (on_trace ? FL_ON_TRACE : 0) | (too_close ? FL_TOO_CLOSE : 0) | (mission << FL_MISSION_SHIFT) |
-                  (agent << FL_AGENT_SHIFT) | (leader_st << FL_LEADER_SHIFT);
     }
     sense_serial<NB>(cfg, s, i, w, t, &snap_pushes, &e.overflow);
     cache_store(s, i, gc, t, snap_pushes);

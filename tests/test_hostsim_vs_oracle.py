@@ -22,6 +22,8 @@ CASES = [
     # BASELINE.json configs[4]: ray-count sweep up to 360 lasers (the reference only accepts 12/20/24/36, SEN:761)
     ("rays_360", dict(bear_number=2, frames_per_step=3, follower_sensors=cfg3_sensors(72, 360, 4)), 24, 40),
     ("rays_120_f1", dict(bear_number=1, frames_per_step=2, follower_sensors=cfg3_sensors(20, 120, 8)), 24, 60),
+    # more frames per step than one chunk of the two-pass frame loop (kFrameChunk = 10)
+    ("cfg3_f13", dict(bear_number=2, frames_per_step=13, follower_sensors=cfg3_sensors(), max_steps=400, auto_reset=True), 48, 50),
     # sensors without history, FollowerInfo, LeaderTrackDetector_vector (kwargs of the golden trace)
     ("flat_sensors", dict(FLAT_SENSOR_KWARGS, auto_reset=True, max_steps=300), 48, 80),
     # LeaderTrackDetector_radar in its three modes (SEN:394-461)
