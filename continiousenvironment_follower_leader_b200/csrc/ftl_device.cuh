@@ -352,8 +352,13 @@ FTL_HD void robot_move(Robot& r, const FtlRobotConfig& c) {  // CLS:129-182
         r.rx = cx - (nw >> 1);
         r.ry = cy - (nh >> 1);
     }
+#ifdef FTL_INLINE_SINCOS
+    double sn, cs;
+    sincos_deg(r.dir, &sn, &cs);
+#else
     const SinCos sc_ = sincos_deg_nv(r.dir);
     const double sn = sc_.s, cs = sc_.c;
+#endif
     float mx = (float)(cs * r.speed), my = (float)(sn * r.speed);
     r.px = r.px + mx;
     r.py = r.py + my;

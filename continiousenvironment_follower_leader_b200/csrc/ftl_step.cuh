@@ -335,11 +335,13 @@ FTL_HD void env_step(const DevCfg& cfg, const DevState& s, const DevPool& pool, 
     GreenCache gc;
     Tracker t;
     int snap_pushes;
-    cache_load(s, i, gc, t, &snap_pushes);
     float2* trail = s.trail + (size_t)i * c.trail_cap;
     float* trail_d = s.trail_d + (size_t)i * c.trail_cap;
     double* trail_s = s.trail_s + (size_t)i * c.trail_cap;
+#ifdef FTL_EARLY_GREEN_LOAD
+    cache_load(s, i, gc, t, &snap_pushes);
     green_cache_hydrate(trail, trail_s, e.trail_len, gc);
+#endif
     const int4* statics = pool.static_rects + (size_t)e.scenario * c.static_cap;
     const int n_static = pool.n_static[e.scenario];
     const int n_route = pool.n_route[e.scenario];
@@ -373,7 +375,11 @@ FTL_HD void env_step(const DevCfg& cfg, const DevState& s, const DevPool& pool, 
             FTL_FRAME_SYNC(f0 + j);
             int bits = 0;
             // (1) follower, ENV:957-964
+#ifndef FTL_OUTLINE_ROBOTS
+            robot_move(w.follower, c.follower);
+#else
             w.follower = robot_move_nv(w.follower, &c.follower);
+#endif
             if (!c.ignore_follower_collisions) {
                 bool hit = robots_collide(w.follower, w.leader) || collide_static_masked(w.follower, statics, fmask) ||
                            out_of_bounds(c, w.follower);
@@ -394,14 +400,22 @@ FTL_HD void env_step(const DevCfg& cfg, const DevState& s, const DevPool& pool, 
 #pragma unroll
             for (int b = 0; b < NB; b++) {
                 bear_target(c, b, w.bear[b], w.leader, &w.btx[b], &w.bty[b], &w.bidx[b]);
+#ifndef FTL_OUTLINE_ROBOTS
+                move_to_the_point(w.bear[b], c.bear, w.btx[b], w.bty[b], false, 0.0);
+#else
                 w.bear[b] = move_to_the_point_nv(w.bear[b], &c.bear, w.btx[b], w.bty[b], 0, 0.0);
+#endif
             }
             // (5) leader, ENV:1048-1072
             if (!lfin) {
                 e.step_count = sc_base + j;   // the regimes are keyed by the frame counter
                 double speed = c.n_speed_regime > 0 ? leader_speed(cfg, e, i) : c.leader.max_speed;
                 double accel = c.n_accel_regime > 0 ? leader_accel(cfg, e) / c.frames_per_step : 0.0;
+#ifndef FTL_OUTLINE_ROBOTS
+                move_to_the_point(w.leader, c.leader, (double)target.x, (double)target.y, true, speed + accel);
+#else
                 w.leader = move_to_the_point_nv(w.leader, &c.leader, (double)target.x, (double)target.y, 1, speed + accel);
+#endif
             } else {
                 command_forward(w.leader, c.leader, 0);
                 command_turn(w.leader, c.leader, 0, 0);
@@ -415,6 +429,12 @@ FTL_HD void env_step(const DevCfg& cfg, const DevState& s, const DevPool& pool, 
             rec_bits[j] = (unsigned char)bits;
         }
         e.step_count = sc_base;
+#ifndef FTL_EARLY_GREEN_LOAD
+        if (f0 == 0) {   // the green-zone cache is only needed from here on: not live (or spilled) during pass 1
+            cache_load(s, i, gc, t, &snap_pushes);
+            green_cache_hydrate(trail, trail_s, e.trail_len, gc);
+        }
+#endif
         // ---- pass 2: flags, trail, timers, reward ------------------------------------------------------------------
         for (int j = 0; j < nf; j++) {
             const int bits = rec_bits[j];
