@@ -278,8 +278,10 @@ FTL_HD void robot_init(Robot& r, const FtlRobotConfig& c, float x, float y, doub
 // pygame 2.1.2 transform.rotate bounding box (third party; see oracle/shims/pygame/transform.py)
 FTL_HD void rotated_size(int w, int h, double angle_py, int* ow, int* oh) {
     float angle = (float)angle_py;
-    double q = rint((double)angle / 90.0);
-    if ((double)angle == 90.0 * q) {  // fmod(angle, 90) == 0
+    // fmod(angle, 90) == 0.  q only has to be the right candidate when angle IS a multiple of 90 (|q| <= 4: the
+    // product with the rounded reciprocal is within 1e-15 of the integer), so no float64 division is needed
+    double q = rint((double)angle * (1.0 / 90.0));
+    if ((double)angle == 90.0 * q) {
         int turns = ((int)angle / 90) % 4;
         if (turns < 0) turns += 4;
         if (turns & 1) { *ow = h; *oh = w; } else { *ow = w; *oh = h; }
