@@ -458,3 +458,35 @@ def test_gym_surface_returns_the_radar_like_the_reference():
         assert obs["LeaderTrackDetector_radar"].shape == (12,)
         bad += _radar_outliers(obs["LeaderTrackDetector_radar"], d["t_radar"][t + 1])
     assert bad <= 1
+
+
+@pytest.mark.gpu
+def test_overlapped_ray_kernel_with_a_multi_wave_step_kernel():
+    """100 000 envs are more blocks of k_step than fit the GPU at once, so the programmatic dependent launch of k_rays
+     starts while later waves of k_step are still queued: every ray warp must still see the state its
+    env's step published.  A slice of the big batch run on its own (same global env ids) is the reference."""
+    import torch
+    from continiousenvironment_follower_leader_b200.batch_env import FtlBatchEnv
+    gc = GameConfig(bear_number=1, follower_sensors=cfg3_sensors(), auto_reset=True, max_steps=150)
+    pool = synthetic_pool(gc, 96, seed=3)
+    n, first, m = 100000, 61440, 2048
+
+    def run(n_envs, base):
+        env = FtlBatchEnv(n_envs, game_config=gc, scenario_pool=pool, env_id_base=base)
+        env.reset()
+        g = torch.Generator(device="cuda").manual_seed(7)
+        lo, hi = [torch.tensor(x, device="cuda") for x in gc.action_bounds()]
+        acts = lo + (hi - lo) * torch.rand((30, n, 2), generator=g, device="cuda")
+        rays, feats = [], []
+        for t in range(30):
+            obs, rew, done, info = env.step(acts[t, base:base + n_envs].contiguous())
+            rays.append(env.rays.clone())
+            feats.append(obs["numerical_features"].clone())
+        env.close()
+        return rays, feats
+
+    big_r, big_f = run(n, 0)
+    small_r, small_f = run(m, first)
+    for t in range(30):
+        assert torch.equal(big_f[t][first:first + m], small_f[t]), "state differs at step %d" % t
+        assert torch.equal(big_r[t][first:first + m], small_r[t]), "rays differ at step %d" % t
