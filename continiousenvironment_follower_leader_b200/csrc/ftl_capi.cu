@@ -1,10 +1,13 @@
 // ftl_capi.cu -- the C-ABI of include/ftl.h (libftl.so), the ray kernel and the state-exchange kernels.
 //
 // Launch structure of one ftl_step():
-//   k_step<NB>   (ftl_step_nb.cu) one thread per env: the F sub-frames fused in registers, tracker scans,
-//                history snapshot, non-ray outputs, episode statistics, optional in-place auto-reset
-//   k_rays       one thread per (env, ray): history ray casting with static/corridor de-duplication
-// Both are HBM/ALU streaming kernels without tensor-core work (ray casting is not a contraction).
+//   k_step<NB>    (ftl_step_nb.cu) one thread per env: the F sub-frames fused in registers (a kinematics pass and a
+//                 bookkeeping pass), tracker scans, history snapshot, non-ray outputs, episode statistics, optional
+//                 in-place auto-reset (a copy of the scenario's reset image)
+//   k_rays        one warp per env: history ray casting with static/corridor de-duplication; launched as a programmatic
+//                 dependent of k_step, it waits per group of 32 envs on the flag the owning warp of k_step publishes
+//   k_rays_exact  one thread per env, almost always idle: the pairs whose float32 predicates were inconclusive
+// All are HBM/ALU streaming kernels without tensor-core work (ray casting is not a contraction).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false (see build.py); fused
 // multiply-adds are written explicitly where wanted so float results match the reference's rounding.
 #include <cuda_runtime.h>
