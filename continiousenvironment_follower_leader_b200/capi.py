@@ -29,10 +29,46 @@ class FtlError(RuntimeError):
 
 _LIBS = {}
 
+_vp, _i32, _i64 = C.c_void_p, C.c_int32, C.c_int64
+# every entry point include/ftl.h declares: name -> (argtypes, restype)
+SIGNATURES = {
+    "ftl_abi_version": ([], C.c_int),
+    "ftl_last_error": ([], C.c_char_p),
+    "ftl_create": ([C.POINTER(abi.FtlConfig), _i32, _i32, _i64, C.POINTER(_vp)], C.c_int),
+    "ftl_destroy": ([_vp], C.c_int),
+    "ftl_rays_per_env": ([_vp], C.c_int),
+    "ftl_num_envs": ([_vp], C.c_int),
+    "ftl_upload_scenarios": ([_vp, C.POINTER(abi.FtlScenarioPool)], C.c_int),
+    "ftl_reset": ([_vp, _vp, _vp, C.POINTER(abi.FtlOutputs), _vp], C.c_int),
+    "ftl_step": ([_vp, _vp, C.POINTER(abi.FtlOutputs), _vp], C.c_int),
+    "ftl_reset_host": ([_vp, _vp, _vp, C.POINTER(abi.FtlOutputs), _vp], C.c_int),
+    "ftl_step_host": ([_vp, _vp, C.POINTER(abi.FtlOutputs), _vp], C.c_int),
+    "ftl_step_host_begin": ([_vp, _vp, C.POINTER(abi.FtlOutputs), _vp], C.c_int),
+    "ftl_step_host_wait": ([_vp], C.c_int),
+    "ftl_host_stream": ([_vp], _vp),
+    "ftl_get_state": ([_vp, _i32, _i32, C.POINTER(abi.FtlStateBuffers)], C.c_int),
+    "ftl_set_state": ([_vp, _i32, _i32, C.POINTER(abi.FtlStateBuffers)], C.c_int),
+    "ftl_stats": ([_vp, _vp, _i32, _vp], C.c_int),
+    "ftl_launch_count": ([_vp], _i64),
+    "ftl_profile": ([_vp, _i32], C.c_int),
+    "ftl_profile_read": ([_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i64)], C.c_int),
+    "ftl_generate_scenarios": ([C.POINTER(abi.FtlScenarioGenConfig), _vp, _i32, C.POINTER(abi.FtlScenarioPool), _i32],
+                               C.c_int),
+}
+
+
+def bind(L, names):
+    """Declare the ctypes signatures of `names` on the loaded library L (AttributeError if one is missing)."""
+    for name in names:
+        fn = getattr(L, name)
+        fn.argtypes, fn.restype = SIGNATURES[name]
+    return L
+
 
 def load(path=None):
-    """dlopen a library exporting the include/ftl.h entry points and declare their signatures."""
-    path = os.path.abspath(path or os.environ.get("FTL_LIB") or DEFAULT_LIB)
+    """dlopen libftl.so (the CUDA build) and declare every include/ftl.h entry point.  A library that lacks one of
+    them is refused: the product path has exactly one implementation."""
+    path = os.path.abspath(path or DEFAULT_LIB)
     if path in _LIBS:
         return _LIBS[path]
     if not os.path.exists(path):
@@ -40,34 +76,13 @@ def load(path=None):
             "%s not found: build the CUDA extension first (python -m continiousenvironment_follower_leader_b200.build); "
             "there is no CPU fallback" % path)
     L = C.CDLL(path)
-    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
-    L.ftl_last_error.restype = C.c_char_p
-    L.ftl_create.argtypes = [C.POINTER(abi.FtlConfig), i32, i32, i64, C.POINTER(vp)]
-    L.ftl_destroy.argtypes = [vp]
-    L.ftl_rays_per_env.argtypes = [vp]
-    L.ftl_num_envs.argtypes = [vp]
-    L.ftl_upload_scenarios.argtypes = [vp, C.POINTER(abi.FtlScenarioPool)]
-    L.ftl_reset_host.argtypes = [vp, vp, vp, C.POINTER(abi.FtlOutputs), vp]
-    L.ftl_step_host.argtypes = [vp, vp, C.POINTER(abi.FtlOutputs), vp]
-    for name, argtypes, restype in (("ftl_step_host_begin", [vp, vp, C.POINTER(abi.FtlOutputs), vp], C.c_int),
-                                    ("ftl_step_host_wait", [vp], C.c_int),
-                                    ("ftl_host_stream", [vp], vp)):
-        if hasattr(L, name):   # not in the host-compiled test harness
-            getattr(L, name).argtypes = argtypes
-            getattr(L, name).restype = restype
-    L.ftl_get_state.argtypes = [vp, i32, i32, C.POINTER(abi.FtlStateBuffers)]
-    L.ftl_set_state.argtypes = [vp, i32, i32, C.POINTER(abi.FtlStateBuffers)]
-    L.ftl_generate_scenarios.argtypes = [C.POINTER(abi.FtlScenarioGenConfig), vp, i32, C.POINTER(abi.FtlScenarioPool), i32]
-    for name, argtypes, restype in (
-            ("ftl_reset", [vp, vp, vp, C.POINTER(abi.FtlOutputs), vp], C.c_int),
-            ("ftl_step", [vp, vp, C.POINTER(abi.FtlOutputs), vp], C.c_int),
-            ("ftl_stats", [vp, vp, i32, vp], C.c_int),
-            ("ftl_launch_count", [vp], i64),
-            ("ftl_profile", [vp, i32], C.c_int),
-            ("ftl_profile_read", [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)], C.c_int)):
-        if hasattr(L, name):  # the host-compiled test harness only has the *_host entry points
-            getattr(L, name).argtypes = argtypes
-            getattr(L, name).restype = restype
+    try:
+        bind(L, SIGNATURES)
+    except AttributeError as e:
+        raise FtlLibraryMissing("%s does not export the whole include/ftl.h C-ABI (%s)" % (path, e)) from None
+    if L.ftl_abi_version() != abi.FTL_ABI_VERSION:
+        raise FtlLibraryMissing("%s has ABI version %d, this package needs %d: rebuild it"
+                                % (path, L.ftl_abi_version(), abi.FTL_ABI_VERSION))
     _LIBS[path] = L
     return L
 

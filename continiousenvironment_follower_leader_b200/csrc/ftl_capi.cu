@@ -418,6 +418,19 @@ int ftl_create(const FtlConfig* cfg, int32_t n_envs, int32_t device, int64_t env
     ray_static_tables(d);
     h->rays_total = total_rays(c);
     d.rays_total = h->rays_total;
+    if (h->rays_total > 0) {   // the ray kernel keeps its tables in dynamic shared memory: refuse what cannot fit, here
+        int optin = 0;
+        CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        const size_t need = ((ray_shared_bytes(h->rays_total, d.ray_hmax) + 15) & ~(size_t)15) * FTL_RAYS_WARPS;
+        if (need > (size_t)optin) {
+            const int rt = h->rays_total;
+            delete h;
+            return fail(FTL_ERR_INVALID, "ray sensors need " + std::to_string(need) + " bytes of shared memory per block (" +
+                                             std::to_string(rt) + " rays, " + std::to_string(ray_hmax(c)) +
+                                             " history rows); the device allows " + std::to_string(optin) +
+                                             ": reduce lasers_count or max_prev_obs");
+        }
+    }
     d.eps_f32 = (float)c.leader_pos_epsilon;
     d.dev_f32 = (float)c.max_dev;
     d.eps2_f32 = sq_threshold(c.leader_pos_epsilon);
@@ -508,6 +521,12 @@ int ftl_upload_scenarios(ftl_handle h, const FtlScenarioPool* p) {
     }
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaDeviceSynchronize());
+    // the old pool dies here: whatever fails below, no step may run on freed memory, and envs keep scenario ids of
+    // the old pool, so a full ftl_reset is required after every upload
+    h->have_pool = false;
+    h->was_reset = false;
+    h->pool = DevPool{};
+    h->image = DevState{};
     for (void* q : h->pool_allocs) cudaFree(q);
     h->pool_allocs.clear();
     const size_t S = p->n_scenarios;
@@ -626,7 +645,11 @@ int ftl_step(ftl_handle h, const void* actions_dev, const FtlOutputs* out_dev, v
     if (rc) return rc;
     // The ray kernel overlaps the tail of k_step (programmatic dependent launch + per-group flags) unless something
     // was launched in between or per-kernel timing is on.
-    const bool overlap = !h->profiling && !FTL_NO_PDL &&
+    // Not while the stream is being captured either: the sequence number is a kernel argument, so a replayed graph
+    // would find last replay's flags already equal to it and skip the wait -- captured steps use plain stream order.
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    CUDA_TRY(cudaStreamIsCapturing(st, &cap));
+    const bool overlap = !h->profiling && !FTL_NO_PDL && cap == cudaStreamCaptureStatusNone &&
                          !(o.follower_info || (o.track_vectors && h->cfg.c.track_vector_len > 0) ||
                            (o.radar && h->cfg.c.radar_sectors > 0));
     if (h->profiling) prof_event(h, st);
@@ -757,10 +780,33 @@ int ftl_set_state(ftl_handle h, int32_t first, int32_t count, const FtlStateBuff
     if (!h || !b) return fail(FTL_ERR_INVALID, "NULL argument");
     if (first < 0 || count < 0 || first + count > h->n) return fail(FTL_ERR_INVALID, "env range out of bounds");
     if (!b->env || !b->trail) return fail(FTL_ERR_INVALID, "set_state needs at least env and trail");
+    if (!h->have_pool) return fail(FTL_ERR_STATE, "ftl_upload_scenarios must be called before ftl_set_state");
     if (count == 0) return FTL_OK;
+    const FtlConfig& c = h->cfg.c;
+    // every index the kernels will follow is checked here, on the host, before anything reaches the device
+    for (int k = 0; k < count; k++) {
+        const FtlEnvState& e = b->env[k];
+        const char* bad = nullptr;
+        const int64_t live = (int64_t)e.ring_head - (int64_t)e.ring_tail;
+        if (e.trail_len < 0 || e.trail_len > c.trail_cap) bad = "trail_len outside [0, trail_cap]";
+        else if (e.ring_tail < 0 || live < 0 || live > c.corridor_cap) bad = "ring_head - ring_tail outside [0, corridor_cap]";
+        else if (e.scenario_id < 0 || e.scenario_id >= h->pool.n_scenarios) bad = "scenario_id outside the uploaded pool";
+        else if (e.snap_pushes < 0) bad = "snap_pushes is negative";
+        else if (e.cur_target_id < 0) bad = "cur_target_id is negative";
+        else if (e.mission_status < 0 || e.mission_status > 3 || e.agent_status < 0 || e.agent_status > 7 ||
+                 e.leader_status < 0 || e.leader_status > 3) bad = "status code out of range";
+        for (int q = 0; !bad && q < c.n_bears; q++)
+            if (e.bear_index[q] < 0 || e.bear_index[q] > 3) bad = "bear_index outside 0..3";
+        for (int q = 0; !bad && q < FTL_MAX_HIST; q++) {
+            const FtlSnapshot& sn = e.snap[q];
+            if (!sn.valid) continue;
+            const int64_t span = (int64_t)sn.corr_head - (int64_t)sn.corr_tail;
+            if (sn.corr_tail < 0 || span < 0 || span > c.corridor_cap) bad = "history snapshot range outside the corridor ring";
+        }
+        if (bad) return fail(FTL_ERR_INVALID, "ftl_set_state: env " + std::to_string(first + k) + ": " + bad);
+    }
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaDeviceSynchronize());
-    const FtlConfig& c = h->cfg.c;
     CUDA_TRY(cudaMemcpy(h->st.trail + (size_t)first * c.trail_cap, b->trail, sizeof(float2) * (size_t)c.trail_cap * count, cudaMemcpyHostToDevice));
     if (b->hist) CUDA_TRY(cudaMemcpy(h->st.hist + (size_t)first * c.corridor_cap, b->hist, sizeof(double2) * (size_t)c.corridor_cap * count, cudaMemcpyHostToDevice));
     if (b->corridor) CUDA_TRY(cudaMemcpy(h->st.corridor + (size_t)first * c.corridor_cap, b->corridor, sizeof(float4) * (size_t)c.corridor_cap * count, cudaMemcpyHostToDevice));

@@ -1,18 +1,43 @@
-"""The wrappers the shipped trained configurations stack on the env (utils/wrappers.py):
-``ContinuousObserveModifier_sensorPrev`` (WRP:169-221) and ``SkipBadSeeds`` (WRP:814-825), plus
-``MyFrameStack`` (WRP:17-70).  They work on ``gym_surface.Game`` exactly as upstream; for batched
-training ``sensor_prev_observation`` applies the same normalise-and-concatenate to the device tensors.
+"""Observation post-processing of the shipped trained configurations, for ``gym_surface.Game`` and for the batch.
+
+The reference stacks ``ContinuousObserveModifier_sensorPrev`` (utils/wrappers.py:169-221), ``SkipBadSeeds``
+(utils/wrappers.py:814-825) and sometimes ``MyFrameStack`` (utils/wrappers.py:17-70) on its env.  The reference's OWN
+wrapper classes run unmodified on ``gym_surface.Game`` (tests/test_reference_wrappers.py proves it on a golden
+trace); the classes below are independent implementations of the same contracts -- same names, constructor
+arguments, spaces and results -- for installations that do not carry the reference tree, built around one
+table-driven normaliser that also serves the device tensors of ``FtlBatchEnv`` (``sensor_prev_observation``).
 """
-from collections import deque
+import collections
 
 import numpy as np
 
 from .gym_surface import Box
 
+# sensor classes whose (H, W) history blocks the sensorPrev contract normalises and concatenates (WRP:206, 214)
 PREV_CLASSES = ("LeaderCorridor_Prev_lasers_v2", "LeaderCorridor_Prev_lasers_v3")
+COMPAS_CLASS = "LeaderCorridor_lasers_compas"
 
 
-class Wrapper:
+def _sensor_prev_plan(follower_sensors):
+    """[(dict key, width in features)] of the sensors the sensorPrev contract consumes, in dict order.
+
+    Every entry must name its ``sensor_class`` (the reference indexes it unconditionally, WRP:181, so a config
+    without it is a KeyError there as well); a sensor also counts when its dict KEY is one of the class names."""
+    plan = []
+    for key, conf in follower_sensors.items():
+        cls = conf["sensor_class"]
+        if cls in PREV_CLASSES:
+            plan.append((key, conf["lasers_count"] * (4 if conf["pad_sectors"] else 1), True))
+        elif cls == COMPAS_CLASS:
+            plan.append((key, 5 * conf["lasers_count"], True))
+        elif key in PREV_CLASSES or key == COMPAS_CLASS:
+            plan.append((key, 0, False))   # consumed by observation() but never counted by the constructor upstream
+    return plan
+
+
+class _Delegate:
+    """Minimal stand-in for gym.Wrapper: public attributes fall through to the wrapped env."""
+
     def __init__(self, env):
         self.env = env
         self.action_space = env.action_space
@@ -23,11 +48,9 @@ class Wrapper:
             raise AttributeError("attempted to get missing private attribute '{}'".format(name))
         return getattr(self.env, name)
 
-    def step(self, action):
-        return self.env.step(action)
-
-    def reset(self, **kwargs):
-        return self.env.reset(**kwargs)
+    @property
+    def unwrapped(self):
+        return self.env.unwrapped
 
     def seed(self, seed=None):
         return self.env.seed(seed)
@@ -35,105 +58,112 @@ class Wrapper:
     def close(self):
         return self.env.close()
 
-    @property
-    def unwrapped(self):
-        return self.env.unwrapped
+    def reset(self, **kwargs):
+        return self.env.reset(**kwargs)
+
+    def step(self, action):
+        return self.env.step(action)
 
 
-class ObservationWrapper(Wrapper):
+# names other code may import from here, as from gym
+Wrapper = _Delegate
+
+
+class ObservationWrapper(_Delegate):
     def reset(self, **kwargs):
         return self.observation(self.env.reset(**kwargs))
 
     def step(self, action):
-        observation, reward, done, info = self.env.step(action)
-        return self.observation(observation), reward, done, info
+        obs, reward, done, info = self.env.step(action)
+        return self.observation(obs), reward, done, info
 
 
 class ContinuousObserveModifier_sensorPrev(ObservationWrapper):
-    """History-sensor features, each divided by its laser_length, clipped to [0, 1], concatenated on axis 1."""
+    """obs dict -> float matrix [max_prev_obs, sum of sensor widths], each block ``clip(block / laser_length, 0, 1)``.
+
+    ``action_values_range`` only re-declares the action space as [-1, 1]; like upstream (WRP:193-201, no ``step``
+    override) this wrapper never rescales the actions it forwards."""
 
     def __init__(self, env, action_values_range=None, lz4_compress=False, max_prev_obs=0):
         super().__init__(env)
-        self.observations_list = None
-        features_number = 0
         self.max_prev_obs = max_prev_obs
-        for sensor_name, sensor_config in env.follower_sensors.items():
-            if sensor_config["sensor_class"] in PREV_CLASSES:   # KeyError without "sensor_class", as upstream (WRP:181)
-                if sensor_config["pad_sectors"]:
-                    features_number += 4 * sensor_config["lasers_count"]
-                else:
-                    features_number += sensor_config["lasers_count"]
-            if sensor_config["sensor_class"] == "LeaderCorridor_lasers_compas":
-                features_number += 5 * sensor_config["lasers_count"]
-        self.features_number_num = features_number
-        self.observation_space = Box(-np.ones([self.max_prev_obs, features_number]),
-                                     np.ones([self.max_prev_obs, features_number]))
+        self.observations_list = None
+        self._plan = _sensor_prev_plan(env.follower_sensors)
+        self.features_number_num = sum(width for _, width, counted in self._plan if counted)
+        bound = np.ones([max_prev_obs, self.features_number_num])
+        self.observation_space = Box(-bound, bound)
         self.action_values_range = action_values_range
-        if self.action_values_range is not None:   # declared only: this wrapper never rescales in step (WRP:193-201)
-            low_bound, high_bound = self.action_values_range
-            self.scale = (high_bound - low_bound) / (env.action_space.high - env.action_space.low)
-            self.min = low_bound - env.action_space.low * self.scale
-            self.action_space = Box(low=-np.ones_like(env.action_space.low), high=np.ones_like(env.action_space.high),
-                                    shape=env.action_space.shape, dtype=env.action_space.dtype)
+        if action_values_range is not None:
+            lo, hi = action_values_range
+            inner = env.action_space
+            self.scale = (hi - lo) / (inner.high - inner.low)
+            self.min = lo - inner.low * self.scale
+            self.action_space = Box(low=-np.ones_like(inner.low), high=np.ones_like(inner.high), shape=inner.shape,
+                                    dtype=inner.dtype)
 
     def observation(self, obs):
-        features_list = []
-        for sensor_name in self.follower_sensors.keys():
-            sensor_config = self.follower_sensors[sensor_name]
-            if sensor_name in PREV_CLASSES or sensor_config["sensor_class"] in PREV_CLASSES:
-                corridor_obs = obs[sensor_name]
-                assert len(corridor_obs.shape) == 2
-                assert corridor_obs.shape[0] == self.max_prev_obs
-                corridor_obs = np.clip(corridor_obs / self.follower.sensors[sensor_name].laser_length, 0, 1)
-                features_list.append(corridor_obs)
-        self.observations_list = np.concatenate(features_list, axis=1)
+        blocks = []
+        for key, _, _ in self._plan:
+            block = obs[key]
+            assert block.ndim == 2 and block.shape[0] == self.max_prev_obs
+            blocks.append(np.clip(block / self.follower.sensors[key].laser_length, 0, 1))
+        self.observations_list = np.concatenate(blocks, axis=1)
         return self.observations_list
 
 
-class SkipBadSeeds(Wrapper):
-    """Re-reset until the planner reached the target (WRP:814-825)."""
+class SkipBadSeeds(_Delegate):
+    """``reset`` repeats until the route planner reached its target (``found_target_point``)."""
 
     def reset(self, **kwargs):
-        observation = self.env.reset(**kwargs)
-        while not self.env.found_target_point:
-            observation = self.env.reset(**kwargs)
-        return observation
+        while True:
+            obs = self.env.reset(**kwargs)
+            if self.env.found_target_point:
+                return obs
 
 
 class MyFrameStack(ObservationWrapper):
+    """Rolling concatenation (axis 0) of the last ``framestack`` observations; ``reset`` fills the window with
+    copies of the first one."""
+
     def __init__(self, env, framestack, lz4_compress=False):
         super().__init__(env)
         self.framestack = framestack
-        self.frames = deque(maxlen=framestack)
-        low = np.tile(self.observation_space.low[...], framestack)
-        high = np.tile(self.observation_space.high[...], framestack)
-        self.observation_space = Box(low=low, high=high, dtype=self.observation_space.dtype)
+        self.lz4_compress = lz4_compress
+        self.frames = collections.deque(maxlen=framestack)
+        space = self.observation_space
+        self.observation_space = Box(low=np.tile(space.low, framestack), high=np.tile(space.high, framestack),
+                                     dtype=space.dtype)
 
     def observation(self, observation=None):
         assert len(self.frames) == self.framestack, (len(self.frames), self.framestack)
         return np.concatenate(self.frames)
 
     def step(self, action):
-        observation, reward, done, info = self.env.step(action)
-        self.frames.append(observation)
+        obs, reward, done, info = self.env.step(action)
+        self.frames.append(obs)
         return self.observation(), reward, done, info
 
     def reset(self, **kwargs):
-        observation = self.env.reset(**kwargs)
-        [self.frames.append(observation) for _ in range(self.framestack)]
+        first = self.env.reset(**kwargs)
+        self.frames.extend([first] * self.framestack)
         return self.observation()
 
 
 def sensor_prev_observation(batch_env):
-    """Batched ContinuousObserveModifier_sensorPrev.observation on device tensors: [N, H, sum of widths]."""
+    """The sensorPrev matrix for every env of an ``FtlBatchEnv``, on the device: [N, H, sum of widths].
+
+    Only sensors the single-env wrapper would consume take part (history sensors of PREV_CLASSES; a flat
+    ``LeaderCorridor_lasers(_v2)`` configured next to them is skipped, as WRP:206-213 skips it)."""
     import torch
     if batch_env.cfg.fused_sensor_prev:   # the ray kernel already wrote this matrix
         return batch_env.sensor_prev()
+    gc = batch_env.gc
+    wanted = {key for key, _, _ in _sensor_prev_plan(gc.follower_sensors)}
     feats = []
-    layout = batch_env.gc.ray_layout()
-    for i, (name, off, h, w) in enumerate(layout):
-        L = batch_env.gc.c.ray[i].laser_length
+    for i, (name, off, h, w) in enumerate(gc.ray_layout()):
+        if name not in wanted or gc.ray_sensor_flat[i]:
+            continue
         # a tensor divisor: torch turns division by a python scalar into a multiplication by 1/L (1 ulp off numpy's)
-        div = torch.tensor(L, dtype=torch.float32, device=batch_env.rays.device)
+        div = torch.tensor(gc.c.ray[i].laser_length, dtype=torch.float32, device=batch_env.rays.device)
         feats.append(torch.clamp(batch_env.rays[:, off:off + h * w].view(batch_env.n, h, w) / div, 0, 1))
     return torch.cat(feats, dim=2)

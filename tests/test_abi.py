@@ -52,3 +52,16 @@ def test_invalid_configuration_is_rejected_without_a_gpu():
     h = C.c_void_p()
     rc = lib.ftl_create(C.byref(gc.c), 4, 0, 0, C.byref(h))
     assert rc == abi.FTL_ERR_INVALID and b"corridor_cap" in lib.ftl_last_error()
+
+
+def test_product_loader_refuses_a_library_without_the_device_entry_points():
+    """The host build of the device functions (tests/hostsim) lacks ftl_step / ftl_stats ...: only the tests' own loader
+    (tests/hostsim_py.py) binds it; capi.load must not accept it as a stand-in for libftl.so."""
+    import hostsim_py
+    hostsim_py.lib()
+    with pytest.raises(capi.FtlLibraryMissing):
+        capi.load(os.path.join(ROOT, "tests", "hostsim", "libftl_hostsim.so"))
+
+
+def test_every_declared_entry_point_has_a_ctypes_signature():
+    assert set(_declared_symbols()) - {"ftl_set_error_message"} <= set(capi.SIGNATURES)

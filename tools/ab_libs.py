@@ -1,4 +1,4 @@
-"""Time the two kernels for several builds of libftl.so (FTL_LIB override) on one box, with a checksum of the
+"""Time the two kernels for several builds of libftl.so (the tool passes the variant to FtlBatchEnv(lib_path=...) through AB_LIB) on one box, with a checksum of the
 state after the run so that a variant that changes results is visible; diagnostic.
 
     python tools/ab_libs.py [glob]         (default glob: tools/libftl_*.so)
@@ -15,6 +15,6 @@ print('k_step %.4f k_rays %.4f sum %.4f  step(no events) %.4f  %s' % (a,b,a+b,sw
 for rep in range(int(os.environ.get("AB_REPS", "1"))):
     for lib in libs:
         env = dict(os.environ)
-        if lib: env["FTL_LIB"] = os.path.abspath(lib)
+        if lib: env["AB_LIB"] = os.path.abspath(lib)
         out = subprocess.run([sys.executable, "-c", CODE], env=env, capture_output=True, text=True)
         print("%-28s" % (os.path.basename(lib) if lib else "default"), out.stdout.strip().splitlines()[-1] if out.stdout.strip() else out.stderr[-600:], flush=True)

@@ -1,4 +1,4 @@
-"""Build tools/libftl_<tag>.so with extra -D flags (A/B timing with tools/ab_libs.py; FTL_LIB selects a build).
+"""Build tools/libftl_<tag>.so with extra -D flags (A/B timing with tools/ab_libs.py; AB_LIB selects a build for tools/sweep_f.py).
 
     python tools/build_variant.py <tag> [-DNAME=VALUE ...] [--nb-only]
 """

@@ -1,5 +1,5 @@
 """Device-time of the two kernels versus frames_per_step / ray count / env count (diagnostic sweep)."""
-import sys, json
+import os, sys, json
 import torch
 sys.path.insert(0, ".")
 from continiousenvironment_follower_leader_b200.batch_env import FtlBatchEnv
@@ -13,7 +13,7 @@ def run(n, F, rays=(12, 36), steps=200, warm=100, auto_reset=True, max_steps=500
         import numpy as np
         from continiousenvironment_follower_leader_b200.scenario import ScenarioPool
         pool = ScenarioPool.from_arrays(np.load('continiousenvironment_follower_leader_b200/data/pool_cfg3_reference.npz'))
-    env = FtlBatchEnv(n, game_config=gc, scenario_pool=pool)
+    env = FtlBatchEnv(n, game_config=gc, scenario_pool=pool, lib_path=os.environ.get('AB_LIB'))   # AB_LIB: a tools/libftl_<tag>.so variant (tools/ab_libs.py)
     env.reset()
     g = torch.Generator(device="cuda").manual_seed(1)
     lo, hi = [torch.tensor(x, device="cuda") for x in gc.action_bounds()]
