@@ -1,24 +1,37 @@
 #!/usr/bin/env python
 """bench.py -- env-steps/sec of the batched "follow the leader" simulator (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--envs-per-gpu E]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config cfg2|cfg3|cfg4|cfg5]
+                    [--envs-per-gpu E] [--settle S]
 
-One "step" = one Game.step for every env of the batch: frames_per_step physics frames + one sensor
-scan (reference: follow_the_leader_continuous_env.py:908-945).  Workload at every N: BASELINE.json
-configs[2] per GPU -- 65536 envs, 35 static + 1 dynamic obstacles, LeaderPositionsTracker_v2 +
-LeaderCorridor_Prev_lasers_v2 (12 rays) + LaserPrevSensor (36 rays), H = 5, F = 10 -- i.e. weak scaling,
-each rank owns a disjoint env slice keyed by global env id; NCCL is used only to all-reduce the episode
-statistics vector every 64 steps.
+One "step" = one Game.step for every env of the batch: frames_per_step physics frames + one sensor scan (reference:
+follow_the_leader_continuous_env.py:908-945).  Workloads (BASELINE.json `configs`):
+
+  cfg3 (default; the configuration the metric is quoted on)  65 536 envs per GPU, 35 static + 1 dynamic obstacles,
+        LeaderPositionsTracker_v2 + LeaderCorridor_Prev_lasers_v2 (12 rays) + LaserPrevSensor (36 rays), H = 5, F = 10,
+        scenario pool exported from the reference's own reset()
+  cfg2  4 096 envs, no obstacles, tracker only (kinematics + reward plumbing)
+  cfg4  1 048 576 envs over all ranks (at most 262 144 per GPU), the "gazebo" hardcore preset (ENV:2013-2107: 2 bears,
+        list-valued speed regimes, acceleration regime, early stopping, 12 + 24 rays, F = 5)
+  cfg5  32 768 envs per GPU (262 144 on 8 GPUs): frames_per_step sweep and obstacle-sensor ray-count sweep; `value` is the
+        F = 10 / 36-ray point, the sweep is in `sweep`
+
+Weak scaling at every N: each rank owns a disjoint env slice keyed by global env id; NCCL only all-reduces the
+episode-statistics vector (at least once inside the timed region).  Before the warm-up the batch is advanced `--settle`
+untimed steps (default 150) so that the timed steps see the steady-state mix of episode ages, not the first steps after a
+reset.
 
 The printed JSON line carries
   value     device-timed whole-job env-steps/s with actions resident in HBM (CUDA events, max over ranks)
-  e2e       the same metric through the host-buffer C-ABI call (ftl_step_host): actions copied from pinned
-            host memory and observation/reward/done copied back to pinned host memory every step
-  roofline  algorithmic bytes of the dominant kernel / its CUDA-event time, against the measured HBM peak
-  cpu_baseline  the CPU oracle (a C port of the reference's algorithm, oracle/ftl_oracle.c) on the box's
-            host cores, bounded sample
-`--impl reference` times that CPU oracle alone (the reference itself is pure Python + pygame and cannot
-travel to the GPU box; its measured speed in the build container is quoted in BASELINE.md/DESIGN.md).
+  e2e       the same metric through the host-buffer C-ABI (ftl_step_host_begin/_wait): actions from pinned host memory,
+            every output copied back to pinned host memory each step; with the box's measured concurrent D2H ceiling
+  rollout   the same metric with a device-resident consumer (rollout.DeviceRollout: a torch policy reads the fused
+            sensorPrev matrix in place, trajectory stored in device rings): zero host copies per step
+  roofline  algorithmic bytes of the dominant kernel / its CUDA-event time against the measured HBM peak, plus the
+            measured FP32 FMA peak and the issue-slot utilisation from the committed ncu capture
+  cpu_baseline  the CPU oracle (a C port of the reference's algorithm, oracle/ftl_oracle.c) on the box's host cores
+`--impl reference` times that CPU oracle alone on the same configuration (the reference itself is pure Python + pygame
+and cannot travel to the GPU box; its measured speed in the build container is quoted in BASELINE.md / DESIGN.md).
 """
 import argparse
 import json
@@ -34,38 +47,82 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-from continiousenvironment_follower_leader_b200.config import GameConfig, cfg3_sensors  # noqa: E402
+from continiousenvironment_follower_leader_b200.config import (  # noqa: E402
+    GameConfig, cfg3_sensors, TEST_GAME_MANUAL_GAZEBO_KWARGS)
 from continiousenvironment_follower_leader_b200.scenario import ScenarioPool, synthetic_pool  # noqa: E402
 
 METRIC = "env-steps/sec (device-timed, whole box)"
 UNIT = "env-steps/s"
-WORKLOAD = ("cfg3: 65536 envs/GPU, 35 static + 1 dynamic obstacles, LeaderPositionsTracker_v2 + "
-            "LeaderCorridor_Prev_lasers_v2(12 rays) + LaserPrevSensor(36 rays), H=5, frames_per_step=10")
-
-# Algorithmic bytes per env-step (DESIGN.md "Measurement"; SURVEY.md section 8(d) gives 4.3 KB for both kernels)
-BYTES_STEP_KERNEL = 2400   # robot/bookkeeping state R+W, static rect table, green window, action, small outputs
-BYTES_RAY_KERNEL = 2500    # corridor ring, static rect table, dynamic snapshots, 240 ray floats out
-FLOP_PER_ENV_STEP = 3.9e5  # SURVEY.md section 8(d), de-duplicated ray casting + F * controllers
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r02_traffic.json")
 
 
-def workload_config(auto_reset=True):
-    return GameConfig(bear_number=1, follower_sensors=cfg3_sensors(), auto_reset=auto_reset)
+# ---------------------------------------------------------------------------------------------------
+# workloads
+# ---------------------------------------------------------------------------------------------------
+def workload_config(auto_reset=True, frames_per_step=10, rays=(12, 36), fused_sensor_prev=False):
+    """BASELINE.json configs[2] ("cfg3")."""
+    return GameConfig(bear_number=1, follower_sensors=cfg3_sensors(rays[0], rays[1]), auto_reset=auto_reset,
+                      frames_per_step=frames_per_step, fused_sensor_prev=fused_sensor_prev)
 
 
 def workload_pool(gc, n_scenarios=1024, seed=0):
     ref = os.path.join(ROOT, "continiousenvironment_follower_leader_b200", "data", "pool_cfg3_reference.npz")
-    if os.path.exists(ref):   # scenarios exported from the reference's own reset() (oracle/gen_scenario_pool.py)
-        d = np.load(ref)
+    if os.path.exists(ref) and gc.c.n_bears == 1 and gc.c.game_width == 1500:
+        d = np.load(ref)   # scenarios exported from the reference's own reset() (oracle/gen_scenario_pool.py)
         if d["static_rects"].shape[1] == gc.c.static_cap and d["route"].shape[1] == gc.c.route_cap:
             return ScenarioPool.from_arrays(d), "reference-reset"
     return synthetic_pool(gc, n_scenarios, seed=seed), "synthetic"
 
 
+def build_workload(name, world, envs_override=None, frames_per_step=None, obstacle_rays=None):
+    """(GameConfig, pool, pool kind, envs per GPU, description) of a BASELINE.json configuration."""
+    F = frames_per_step
+    if name == "cfg2":
+        tracker = {"LeaderPositionsTracker_v2": cfg3_sensors()["LeaderPositionsTracker_v2"]}
+        gc = GameConfig(add_obstacles=False, add_bear=False, follower_sensors=tracker, auto_reset=True,
+                        frames_per_step=F or 10)
+        n = envs_override or 4096
+        desc = "cfg2: %d envs/GPU, no obstacles, LeaderPositionsTracker_v2 only, frames_per_step=%d" % (n, gc.c.frames_per_step)
+        pool, kind = synthetic_pool(gc, 256, seed=0), "synthetic"
+    elif name == "cfg4":
+        kw = dict(TEST_GAME_MANUAL_GAZEBO_KWARGS, auto_reset=True)
+        if F:
+            kw["frames_per_step"] = F
+        gc = GameConfig(**kw)
+        n = envs_override or min(1048576 // world, 262144)
+        desc = ("cfg4: %d envs/GPU (%d in the job; 1 048 576 needs >= 4 GPUs at 262 144 per GPU), 'gazebo' hardcore preset "
+                "(20 static + 2 dynamic obstacles, speed/acceleration regimes, early stopping), "
+                "LeaderPositionsTracker_v2 + 12-ray + 24-ray history sensors, H=5, frames_per_step=%d"
+                % (n, n * world, gc.c.frames_per_step))
+        pool, kind = synthetic_pool(gc, 256, seed=0), "synthetic"
+    else:   # cfg3 and the points of the cfg5 sweep
+        gc = workload_config(True, F or 10, (12, obstacle_rays or 36))
+        n = envs_override or (32768 if name == "cfg5" else 65536)
+        desc = ("%s: %d envs/GPU, 35 static + 1 dynamic obstacles, LeaderPositionsTracker_v2 + "
+                "LeaderCorridor_Prev_lasers_v2(12 rays) + LaserPrevSensor(%d rays), H=5, frames_per_step=%d"
+                % (name, n, obstacle_rays or 36, gc.c.frames_per_step))
+        pool, kind = workload_pool(gc)
+    return gc, pool, kind, n, desc
+
+
+def algorithmic_bytes(gc):
+    """Algorithmic HBM bytes per env-step of the two kernel groups, SURVEY.md section 8(d)'s accounting: state read and
+    written once, static rectangle table, green window, corridor ring, history snapshots, action and outputs."""
+    c = gc.c
+    robots = 2 + c.n_bears
+    statics = 16 * (2 + (gc.kwargs["obstacle_number"] if gc.kwargs["add_obstacles"] else 0))
+    rays_out = 4 * gc.rays_per_env
+    H = max([c.ray[i].max_prev_obs for i in range(c.n_ray_sensors)] or [0])
+    ring = 36 * 24 if c.tracker_enabled else 0      # ~36 live corridor entries of 24 B (SURVEY: C = 36 at F = 10)
+    step = robots * 72 * 2 + 64 + statics + 160 * 8 + 8 + 40 + 12
+    rays = (ring + statics + H * (8 + 16 * (1 + c.n_bears)) + rays_out) if c.n_ray_sensors else 0
+    return {"k_step": step, "k_rays": rays}
+
+
 def measured_traffic():
-    """DRAM bytes per launch of each kernel from the committed ncu --set full capture (profiles/r01_traffic.json)."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    """Per-launch DRAM bytes / warp instructions of each kernel from the committed ncu --set full capture."""
     try:
-        return json.load(open(p))
+        return json.load(open(TRAFFIC_FILE))
     except Exception:
         return {}
 
@@ -129,30 +186,33 @@ class ClockSampler(threading.Thread):
 # ---------------------------------------------------------------------------------------------------
 # CPU oracle leg (cpu_baseline and --impl reference)
 # ---------------------------------------------------------------------------------------------------
+def _host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def _oracle_actions(gc, n, rng, k=8):
+    lo, hi = gc.action_bounds()
+    return [rng.uniform(lo, hi, size=(n, len(lo))).astype(np.float32) for _ in range(k)]
+
+
 def cpu_oracle_throughput(gc, pool, budget_s=12.0, n_envs=None, min_steps=4, warmup=1):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     from oracle_py import OracleEnv
-    cores = os.cpu_count() or 1
-    try:
-        cores = len(os.sched_getaffinity(0))
-    except Exception:
-        pass
+    cores = _host_cores()
     n = n_envs or max(256, 128 * cores)
     env = OracleEnv(gc, n, n_threads=cores)
     env.upload_scenarios(pool)
     env.reset()
-    rng = np.random.RandomState(0)
-    lo, hi = gc.action_bounds()
-    acts = [rng.uniform(lo, hi, size=(n, 2)).astype(np.float32) for _ in range(8)]
+    acts = _oracle_actions(gc, n, np.random.RandomState(0))
     for w in range(warmup):
         env.step(acts[w % 8])
     t0 = time.perf_counter()
     steps = 0
-    per_step = []
     while True:
-        t1 = time.perf_counter()
         env.step(acts[steps % 8])
-        per_step.append(time.perf_counter() - t1)
         steps += 1
         el = time.perf_counter() - t0
         if steps >= min_steps and el >= budget_s:
@@ -161,29 +221,23 @@ def cpu_oracle_throughput(gc, pool, budget_s=12.0, n_envs=None, min_steps=4, war
     env.close()
     return {"value": n * steps / el, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": "%d envs x %d steps of the same workload (%.1f s) through oracle/ftl_oracle.c, %d OpenMP threads"
-                      % (n, steps, el, cores)}, per_step, n
+                      % (n, steps, el, cores)}
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    gc = workload_config()
-    pool, pool_kind = workload_pool(gc)
-    cores = os.cpu_count() or 1
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    gc, pool, pool_kind, _, desc = build_workload(args.config, world, args.envs_per_gpu)
+    cores = _host_cores()
     n = max(256, 128 * cores)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     from oracle_py import OracleEnv
-    try:
-        cores = len(os.sched_getaffinity(0))
-    except Exception:
-        pass
     env = OracleEnv(gc, n, n_threads=cores)
     env.upload_scenarios(pool)
     env.reset()
-    rng = np.random.RandomState(0)
-    lo, hi = gc.action_bounds()
-    acts = [rng.uniform(lo, hi, size=(n, 2)).astype(np.float32) for _ in range(8)]
+    acts = _oracle_actions(gc, n, np.random.RandomState(0))
     # bound the run: at most ~150 s of CPU work in total
     t0 = time.perf_counter()
     env.step(acts[0])
@@ -197,13 +251,13 @@ def run_reference_arm(args):
         env.step(acts[k % 8])
     el = time.perf_counter() - t0
     value = n * steps / el
-    sample = ("%d envs x %d steps per run of the cfg3 workload through oracle/ftl_oracle.c (C port of the reference "
+    sample = ("%d envs x %d steps per run of the %s workload through oracle/ftl_oracle.c (C port of the reference "
               "algorithm), %d OpenMP threads; the pure-Python reference itself measured 16 env-steps/s/process in the "
-              "build container" % (n, steps, cores))
+              "build container" % (n, steps, args.config, cores))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": 1e3 * el / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64+f32", "data": "synthetic (seeded scenario pool: %s)" % pool_kind,
-            "config": {"workload": WORKLOAD, "envs_in_sample": n},
+            "config": {"workload": desc, "envs_in_sample": n},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -213,14 +267,218 @@ def run_reference_arm(args):
 # ---------------------------------------------------------------------------------------------------
 # GPU leg
 # ---------------------------------------------------------------------------------------------------
+class Job:
+    """rank / world plumbing shared by the measurement legs."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback for the product path")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        self.torch.cuda.synchronize(self.dev)
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def all_max(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_sum(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+
+def device_actions(job, gc, n, n_act=16):
+    """A ring of uniform action batches in the action Box, generated on the device from a per-rank seed."""
+    torch = job.torch
+    g = torch.Generator(device=job.dev).manual_seed(1234 + job.rank)
+    lo, hi = [torch.tensor(x, device=job.dev) for x in gc.action_bounds()]
+    return (lo + (hi - lo) * torch.rand((n_act, n, len(lo)), generator=g, device=job.dev)).contiguous()
+
+
+def time_device_steps(job, env, actions, steps, warmup, settle, sampler=None):
+    """ms for `steps` steps of `env` (max over ranks), after `settle` + `warmup` untimed steps; the statistics vector is
+    all-reduced every stats_every steps inside the timed region (at least once)."""
+    torch = job.torch
+    n_act = actions.shape[0]
+    stats_every = min(64, max(1, steps // 2))
+    for w in range(settle + warmup):
+        env.step_raw(actions[w % n_act])
+    if job.world > 1:
+        env.stats(reduce_across_ranks=True)
+    job.barrier()
+    if sampler is not None and job.rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = env.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reduces = 0
+    job.barrier()
+    e0.record()
+    for k in range(steps):
+        env.step_raw(actions[k % n_act])
+        if job.world > 1 and (k + 1) % stats_every == 0:
+            env.stats(reduce_across_ranks=True)
+            reduces += 1
+    e1.record()
+    job.barrier()
+    ms = job.all_max(e0.elapsed_time(e1))
+    return ms, env.launch_count - launches0, stats_every, reduces
+
+
+def kernel_split(env, actions, steps):
+    """Per-kernel device time from a separate pass with CUDA events between the launches (which switches the overlap of
+    the kernels off, so the parts add up to more than a step)."""
+    env.profile(True)
+    n_act = actions.shape[0]
+    for k in range(steps):
+        env.step_raw(actions[k % n_act])
+    step_ms, rays_ms, prof_steps = env.profile_read()
+    env.profile(False)
+    return {"k_step": step_ms / max(prof_steps, 1), "k_rays": rays_ms / max(prof_steps, 1)}
+
+
+def d2h_ceiling(job, nbytes, reps=40):
+    """Concurrent pinned D2H bandwidth of all ranks copying `nbytes` each, no kernels: the ceiling of the e2e leg."""
+    torch = job.torch
+    n = max(int(nbytes) // 4, 1)
+    src = torch.empty(n, dtype=torch.float32, device=job.dev).normal_()
+    dst = torch.empty(n, dtype=torch.float32).pin_memory()
+    for _ in range(3):
+        dst.copy_(src, non_blocking=True)
+    job.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize(job.dev)
+    el = job.all_max(time.perf_counter() - t0)
+    return job.world * n * 4 * reps / el / 1e9
+
+
+def e2e_leg(job, gc, pool, n, actions, steps):
+    """The metric through the host-buffer C-ABI, pinned host memory both ways.  (1) one synchronous ftl_step_host per
+    step over the whole batch; (2) the batch as two halves driven alternately with ftl_step_host_begin / _wait on
+    handle-owned streams (a double-buffered rollout loop: while one half's observations cross PCIe -- and its policy
+    would run -- the other half's kernels execute).  Every step of every env pays its H2D action copy and the D2H copy
+    of all outputs.  (2) is the headline.  The rank is bound to the cores of its GPU's NUMA node first, so that the
+    pinned buffers live next to the GPU."""
+    from continiousenvironment_follower_leader_b200 import capi, parallel
+    torch = job.torch
+    old_aff = os.sched_getaffinity(0)
+    binding = parallel.bind_to_gpu_numa(job.local_rank)
+    try:
+        host_actions = [actions[k].cpu().numpy() for k in range(4)]
+        host = capi.HostEnv(gc, n, device=job.local_rank, env_id_base=job.rank * n, pinned=True)
+        host.upload_scenarios(pool)
+        host.reset()
+        for w in range(3):
+            host.step(host_actions[w % 4])
+        job.barrier()
+        t0 = time.perf_counter()
+        for k in range(steps):
+            host.step(host_actions[k % 4])
+        torch.cuda.synchronize(job.dev)
+        sync_value = job.world * n * steps / job.all_max(time.perf_counter() - t0)
+        host.close()
+
+        half = n // 2
+        parts = [capi.HostEnv(gc, m, device=job.local_rank, env_id_base=job.rank * n + first, pinned=True,
+                              own_stream=True) for first, m in ((0, half), (half, n - half))]
+        acts = [[a[:half] for a in host_actions], [a[half:] for a in host_actions]]
+        for hpart in parts:
+            hpart.upload_scenarios(pool)
+            hpart.reset()
+        A, B = parts
+
+        def run(k_steps):
+            A.step_begin(acts[0][0])
+            for k in range(k_steps):
+                B.step_begin(acts[1][k % 4])
+                A.step_wait()                      # A's observation of step k is in host memory here
+                if k + 1 < k_steps:
+                    A.step_begin(acts[0][(k + 1) % 4])
+                B.step_wait()
+
+        run(3)
+        job.barrier()
+        t0 = time.perf_counter()
+        run(steps)
+        torch.cuda.synchronize(job.dev)
+        value = job.world * n * steps / job.all_max(time.perf_counter() - t0)
+        h2d = sum(x.h2d_bytes_per_step for x in parts)
+        d2h = sum(x.d2h_bytes_per_step for x in parts)
+        for hpart in parts:
+            hpart.close()
+        ceiling = d2h_ceiling(job, d2h)
+    finally:
+        try:
+            os.sched_setaffinity(0, old_aff)
+        except Exception:
+            pass
+    moved = value / (job.world * n) * d2h * job.world / 1e9     # GB/s of D2H the e2e leg sustained, whole job
+    return {"value": value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": steps,
+            "api": "two capi.HostEnv halves, step_begin/step_wait alternating -> ftl_step_host_begin/_wait "
+                   "(pinned host buffers, handle-owned streams)",
+            "synchronous_whole_batch": sync_value,
+            "synchronous_api": "capi.HostEnv.step -> ftl_step_host, one call per step for all envs",
+            "d2h_gbs": moved, "d2h_ceiling_gbs": ceiling, "frac_of_d2h_ceiling": moved / ceiling if ceiling else None,
+            "ceiling_note": "ceiling = all ranks copying d2h_bytes_per_step to pinned host memory concurrently, no kernels",
+            "numa_binding": {k: v for k, v in binding.items() if k != "cpus"}}
+
+
+def rollout_leg(job, n, steps, horizon=16):
+    """Device-resident consumer: rollout.DeviceRollout on the cfg3 workload with the fused sensorPrev output."""
+    from continiousenvironment_follower_leader_b200.rollout import DeviceRollout
+    torch = job.torch
+    gc = workload_config(True, fused_sensor_prev=True)
+    pool, _ = workload_pool(gc)
+    ro = DeviceRollout(n, horizon, game_config=gc, scenario_pool=pool, device=job.dev, env_id_base=job.rank * n)
+    for _ in range(max(1, 160 // horizon)):   # settle + warm-up
+        ro.collect()
+    rounds = max(1, steps // horizon)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    job.barrier()
+    e0.record()
+    for _ in range(rounds):
+        ro.collect()
+    e1.record()
+    job.barrier()
+    ms = job.all_max(e0.elapsed_time(e1))
+    ro.close()
+    return {"value": job.world * n * rounds * horizon / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / (rounds * horizon),
+            "steps": rounds * horizon, "host_copies_per_step": 0,
+            "api": "rollout.DeviceRollout.collect: MlpPolicy (240 -> 128 -> 128 -> 2 + value head, torch) reads the fused "
+                   "sensorPrev matrix in place, writes actions into the tensor ftl_step consumes; obs/actions/rewards/"
+                   "dones/values stored in device rings"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--envs-per-gpu", type=int, default=65536)
+    ap.add_argument("--config", default="cfg3", choices=["cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--envs-per-gpu", type=int, default=None)
+    ap.add_argument("--settle", type=int, default=150, help="untimed steps before the warm-up (steady-state episode mix)")
     ap.add_argument("--e2e-steps", type=int, default=30)
+    ap.add_argument("--rollout-steps", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -228,191 +486,112 @@ def main():
     if args.impl == "reference":
         return run_reference_arm(args)
 
-    import torch
-    import torch.distributed as dist
     from continiousenvironment_follower_leader_b200 import capi
     from continiousenvironment_follower_leader_b200.batch_env import FtlBatchEnv
+    job = Job()
+    rank, world, dev = job.rank, job.world, job.dev
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback for the product path")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-
-    n = args.envs_per_gpu
-    gc = workload_config(auto_reset=True)
-    pool, pool_kind = workload_pool(gc)
+    gc, pool, pool_kind, n, desc = build_workload(args.config, world, args.envs_per_gpu)
     env = FtlBatchEnv(n, game_config=gc, scenario_pool=pool, device=dev, env_id_base=rank * n)
     env.reset()
-
-    # actions: uniform in the action Box, generated on the device from a per-rank seed; a ring of 16 batches
-    g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    lo, hi = [torch.tensor(x, device=dev) for x in gc.action_bounds()]
-    n_act = 16
-    actions = (lo + (hi - lo) * torch.rand((n_act, n, 2), generator=g, device=dev)).contiguous()
-
-    def barrier():
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    stats_every = 64
-    for w in range(args.warmup):
-        env.step_raw(actions[w % n_act])
-    if world > 1:
-        env.stats(reduce_across_ranks=True)
-    barrier()
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
-    launches0 = env.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for k in range(args.steps):
-        env.step_raw(actions[k % n_act])
-        if world > 1 and (k + 1) % stats_every == 0:
-            env.stats(reduce_across_ranks=True)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = env.launch_count - launches0
-    # per-kernel split from a separate pass with CUDA events around each kernel on the launching stream: the events
-    # switch off the overlap of the ray kernel with the step kernel's tail, so these add up to more than ms_per_step
-    env.profile(True)
-    for k in range(min(args.steps, 100)):
-        env.step_raw(actions[k % n_act])
-    step_ms, rays_ms, prof_steps = env.profile_read()
-    env.profile(False)
+    actions = device_actions(job, gc, n)
+    sampler = ClockSampler(job.local_rank)
+    ms_max, launches, stats_every, reduces = time_device_steps(job, env, actions, args.steps, args.warmup, args.settle,
+                                                               sampler)
+    k_ms = kernel_split(env, actions, min(args.steps, 100))
     if rank == 0:
         time.sleep(0.2)
         sampler.stop()
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
     value = world * n * args.steps / (ms_max * 1e-3)
-
-    # ---- end to end through the host-buffer C-ABI (pinned host memory both ways) ---------------------
-    # (1) one synchronous ftl_step_host per step over the whole batch; (2) the batch as two halves driven alternately
-    # with ftl_step_host_begin / _wait on handle-owned streams (what a double-buffered rollout loop does: while one
-    # half's observations cross PCIe -- and its policy would run -- the other half's kernels execute).  Every step of
-    # every env still pays its H2D action copy and the D2H copy of all outputs.  (2) is the headline e2e.
-    host_actions = [actions[k].cpu().numpy() for k in range(4)]
-
-    def all_max(seconds):
-        tt = torch.tensor([seconds], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        return float(tt.item())
-
-    e2e_sync_value = None
-    if args.e2e_steps > 0:
-        host = capi.HostEnv(gc, n, device=local_rank, env_id_base=rank * n, pinned=True)
-        host.upload_scenarios(pool)
-        host.reset()
-        for w in range(3):
-            host.step(host_actions[w % 4])
-        barrier()
-        t0 = time.perf_counter()
-        for k in range(args.e2e_steps):
-            host.step(host_actions[k % 4])
-        torch.cuda.synchronize(dev)
-        e2e_sync_value = world * n * args.e2e_steps / all_max(time.perf_counter() - t0)
-        host.close()
-
-    e2e_value, h2d, d2h = None, 0, 0
-    if args.e2e_steps > 0:
-        half = n // 2
-        parts = [capi.HostEnv(gc, m, device=local_rank, env_id_base=rank * n + first, pinned=True, own_stream=True)
-                 for first, m in ((0, half), (half, n - half))]
-        acts = [[a[:half] for a in host_actions], [a[half:] for a in host_actions]]
-        for hpart in parts:
-            hpart.upload_scenarios(pool)
-            hpart.reset()
-        A, B = parts
-
-        def run(steps):
-            A.step_begin(acts[0][0])
-            for k in range(steps):
-                B.step_begin(acts[1][k % 4])
-                A.step_wait()                      # A's observation of step k is in host memory here
-                if k + 1 < steps:
-                    A.step_begin(acts[0][(k + 1) % 4])
-                B.step_wait()
-
-        run(3)
-        barrier()
-        t0 = time.perf_counter()
-        run(args.e2e_steps)
-        torch.cuda.synchronize(dev)
-        e2e_value = world * n * args.e2e_steps / all_max(time.perf_counter() - t0)
-        h2d = sum(x.h2d_bytes_per_step for x in parts)
-        d2h = sum(x.d2h_bytes_per_step for x in parts)
-        for hpart in parts:
-            hpart.close()
-
     stats = env.stats_dict(reduce_across_ranks=world > 1)
+    env.close()
+
+    sweep = None
+    if args.config == "cfg5":   # BASELINE.json configs[4]: frames_per_step sweep and ray-count sweep
+        sweep = []
+        points = [("frames_per_step", F, 36) for F in (1, 2, 3, 5, 8, 10)] + \
+                 [("obstacle_rays", 10, R) for R in (12, 24, 72, 120, 180, 360)]
+        for what, F, R in points:
+            gcs, pools, _, ns, _ = build_workload("cfg5", world, args.envs_per_gpu, frames_per_step=F, obstacle_rays=R)
+            e = FtlBatchEnv(ns, game_config=gcs, scenario_pool=pools, device=dev, env_id_base=rank * ns)
+            e.reset()
+            ms, _, _, _ = time_device_steps(job, e, actions[:, :ns], min(args.steps, 100), 5, args.settle)
+            e.close()
+            sweep.append({"swept": what, "frames_per_step": F, "obstacle_rays": R,
+                          "value": world * ns * min(args.steps, 100) / (ms * 1e-3),
+                          "ms_per_step": ms / min(args.steps, 100)})
+
+    e2e = None
+    if args.e2e_steps > 0:
+        e2e = e2e_leg(job, gc, pool, n, actions, args.e2e_steps)
+    rollout = None
+    if args.rollout_steps > 0 and args.config == "cfg3":
+        rollout = rollout_leg(job, n, args.rollout_steps)
+        rollout["frac_of_value"] = rollout["value"] / value
+
     if rank == 0:
         peaks, peak_kind = measured_peaks()
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        # k_rays includes the (almost always idle) exact-resolution launch k_rays_exact that follows it
-        k_ms = {"k_step": step_ms / max(prof_steps, 1), "k_rays": rays_ms / max(prof_steps, 1)}
+        # k_rays includes the (almost always idle) finishing launch that follows it
         dominant = max(k_ms, key=k_ms.get)
-        alg_bytes = (BYTES_STEP_KERNEL if dominant == "k_step" else BYTES_RAY_KERNEL) * n
-        achieved = alg_bytes / (k_ms[dominant] * 1e-3) / 1e9
-        traffic = measured_traffic().get(dominant)
-        if traffic is not None and n != 65536:
-            traffic = None   # the capture was taken at 65536 envs per GPU
+        alg = algorithmic_bytes(gc)
+        achieved = alg[dominant] * n / (k_ms[dominant] * 1e-3) / 1e9
+        prof = measured_traffic() if (args.config == "cfg3" and n == 65536) else {}   # the capture is of this workload
+        traffic = prof.get(dominant)
         clocks = sampler.summary()
-        sm_mhz = clocks["sm_mhz"] or peaks.get("sm_max_mhz", 1965.0)
-        fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+        try:
+            fp32_peak = capi.measure_fp32_peak(job.local_rank)
+        except Exception:
+            fp32_peak = None
+        issue = None
+        inst = (prof.get("warp_inst") or {}).get(dominant)
+        if inst:   # issue slots: 148 SMs x 4 schedulers x 1 warp instruction per cycle
+            sm_hz = (clocks["sm_mhz"] or peaks.get("sm_max_mhz", 1965.0)) * 1e6
+            issue = {"kernel": dominant, "warp_inst_per_launch": inst,
+                     "lanes_per_inst": (prof.get("lanes_per_inst") or {}).get(dominant),
+                     "frac_of_issue_slots": inst / (k_ms[dominant] * 1e-3 * 148 * 4 * sm_hz),
+                     "note": "warp instructions of the committed ncu capture / (launch time x 148 SMs x 4 schedulers x SM clock)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64 controllers + f32 positions/rays + i32 hitboxes", "data": "synthetic (seeded scenario pool: %s, %d scenarios; "
             "uniform random actions)" % (pool_kind, pool.n),
-            "config": {"workload": WORKLOAD, "envs_per_gpu": n, "global_envs": n * world, "auto_reset": True,
+            "config": {"workload": desc, "name": args.config, "envs_per_gpu": n, "global_envs": n * world,
+                       "auto_reset": True, "settle_steps": args.settle,
                        "cache": "state touched per step (%.0f MB) exceeds the 126 MB L2; no explicit flush" % (
-                           n * (BYTES_STEP_KERNEL + BYTES_RAY_KERNEL) / 1e6),
-                       "stats_allreduce_every": stats_every if world > 1 else None},
+                           n * (alg["k_step"] + alg["k_rays"]) / 1e6) if n * (alg["k_step"] + alg["k_rays"]) > 126e6 else
+                       "state touched per step (%.0f MB) fits the 126 MB L2 at this batch size (BASELINE.json's size for "
+                       "this configuration); no explicit flush" % (n * (alg["k_step"] + alg["k_rays"]) / 1e6),
+                       "stats_allreduce_every": stats_every if world > 1 else None,
+                       "stats_allreduces_in_timed_region": reduces if world > 1 else None},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": args.e2e_steps,
-                    "api": "two capi.HostEnv halves, step_begin/step_wait alternating -> ftl_step_host_begin/_wait "
-                           "(pinned host buffers, handle-owned streams)",
-                    "synchronous_whole_batch": e2e_sync_value,
-                    "synchronous_api": "capi.HostEnv.step -> ftl_step_host, one call per step for all envs"},
+            "e2e": e2e,
+            "rollout": rollout,
             "gpu_launches": int(launches),
             "kernels_ms_per_step": k_ms,
-            "kernels_note": "each kernel timed alone (events between the launches disable the overlap): k_rays is a "
-                            "programmatic dependent launch of k_step and fills its tail, so ms_per_step < k_step + k_rays",
+            "kernels_note": "each kernel group timed alone (events between the launches disable their overlap), so "
+                            "ms_per_step < k_step + k_rays",
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_kind,
-                         "note": "k_rays is issue-bound (62% of issue slots busy, ncu), not HBM-bound: measured DRAM traffic is 1.3 KB/env-step",
-                         "algorithmic_bytes_per_env_step": BYTES_STEP_KERNEL if dominant == "k_step" else BYTES_RAY_KERNEL,
-                         "fp32_alu": {"flop_per_env_step": FLOP_PER_ENV_STEP,
-                                      "achieved_tflops": FLOP_PER_ENV_STEP * n * args.steps / (ms * 1e-3) / 1e12,
-                                      "peak_tflops_at_measured_clock": fp32_peak}},
+                         "algorithmic_bytes_per_env_step": alg[dominant],
+                         "whole_step": {"algorithmic_bytes_per_env_step": alg["k_step"] + alg["k_rays"],
+                                        "achieved": (alg["k_step"] + alg["k_rays"]) * n * args.steps / (ms_max * 1e-3) / 1e9,
+                                        "frac": (alg["k_step"] + alg["k_rays"]) * n * args.steps / (ms_max * 1e-3) / 1e9 / hbm_peak},
+                         "fp32_fma_peak_tflops_measured": fp32_peak,
+                         "issue_slots": issue,
+                         "note": "neither kernel is HBM-bound (measured DRAM traffic is below the algorithmic bytes): "
+                                 "the ray kernel is bound by instruction issue, the step kernels by dependent latency"},
             "episode_stats": stats,
         }
+        if sweep is not None:
+            line["sweep"] = sweep
         if not args.no_cpu_baseline and world == 1:
-            cb, _, _ = cpu_oracle_throughput(gc, pool)
-            line["cpu_baseline"] = cb
+            line["cpu_baseline"] = cpu_oracle_throughput(gc, pool)
         elif world > 1:
             line["cpu_baseline"] = None
         print(json.dumps(line))
-    env.close()
     if world > 1:
-        dist.destroy_process_group()
+        job.dist.destroy_process_group()
     return 0
 
 

@@ -52,6 +52,7 @@ SIGNATURES = {
     "ftl_launch_count": ([_vp], _i64),
     "ftl_profile": ([_vp, _i32], C.c_int),
     "ftl_profile_read": ([_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i64)], C.c_int),
+    "ftl_measure_fp32_peak": ([_i32, C.POINTER(C.c_double)], C.c_int),
     "ftl_generate_scenarios": ([C.POINTER(abi.FtlScenarioGenConfig), _vp, _i32, C.POINTER(abi.FtlScenarioPool), _i32],
                                C.c_int),
 }
@@ -85,6 +86,14 @@ def load(path=None):
                                 % (path, L.ftl_abi_version(), abi.FTL_ABI_VERSION))
     _LIBS[path] = L
     return L
+
+
+def measure_fp32_peak(device=0):
+    """FP32 FMA peak of `device` in TFLOP/s (ftl_measure_fp32_peak)."""
+    L = load()
+    v = C.c_double()
+    check(L, L.ftl_measure_fp32_peak(int(device), C.byref(v)), "ftl_measure_fp32_peak")
+    return v.value
 
 
 def check(L, rc, what):

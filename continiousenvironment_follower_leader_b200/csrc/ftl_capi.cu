@@ -101,6 +101,18 @@ __global__ void k_unpack_state(const __grid_constant__ DevCfg cfg, const DevStat
     unpack_env(cfg, s, first + j, src[j]);
 }
 
+// ---- FP32 FMA microbenchmark (ftl_measure_fp32_peak): 8 independent chains per thread, all in registers ---------
+__global__ void __launch_bounds__(256) k_fma_peak(float* out, int iters, float a, float b) {
+    float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f, x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f,
+          x7 = x0 + 7.f;
+#pragma unroll 4
+    for (int i = 0; i < iters; i++) {
+        x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+        x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
 // =================================================================================================
 // host side: handle, C-ABI
 // =================================================================================================
@@ -827,6 +839,36 @@ int ftl_stats(ftl_handle h, double* stats_dev, int32_t reset_after, void* cuda_s
     cudaStream_t st = (cudaStream_t)cuda_stream;
     CUDA_TRY(cudaMemcpyAsync(stats_dev, h->d_stats, sizeof(double) * FTL_STAT_COUNT, cudaMemcpyDeviceToDevice, st));
     if (reset_after) CUDA_TRY(cudaMemsetAsync(h->d_stats, 0, sizeof(double) * FTL_STAT_COUNT, st));
+    return FTL_OK;
+}
+
+int ftl_measure_fp32_peak(int32_t device, double* tflops_out) {
+    if (!tflops_out) return fail(FTL_ERR_INVALID, "NULL argument");
+    CUDA_TRY(cudaSetDevice(device));
+    int sms = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const int blocks = sms * 8, threads = 256, iters = 1 << 15;
+    float* buf = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&buf, sizeof(float) * (size_t)blocks * threads));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 6; rep++) {   // the first launches warm the clocks up; the best of the rest is the peak
+        cudaEventRecord(e0);
+        k_fma_peak<<<blocks, threads>>>(buf, iters, 0.999f, 1e-3f);
+        cudaEventRecord(e1);
+        cudaError_t err = cudaEventSynchronize(e1);
+        if (err != cudaSuccess) { cudaFree(buf); return fail(FTL_ERR_CUDA, cudaGetErrorString(err)); }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double tf = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+        if (rep >= 2 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(buf);
+    *tflops_out = best;
     return FTL_OK;
 }
 

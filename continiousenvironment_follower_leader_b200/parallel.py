@@ -21,6 +21,69 @@ def shard(global_envs, rank=None, world=None):
     return base, count
 
 
+def gpu_numa_node(gpu_index):
+    """NUMA node of a GPU from sysfs (PCI bus id through NVML), or None when the platform does not say."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(gpu_index))
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:       # NVML prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        return node if node >= 0 else None
+    except Exception:
+        return None
+
+
+def _cpus_of_node(node):
+    try:
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            text = f.read().strip()
+    except Exception:
+        return None
+    cpus = set()
+    for part in text.split(","):
+        if "-" in part:
+            a, b = part.split("-")
+            cpus.update(range(int(a), int(b) + 1))
+        elif part:
+            cpus.add(int(part))
+    return cpus
+
+
+def bind_to_gpu_numa(gpu_index, local_world=None):
+    """Pin the calling process to the cores of the NUMA node nearest `gpu_index` (so that pinned host buffers
+    allocated AFTERWARDS land on that node and the D2H copies of the host path do not cross sockets).  When several
+    ranks share a node its cores are split evenly between them.  Returns what was done; never raises."""
+    info = {"gpu": int(gpu_index), "numa_node": None, "bound": False}
+    try:
+        allowed = os.sched_getaffinity(0)
+        node = gpu_numa_node(gpu_index)
+        info["numa_node"] = node
+        cpus = _cpus_of_node(node) if node is not None else None
+        if not cpus:
+            return info
+        cpus = sorted(cpus & allowed)
+        if not cpus:
+            return info
+        if local_world is None:
+            local_world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
+        # ranks whose GPUs sit on the same node share its cores
+        same = [g for g in range(local_world) if gpu_numa_node(g) == node] or [int(gpu_index)]
+        k = same.index(int(gpu_index)) if int(gpu_index) in same else 0
+        share = max(1, len(cpus) // len(same))
+        mine = cpus[k * share:(k + 1) * share] or cpus
+        os.sched_setaffinity(0, set(mine))
+        info.update(bound=True, cpus=mine)
+    except Exception as e:   # noqa: BLE001 - binding is an optimisation
+        info["error"] = repr(e)
+    return info
+
+
 def reduce_stats(stats):
     """Sum a statistics tensor over all ranks (no-op without an initialised process group)."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:

@@ -307,6 +307,10 @@ int64_t ftl_launch_count(ftl_handle h);
 int ftl_profile(ftl_handle h, int32_t enable);
 int ftl_profile_read(ftl_handle h, double* step_kernel_ms, double* ray_kernel_ms, int64_t* steps);
 
+/* Diagnostic for the roofline report: FP32 FMA throughput of `device` measured with a
+ * register-resident kernel of independent fused multiply-add chains (2 flop per FMA), in TFLOP/s.  No handle needed. */
+int ftl_measure_fp32_peak(int32_t device, double* tflops_out);
+
 /* Replaces the scenario-building part of Game.reset() (ENV:434-543: _create_robots, _create_obstacles,
  * generate_finish_point, trajectory planning, _pos_follower_behind_leader) after env.seed(seeds[i]) (ENV:429-432),
  * for n seeds on n_threads host threads (0 = all cores).  Fills the first n scenarios of `out`, whose arrays are

@@ -223,6 +223,21 @@ def check_final_arrays(st, d, gc, env_index=0):
         _equal(st.corridor[env_index, idx], d["final_corridor"].astype(np.float32), "whole corridor (f32)", -1)
 
 
+def sample_actions(gc, rng, n, t=0):
+    """Uniform actions of the configured action space; every third step half of the batch drives straight ahead at
+    full speed so that part of it stays near the trail (in-box rewards, finish timers)."""
+    if gc.discrete_action_space:
+        a = rng.randint(0, 5, size=n).astype(np.int32)
+        if t % 3 == 0:
+            a[: n // 2] = 2
+        return a
+    lo, hi = gc.action_bounds()
+    a = rng.uniform(lo, hi, size=(n, len(lo))).astype(np.float32)
+    if t % 3 == 0:
+        a[: n // 2] = (0.0,) if len(lo) == 1 else (hi[0], 0.0)
+    return a
+
+
 def sensor_prev_expected(gc, rays):
     """ContinuousObserveModifier_sensorPrev.observation (WRP:203-221) applied with numpy to raw sensor blocks
     [N, rays_per_env]: clip(block / laser_length, 0, 1) per sensor, concatenated along the ray axis -> [N, H, sum W]."""

@@ -1,0 +1,219 @@
+"""GPU parity, part 2 (`pytest -m gpu`): the sub-paths of Game.step that round 1 only covered on the CPU build.
+
+  * constant_follower_speed / aggregate_reward (ENV:918-925, 1136), frames_per_step in {1, 2, 13} (the chunk boundary of
+    the frame loop and the low end of BASELINE.json's F sweep), 120 rays -- libftl.so against the oracle on seeded batches
+  * the episode-statistics vector the step kernel accumulates with atomics (what NCCL reduces) against the same sums
+    recomputed from the oracle's outputs, with and without auto-reset
+  * the bench workload itself: 65 536 envs on the 512-layout reference pool with auto-reset; a 1 024-env slice is
+    re-simulated by the oracle from the same actions and compared after 100 / 200 / 300 steps
+
+Bars as everywhere: integers bit-exact, floats within 1e-4 relative, ray outliers counted.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import parity
+from continiousenvironment_follower_leader_b200 import abi, capi
+from continiousenvironment_follower_leader_b200.config import GameConfig, cfg3_sensors
+from continiousenvironment_follower_leader_b200.scenario import ScenarioPool, synthetic_pool
+from test_gpu_parity import _compare_states, _ray_outliers
+
+pytestmark = pytest.mark.gpu
+
+
+sample_actions = parity.sample_actions
+
+
+GAP_CASES = [
+    ("const_speed", dict(bear_number=1, constant_follower_speed=True, follower_sensors=cfg3_sensors()), 1024, 60),
+    ("aggregate_reward", dict(bear_number=1, aggregate_reward=True, follower_sensors=cfg3_sensors(), max_steps=400,
+                              auto_reset=True), 1024, 70),
+    ("f1", dict(bear_number=1, frames_per_step=1, follower_sensors=cfg3_sensors()), 1024, 150),
+    ("f2_120rays", dict(bear_number=1, frames_per_step=2, follower_sensors=cfg3_sensors(12, 120, 5)), 512, 90),
+    ("f13_2bears", dict(bear_number=2, frames_per_step=13, follower_sensors=cfg3_sensors(), max_steps=400,
+                        auto_reset=True), 1024, 50),
+    ("f10_warm0_es", dict(bear_number=1, warm_start=0, early_stopping={"max_distance_coef": 1.3, "low_reward": -60},
+                          follower_sensors=cfg3_sensors(), auto_reset=True), 1024, 80),
+]
+
+
+@pytest.mark.parametrize("name,kwargs,n,steps", GAP_CASES, ids=[c[0] for c in GAP_CASES])
+def test_cuda_matches_oracle_on_the_uncovered_step_options(name, kwargs, n, steps):
+    from oracle_py import OracleEnv
+    gc = GameConfig(**kwargs)
+    pool = synthetic_pool(gc, 64, seed=2)
+    cuda, orc = capi.HostEnv(gc, n, lib=capi.load()), OracleEnv(gc, n, n_threads=8)
+    cuda.upload_scenarios(pool)
+    orc.upload_scenarios(pool)
+    ids = (np.arange(n) % pool.n).astype(np.int32)
+    cuda.reset(scenario_ids=ids)
+    orc.reset(scenario_ids=ids)
+    rng = np.random.RandomState(17)
+    bad, total, dones = 0, 0, 0
+    for t in range(steps):
+        a = sample_actions(gc, rng, n, t)
+        oc, oo = cuda.step(a), orc.step(a)
+        assert np.array_equal(oc.done, oo.done), "done differs at step %d" % t
+        assert np.array_equal(oc.status, oo.status), "status differs at step %d" % t
+        assert np.allclose(oc.reward, oo.reward, rtol=1e-5, atol=1e-5), "reward differs at step %d" % t
+        assert np.array_equal(oc.leader_target, oo.leader_target)
+        assert np.allclose(oc.numerical_features, oo.numerical_features, rtol=parity.RTOL, atol=1e-4)
+        bad += _ray_outliers(oc.rays, oo.rays)
+        total += oc.rays.size
+        dones += int(oo.done.sum())
+        if t % 10 == 9 or t == steps - 1:
+            _compare_states(cuda.get_state(), orc.get_state(), gc, n, parity.RTOL)
+    assert bad <= 2, "%d of %d ray values outside tolerance" % (bad, total)
+    if gc.c.aggregate_reward:   # the returned reward is the running total (ENV:1136), not the last frame's
+        live = ~oo.done.astype(bool)
+        assert live.sum() > n // 2
+        assert np.allclose(oc.reward[live], orc.get_state().env["overall_reward"][live], rtol=1e-5, atol=1e-5)
+        assert np.abs(oc.reward).max() > 5, "aggregate rewards should have grown beyond a single frame's reward"
+    cuda.close()
+
+
+def _stats_from_outputs(done_prev, out, state):
+    """FTL_STAT_* sums of the envs that finished in this step, from host arrays."""
+    new = (~done_prev) & out.done.astype(bool)
+    v = np.zeros(abi.STAT_COUNT, np.float64)
+    v[abi.STAT_EPISODES] = new.sum()
+    v[abi.STAT_RETURN_SUM] = state.env["overall_reward"][new].sum()
+    v[abi.STAT_LENGTH_SUM] = state.env["step_count"][new].sum()
+    st = out.status[new]
+    v[abi.STAT_CRASH] = (st[:, 3] != 0).sum()
+    v[abi.STAT_SUCCESS] = (st[:, 0] == 2).sum()
+    v[abi.STAT_TIMEOUT] = (st[:, 0] == 3).sum()
+    v[abi.STAT_LEADER_CRASH] = (st[:, 2] == 2).sum()
+    return v
+
+
+@pytest.mark.parametrize("auto_reset", [False, True], ids=["no_reset", "auto_reset"])
+def test_device_episode_statistics_equal_the_sums_over_the_oracle(auto_reset):
+    """ftl_stats (atomics in the step kernel; the vector NCCL all-reduces) against sums over the oracle.  Without
+    auto-reset the oracle's state still holds the finished episode's return and length when it is read; with
+    auto-reset the env is already re-initialised, so the run uses aggregate_reward (the returned reward of the last
+    step IS the episode return, ENV:1136) and counts the steps of each episode (step_count advances by F per step)."""
+    import torch
+    from oracle_py import OracleEnv
+    from continiousenvironment_follower_leader_b200.batch_env import FtlBatchEnv
+    gc = GameConfig(bear_number=1, follower_sensors=cfg3_sensors(), max_steps=250, auto_reset=auto_reset,
+                    aggregate_reward=auto_reset)
+    pool = synthetic_pool(gc, 48, seed=4)
+    n = 4000     # not a multiple of 32: the filler envs of the last warp must not be counted
+    env = FtlBatchEnv(n, game_config=gc, scenario_pool=pool)
+    orc = OracleEnv(gc, n, n_threads=8)
+    orc.upload_scenarios(pool)
+    env.reset()
+    orc.reset()
+    rng = np.random.RandomState(5)
+    want = np.zeros(abi.STAT_COUNT, np.float64)
+    done_prev = np.zeros(n, bool)
+    ep_steps = np.zeros(n, np.int64)
+    for t in range(60 if auto_reset else 40):
+        a = sample_actions(gc, rng, n, t)
+        obs, rew, done, info = env.step(torch.from_numpy(a).cuda())
+        oo = orc.step(a)
+        assert np.array_equal(done.cpu().numpy(), oo.done.astype(bool))
+        ep_steps += 1
+        if auto_reset:
+            new = oo.done.astype(bool)
+            v = _stats_from_outputs(np.zeros(n, bool), oo, orc.get_state())
+            v[abi.STAT_RETURN_SUM] = oo.reward[new].astype(np.float64).sum()
+            v[abi.STAT_LENGTH_SUM] = (ep_steps[new] * gc.c.frames_per_step).sum()
+            ep_steps[new] = 0
+            want += v
+        else:
+            want += _stats_from_outputs(done_prev, oo, orc.get_state())
+            done_prev = oo.done.astype(bool).copy()
+    got = env.stats().cpu().numpy()
+    if auto_reset:
+        assert want[abi.STAT_EPISODES] > 2 * n     # 26 steps per episode at most
+    else:
+        assert want[abi.STAT_EPISODES] == n        # max_steps = 250 frames: every env finished exactly once
+    for k in (abi.STAT_EPISODES, abi.STAT_LENGTH_SUM, abi.STAT_CRASH, abi.STAT_SUCCESS, abi.STAT_TIMEOUT,
+              abi.STAT_LEADER_CRASH):
+        assert got[k] == want[k], (abi.STAT_NAMES[k], got[k], want[k])
+    assert got[abi.STAT_RETURN_SUM] == pytest.approx(want[abi.STAT_RETURN_SUM], rel=1e-6 if auto_reset else 1e-9, abs=1e-6)
+    assert got[abi.STAT_OVERFLOW] == 0
+    # reset_after zeroes the vector
+    env.stats(reset=True)
+    assert float(env.stats().abs().sum()) == 0.0
+    env.close()
+
+
+def test_bench_workload_sample_matches_the_oracle_after_hundreds_of_steps():
+    """The configuration bench.py times (BASELINE.json configs[2]: 65 536 envs, reference scenario pool, auto-reset,
+    uniform random actions): envs [first, first + m) are re-simulated by the oracle with the same global env ids
+    and the same actions; states are compared after 100, 200 and 300 steps -- i.e. across many in-step resets."""
+    import torch
+    from oracle_py import OracleEnv
+    from continiousenvironment_follower_leader_b200.batch_env import FtlBatchEnv
+    import bench
+    gc = bench.workload_config(auto_reset=True)
+    pool, kind = bench.workload_pool(gc)
+    n, first, m = 65536, 40960, 1024
+    env = FtlBatchEnv(n, game_config=gc, scenario_pool=pool)
+    orc = OracleEnv(gc, m, env_id_base=first, n_threads=os.cpu_count() or 8)
+    orc.upload_scenarios(pool)
+    env.reset()
+    orc.reset()
+    _compare_states(env.get_state(first, m), orc.get_state(), gc, m, parity.RTOL)
+    g = torch.Generator(device="cuda").manual_seed(99)
+    lo, hi = [torch.tensor(x, device="cuda") for x in gc.action_bounds()]
+    bad, total, episodes = 0, 0, 0
+    for t in range(300):
+        a = (lo + (hi - lo) * torch.rand((n, 2), generator=g, device="cuda")).contiguous()
+        obs, rew, done, info = env.step(a)
+        oo = orc.step(a[first:first + m].cpu().numpy())
+        episodes += int(oo.done.sum())
+        if t % 20 == 19:
+            assert np.array_equal(done[first:first + m].cpu().numpy(), oo.done.astype(bool)), "done differs at step %d" % t
+            assert np.allclose(rew[first:first + m].cpu().numpy(), oo.reward, rtol=1e-5, atol=1e-5)
+            bad += _ray_outliers(env.rays[first:first + m].cpu().numpy(), oo.rays)
+            total += oo.rays.size
+        if t + 1 in (100, 200, 300):
+            _compare_states(env.get_state(first, m), orc.get_state(), gc, m, parity.RTOL)
+    assert episodes > m // 2, "the sample saw too few in-step resets (%d)" % episodes
+    assert bad <= 3, "%d of %d ray values outside tolerance" % (bad, total)
+    env.close()
+
+
+def test_device_rollout_matches_a_manual_loop_and_stays_on_the_device():
+    """rollout.DeviceRollout: the trajectory it stores must be the one a hand-written loop over
+    FtlBatchEnv.step with the same policy produces, the observation it feeds the policy is the fused sensorPrev matrix
+    (WRP:203-221) of the raw sensor blocks, and nothing in it lives on the host."""
+    import torch
+    from continiousenvironment_follower_leader_b200.batch_env import FtlBatchEnv
+    from continiousenvironment_follower_leader_b200.rollout import DeviceRollout
+    from continiousenvironment_follower_leader_b200.wrappers import sensor_prev_observation
+    kwargs = dict(bear_number=1, follower_sensors=cfg3_sensors(), auto_reset=True, max_steps=200)
+    gc_f, gc_raw = GameConfig(fused_sensor_prev=True, **kwargs), GameConfig(**kwargs)
+    pool = synthetic_pool(gc_f, 32, seed=6)
+    n, T = 2048, 24
+    ro = DeviceRollout(n, T, game_config=gc_f, scenario_pool=pool, seed=3)
+    traj = ro.collect(explore=False)
+    for k, v in traj.items():
+        assert v.is_cuda, k
+    assert traj["obs"].shape == (T + 1, n, 240) and traj["actions"].shape == (T, n, 2)
+    assert float(traj["obs"].min()) >= 0 and float(traj["obs"].max()) <= 1
+    lo, hi = gc_f.action_bounds()
+    assert bool((traj["actions"] >= torch.tensor(lo, device="cuda") - 1e-6).all())
+    assert bool((traj["actions"] <= torch.tensor(hi, device="cuda") + 1e-6).all())
+    assert int(traj["dones"].sum()) > 0          # max_steps = 200 frames: episodes end inside the window
+    # the same policy driven by hand over the raw-sensor configuration
+    env = FtlBatchEnv(n, game_config=gc_raw, scenario_pool=pool)
+    env.reset()
+    with torch.no_grad():
+        for t in range(T):
+            obs = sensor_prev_observation(env).reshape(n, -1)
+            assert torch.equal(obs, traj["obs"][t]), "observation differs at step %d" % t
+            act, val = ro.policy(obs, None)
+            assert torch.equal(act, traj["actions"][t])
+            _, rew, done, _ = env.step(act.contiguous())
+            assert torch.equal(rew, traj["rewards"][t]) and torch.equal(done, traj["dones"][t].bool())
+    adv, ret = ro.advantages()
+    assert adv.shape == (T, n) and bool(torch.isfinite(adv).all())
+    env.close()
+    ro.close()

@@ -31,6 +31,11 @@ CASES = [
                        max_steps=300), 48, 70),
     ("radar_new", dict(parity.load_trace(parity.GOLDEN_DIR + "/radar_new_seed19.npz")[1]["kwargs"]), 32, 60),
     ("radar_near", dict(parity.load_trace(parity.GOLDEN_DIR + "/radar_near_seed21.npz")[1]["kwargs"]), 32, 60),
+    # the remaining action decode and reward options of Game.step (ENV:918-925, 1136) and the shortest step
+    ("const_speed", dict(bear_number=1, constant_follower_speed=True, follower_sensors=cfg3_sensors()), 48, 60),
+    ("aggregate_reward", dict(bear_number=1, aggregate_reward=True, follower_sensors=cfg3_sensors(), max_steps=300,
+                              auto_reset=True), 48, 60),
+    ("f1", dict(bear_number=1, frames_per_step=1, follower_sensors=cfg3_sensors()), 48, 120),
 ]
 
 
@@ -48,12 +53,7 @@ def test_hostsim_matches_oracle(name, kwargs, n, steps):
     bounds = gc.action_bounds()
     bad, total = 0, 0
     for t in range(steps):
-        if gc.discrete_action_space:
-            a = rng.randint(0, 5, size=n).astype(np.int32)
-        else:
-            a = rng.uniform(bounds[0], bounds[1], size=(n, 2)).astype(np.float32)
-            if t % 3 == 0:      # keep some followers moving straight so they stay near the trail
-                a[: n // 2, 0], a[: n // 2, 1] = bounds[1][0], 0.0
+        a = parity.sample_actions(gc, rng, n, t)
         os_, oo = sim.step(a), orc.step(a)
         assert np.array_equal(os_.done, oo.done), "done differs at step %d" % t
         assert np.array_equal(os_.status, oo.status)
