@@ -150,6 +150,11 @@ class FtlOutputs(C.Structure):
                 ("follower_info", C.c_void_p), ("track_vectors", C.c_void_p), ("radar", C.c_void_p)]
 
 
+class FtlStepInputs(C.Structure):
+    """Optional per-step inputs of ftl_step_ex / ftl_step_host_ex (include/ftl.h)."""
+    _fields_ = [("frames_per_step", C.c_void_p), ("regime_draws", C.c_void_p)]
+
+
 ENV_STATE_DTYPE = np.dtype(FtlEnvState)
 
 

@@ -61,6 +61,9 @@ class FtlBatchEnv:
                                    None if self.radar is None else self.radar.data_ptr())
         self._stats = torch.zeros(abi.STAT_COUNT, dtype=torch.float64, device=dev)
         self._ray_layout = self.gc.ray_layout()
+        self._env_id_base = int(env_id_base)
+        self._frames_gen = None
+        self.last_frames = None
         self._pool = None
         if scenario_pool is not None:
             self.upload_scenarios(scenario_pool)
@@ -119,11 +122,30 @@ class FtlBatchEnv:
                    "ftl_reset")
         return self._obs()
 
-    def step(self, actions):
+    def step(self, actions, frames=None, regime_draws=None):
+        """frames: int32 CUDA tensor [N], frames this step runs per env (random_frames_per_step, ENV:939-940; drawn
+        on the device from `random_frames_per_step` when the configuration has it and none is given); regime_draws:
+        float64 CUDA tensor [N, frames_per_step], see FtlStepInputs in include/ftl.h."""
         want = torch.int32 if self.cfg.action_mode == abi.ACTION_DISCRETE else torch.float32
         if actions.dtype != want or not actions.is_contiguous() or actions.device != self.device:
             actions = actions.to(device=self.device, dtype=want).contiguous()
-        capi.check(self._L, self._L.ftl_step(self._h, actions.data_ptr(), C.byref(self._out), self._stream()), "ftl_step")
+        if frames is None and self.gc.random_frames_per_step is not None:
+            lo, hi = self.gc.random_frames_per_step     # np.random.randint(lo, hi): hi exclusive
+            if self._frames_gen is None:
+                self._frames_gen = torch.Generator(device=self.device).manual_seed(0x5eed + int(self._env_id_base))
+            frames = torch.randint(int(lo), int(hi), (self.n,), generator=self._frames_gen, device=self.device,
+                                   dtype=torch.int32)
+        if frames is None and regime_draws is None:
+            capi.check(self._L, self._L.ftl_step(self._h, actions.data_ptr(), C.byref(self._out), self._stream()), "ftl_step")
+        else:
+            f = None if frames is None else frames.to(device=self.device, dtype=torch.int32).contiguous()
+            d = None if regime_draws is None else regime_draws.to(device=self.device, dtype=torch.float64).contiguous()
+            if d is not None and tuple(d.shape) != (self.n, self.cfg.frames_per_step):
+                raise ValueError("regime_draws must have shape (n_envs, frames_per_step)")
+            ins = abi.FtlStepInputs(None if f is None else f.data_ptr(), None if d is None else d.data_ptr())
+            capi.check(self._L, self._L.ftl_step_ex(self._h, actions.data_ptr(), C.byref(ins), C.byref(self._out),
+                                                    self._stream()), "ftl_step_ex")
+            self.last_frames = f
         return self._obs(), self.reward, self.done.bool(), {"status": self.status}
 
     def step_raw(self, actions):
@@ -160,6 +182,13 @@ class FtlBatchEnv:
         a, b, k = C.c_double(), C.c_double(), C.c_int64()
         capi.check(self._L, self._L.ftl_profile_read(self._h, C.byref(a), C.byref(b), C.byref(k)), "ftl_profile_read")
         return a.value, b.value, k.value
+
+    def profile_read_kernels(self):
+        """{"k_kin", "k_book", "k_rays"} ms accumulated since profile(True) (k_rays includes k_finish), and the steps."""
+        a, b, r, k = C.c_double(), C.c_double(), C.c_double(), C.c_int64()
+        capi.check(self._L, self._L.ftl_profile_read_kernels(self._h, C.byref(a), C.byref(b), C.byref(r), C.byref(k)),
+                   "ftl_profile_read_kernels")
+        return {"k_kin": a.value, "k_book": b.value, "k_rays": r.value}, k.value
 
     @property
     def launch_count(self):

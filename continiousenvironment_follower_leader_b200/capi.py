@@ -41,6 +41,8 @@ SIGNATURES = {
     "ftl_upload_scenarios": ([_vp, C.POINTER(abi.FtlScenarioPool)], C.c_int),
     "ftl_reset": ([_vp, _vp, _vp, C.POINTER(abi.FtlOutputs), _vp], C.c_int),
     "ftl_step": ([_vp, _vp, C.POINTER(abi.FtlOutputs), _vp], C.c_int),
+    "ftl_step_ex": ([_vp, _vp, C.POINTER(abi.FtlStepInputs), C.POINTER(abi.FtlOutputs), _vp], C.c_int),
+    "ftl_step_host_ex": ([_vp, _vp, C.POINTER(abi.FtlStepInputs), C.POINTER(abi.FtlOutputs), _vp], C.c_int),
     "ftl_reset_host": ([_vp, _vp, _vp, C.POINTER(abi.FtlOutputs), _vp], C.c_int),
     "ftl_step_host": ([_vp, _vp, C.POINTER(abi.FtlOutputs), _vp], C.c_int),
     "ftl_step_host_begin": ([_vp, _vp, C.POINTER(abi.FtlOutputs), _vp], C.c_int),
@@ -52,6 +54,8 @@ SIGNATURES = {
     "ftl_launch_count": ([_vp], _i64),
     "ftl_profile": ([_vp, _i32], C.c_int),
     "ftl_profile_read": ([_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i64)], C.c_int),
+    "ftl_profile_read_kernels": ([_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i64)],
+                                 C.c_int),
     "ftl_measure_fp32_peak": ([_i32, C.POINTER(C.c_double)], C.c_int),
     "ftl_generate_scenarios": ([C.POINTER(abi.FtlScenarioGenConfig), _vp, _i32, C.POINTER(abi.FtlScenarioPool), _i32],
                                C.c_int),
@@ -212,10 +216,22 @@ class HostEnv:
               "ftl_reset_host")
         return self.out
 
-    def step(self, actions):
+    def step(self, actions, frames=None, regime_draws=None):
+        """One Game.step for every env.  Optional per-step inputs (FtlStepInputs, include/ftl.h): `frames` int32[N] =
+        frames this step runs per env (random_frames_per_step, ENV:939-940); `regime_draws` float64[N, frames_per_step]
+        = the random() behind random.uniform of list-valued leader_speed_regime entries (ENV:1155-1156)."""
         np.copyto(self._actions, np.asarray(actions).reshape(self._actions.shape), casting="same_kind")
-        check(self._L, self._L.ftl_step_host(self._h, abi.ptr(self._actions), C.byref(self.out.c), self._stream),
-              "ftl_step_host")
+        if frames is None and regime_draws is None:
+            check(self._L, self._L.ftl_step_host(self._h, abi.ptr(self._actions), C.byref(self.out.c), self._stream),
+                  "ftl_step_host")
+            return self.out
+        f = None if frames is None else np.ascontiguousarray(np.broadcast_to(frames, (self.n,)), np.int32)
+        d = None if regime_draws is None else np.ascontiguousarray(regime_draws, np.float64)
+        if d is not None and d.shape != (self.n, self.cfg.frames_per_step):
+            raise ValueError("regime_draws must have shape (n_envs, frames_per_step)")
+        ins = abi.FtlStepInputs(abi.ptr(f), abi.ptr(d))
+        check(self._L, self._L.ftl_step_host_ex(self._h, abi.ptr(self._actions), C.byref(ins), C.byref(self.out.c),
+                                                self._stream), "ftl_step_host_ex")
         return self.out
 
     def step_begin(self, actions):

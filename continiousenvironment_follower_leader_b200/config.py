@@ -86,8 +86,20 @@ class GameConfig:
             raise NotImplementedError("manual_control needs a pygame window; the batched simulator is head-less")
         if g["simulation_time_limit"] is not None:
             raise NotImplementedError("simulation_time_limit is wall-clock based (ENV:1119-1123) and not supported")
+        # random_frames_per_step (ENV:398-405, 939-940): the reference redraws self.frames_per_step with
+        # np.random.randint(lo, hi) after every step.  Here the kernels take the per-env count of each step as an input
+        # (FtlStepInputs.frames_per_step) and FtlConfig.frames_per_step becomes the capacity hi - 1.
+        self.random_frames_per_step = None
         if g["random_frames_per_step"] is not None:
-            raise NotImplementedError("random_frames_per_step (ENV:405, 939-940) is not supported by the fused kernel")
+            rf = g["random_frames_per_step"]
+            if g["frames_per_step"] is not None:
+                warn("random_frames_per_step and frames_per_step are both given; random_frames_per_step is used")
+            assert len(rf) == 2, ("random_frames_per_step must be the two bounds of the random draw. "
+                                  "Given: {}".format(rf))
+            lo_f, hi_f = int(rf[0]), int(rf[1])
+            if lo_f < 1 or hi_f <= lo_f:
+                raise ValueError("random_frames_per_step needs 1 <= low < high (np.random.randint(low, high))")
+            self.random_frames_per_step = (lo_f, hi_f)
 
         ptm = g["pixels_to_meter"]
         px = lambda m: m * ptm  # noqa: E731  ENV:1942-1943
@@ -97,7 +109,7 @@ class GameConfig:
         # library option: `rays` carries ContinuousObserveModifier_sensorPrev's output (WRP:203-221) directly
         c.fused_sensor_prev = int(bool(fused_sensor_prev))
         c.game_width, c.game_height = int(g["game_width"]), int(g["game_height"])
-        c.frames_per_step = int(g["frames_per_step"])
+        c.frames_per_step = self.random_frames_per_step[1] - 1 if self.random_frames_per_step else int(g["frames_per_step"])
         c.max_steps, c.warm_start = int(g["max_steps"]), int(g["warm_start"])
         c.trajectory_saving_period = 5  # ENV:262
         c.aggregate_reward = int(bool(g["aggregate_reward"]))
@@ -176,7 +188,8 @@ class GameConfig:
         if corridor_cap is None:
             corridor_cap = 64
             if c.tracker_enabled:
-                per_save = max(lead_v * c.frames_per_step * c.saving_period / max(c.tracker_scans_per_step, 1), 1e-6)
+                f_min = self.random_frames_per_step[0] if self.random_frames_per_step else c.frames_per_step
+                per_save = max(lead_v * f_min * c.saving_period / max(c.tracker_scans_per_step, 1), 1e-6)
                 corridor_cap = min(_pow2_at_least(int(1.5 * c.corridor_length / per_save) + 32), 512)
         if corridor_cap & (corridor_cap - 1) or corridor_cap > 512:
             raise ValueError("corridor_cap must be a power of two <= 512")

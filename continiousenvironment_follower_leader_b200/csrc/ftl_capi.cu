@@ -1,12 +1,16 @@
-// ftl_capi.cu -- the C-ABI of include/ftl.h (libftl.so), the ray kernel and the state-exchange kernels.
+// ftl_capi.cu -- the C-ABI of include/ftl.h (libftl.so), the ray kernel, the bookkeeping / finishing kernels and the
+// state-exchange kernels.
 //
-// Launch structure of one ftl_step():
-//   k_step<NB>    (ftl_step_nb.cu) one thread per env: the F sub-frames fused in registers (a kinematics pass and a
-//                 bookkeeping pass), tracker scans, history snapshot, non-ray outputs, episode statistics, optional
-//                 in-place auto-reset (a copy of the scenario's reset image)
-//   k_rays        one warp per env: history ray casting with static/corridor de-duplication; launched as a programmatic
-//                 dependent of k_step, it waits per group of 32 envs on the flag the owning warp of k_step publishes
-//   k_rays_exact  one thread per env, almost always idle: the pairs whose float32 predicates were inconclusive
+// Launch structure of one ftl_step() -- a chain of programmatic dependent launches on the caller's stream; each kernel
+// waits per group of 32 envs on a flag the kernel it depends on publishes, so they overlap wherever the data allows:
+//   k_kin<NB>   (ftl_step_nb.cu) one thread per env: the F sub-frames of robot kinematics fused in registers, per-frame
+//               records, tracker scans, history snapshot, observation outputs            -> kin_flag
+//   k_book      one thread per env: the bookkeeping of the F recorded frames (exact green-zone flags, trail, timers,
+//               early stopping, reward, done), episode statistics.  Needs kin_flag; runs BESIDE k_rays -> book_flag
+//   k_rays      one warp per env: history ray casting with static/corridor de-duplication.  Needs kin_flag only
+//   k_finish    one thread per env, almost always idle: the (edge, ray) pairs whose float32 predicates were inconclusive,
+//               then the in-place auto-reset of finished envs as a copy of the scenario's reset image (state, first
+//               observation and its rays).  Needs all of k_rays and book_flag
 // All are HBM/ALU streaming kernels without tensor-core work (ray casting is not a contraction).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false (see build.py); fused
 // multiply-adds are written explicitly where wanted so float results match the reference's rounding.
@@ -23,6 +27,8 @@
 #include "ftl_rays.cuh"
 #include "ftl_step.cuh"
 #include "ftl_state_io.cuh"
+#include "ftl_reset_image.cuh"
+#include "ftl_book.cuh"
 
 using namespace ftl;
 
@@ -30,55 +36,79 @@ using namespace ftl;
 // kernels
 // =================================================================================================
 #ifndef FTL_NO_PDL
-#define FTL_NO_PDL 0   // 1: plain stream order between k_step and k_rays
+#define FTL_NO_PDL 0   // 1: plain stream order between the kernels of a step
 #endif
-#ifndef FTL_EXACT_PDL
-#define FTL_EXACT_PDL 1   // k_rays_exact as a programmatic dependent launch of k_rays (hides its launch latency)
+#ifndef FTL_FUSED_BOOK
+#define FTL_FUSED_BOOK 1   // 1: k_kin also does the bookkeeping of its env (no k_book launch); 0: separate k_book beside k_rays.
+                           // Same-box A/B (profiles/r02_ab_log.txt): fused 0.370 ms per step, split 0.408 -- the bookkeeping is
+                           // latency-bound either way and a separate kernel holds registers the ray kernel wants
 #endif
 #ifndef FTL_RAYS_WARPS
 #define FTL_RAYS_WARPS 2   // envs per block.  A block lives as long as its slowest env: 2-warp blocks measured 2.3 % faster
-#endif                     // than 4-warp ones (and they fit sooner into what a finished k_step block frees, section 4.5)
+#endif                     // than 4-warp ones (and they fit sooner into what a finished block of the step kernels frees)
 #ifndef FTL_RAYS_MINB
 #define FTL_RAYS_MINB (28 / FTL_RAYS_WARPS)   // 28 warps per SM: 72 registers, no spills; shared memory (7.2 KB per warp) allows no more
 #endif
+
 __global__ void __launch_bounds__(32 * FTL_RAYS_WARPS, FTL_RAYS_MINB)
 k_rays(const __grid_constant__ DevCfg cfg, const DevState s, const DevPool pool, const double2* __restrict__ rot,
        float* __restrict__ rays_out, int smem_per_warp, int first_env, int end_env, int wait_seq) {
-#if FTL_EXACT_PDL
-    asm volatile("griddepcontrol.launch_dependents;");   // k_rays_exact may be scheduled behind the last wave of this grid
-#endif
+    asm volatile("griddepcontrol.launch_dependents;");   // k_finish may be scheduled behind the last wave of this grid
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5;
     const int i = first_env + blockIdx.x * (blockDim.x >> 5) + warp;  // one warp per env
     if (i >= end_env) return;
-    if (wait_seq) {
-        // launched as a programmatic dependent of k_step (see there): wait until the warp of k_step that owns this
-        // env's group of 32 has published step `wait_seq`.  Bounded: a flag that never arrives is a bug, not a hang.
-        if ((threadIdx.x & 31) == 0) {
-            const int* flag = s.step_flag + (i >> 5);
-            int seen, spins = 0;
-            for (;;) {
-                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
-                if (seen == wait_seq) break;
-                __nanosleep(200);
-                if (++spins > (1 << 24)) __trap();
-            }
-        }
-        __syncwarp();
-    }
+    if (wait_seq) wait_group_flag(s.kin_flag, i >> 5, wait_seq);   // launched early: wait for this env's kinematics
     RayShared& sh = *reinterpret_cast<RayShared*>(smem + (size_t)warp * smem_per_warp);
     rays_warp(cfg, s, pool, rot, i, sh, rays_out);
 }
 
-__global__ void __launch_bounds__(128)
-k_rays_exact(const __grid_constant__ DevCfg cfg, const DevState s, const DevPool pool, float* __restrict__ rays_out,
-             int first_env, int end_env) {
-#if FTL_EXACT_PDL
-    asm volatile("griddepcontrol.wait;" ::: "memory");   // launched early (programmatic dependent of k_rays): wait for all of it
+#ifndef FTL_BOOK_THREADS
+#define FTL_BOOK_THREADS 64
 #endif
-    const int i = first_env + blockIdx.x * blockDim.x + threadIdx.x;   // one thread per env, idle unless a pair was inconclusive
-    if (i >= end_env) return;
-    rays_exact_env(cfg, s, pool, i, rays_out);
+__global__ void __launch_bounds__(FTL_BOOK_THREADS)
+k_book(const __grid_constant__ DevCfg cfg, const __grid_constant__ DevState s, const __grid_constant__ DevOutputs img_out,
+       const __grid_constant__ DevOutputs out, double* __restrict__ stats, int n_scenarios, int wait_seq, int seq) {
+    asm volatile("griddepcontrol.launch_dependents;");
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // whole warps: n is padded to a multiple of 32
+    if (i >= s.n) return;
+    if (wait_seq) wait_group_flag(s.kin_flag, i >> 5, wait_seq);
+    book_env(cfg, s, img_out, out, stats, n_scenarios, i);
+    publish_group_flag(s.book_flag, i >> 5, seq);
+}
+
+// One thread per env, almost always idle: the (edge, ray) pairs of k_rays whose float32 predicates were inconclusive are
+// redone in float64, and the rays of envs that finished in this step are replaced by those of their next episode's first
+// observation (ftl_reset_image.cuh).  Serial behind k_rays, so it does as little as possible.
+__global__ void __launch_bounds__(128, 12)   // 40 registers: its blocks are resident (waiting) beside the last ray blocks
+k_finish(const __grid_constant__ DevCfg cfg, const __grid_constant__ DevState s, const __grid_constant__ DevPool pool,
+         const __grid_constant__ DevOutputs img_out, float* __restrict__ rays_out, int first_env, int end_env, int wait_seq,
+         int renew, int pdl) {
+    if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");   // launched early: wait for all of k_rays
+    const int i = first_env + blockIdx.x * blockDim.x + threadIdx.x;   // first_env is a multiple of 32: a warp = one group
+    const int lane = threadIdx.x & 31;
+    if (i - lane >= end_env) return;                              // whole warps leave together
+    if (i < end_env) rays_exact_env(cfg, s, pool, i, rays_out);
+    if (!renew) return;
+    if (wait_seq) wait_group_flag(s.book_flag, (i - lane) >> 5, wait_seq);   // `done` is the bookkeeping kernel's
+    const int scen = i < end_env ? pending_reset_scenario(cfg, s, pool.n_scenarios, i) : -1;
+    unsigned todo = __ballot_sync(0xffffffffu, scen >= 0);
+    const int rpe = cfg.rays_per_env;
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int env = __shfl_sync(0xffffffffu, i, src), sc = __shfl_sync(0xffffffffu, scen, src);
+        for (int k = lane; k < rpe; k += 32) rays_out[(size_t)env * rpe + k] = img_out.rays[(size_t)sc * rpe + k];
+    }
+}
+
+// the state half of the auto-reset outside a step (ftl_get_state / ftl_set_state / ftl_reset after a step)
+__global__ void __launch_bounds__(128)
+k_apply_resets(const __grid_constant__ DevCfg cfg, const __grid_constant__ DevState s, const __grid_constant__ DevPool pool,
+               const __grid_constant__ DevState img) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= s.n) return;
+    apply_pending_resets(cfg, s, pool, img, i);
 }
 
 // ---- state exchange: SoA <-> FtlEnvState (AoS) ----------------------------------------------------
@@ -135,19 +165,23 @@ struct FtlHandle_ {
     int n_robots = 2;
     DevState st{};
     DevState image{};   // env s = scenario s right after reset (built by ftl_upload_scenarios); the in-step auto-reset copies from it
+    DevOutputs image_out{};   // ... and its first observation (numerical_features, leader_target, rays)
     DevPool pool{};
     bool have_pool = false, was_reset = false;
+    bool maybe_pending_resets = false;   // a step ran since the last k_apply_resets: finished envs may await their state copy
     std::vector<void*> allocs, pool_allocs;
     double* d_stats = nullptr;
     // device-side staging for the host-buffer entry points
     void* d_actions = nullptr;
+    int* d_in_frames = nullptr;       // FtlStepInputs staging of the host path (allocated on first use)
+    double* d_in_draws = nullptr;
     uint8_t* d_mask = nullptr;
     int* d_scen_ids = nullptr;
     DevOutputs d_out{};
     FtlEnvState* d_state_stage = nullptr;
     int state_stage_cap = 0;
     int64_t launches = 0;
-    int step_seq = 0;          // sequence number of the last k_step launch (step_flag protocol)
+    int step_seq = 0;          // sequence number of the last ftl_step (kin_flag / book_flag protocol)
     int rays_total = 0;
     bool rays_smem_opted = false;
     double2* d_rot = nullptr;   // (cos, sin)(k * 360/R) per flat ray
@@ -156,12 +190,13 @@ struct FtlHandle_ {
     cudaStream_t pending_stream = nullptr;   // stream of an ftl_step_host_begin that has not been waited for
     bool pending = false;
     cudaEvent_t chunk_ev[8] = {};
-    // optional per-kernel timing (ftl_profile): three events per step on the launching stream
+    // optional per-kernel timing (ftl_profile): kProfEvents events per step on the launching stream
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;
     size_t prof_used = 0;
 };
 
+constexpr int kProfEvents = 4;
 static cudaEvent_t prof_event(FtlHandle_* h, cudaStream_t st) {
     if (h->prof_used == h->prof_events.size()) {
         cudaEvent_t e;
@@ -235,7 +270,12 @@ static cudaError_t alloc_state(FtlHandle_* h, DevState& s, const FtlConfig& c, s
     ok(dalloc(h, &s.snap_rect, (size_t)FTL_MAX_HIST * (1 + nb) * n, list));
     ok(dalloc(h, &s.unc_rec, n * kUncPerEnv, list));
     ok(dalloc(h, &s.unc_count, n, list));
-    ok(dalloc(h, &s.step_flag, n / 32 + 1, list));
+    ok(dalloc(h, &s.rec_f, n * (size_t)c.frames_per_step, list));
+    ok(dalloc(h, &s.rec_l, n * (size_t)c.frames_per_step, list));
+    ok(dalloc(h, &s.rec_bits, n * (size_t)c.frames_per_step, list));
+    ok(dalloc(h, &s.rec_lbits, n * (size_t)c.frames_per_step, list));
+    ok(dalloc(h, &s.kin_flag, n / 32 + 1, list));
+    ok(dalloc(h, &s.book_flag, n / 32 + 1, list));
     return e;
 }
 
@@ -305,20 +345,40 @@ static void launch_reset(FtlHandle_* h, const DevState& s, const uint8_t* mask, 
     }
 }
 
+static int flush_pending_resets(ftl_handle h, cudaStream_t st);
 static int launch_optional_sensors(ftl_handle h, const DevOutputs& o, cudaStream_t st) {
     if (!o.follower_info && !(o.track_vectors && h->cfg.c.track_vector_len > 0) &&
         !(o.radar && h->cfg.c.radar_sectors > 0))
         return FTL_OK;
+    // FollowerInfo / LeaderTrackDetector_* read the stored state, which for an env that just finished must already be
+    // the first state of its next episode, like the rest of the observation
+    int rc = flush_pending_resets(h, st);
+    if (rc) return rc;
     k_optional_sensors<<<(h->n + 127) / 128, 128, 0, st>>>(h->cfg, h->st, o);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return FTL_OK;
 }
 
-static int launch_rays(ftl_handle h, float* rays, cudaStream_t st, int first_env = 0, int end_env = -1, int wait_seq = 0) {
-    if (!rays || h->rays_total == 0) return FTL_OK;
-    if (end_env < 0) end_env = h->n;
-    if (end_env <= first_env) return FTL_OK;
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                              Args&&... args) {
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = grid; lc.blockDim = block; lc.dynamicSmemBytes = smem; lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at; lc.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&lc, kernel, std::forward<Args>(args)...);
+}
+
+// k_rays + k_finish for the envs [first_env, end_env) of state `s` (first_env a multiple of 32).  wait_seq != 0: the
+// kernels are programmatic dependents of what is in front of them in the stream and wait on the step's flags instead.
+// renew: inside ftl_step -- k_finish also delivers the first rays of the next episode of envs that finished.
+static int launch_rays_and_finish(ftl_handle h, const DevState& s, const DevOutputs& o, cudaStream_t st, int first_env,
+                                  int end_env, int wait_seq, bool renew) {
+    if (end_env <= first_env || !o.rays || h->rays_total == 0) return FTL_OK;
+    const bool pdl = wait_seq != 0;
     const int warps = FTL_RAYS_WARPS, threads = warps * 32;
     const int per_warp = (int)((ray_shared_bytes(h->rays_total, h->cfg.ray_hmax) + 15) & ~(size_t)15);
     const int smem = per_warp * warps;
@@ -326,35 +386,24 @@ static int launch_rays(ftl_handle h, float* rays, cudaStream_t st, int first_env
         CUDA_TRY(cudaFuncSetAttribute(k_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         h->rays_smem_opted = true;
     }
-    int blocks = (end_env - first_env + warps - 1) / warps;
-    if (wait_seq) {
-        // programmatic dependent launch behind k_step: the blocks start while k_step's last warps are still running
-        cudaLaunchConfig_t lc{};
-        lc.gridDim = dim3(blocks); lc.blockDim = dim3(threads); lc.dynamicSmemBytes = smem; lc.stream = st;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = 1;
-        lc.attrs = at; lc.numAttrs = 1;
-        const double2* rot = h->d_rot;
-        CUDA_TRY(cudaLaunchKernelEx(&lc, k_rays, h->cfg, h->st, h->pool, rot, rays, per_warp, first_env, end_env, wait_seq));
-    } else {
-        k_rays<<<blocks, threads, smem, st>>>(h->cfg, h->st, h->pool, h->d_rot, rays, per_warp, first_env, end_env, 0);
-    }
-#if FTL_EXACT_PDL
-    {   // its blocks are scheduled while the last ray blocks run; griddepcontrol.wait at its top keeps the order
-        cudaLaunchConfig_t lc{};
-        lc.gridDim = dim3((end_env - first_env + 127) / 128); lc.blockDim = dim3(128); lc.dynamicSmemBytes = 0; lc.stream = st;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = 1;
-        lc.attrs = at; lc.numAttrs = 1;
-        CUDA_TRY(cudaLaunchKernelEx(&lc, k_rays_exact, h->cfg, h->st, h->pool, rays, first_env, end_env));
-    }
-#else
-    k_rays_exact<<<(end_env - first_env + 127) / 128, 128, 0, st>>>(h->cfg, h->st, h->pool, rays, first_env, end_env);
-#endif
+    const int blocks = (end_env - first_env + warps - 1) / warps;
+    const double2* rot = h->d_rot;
+    CUDA_TRY(launch_pdl(k_rays, dim3(blocks), dim3(threads), smem, st, pdl, h->cfg, s, h->pool, rot, o.rays, per_warp,
+                        first_env, end_env, wait_seq));
+    CUDA_TRY(launch_pdl(k_finish, dim3((end_env - first_env + 127) / 128), dim3(128), 0, st, pdl, h->cfg, s, h->pool,
+                        h->image_out, o.rays, first_env, end_env, renew ? wait_seq : 0, renew ? 1 : 0, pdl ? 1 : 0));
     h->launches += 2;
     CUDA_TRY(cudaGetLastError());
+    return FTL_OK;
+}
+
+// the state half of pending auto-resets, for callers that look at or replace state between steps
+static int flush_pending_resets(ftl_handle h, cudaStream_t st) {
+    if (!h->maybe_pending_resets || !h->have_pool) return FTL_OK;
+    k_apply_resets<<<(h->st.n + 127) / 128, 128, 0, st>>>(h->cfg, h->st, h->pool, h->image);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    h->maybe_pending_resets = false;
     return FTL_OK;
 }
 
@@ -539,6 +588,7 @@ int ftl_upload_scenarios(ftl_handle h, const FtlScenarioPool* p) {
     h->was_reset = false;
     h->pool = DevPool{};
     h->image = DevState{};
+    h->image_out = DevOutputs{};
     for (void* q : h->pool_allocs) cudaFree(q);
     h->pool_allocs.clear();
     const size_t S = p->n_scenarios;
@@ -610,10 +660,18 @@ int ftl_upload_scenarios(ftl_handle h, const FtlScenarioPool* p) {
     std::vector<int> iota(im.n);
     for (int k = 0; k < im.n; k++) iota[k] = k < p->n_scenarios ? k : 0;
     CUDA_TRY(cudaMemcpy(ids, iota.data(), sizeof(int) * iota.size(), cudaMemcpyHostToDevice));
-    DevOutputs none{};
-    launch_reset(h, im, nullptr, ids, none, 1, nullptr);
+    // the first observation of every scenario: k_reset writes numerical_features / leader_target, the ray kernels the rays
+    DevOutputs io{};
+    io.n = p->n_scenarios;
+    CUDA_TRY(dalloc(h, &io.numerical_features, (size_t)im.n * 10, &h->pool_allocs));
+    CUDA_TRY(dalloc(h, &io.leader_target, (size_t)im.n * 2, &h->pool_allocs));
+    CUDA_TRY(dalloc(h, &io.rays, (size_t)im.n * (h->cfg.rays_per_env ? h->cfg.rays_per_env : 1), &h->pool_allocs));
+    launch_reset(h, im, nullptr, ids, io, 1, nullptr);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
+    h->image_out = io;
+    int rc = launch_rays_and_finish(h, im, io, nullptr, 0, p->n_scenarios, 0, false);
+    if (rc) return rc;
     CUDA_TRY(cudaDeviceSynchronize());
     h->have_pool = true;
     return FTL_OK;
@@ -626,48 +684,85 @@ int ftl_reset(ftl_handle h, const uint8_t* mask_dev, const int32_t* scenario_ids
     CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
     DevOutputs o = to_dev_outputs(out_dev, h->n);
+    if (h->was_reset && mask_dev) {   // envs outside the mask that finished in the last step keep their auto-reset
+        int rc0 = flush_pending_resets(h, st);
+        if (rc0) return rc0;
+    }
+    h->maybe_pending_resets = false;
     const int reset_filler = (!mask_dev || !h->was_reset) ? 1 : 0;
     launch_reset(h, h->st, mask_dev, scenario_ids_dev, o, reset_filler, st);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     h->was_reset = true;
-    int rc = launch_optional_sensors(h, o, st);
+    int rc = launch_rays_and_finish(h, h->st, o, st, 0, h->n, 0, false);
     if (rc) return rc;
-    return launch_rays(h, o.rays, st);
+    return launch_optional_sensors(h, o, st);
 }
 
-int ftl_step(ftl_handle h, const void* actions_dev, const FtlOutputs* out_dev, void* cuda_stream) {
+static void launch_kin(FtlHandle_* h, const void* actions, const DevOutputs& o, int seq, cudaStream_t st) {
+    switch (h->cfg.c.n_bears) {
+        case 0: ftl_launch_kin_nb0(h->cfg, h->st, h->pool, h->image, h->image_out, actions, o, h->d_stats, seq, FTL_FUSED_BOOK, st); break;
+        case 1: ftl_launch_kin_nb1(h->cfg, h->st, h->pool, h->image, h->image_out, actions, o, h->d_stats, seq, FTL_FUSED_BOOK, st); break;
+        case 2: ftl_launch_kin_nb2(h->cfg, h->st, h->pool, h->image, h->image_out, actions, o, h->d_stats, seq, FTL_FUSED_BOOK, st); break;
+        case 3: ftl_launch_kin_nb3(h->cfg, h->st, h->pool, h->image, h->image_out, actions, o, h->d_stats, seq, FTL_FUSED_BOOK, st); break;
+        default: ftl_launch_kin_nb4(h->cfg, h->st, h->pool, h->image, h->image_out, actions, o, h->d_stats, seq, FTL_FUSED_BOOK, st); break;
+    }
+    h->launches++;
+}
+
+// k_kin and k_book of one step.  *wait_seq = the sequence number the dependent kernels wait for, or 0 when the kernels
+// run in plain stream order (per-kernel timing, a stream that is being captured, FTL_NO_PDL).
+static int launch_step_front(ftl_handle h, const void* actions_dev, const DevOutputs& o, cudaStream_t st, int* wait_seq) {
+    // While the stream is being captured the sequence number would be frozen into the graph: a replay would find the
+    // previous replay's flags already equal to it and skip the wait.  Captured steps therefore use plain stream order.
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    CUDA_TRY(cudaStreamIsCapturing(st, &cap));
+    const bool overlap = !h->profiling && !FTL_NO_PDL && cap == cudaStreamCaptureStatusNone;
+    const int seq = h->step_seq = (h->step_seq % 0x3fffffff) + 1;   // never 0
+    if (h->profiling) prof_event(h, st);
+    launch_kin(h, actions_dev, o, seq, st);
+    CUDA_TRY(cudaGetLastError());
+    if (h->profiling) prof_event(h, st);
+    if (!FTL_FUSED_BOOK) {
+        CUDA_TRY(launch_pdl(k_book, dim3((h->st.n + FTL_BOOK_THREADS - 1) / FTL_BOOK_THREADS), dim3(FTL_BOOK_THREADS), 0, st,
+                            overlap, h->cfg, h->st, h->image_out, o, h->d_stats, h->pool.n_scenarios, overlap ? seq : 0, seq));
+        h->launches++;
+    }
+    if (h->profiling) prof_event(h, st);
+    *wait_seq = overlap ? seq : 0;
+    h->maybe_pending_resets = true;
+    return FTL_OK;
+}
+
+// the per-step inputs travel inside the DevState argument of the launches of this step only
+struct StepInputsScope {
+    ftl_handle h;
+    StepInputsScope(ftl_handle h_, const FtlStepInputs* in) : h(h_) {
+        h->st.in_frames = in ? in->frames_per_step : nullptr;
+        h->st.in_draws = in ? in->regime_draws : nullptr;
+    }
+    ~StepInputsScope() { h->st.in_frames = nullptr; h->st.in_draws = nullptr; }
+};
+
+int ftl_step_ex(ftl_handle h, const void* actions_dev, const FtlStepInputs* in_dev, const FtlOutputs* out_dev,
+                void* cuda_stream) {
     if (!h || !actions_dev) return fail(FTL_ERR_INVALID, "NULL argument");
     if (!h->was_reset) return fail(FTL_ERR_STATE, "ftl_reset must be called before ftl_step");
     CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
     DevOutputs o = to_dev_outputs(out_dev, h->n);
-    if (h->profiling) prof_event(h, st);
-    const int seq = h->step_seq = (h->step_seq % 0x3fffffff) + 1;   // never 0
-    switch (h->cfg.c.n_bears) {
-        case 0: ftl_launch_step_nb0(h->cfg, h->st, h->pool, h->image, actions_dev, o, h->d_stats, seq, st); break;
-        case 1: ftl_launch_step_nb1(h->cfg, h->st, h->pool, h->image, actions_dev, o, h->d_stats, seq, st); break;
-        case 2: ftl_launch_step_nb2(h->cfg, h->st, h->pool, h->image, actions_dev, o, h->d_stats, seq, st); break;
-        case 3: ftl_launch_step_nb3(h->cfg, h->st, h->pool, h->image, actions_dev, o, h->d_stats, seq, st); break;
-        default: ftl_launch_step_nb4(h->cfg, h->st, h->pool, h->image, actions_dev, o, h->d_stats, seq, st); break;
-    }
-    h->launches++;
-    CUDA_TRY(cudaGetLastError());
-    int rc = launch_optional_sensors(h, o, st);
+    StepInputsScope scope(h, in_dev);
+    int wait_seq = 0;
+    int rc = launch_step_front(h, actions_dev, o, st, &wait_seq);
     if (rc) return rc;
-    // The ray kernel overlaps the tail of k_step (programmatic dependent launch + per-group flags) unless something
-    // was launched in between or per-kernel timing is on.
-    // Not while the stream is being captured either: the sequence number is a kernel argument, so a replayed graph
-    // would find last replay's flags already equal to it and skip the wait -- captured steps use plain stream order.
-    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    CUDA_TRY(cudaStreamIsCapturing(st, &cap));
-    const bool overlap = !h->profiling && !FTL_NO_PDL && cap == cudaStreamCaptureStatusNone &&
-                         !(o.follower_info || (o.track_vectors && h->cfg.c.track_vector_len > 0) ||
-                           (o.radar && h->cfg.c.radar_sectors > 0));
+    rc = launch_rays_and_finish(h, h->st, o, st, 0, h->n, wait_seq, true);
     if (h->profiling) prof_event(h, st);
-    rc = launch_rays(h, o.rays, st, 0, -1, overlap ? seq : 0);
-    if (h->profiling) prof_event(h, st);
-    return rc;
+    if (rc) return rc;
+    return launch_optional_sensors(h, o, st);
+}
+
+int ftl_step(ftl_handle h, const void* actions_dev, const FtlOutputs* out_dev, void* cuda_stream) {
+    return ftl_step_ex(h, actions_dev, nullptr, out_dev, cuda_stream);
 }
 
 void* ftl_host_stream(ftl_handle h) {
@@ -689,13 +784,28 @@ int ftl_step_host_wait(ftl_handle h) {
     return FTL_OK;
 }
 
+static int step_host_begin(ftl_handle h, const void* actions_host, const FtlStepInputs* in_host, const FtlOutputs* out_host,
+                           void* cuda_stream);
+
 int ftl_step_host(ftl_handle h, const void* actions_host, const FtlOutputs* out_host, void* cuda_stream) {
-    int rc = ftl_step_host_begin(h, actions_host, out_host, cuda_stream);
+    int rc = step_host_begin(h, actions_host, nullptr, out_host, cuda_stream);
+    if (rc) return rc;
+    return ftl_step_host_wait(h);
+}
+
+int ftl_step_host_ex(ftl_handle h, const void* actions_host, const FtlStepInputs* in_host, const FtlOutputs* out_host,
+                     void* cuda_stream) {
+    int rc = step_host_begin(h, actions_host, in_host, out_host, cuda_stream);
     if (rc) return rc;
     return ftl_step_host_wait(h);
 }
 
 int ftl_step_host_begin(ftl_handle h, const void* actions_host, const FtlOutputs* out_host, void* cuda_stream) {
+    return step_host_begin(h, actions_host, nullptr, out_host, cuda_stream);
+}
+
+static int step_host_begin(ftl_handle h, const void* actions_host, const FtlStepInputs* in_host, const FtlOutputs* out_host,
+                           void* cuda_stream) {
     if (!h || !actions_host) return fail(FTL_ERR_INVALID, "NULL argument");
     if (!h->was_reset) return fail(FTL_ERR_STATE, "ftl_reset must be called before ftl_step");
     if (h->pending) return fail(FTL_ERR_STATE, "ftl_step_host_begin: the previous step has not been waited for");
@@ -709,45 +819,63 @@ int ftl_step_host_begin(ftl_handle h, const void* actions_host, const FtlOutputs
     cudaStream_t cs = h->copy_stream;
     size_t action_bytes = (h->cfg.c.action_mode == FTL_ACTION_CONTINUOUS ? 8 : 4) * n;
     CUDA_TRY(cudaMemcpyAsync(h->d_actions, actions_host, action_bytes, cudaMemcpyHostToDevice, st));
-    FtlOutputs o = staged_outputs(h, out_host);
-    // fused step kernel, everything except the rays
-    FtlOutputs no_rays = o;
-    no_rays.rays = nullptr;
-    int rc = ftl_step(h, h->d_actions, &no_rays, cuda_stream);
-    if (rc) return rc;
-    h->pending_stream = st;
-    if (!out_host) {
-        rc = launch_rays(h, h->d_out.rays, st);
-        if (rc) return rc;
-        h->pending = true;
-        return FTL_OK;
+    FtlStepInputs in_dev{};
+    if (in_host && in_host->frames_per_step) {
+        if (!h->d_in_frames) CUDA_TRY(dalloc(h, &h->d_in_frames, (size_t)h->n_pad));
+        CUDA_TRY(cudaMemcpyAsync(h->d_in_frames, in_host->frames_per_step, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+        in_dev.frames_per_step = h->d_in_frames;
     }
-    const DevOutputs& d = h->d_out;
-    CUDA_TRY(cudaEventRecord(h->chunk_ev[0], st));
-    CUDA_TRY(cudaStreamWaitEvent(cs, h->chunk_ev[0], 0));
-    if (out_host->numerical_features) CUDA_TRY(cudaMemcpyAsync(out_host->numerical_features, d.numerical_features, 40 * n, cudaMemcpyDeviceToHost, cs));
-    if (out_host->leader_target) CUDA_TRY(cudaMemcpyAsync(out_host->leader_target, d.leader_target, 8 * n, cudaMemcpyDeviceToHost, cs));
-    if (out_host->reward) CUDA_TRY(cudaMemcpyAsync(out_host->reward, d.reward, 4 * n, cudaMemcpyDeviceToHost, cs));
-    if (out_host->done) CUDA_TRY(cudaMemcpyAsync(out_host->done, d.done, n, cudaMemcpyDeviceToHost, cs));
-    if (out_host->status) CUDA_TRY(cudaMemcpyAsync(out_host->status, d.status, 4 * n, cudaMemcpyDeviceToHost, cs));
-    if (out_host->follower_info) CUDA_TRY(cudaMemcpyAsync(out_host->follower_info, d.follower_info, 8 * n, cudaMemcpyDeviceToHost, cs));
-    if (out_host->track_vectors && h->cfg.c.track_vector_len)
-        CUDA_TRY(cudaMemcpyAsync(out_host->track_vectors, d.track_vectors, 8 * n * h->cfg.c.track_vector_len, cudaMemcpyDeviceToHost, cs));
-    if (out_host->radar && h->cfg.c.radar_sectors)
-        CUDA_TRY(cudaMemcpyAsync(out_host->radar, d.radar, 4 * n * h->cfg.c.radar_sectors, cudaMemcpyDeviceToHost, cs));
-    // ray kernel in chunks of envs: the D2H copy of chunk c runs while chunk c+1 is being cast
-    if (out_host->rays && h->cfg.rays_per_env) {
+    if (in_host && in_host->regime_draws) {
+        const size_t cnt = (size_t)h->cfg.c.frames_per_step;
+        if (!h->d_in_draws) CUDA_TRY(dalloc(h, &h->d_in_draws, (size_t)h->n_pad * cnt));
+        CUDA_TRY(cudaMemcpyAsync(h->d_in_draws, in_host->regime_draws, sizeof(double) * n * cnt, cudaMemcpyHostToDevice, st));
+        in_dev.regime_draws = h->d_in_draws;
+    }
+    StepInputsScope scope(h, &in_dev);
+    FtlOutputs so = staged_outputs(h, out_host);
+    if (!out_host) so.rays = h->d_out.rays;   // nobody reads them, but the step stays the same work
+    h->pending_stream = st;
+    const bool want_rays = out_host && out_host->rays && h->cfg.rays_per_env;
+    if (!want_rays) {   // the whole step in one go, then the copies
+        int rc = ftl_step_ex(h, h->d_actions, &in_dev, &so, cuda_stream);
+        if (rc) return rc;
+    } else {
+        // kinematics + bookkeeping for everybody, then the ray and finishing kernels in chunks of envs: the D2H copy of
+        // chunk c runs on the copy stream while chunk c+1 is being cast
+        DevOutputs o = to_dev_outputs(&so, h->n);
+        int wait_seq = 0;
+        int rc = launch_step_front(h, h->d_actions, o, st, &wait_seq);
+        if (rc) return rc;
         const int chunks = h->n >= 8192 ? 6 : 1;
         const size_t row = sizeof(float) * (size_t)h->cfg.rays_per_env;
         for (int c = 0; c < chunks; c++) {
-            int first = (int)((long long)h->n * c / chunks), end = (int)((long long)h->n * (c + 1) / chunks);
-            rc = launch_rays(h, h->d_out.rays, st, first, end);
+            int first = (int)(((long long)h->n * c / chunks) & ~31LL), end = (int)(((long long)h->n * (c + 1) / chunks) & ~31LL);
+            if (c == chunks - 1) end = h->n;
+            rc = launch_rays_and_finish(h, h->st, o, st, first, end, wait_seq, true);
             if (rc) return rc;
             CUDA_TRY(cudaEventRecord(h->chunk_ev[1 + c], st));
             CUDA_TRY(cudaStreamWaitEvent(cs, h->chunk_ev[1 + c], 0));
-            CUDA_TRY(cudaMemcpyAsync((char*)out_host->rays + row * first, (const char*)d.rays + row * first,
+            CUDA_TRY(cudaMemcpyAsync((char*)out_host->rays + row * first, (const char*)h->d_out.rays + row * first,
                                      row * (size_t)(end - first), cudaMemcpyDeviceToHost, cs));
         }
+        if (h->profiling) prof_event(h, st);
+        rc = launch_optional_sensors(h, o, st);
+        if (rc) return rc;
+    }
+    if (out_host) {   // the small outputs: after the last finishing kernel (it rewrites the observation of reset envs)
+        const DevOutputs& d = h->d_out;
+        CUDA_TRY(cudaEventRecord(h->chunk_ev[0], st));
+        CUDA_TRY(cudaStreamWaitEvent(cs, h->chunk_ev[0], 0));
+        if (out_host->numerical_features) CUDA_TRY(cudaMemcpyAsync(out_host->numerical_features, d.numerical_features, 40 * n, cudaMemcpyDeviceToHost, cs));
+        if (out_host->leader_target) CUDA_TRY(cudaMemcpyAsync(out_host->leader_target, d.leader_target, 8 * n, cudaMemcpyDeviceToHost, cs));
+        if (out_host->reward) CUDA_TRY(cudaMemcpyAsync(out_host->reward, d.reward, 4 * n, cudaMemcpyDeviceToHost, cs));
+        if (out_host->done) CUDA_TRY(cudaMemcpyAsync(out_host->done, d.done, n, cudaMemcpyDeviceToHost, cs));
+        if (out_host->status) CUDA_TRY(cudaMemcpyAsync(out_host->status, d.status, 4 * n, cudaMemcpyDeviceToHost, cs));
+        if (out_host->follower_info) CUDA_TRY(cudaMemcpyAsync(out_host->follower_info, d.follower_info, 8 * n, cudaMemcpyDeviceToHost, cs));
+        if (out_host->track_vectors && h->cfg.c.track_vector_len)
+            CUDA_TRY(cudaMemcpyAsync(out_host->track_vectors, d.track_vectors, 8 * n * h->cfg.c.track_vector_len, cudaMemcpyDeviceToHost, cs));
+        if (out_host->radar && h->cfg.c.radar_sectors)
+            CUDA_TRY(cudaMemcpyAsync(out_host->radar, d.radar, 4 * n * h->cfg.c.radar_sectors, cudaMemcpyDeviceToHost, cs));
     }
     h->pending = true;
     return FTL_OK;
@@ -773,6 +901,10 @@ int ftl_get_state(ftl_handle h, int32_t first, int32_t count, const FtlStateBuff
     if (count == 0) return FTL_OK;
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaDeviceSynchronize());
+    {
+        int rc0 = flush_pending_resets(h, nullptr);
+        if (rc0) return rc0;
+    }
     const FtlConfig& c = h->cfg.c;
     if (b->env) {
         int rc = ensure_stage(h, count);
@@ -819,6 +951,11 @@ int ftl_set_state(ftl_handle h, int32_t first, int32_t count, const FtlStateBuff
     }
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaDeviceSynchronize());
+    {
+        int rc0 = flush_pending_resets(h, nullptr);
+        if (rc0) return rc0;
+        CUDA_TRY(cudaDeviceSynchronize());
+    }
     CUDA_TRY(cudaMemcpy(h->st.trail + (size_t)first * c.trail_cap, b->trail, sizeof(float2) * (size_t)c.trail_cap * count, cudaMemcpyHostToDevice));
     if (b->hist) CUDA_TRY(cudaMemcpy(h->st.hist + (size_t)first * c.corridor_cap, b->hist, sizeof(double2) * (size_t)c.corridor_cap * count, cudaMemcpyHostToDevice));
     if (b->corridor) CUDA_TRY(cudaMemcpy(h->st.corridor + (size_t)first * c.corridor_cap, b->corridor, sizeof(float4) * (size_t)c.corridor_cap * count, cudaMemcpyHostToDevice));
@@ -881,23 +1018,40 @@ int ftl_profile(ftl_handle h, int32_t enable) {
     return FTL_OK;
 }
 
-int ftl_profile_read(ftl_handle h, double* step_kernel_ms, double* ray_kernel_ms, int64_t* steps) {
-    if (!h) return fail(FTL_ERR_INVALID, "NULL handle");
+static int profile_collect(ftl_handle h, double ms_out[3], int64_t* steps) {
     CUDA_TRY(cudaSetDevice(h->device));
     CUDA_TRY(cudaDeviceSynchronize());
-    double a = 0, b = 0;
-    size_t n = h->prof_used / 3;
-    for (size_t k = 0; k < n; k++) {
-        float ms = 0;
-        CUDA_TRY(cudaEventElapsedTime(&ms, h->prof_events[3 * k], h->prof_events[3 * k + 1]));
-        a += ms;
-        CUDA_TRY(cudaEventElapsedTime(&ms, h->prof_events[3 * k + 1], h->prof_events[3 * k + 2]));
-        b += ms;
-    }
-    if (step_kernel_ms) *step_kernel_ms = a;
-    if (ray_kernel_ms) *ray_kernel_ms = b;
+    ms_out[0] = ms_out[1] = ms_out[2] = 0.0;
+    const size_t n = h->prof_used / kProfEvents;   // per step: before k_kin, after it, after k_book, after k_rays + k_finish
+    for (size_t k = 0; k < n; k++)
+        for (int j = 0; j < 3; j++) {
+            float ms = 0;
+            CUDA_TRY(cudaEventElapsedTime(&ms, h->prof_events[kProfEvents * k + j], h->prof_events[kProfEvents * k + j + 1]));
+            ms_out[j] += ms;
+        }
     if (steps) *steps = (int64_t)n;
     h->prof_used = 0;
+    return FTL_OK;
+}
+
+int ftl_profile_read(ftl_handle h, double* step_kernel_ms, double* ray_kernel_ms, int64_t* steps) {
+    if (!h) return fail(FTL_ERR_INVALID, "NULL handle");
+    double ms[3];
+    int rc = profile_collect(h, ms, steps);
+    if (rc) return rc;
+    if (step_kernel_ms) *step_kernel_ms = ms[0] + ms[1];
+    if (ray_kernel_ms) *ray_kernel_ms = ms[2];
+    return FTL_OK;
+}
+
+int ftl_profile_read_kernels(ftl_handle h, double* kin_ms, double* book_ms, double* rays_ms, int64_t* steps) {
+    if (!h) return fail(FTL_ERR_INVALID, "NULL handle");
+    double ms[3];
+    int rc = profile_collect(h, ms, steps);
+    if (rc) return rc;
+    if (kin_ms) *kin_ms = ms[0];
+    if (book_ms) *book_ms = ms[1];
+    if (rays_ms) *rays_ms = ms[2];
     return FTL_OK;
 }
 

@@ -96,7 +96,16 @@ struct DevState {
     int4* snap_rect;   // [FTL_MAX_HIST][1+n_bears][n]
     UncRec* unc_rec;   // [n][kUncPerEnv]  scratch of the ray pass
     int* unc_count;    // [n]
-    int* step_flag;    // [n / 32]  sequence number of the last step whose state the owning warp of k_step has published
+    // per-frame records the kinematics kernel leaves for the bookkeeping kernel (frame-major, env fastest)
+    float2* rec_f;     // [frames_per_step][n]  follower position after frame j
+    float2* rec_l;     // [frames_per_step][n]  leader position after frame j
+    unsigned char* rec_bits;   // [frames_per_step][n]  REC_* bits of frame j
+    unsigned char* rec_lbits;  // [frames_per_step][n]  ... the leader's bits when a separate warp computes them
+    // optional per-step inputs (FtlStepInputs; NULL = configuration value / Philox), set by the host before each launch
+    const int* in_frames;      // [n]  frames of this step per env
+    const double* in_draws;    // [n][frames_per_step]  uniform draws of list-valued speed regimes, per frame
+    int* kin_flag;     // [n / 32]  sequence number of the last step whose kinematics the owning warp of k_kin has published
+    int* book_flag;    // [n / 32]  ... whose bookkeeping the owning warp of k_book has published
 };
 
 struct DevPool {  // scenario pool in device (or host, for hostsim) memory
@@ -488,6 +497,19 @@ FTL_HD void near_static_masks_grid(const DevPool& pool, int scenario, const int4
     }
     near_static_masks(rects, n_static, p0, inflate0, p1, inflate1, m0, m1);
 }
+// one robot's mask (the role-split kinematics kernel computes the follower's and the leader's in different warps)
+FTL_HD uint64_t near_static_mask_one(const DevPool& pool, int scenario, const int4* rects, int n_static, float2 p,
+                                     float inflate) {
+    int cell;
+    if (pool.near_grid && near_grid_cell(pool, p, &cell)) {
+        const uint64_t* g = pool.near_grid + (size_t)scenario * pool.near_grid_w * pool.near_grid_h;
+        return near_refine(rects, g[cell], p, inflate);
+    }
+    uint64_t a = 0;
+    for (int k = 0; k < n_static; k++)
+        if (near_rect(rects[k], p.x, p.y, inflate)) a |= (uint64_t)1 << k;
+    return a;
+}
 FTL_HD bool collide_static_masked(const Robot& r, const int4* rects, uint64_t mask) {
     while (mask) {
 #if defined(__CUDA_ARCH__)
@@ -612,6 +634,9 @@ FTL_HD int bound_decide(float ub2, float lb, float disp2, float thr, float thr2)
 // each request together (coalesced loads, ~60 warp instructions instead of a ~200-iteration serial loop in one
 // lane while 31 wait); the host build runs the same arithmetic serially.
 struct ScanMin { float best; int arg; };
+#ifndef FTL_SCAN_UNROLL
+#define FTL_SCAN_UNROLL 4
+#endif
 #ifndef FTL_OUTLINE_SCAN   // measured: out of line is 2% slower (k_step 0.2045 -> 0.2091 ms)
 FTL_HD ScanMin warp_scan_min_impl(bool need, const float2* trail, int lo, int hi, float fx, float fy) {
 #else
@@ -633,7 +658,21 @@ FTL_HD_NOINLINE ScanMin warp_scan_min_impl(bool need, const float2* trail, int l
         const float bfx = __shfl_sync(full, fx, src), bfy = __shfl_sync(full, fy, src);
         float best = 3.0e38f;
         int bi = -1;
-        for (int k = bhi - lane; k >= blo; k -= 32) {
+        int k = bhi - lane;
+#if FTL_SCAN_UNROLL > 1
+        // several loads in flight per lane (the scan is a chain of DRAM round trips otherwise); same visiting order
+        for (; k - 32 * (FTL_SCAN_UNROLL - 1) >= blo; k -= 32 * FTL_SCAN_UNROLL) {
+            float2 p[FTL_SCAN_UNROLL];
+#pragma unroll
+            for (int u = 0; u < FTL_SCAN_UNROLL; u++) p[u] = t[k - 32 * u];
+#pragma unroll
+            for (int u = 0; u < FTL_SCAN_UNROLL; u++) {
+                float d2 = d2_f32(p[u].x, p[u].y, bfx, bfy);
+                if (d2 < best) { best = d2; bi = k - 32 * u; }
+            }
+        }
+#endif
+        for (; k >= blo; k -= 32) {
             float2 p = t[k];
             float d2 = d2_f32(p.x, p.y, bfx, bfy);
             if (d2 < best) { best = d2; bi = k; }
@@ -677,13 +716,15 @@ FTL_HD void green_resolve(const DevCfg& cfg, const float* trail_d, int n, GreenC
     gc.g_unc = 0;
 }
 
+// `active` = false: the lane has no frame to evaluate (fewer frames this step than its warp's longest env) and only
+// takes part in the warp's collectives.
 FTL_HD void green_flags(const DevCfg& cfg, const float2* trail, const float* trail_d, int n, float fx, float fy,
-                        GreenCache& gc, bool* in_box, bool* on_trace) {  // ENV:1906-1931; all lanes of a warp call this
+                        GreenCache& gc, bool* in_box, bool* on_trace, bool active = true) {  // ENV:1906-1931; all lanes of a warp call this
     FTL_COUNT(3, 1);
     const int hi = n - 2;
     // len(green) > 2 ?  (only ambiguous in the first frames of an episode)
-    if (gc.g_unc > 0 && hi - gc.g_lo + 1 <= 2 && hi - gc.g_lo + 1 + gc.g_unc > 2) green_resolve(cfg, trail_d, n, gc);
-    const bool have_green = hi - gc.g_lo + 1 > 2;
+    if (active && gc.g_unc > 0 && hi - gc.g_lo + 1 <= 2 && hi - gc.g_lo + 1 + gc.g_unc > 2) green_resolve(cfg, trail_d, n, gc);
+    const bool have_green = active && hi - gc.g_lo + 1 > 2;
     int le_eps = 0, le_dev = 0;
     bool need = false;
     if (have_green) {
@@ -840,14 +881,15 @@ FTL_HD double reward_of(const FtlConfig& c, const Episode& e, bool too_close, bo
     return r;
 }
 
-FTL_HD double leader_speed(const DevCfg& cfg, Episode& e, int env_index) {  // ENV:1143-1157
+FTL_HD double leader_speed(const DevCfg& cfg, Episode& e, int env_index, const double* draw) {  // ENV:1143-1157
     const FtlConfig& c = cfg.c;
     int sel = -1;
     for (int k = 0; k < c.n_speed_regime; k++)
         if (c.speed_regime_key[k] <= e.step_count) sel = k;
     if (sel >= 0) {
         if (c.speed_regime_is_range[sel]) {
-            double u = regime_uniform(cfg.env_id_base + env_index, e.episode, e.step_count);
+            // random.uniform(a, b) = a + (b - a) * random(): u is the caller's recorded draw, or Philox
+            double u = draw ? *draw : regime_uniform(cfg.env_id_base + env_index, e.episode, e.step_count);
             e.speed_mult = c.speed_regime_lo[sel] + (c.speed_regime_hi[sel] - c.speed_regime_lo[sel]) * u;
         } else {
             e.speed_mult = c.speed_regime_lo[sel];

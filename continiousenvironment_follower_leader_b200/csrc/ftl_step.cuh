@@ -53,7 +53,7 @@ FTL_HD void episode_store(const DevState& s, int i, const Episode& e) {
     d[GD_LEAD_ACC * n] = e.lead_acc;
     d[GD_LEAD_CUM * n] = e.lead_cum;
 }
-FTL_HD void cache_load(const DevState& s, int i, GreenCache& gc, Tracker& t, int* snap_pushes) {
+FTL_HD void green_load(const DevState& s, int i, GreenCache& gc) {
     const int* g = s.gi + i;
     size_t n = s.n;
     gc.g_lo = g[GI_G_LO * n];
@@ -67,13 +67,8 @@ FTL_HD void cache_load(const DevState& s, int i, GreenCache& gc, Tracker& t, int
     gc.sgy = s.gf[GF_SCAN_GY * n + i];
     gc.sax = s.gf[GF_SCAN_AX * n + i];
     gc.say = s.gf[GF_SCAN_AY * n + i];
-    t.saving_counter = g[GI_SAVING_COUNTER * n];
-    t.ring_tail = g[GI_RING_TAIL * n];
-    t.ring_head = g[GI_RING_HEAD * n];
-    t.hist_f64_end = g[GI_HIST_F64_END * n];
-    *snap_pushes = g[GI_SNAP_PUSHES * n];
 }
-FTL_HD void cache_store(const DevState& s, int i, const GreenCache& gc, const Tracker& t, int snap_pushes) {
+FTL_HD void green_store(const DevState& s, int i, const GreenCache& gc) {
     int* g = s.gi + i;
     size_t n = s.n;
     g[GI_G_LO * n] = gc.g_lo;
@@ -87,11 +82,91 @@ FTL_HD void cache_store(const DevState& s, int i, const GreenCache& gc, const Tr
     s.gf[GF_SCAN_GY * n + i] = gc.sgy;
     s.gf[GF_SCAN_AX * n + i] = gc.sax;
     s.gf[GF_SCAN_AY * n + i] = gc.say;
+}
+FTL_HD void tracker_load(const DevState& s, int i, Tracker& t, int* snap_pushes) {
+    const int* g = s.gi + i;
+    size_t n = s.n;
+    t.saving_counter = g[GI_SAVING_COUNTER * n];
+    t.ring_tail = g[GI_RING_TAIL * n];
+    t.ring_head = g[GI_RING_HEAD * n];
+    t.hist_f64_end = g[GI_HIST_F64_END * n];
+    *snap_pushes = g[GI_SNAP_PUSHES * n];
+}
+FTL_HD void tracker_store(const DevState& s, int i, const Tracker& t, int snap_pushes) {
+    int* g = s.gi + i;
+    size_t n = s.n;
     g[GI_SAVING_COUNTER * n] = t.saving_counter;
     g[GI_RING_TAIL * n] = t.ring_tail;
     g[GI_RING_HEAD * n] = t.ring_head;
     g[GI_HIST_F64_END * n] = t.hist_f64_end;
     g[GI_SNAP_PUSHES * n] = snap_pushes;
+}
+FTL_HD void cache_load(const DevState& s, int i, GreenCache& gc, Tracker& t, int* snap_pushes) {
+    green_load(s, i, gc);
+    tracker_load(s, i, t, snap_pushes);
+}
+FTL_HD void cache_store(const DevState& s, int i, const GreenCache& gc, const Tracker& t, int snap_pushes) {
+    green_store(s, i, gc);
+    tracker_store(s, i, t, snap_pushes);
+}
+
+// The two kernels of a step own disjoint halves of the episode record: the kinematics kernel the leader's route cursor
+// and regime state (it only READS the frame counter and the flags), the bookkeeping kernel everything else.
+FTL_HD void episode_load_kin(const DevState& s, int i, Episode& e) {
+    const int* g = s.gi + i;
+    size_t n = s.n;
+    e.step_count = g[GI_STEP_COUNT * n];
+    e.cur_target_id = g[GI_TARGET_ID * n];
+    e.flags = g[GI_FLAGS * n];
+    e.scenario = g[GI_SCENARIO * n];
+    e.episode = g[GI_EPISODE * n];
+    e.accel_consumed = g[GI_ACCEL_CONSUMED * n];
+    e.overflow = 0;   // bits raised by this step's tracker scans; merged into the stored word by episode_store_kin
+    const double* d = s.gd + i;
+    e.speed_mult = d[GD_SPEED_MULT * n];
+    e.lead_acc = d[GD_LEAD_ACC * n];
+    e.lead_cum = d[GD_LEAD_CUM * n];
+    e.finish_timer = -1; e.trail_len = 0;
+    e.acc_penalty = e.overall = e.last_reward = 0.0;
+}
+FTL_HD void episode_store_kin(const DevState& s, int i, const Episode& e) {
+    int* g = s.gi + i;
+    size_t n = s.n;
+    g[GI_TARGET_ID * n] = e.cur_target_id;
+    g[GI_ACCEL_CONSUMED * n] = e.accel_consumed;
+    if (e.overflow) g[GI_OVERFLOW * n] |= e.overflow;
+    double* d = s.gd + i;
+    d[GD_SPEED_MULT * n] = e.speed_mult;
+    d[GD_LEAD_ACC * n] = e.lead_acc;
+    d[GD_LEAD_CUM * n] = e.lead_cum;
+}
+FTL_HD void episode_load_book(const DevState& s, int i, Episode& e) {
+    const int* g = s.gi + i;
+    size_t n = s.n;
+    e.step_count = g[GI_STEP_COUNT * n];
+    e.finish_timer = g[GI_FINISH_TIMER * n];
+    e.flags = g[GI_FLAGS * n];
+    e.trail_len = g[GI_TRAIL_LEN * n];
+    e.overflow = g[GI_OVERFLOW * n];
+    const double* d = s.gd + i;
+    e.acc_penalty = d[GD_ACC_PENALTY * n];
+    e.overall = d[GD_OVERALL * n];
+    e.last_reward = d[GD_LAST_REWARD * n];
+    e.cur_target_id = 0; e.scenario = 0; e.episode = 0; e.accel_consumed = 0;
+    e.speed_mult = e.lead_acc = e.lead_cum = 0.0;
+}
+FTL_HD void episode_store_book(const DevState& s, int i, const Episode& e) {
+    int* g = s.gi + i;
+    size_t n = s.n;
+    g[GI_STEP_COUNT * n] = e.step_count;
+    g[GI_FINISH_TIMER * n] = e.finish_timer;
+    g[GI_FLAGS * n] = e.flags;
+    g[GI_TRAIL_LEN * n] = e.trail_len;
+    g[GI_OVERFLOW * n] = e.overflow;
+    double* d = s.gd + i;
+    d[GD_ACC_PENALTY * n] = e.acc_penalty;
+    d[GD_OVERALL * n] = e.overall;
+    d[GD_LAST_REWARD * n] = e.last_reward;
 }
 
 FTL_HD int2 route_point(const DevPool& pool, const FtlConfig& c, int scenario, int k) {
@@ -135,27 +210,33 @@ FTL_HD void world_store(const DevState& s, int i, const World<NB>& w) {
 }
 
 // ---- sensors that are cheap and serial: tracker scans + history snapshot (CLS:255-288, SEN:894-895) ----------
-template <int NB>
-FTL_HD void sense_serial(const DevCfg& cfg, const DevState& s, int i, const World<NB>& w, Tracker& t, int* snap_pushes,
-                         int* overflow) {
+FTL_HD void sense_serial_in(const DevCfg& cfg, const DevState& s, int i, const TrackerInput& in, int4 leader_rect,
+                            const int4* bear_rects, int nb, Tracker& t, int* snap_pushes, int* overflow) {
     const FtlConfig& c = cfg.c;
     if (!c.tracker_enabled) return;
     double2* hist = s.hist + (size_t)i * c.corridor_cap;
     float4* corr = s.corridor + (size_t)i * c.corridor_cap;
     double* seg_d = s.seg_d + (size_t)i * c.corridor_cap;
     float* seg_f = s.seg_f + (size_t)i * c.corridor_cap;
-    TrackerInput in = {w.follower.px, w.follower.py, w.leader.px, w.leader.py, w.follower.dir};
     for (int k = 0; k < c.tracker_scans_per_step; k++) tracker_scan(cfg, t, hist, corr, seg_d, seg_f, in, overflow);
     if (c.n_ray_sensors > 0 && t.ring_head - t.ring_tail > 1) {
         int slot = *snap_pushes % FTL_MAX_HIST;
         s.snap_range[(size_t)slot * s.n + i] = make_int2(t.ring_tail, t.ring_head);
-        int4* sr = s.snap_rect + ((size_t)slot * (1 + NB)) * s.n + i;
-        sr[0] = make_int4(w.leader.rx, w.leader.ry, w.leader.rw, w.leader.rh);
-#pragma unroll
-        for (int b = 0; b < NB; b++)
-            sr[(size_t)(1 + b) * s.n] = make_int4(w.bear[b].rx, w.bear[b].ry, w.bear[b].rw, w.bear[b].rh);
+        int4* sr = s.snap_rect + ((size_t)slot * (1 + nb)) * s.n + i;
+        sr[0] = leader_rect;
+        for (int b = 0; b < nb; b++) sr[(size_t)(1 + b) * s.n] = bear_rects[b];
         *snap_pushes += 1;
     }
+}
+template <int NB>
+FTL_HD void sense_serial(const DevCfg& cfg, const DevState& s, int i, const World<NB>& w, Tracker& t, int* snap_pushes,
+                         int* overflow) {
+    TrackerInput in = {w.follower.px, w.follower.py, w.leader.px, w.leader.py, w.follower.dir};
+    int4 bears[NB > 0 ? NB : 1];
+#pragma unroll
+    for (int b = 0; b < NB; b++) bears[b] = make_int4(w.bear[b].rx, w.bear[b].ry, w.bear[b].rw, w.bear[b].rh);
+    sense_serial_in(cfg, s, i, in, make_int4(w.leader.rx, w.leader.ry, w.leader.rw, w.leader.rh), bears, NB, t,
+                    snap_pushes, overflow);
 }
 
 // FollowerInfo.scan (SEN:834-842: float64 quotients stored as float32) and LeaderTrackDetector_vector.scan
@@ -240,9 +321,10 @@ FTL_HD void write_optional_sensors(const FtlConfig& c, const DevState& s, const 
     }
 }
 
+// observation part of the outputs, ENV:1789-1810 (what the kinematics kernel and the reset know)
 template <int NB>
-FTL_HD void write_outputs(const DevCfg& cfg, const DevPool& pool, const DevOutputs& out, int i, const World<NB>& w,
-                          const Episode& e, bool obs_only) {
+FTL_HD void write_outputs_obs(const DevCfg& cfg, const DevPool& pool, const DevOutputs& out, int i, const World<NB>& w,
+                              int scenario, int cur_target_id) {
     const FtlConfig& c = cfg.c;
     if (i >= out.n) return;  // filler env of the last warp
     if (out.numerical_features) {  // ENV:1793-1802
@@ -253,14 +335,17 @@ FTL_HD void write_outputs(const DevCfg& cfg, const DevPool& pool, const DevOutpu
         nf[7] = (float)w.follower.speed; nf[8] = (float)w.follower.dir; nf[9] = (float)w.follower.rot;
     }
     if (out.leader_target) {  // ENV:1803-1806
-        int n_route = pool.n_route[e.scenario];
-        int tid = e.cur_target_id < n_route ? e.cur_target_id : n_route - 1;
-        int2 p = route_point(pool, c, e.scenario, tid), last = route_point(pool, c, e.scenario, n_route - 1);
-        if (n_route > 1 && p.x == last.x && p.y == last.y) p = route_point(pool, c, e.scenario, n_route - 2);
+        int n_route = pool.n_route[scenario];
+        int tid = cur_target_id < n_route ? cur_target_id : n_route - 1;
+        int2 p = route_point(pool, c, scenario, tid), last = route_point(pool, c, scenario, n_route - 1);
+        if (n_route > 1 && p.x == last.x && p.y == last.y) p = route_point(pool, c, scenario, n_route - 2);
         out.leader_target[2 * (size_t)i] = p.x;
         out.leader_target[2 * (size_t)i + 1] = p.y;
     }
-    if (obs_only) return;
+}
+// reward / done / info codes of the step (what the bookkeeping kernel knows)
+FTL_HD void write_outputs_episode(const DevOutputs& out, int i, const Episode& e) {
+    if (i >= out.n) return;
     if (out.reward) out.reward[i] = (float)e.last_reward;
     if (out.done) out.done[i] = (uint8_t)((e.flags & FL_DONE) != 0);
     if (out.status) {
@@ -269,6 +354,12 @@ FTL_HD void write_outputs(const DevCfg& cfg, const DevPool& pool, const DevOutpu
         out.status[4 * (size_t)i + 2] = (uint8_t)((e.flags >> FL_LEADER_SHIFT) & 3);
         out.status[4 * (size_t)i + 3] = (uint8_t)((e.flags & FL_CRASH) != 0);
     }
+}
+template <int NB>
+FTL_HD void write_outputs(const DevCfg& cfg, const DevPool& pool, const DevOutputs& out, int i, const World<NB>& w,
+                          const Episode& e, bool obs_only) {
+    write_outputs_obs<NB>(cfg, pool, out, i, w, e.scenario, e.cur_target_id);
+    if (!obs_only) write_outputs_episode(out, i, e);
 }
 
 // ---- reset: the tail of Game.reset once the scenario exists (ENV:495-543) ---------------------------------------
@@ -328,6 +419,231 @@ FTL_HD void env_reset(const DevCfg& cfg, const DevState& s, const DevPool& pool,
 }
 
 // ---- one step: Game.step without the ray sensors (ENV:908-945, 947-1141) ------------------------------------------
+// The frames of a step are run as two passes that only communicate through per-frame records (FrameRec):
+//   kinematics   (kin_begin + kin_frames)  robots, waypoints, bears, the integer collision tests.  Nothing in it depends
+//                on the green-zone flags, the reward or the counters -- the reference's simulation goes on after a crash
+//                -- so it records, per frame, the two positions and four bits the bookkeeping needs;
+//   bookkeeping  (book_frames)  replays ENV:960-1139 in order: crash flags, exact green-zone flags, trail append, finish
+//                timer, early stopping, reward, counters.
+// On the GPU they are two kernels (k_kin, k_book): the ray kernel only needs the kinematics and the tracker, so the
+// bookkeeping -- whose exact green-zone scans are the long tail of a step -- runs beside the ray kernel instead of in
+// front of it; the records live in HBM, frame-major.  The host build (tests) interleaves the passes chunk by chunk.
+struct FrameRec {   // rec.f[j * stride] = follower position after frame j of the step, ...
+    float2* f;
+    float2* l;
+    unsigned char* bits;
+    unsigned char* lbits;   // optional second byte of bits (the role-split kernel's leader warp writes its own); may be NULL
+    size_t stride;
+};
+
+// frames this env runs in this step (ENV:939-940 via FtlStepInputs.frames_per_step) and its row of regime draws
+FTL_HD int env_frames(const DevCfg& cfg, const DevState& s, int i) {
+    const int cap = cfg.c.frames_per_step;
+    if (!s.in_frames) return cap;
+    const int f = s.in_frames[i];
+    return f < 1 ? 1 : f > cap ? cap : f;
+}
+FTL_HD const double* env_draws(const DevCfg& cfg, const DevState& s, int i) {
+    return s.in_draws ? s.in_draws + (size_t)i * cfg.c.frames_per_step : nullptr;
+}
+
+struct KinCtx {   // per-step constants of the kinematics pass
+    const int4* statics;
+    int n_route;
+    int2 target;            // the leader's current waypoint; re-read only when the index advances
+    uint64_t fmask, lmask;  // static rectangles within reach of the follower / leader during this step
+    bool lfin;
+};
+
+template <int NB>
+FTL_HD void kin_begin(const DevCfg& cfg, const DevPool& pool, double a0, double a1, World<NB>& w, const Episode& e,
+                      KinCtx& k) {
+    const FtlConfig& c = cfg.c;
+    k.statics = pool.static_rects + (size_t)e.scenario * c.static_cap;
+    const int n_static = pool.n_static[e.scenario];
+    k.n_route = pool.n_route[e.scenario];
+    command_forward(w.follower, c.follower, a0);  // ENV:927-933
+    if (a1 < 0) command_turn(w.follower, c.follower, fabs(a1), -1);
+    else if (a1 > 0) command_turn(w.follower, c.follower, a1, 1);
+    else command_turn(w.follower, c.follower, 0, 0);
+    k.target = route_point(pool, c, e.scenario, e.cur_target_id < k.n_route ? e.cur_target_id : k.n_route - 1);
+    near_static_masks_grid(pool, e.scenario, k.statics, n_static, make_float2(w.follower.px, w.follower.py),
+                           cfg.static_inflate[0], make_float2(w.leader.px, w.leader.py), cfg.static_inflate[1], &k.fmask,
+                           &k.lmask);
+    k.lfin = (e.flags & FL_LEADER_FINISHED) != 0;
+}
+
+// frames [frame0, frame0 + nf) of the step; record j of `rec` receives frame frame0 + j.  step_base = the frame counter
+// at the start of the step (the regimes are keyed by the frame counter, ENV:1143-1174).
+template <int NB>
+FTL_HD void kin_frames(const DevCfg& cfg, const DevPool& pool, int i, World<NB>& w, Episode& e, KinCtx& k,
+                       const FrameRec& rec, int step_base, int frame0, int nf, int fps, const double* draws) {
+    const FtlConfig& c = cfg.c;
+    const int4* statics = k.statics;
+    for (int j = 0; j < nf; j++) {
+        FTL_FRAME_SYNC(frame0 + j);
+        int bits = 0;
+        // (1) follower, ENV:957-964
+#ifndef FTL_OUTLINE_ROBOTS
+        robot_move(w.follower, c.follower);
+#else
+        w.follower = robot_move_nv(w.follower, &c.follower);
+#endif
+        if (!c.ignore_follower_collisions) {
+            bool hit = robots_collide(w.follower, w.leader) || collide_static_masked(w.follower, statics, k.fmask) ||
+                       out_of_bounds(c, w.follower);
+#pragma unroll
+            for (int b = 0; b < NB; b++) hit = hit || robots_collide(w.follower, w.bear[b]);
+            if (hit) bits |= REC_FOLLOWER_HIT;
+        }
+        // too_close uses the leader before its move, ENV:973
+        if (d2_f32(w.leader.px, w.leader.py, w.follower.px, w.follower.py) <= cfg.min_dist2_f32) bits |= REC_TOO_CLOSE;
+        // (3) waypoint advance, ENV:978-983
+        if (dist_f64_nv((double)w.leader.px, (double)w.leader.py, (double)k.target.x, (double)k.target.y) <
+            c.leader_pos_epsilon) {
+            e.cur_target_id += 1;
+            if (e.cur_target_id >= k.n_route) k.lfin = true;   // cur_target_point keeps its last value
+            else k.target = route_point(pool, c, e.scenario, e.cur_target_id);
+        }
+        // (4) bears, ENV:987-995
+#pragma unroll
+        for (int b = 0; b < NB; b++) {
+            bear_target(c, b, w.bear[b], w.leader, &w.btx[b], &w.bty[b], &w.bidx[b]);
+#ifndef FTL_OUTLINE_ROBOTS
+            move_to_the_point(w.bear[b], c.bear, w.btx[b], w.bty[b], false, 0.0);
+#else
+            w.bear[b] = move_to_the_point_nv(w.bear[b], &c.bear, w.btx[b], w.bty[b], 0, 0.0);
+#endif
+        }
+        // (5) leader, ENV:1048-1072
+        if (!k.lfin) {
+            e.step_count = step_base + frame0 + j;   // the regimes are keyed by the frame counter
+            double speed = c.n_speed_regime > 0 ? leader_speed(cfg, e, i, draws ? draws + frame0 + j : nullptr)
+                                                : c.leader.max_speed;
+            double accel = c.n_accel_regime > 0 ? leader_accel(cfg, e) / fps : 0.0;
+#ifndef FTL_OUTLINE_ROBOTS
+            move_to_the_point(w.leader, c.leader, (double)k.target.x, (double)k.target.y, true, speed + accel);
+#else
+            w.leader = move_to_the_point_nv(w.leader, &c.leader, (double)k.target.x, (double)k.target.y, 1, speed + accel);
+#endif
+        } else {
+            command_forward(w.leader, c.leader, 0);
+            command_turn(w.leader, c.leader, 0, 0);
+            bits |= REC_LEADER_FINISHED;
+        }
+        if (robots_collide(w.leader, w.follower) || collide_static_masked(w.leader, statics, k.lmask) ||
+            out_of_bounds(c, w.leader))
+            bits |= REC_LEADER_HIT;
+        rec.f[(size_t)j * rec.stride] = make_float2(w.follower.px, w.follower.py);
+        rec.l[(size_t)j * rec.stride] = make_float2(w.leader.px, w.leader.py);
+        rec.bits[(size_t)j * rec.stride] = (unsigned char)bits;
+        if (rec.lbits) rec.lbits[(size_t)j * rec.stride] = 0;
+    }
+    e.step_count = step_base;
+}
+
+// flags, trail, timers, reward of the env's nf recorded frames (ENV:960-1139); e.step_count is the running frame
+// counter, fps the frames_per_step of this step (finish timer).  nf_loop >= nf: the trip count of the warp (every lane
+// takes part in the collectives of the exact scans even when it has no frame left).
+FTL_HD void book_frames(const DevCfg& cfg, float2* trail, float* trail_d, double* trail_s, Episode& e, GreenCache& gc,
+                        const FrameRec& rec, int nf, int fps, int nf_loop) {
+    const FtlConfig& c = cfg.c;
+    for (int j = 0; j < nf_loop; j++) {
+        if (j >= nf) {
+            bool ib, ot;
+            green_flags(cfg, trail, trail_d, e.trail_len, 0.f, 0.f, gc, &ib, &ot, false);
+            continue;
+        }
+        const int bits = rec.bits[(size_t)j * rec.stride] | (rec.lbits ? rec.lbits[(size_t)j * rec.stride] : 0);
+        const float2 fp = rec.f[(size_t)j * rec.stride], lp = rec.l[(size_t)j * rec.stride];
+        int mission = FTL_MISSION_IN_PROGRESS, agent = FTL_AGENT_MOVING, leader_st = FTL_LEADER_MOVING;
+        if (bits & REC_FOLLOWER_HIT) {   // ENV:960-964
+            e.flags |= FL_CRASH | FL_DONE;
+            mission = FTL_MISSION_FAIL;
+            agent = FTL_AGENT_CRASH;
+        }
+        // (2) green zone + flags, ENV:966-973
+        bool in_box, on_trace;
+        green_flags(cfg, trail, trail_d, e.trail_len, fp.x, fp.y, gc, &in_box, &on_trace);
+        const bool too_close = (bits & REC_TOO_CLOSE) != 0;
+        if (bits & REC_LEADER_FINISHED) {
+            e.flags |= FL_LEADER_FINISHED;
+            leader_st = FTL_LEADER_FINISHED;
+        }
+        if (bits & REC_LEADER_HIT) {     // ENV:1068-1072
+            e.flags |= FL_DONE;
+            mission = FTL_MISSION_FAIL;
+            leader_st = FTL_LEADER_CRASH;
+        }
+        // (6) trail append on the virtual clock, ENV:1074-1075
+        if (e.step_count % c.trajectory_saving_period == 0) {
+            if (e.trail_len < c.trail_cap) {
+                // trail_push with the previous tail in registers
+                const int k = e.trail_len;
+                const float2 p = lp, q = gc.last_pt;
+                float dk = 0.f;
+                trail[k] = p;
+                if (k > 0) {
+                    dk = sqrtf(d2_f32(p.x, p.y, q.x, q.y));   // euclidean(newer, older) in float32, ENV:1838
+                    gc.last_s = gc.last_s + (double)dk;
+                } else {
+                    gc.last_s = 0.0;
+                }
+                trail_d[k] = dk;
+                trail_s[k] = gc.last_s;
+                gc.last_pt = p;
+                e.trail_len++;
+                green_cache_appended(cfg, trail_s, e.trail_len, p, q, dk, gc);
+            } else {
+                e.overflow |= 1;
+            }
+        }
+        // (7) finish timer, ENV:1077-1087
+        if ((e.flags & FL_LEADER_FINISHED) && in_box) {
+            if (e.finish_timer < 0) {
+                e.finish_timer = 0;
+            } else {
+                e.finish_timer += 1;
+                if (e.finish_timer > fps * 20) {
+                    mission = FTL_MISSION_SUCCESS;
+                    leader_st = FTL_LEADER_FINISHED;
+                    agent = FTL_AGENT_FINISHED;
+                    e.flags |= FL_DONE;
+                }
+            }
+        }
+        // (8) early stopping, ENV:1088-1107
+        if (e.step_count > c.warm_start) {
+            if (c.es_has_low_reward && e.acc_penalty < c.es_low_reward) {
+                mission = FTL_MISSION_FAIL; leader_st = FTL_LEADER_MOVING; agent = FTL_AGENT_LOW_REWARD;
+                e.flags |= FL_CRASH | FL_DONE;
+            }
+            if (c.es_has_max_distance_coef) {
+                float d = sqrtf(d2_f32(fp.x, fp.y, lp.x, lp.y));
+                if (d > cfg.es_far_f32) {
+                    mission = FTL_MISSION_FAIL; leader_st = FTL_LEADER_MOVING; agent = FTL_AGENT_TOO_FAR;
+                    e.flags |= FL_CRASH | FL_DONE;
+                }
+            }
+        }
+        // (9) reward + counters, ENV:1109-1139
+        double r = reward_of(c, e, too_close, in_box, on_trace);
+        if (r < 0) e.acc_penalty += r; else e.acc_penalty = 0;
+        e.overall += r;
+        e.step_count += 1;
+        if (e.step_count > c.max_steps) {
+            mission = FTL_MISSION_FINISHED_BY_TIME; leader_st = FTL_LEADER_MOVING; agent = FTL_AGENT_MOVING;
+            e.flags |= FL_DONE;
+        }
+        e.last_reward = c.aggregate_reward ? e.overall : r;
+        e.flags = (e.flags & (FL_DONE | FL_CRASH | FL_LEADER_FINISHED)) | (in_box ? FL_IN_BOX : 0) |
+                  (on_trace ? FL_ON_TRACE : 0) | (too_close ? FL_TOO_CLOSE : 0) | (mission << FL_MISSION_SHIFT) |
+                  (agent << FL_AGENT_SHIFT) | (leader_st << FL_LEADER_SHIFT);
+    }
+}
+
+// The whole step for one env with a complete Episode record: the host build of the tests (and the definition of what the
+// two kernels compute together).  The passes alternate over chunks of kFrameChunk frames.
 template <int NB>
 FTL_HD void env_step(const DevCfg& cfg, const DevState& s, const DevPool& pool, int i, double a0, double a1,
                      World<NB>& w, Episode& e) {
@@ -338,191 +654,20 @@ FTL_HD void env_step(const DevCfg& cfg, const DevState& s, const DevPool& pool, 
     float2* trail = s.trail + (size_t)i * c.trail_cap;
     float* trail_d = s.trail_d + (size_t)i * c.trail_cap;
     double* trail_s = s.trail_s + (size_t)i * c.trail_cap;
-#ifdef FTL_EARLY_GREEN_LOAD
     cache_load(s, i, gc, t, &snap_pushes);
     green_cache_hydrate(trail, trail_s, e.trail_len, gc);
-#endif
-    const int4* statics = pool.static_rects + (size_t)e.scenario * c.static_cap;
-    const int n_static = pool.n_static[e.scenario];
-    const int n_route = pool.n_route[e.scenario];
-
-    command_forward(w.follower, c.follower, a0);  // ENV:927-933
-    if (a1 < 0) command_turn(w.follower, c.follower, fabs(a1), -1);
-    else if (a1 > 0) command_turn(w.follower, c.follower, a1, 1);
-    else command_turn(w.follower, c.follower, 0, 0);
-
-    // the leader's current target lives in registers; it is re-read only when the waypoint index advances
-    int2 target = route_point(pool, c, e.scenario, e.cur_target_id < n_route ? e.cur_target_id : n_route - 1);
-
-    uint64_t fmask, lmask;
-    near_static_masks_grid(pool, e.scenario, statics, n_static, make_float2(w.follower.px, w.follower.py),
-                           cfg.static_inflate[0], make_float2(w.leader.px, w.leader.py), cfg.static_inflate[1], &fmask,
-                           &lmask);
-
-    // The frames run in two passes over chunks of kFrameChunk frames.  Pass 1 is the kinematics: nothing in it depends on
-    // the green-zone flags, the reward or the counters (the reference's simulation goes on after a crash), so it only
-    // records, per frame, the two positions and four bits the bookkeeping needs.  Pass 2 replays the bookkeeping in
-    // order (ENV:960-1139).  The split keeps the robot code and the green-zone code out of each other's instruction
-    // footprint and gives pass 2 all follower positions of the chunk at once (batched exact scans).
+    KinCtx k;
+    kin_begin<NB>(cfg, pool, a0, a1, w, e, k);
     float2 rec_f[kFrameChunk], rec_l[kFrameChunk];
     unsigned char rec_bits[kFrameChunk];
-    bool lfin = (e.flags & FL_LEADER_FINISHED) != 0;
-    for (int f0 = 0; f0 < c.frames_per_step; f0 += kFrameChunk) {
-        const int nf = c.frames_per_step - f0 < kFrameChunk ? c.frames_per_step - f0 : kFrameChunk;
-        const int sc_base = e.step_count;
-        // ---- pass 1: robots -------------------------------------------------------------------------------------
-        for (int j = 0; j < nf; j++) {
-            FTL_FRAME_SYNC(f0 + j);
-            int bits = 0;
-            // (1) follower, ENV:957-964
-#ifndef FTL_OUTLINE_ROBOTS
-            robot_move(w.follower, c.follower);
-#else
-            w.follower = robot_move_nv(w.follower, &c.follower);
-#endif
-            if (!c.ignore_follower_collisions) {
-                bool hit = robots_collide(w.follower, w.leader) || collide_static_masked(w.follower, statics, fmask) ||
-                           out_of_bounds(c, w.follower);
-#pragma unroll
-                for (int b = 0; b < NB; b++) hit = hit || robots_collide(w.follower, w.bear[b]);
-                if (hit) bits |= REC_FOLLOWER_HIT;
-            }
-            // too_close uses the leader before its move, ENV:973
-            if (d2_f32(w.leader.px, w.leader.py, w.follower.px, w.follower.py) <= cfg.min_dist2_f32) bits |= REC_TOO_CLOSE;
-            // (3) waypoint advance, ENV:978-983
-            if (dist_f64_nv((double)w.leader.px, (double)w.leader.py, (double)target.x, (double)target.y) <
-                c.leader_pos_epsilon) {
-                e.cur_target_id += 1;
-                if (e.cur_target_id >= n_route) lfin = true;   // cur_target_point keeps its last value
-                else target = route_point(pool, c, e.scenario, e.cur_target_id);
-            }
-            // (4) bears, ENV:987-995
-#pragma unroll
-            for (int b = 0; b < NB; b++) {
-                bear_target(c, b, w.bear[b], w.leader, &w.btx[b], &w.bty[b], &w.bidx[b]);
-#ifndef FTL_OUTLINE_ROBOTS
-                move_to_the_point(w.bear[b], c.bear, w.btx[b], w.bty[b], false, 0.0);
-#else
-                w.bear[b] = move_to_the_point_nv(w.bear[b], &c.bear, w.btx[b], w.bty[b], 0, 0.0);
-#endif
-            }
-            // (5) leader, ENV:1048-1072
-            if (!lfin) {
-                e.step_count = sc_base + j;   // the regimes are keyed by the frame counter
-                double speed = c.n_speed_regime > 0 ? leader_speed(cfg, e, i) : c.leader.max_speed;
-                double accel = c.n_accel_regime > 0 ? leader_accel(cfg, e) / c.frames_per_step : 0.0;
-#ifndef FTL_OUTLINE_ROBOTS
-                move_to_the_point(w.leader, c.leader, (double)target.x, (double)target.y, true, speed + accel);
-#else
-                w.leader = move_to_the_point_nv(w.leader, &c.leader, (double)target.x, (double)target.y, 1, speed + accel);
-#endif
-            } else {
-                command_forward(w.leader, c.leader, 0);
-                command_turn(w.leader, c.leader, 0, 0);
-                bits |= REC_LEADER_FINISHED;
-            }
-            if (robots_collide(w.leader, w.follower) || collide_static_masked(w.leader, statics, lmask) ||
-                out_of_bounds(c, w.leader))
-                bits |= REC_LEADER_HIT;
-            rec_f[j] = make_float2(w.follower.px, w.follower.py);
-            rec_l[j] = make_float2(w.leader.px, w.leader.py);
-            rec_bits[j] = (unsigned char)bits;
-        }
-        e.step_count = sc_base;
-#ifndef FTL_EARLY_GREEN_LOAD
-        if (f0 == 0) {   // the green-zone cache is only needed from here on: not live (or spilled) during pass 1
-            cache_load(s, i, gc, t, &snap_pushes);
-            green_cache_hydrate(trail, trail_s, e.trail_len, gc);
-        }
-#endif
-        // ---- pass 2: flags, trail, timers, reward ------------------------------------------------------------------
-        for (int j = 0; j < nf; j++) {
-            const int bits = rec_bits[j];
-            const float2 fp = rec_f[j], lp = rec_l[j];
-            int mission = FTL_MISSION_IN_PROGRESS, agent = FTL_AGENT_MOVING, leader_st = FTL_LEADER_MOVING;
-            if (bits & REC_FOLLOWER_HIT) {   // ENV:960-964
-                e.flags |= FL_CRASH | FL_DONE;
-                mission = FTL_MISSION_FAIL;
-                agent = FTL_AGENT_CRASH;
-            }
-            // (2) green zone + flags, ENV:966-973
-            bool in_box, on_trace;
-            green_flags(cfg, trail, trail_d, e.trail_len, fp.x, fp.y, gc, &in_box, &on_trace);
-            const bool too_close = (bits & REC_TOO_CLOSE) != 0;
-            if (bits & REC_LEADER_FINISHED) {
-                e.flags |= FL_LEADER_FINISHED;
-                leader_st = FTL_LEADER_FINISHED;
-            }
-            if (bits & REC_LEADER_HIT) {     // ENV:1068-1072
-                e.flags |= FL_DONE;
-                mission = FTL_MISSION_FAIL;
-                leader_st = FTL_LEADER_CRASH;
-            }
-            // (6) trail append on the virtual clock, ENV:1074-1075
-            if (e.step_count % c.trajectory_saving_period == 0) {
-                if (e.trail_len < c.trail_cap) {
-                    // trail_push with the previous tail in registers
-                    const int k = e.trail_len;
-                    const float2 p = lp, q = gc.last_pt;
-                    float dk = 0.f;
-                    trail[k] = p;
-                    if (k > 0) {
-                        dk = sqrtf(d2_f32(p.x, p.y, q.x, q.y));   // euclidean(newer, older) in float32, ENV:1838
-                        gc.last_s = gc.last_s + (double)dk;
-                    } else {
-                        gc.last_s = 0.0;
-                    }
-                    trail_d[k] = dk;
-                    trail_s[k] = gc.last_s;
-                    gc.last_pt = p;
-                    e.trail_len++;
-                    green_cache_appended(cfg, trail_s, e.trail_len, p, q, dk, gc);
-                } else {
-                    e.overflow |= 1;
-                }
-            }
-            // (7) finish timer, ENV:1077-1087
-            if ((e.flags & FL_LEADER_FINISHED) && in_box) {
-                if (e.finish_timer < 0) {
-                    e.finish_timer = 0;
-                } else {
-                    e.finish_timer += 1;
-                    if (e.finish_timer > c.frames_per_step * 20) {
-                        mission = FTL_MISSION_SUCCESS;
-                        leader_st = FTL_LEADER_FINISHED;
-                        agent = FTL_AGENT_FINISHED;
-                        e.flags |= FL_DONE;
-                    }
-                }
-            }
-            // (8) early stopping, ENV:1088-1107
-            if (e.step_count > c.warm_start) {
-                if (c.es_has_low_reward && e.acc_penalty < c.es_low_reward) {
-                    mission = FTL_MISSION_FAIL; leader_st = FTL_LEADER_MOVING; agent = FTL_AGENT_LOW_REWARD;
-                    e.flags |= FL_CRASH | FL_DONE;
-                }
-                if (c.es_has_max_distance_coef) {
-                    float d = sqrtf(d2_f32(fp.x, fp.y, lp.x, lp.y));
-                    if (d > cfg.es_far_f32) {
-                        mission = FTL_MISSION_FAIL; leader_st = FTL_LEADER_MOVING; agent = FTL_AGENT_TOO_FAR;
-                        e.flags |= FL_CRASH | FL_DONE;
-                    }
-                }
-            }
-            // (9) reward + counters, ENV:1109-1139
-            double r = reward_of(c, e, too_close, in_box, on_trace);
-            if (r < 0) e.acc_penalty += r; else e.acc_penalty = 0;
-            e.overall += r;
-            e.step_count += 1;
-            if (e.step_count > c.max_steps) {
-                mission = FTL_MISSION_FINISHED_BY_TIME; leader_st = FTL_LEADER_MOVING; agent = FTL_AGENT_MOVING;
-                e.flags |= FL_DONE;
-            }
-            e.last_reward = c.aggregate_reward ? e.overall : r;
-            e.flags = (e.flags & (FL_DONE | FL_CRASH | FL_LEADER_FINISHED)) | (in_box ? FL_IN_BOX : 0) |
-                      (on_trace ? FL_ON_TRACE : 0) | (too_close ? FL_TOO_CLOSE : 0) | (mission << FL_MISSION_SHIFT) |
-                      (agent << FL_AGENT_SHIFT) | (leader_st << FL_LEADER_SHIFT);
-        }
+    const FrameRec rec = {rec_f, rec_l, rec_bits, nullptr, 1};
+    const int step_base = e.step_count, fps = env_frames(cfg, s, i);
+    const double* draws = env_draws(cfg, s, i);
+    for (int f0 = 0; f0 < fps; f0 += kFrameChunk) {
+        const int nf = fps - f0 < kFrameChunk ? fps - f0 : kFrameChunk;
+        kin_frames<NB>(cfg, pool, i, w, e, k, rec, step_base, f0, nf, fps, draws);
+        e.step_count = step_base + f0;
+        book_frames(cfg, trail, trail_d, trail_s, e, gc, rec, nf, fps, nf);
     }
     sense_serial<NB>(cfg, s, i, w, t, &snap_pushes, &e.overflow);
     cache_store(s, i, gc, t, snap_pushes);

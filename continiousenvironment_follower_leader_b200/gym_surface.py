@@ -128,6 +128,9 @@ class Game(Env):
         self.frames_per_step, self.max_steps, self.warm_start = c.frames_per_step, c.max_steps, c.warm_start
         self.leader_pos_epsilon = g["leader_pos_epsilon"]
         self.early_stopping = g["early_stopping"]
+        self.random_frames_per_step = self.gc.random_frames_per_step
+        if self.random_frames_per_step is not None:   # ENV:405: drawn once here, redrawn after every step (ENV:939-940)
+            self.frames_per_step = int(np.random.randint(*self.random_frames_per_step))
         self.found_target_point = False
         self.trajectory = g["trajectory"]
         self.finish_point = (10, 10)
@@ -187,7 +190,11 @@ class Game(Env):
             a = np.array([int(a)], np.int32)
         else:
             a = np.asarray(action, dtype=np.float32).reshape(1, -1)
-        out = self._env.step(a)
+        if self.random_frames_per_step is not None:
+            out = self._env.step(a, frames=np.array([self.frames_per_step], np.int32))
+            self.frames_per_step = int(np.random.randint(*self.random_frames_per_step))
+        else:
+            out = self._env.step(a)
         self._cached_state = None
         st = out.status[0]
         info = {"mission_status": abi.MISSION_STATUS[int(st[0])], "agent_status": abi.AGENT_STATUS[int(st[1])],

@@ -276,7 +276,27 @@ int ftl_reset(ftl_handle h, const uint8_t* mask_dev, const int32_t* scenario_ids
               const FtlOutputs* out_dev, void* cuda_stream);
 
 /* ---- step: replaces Game.step (ENV:908-945) ---------------------------------------------------- */
+/* Enqueues the kernels of one step on `cuda_stream` (kinematics, bookkeeping, ray casting, finishing; they overlap
+ * through programmatic dependent launches and per-env-group flags).  The call may be captured into a CUDA graph: while
+ * the stream is capturing the kernels are recorded in plain stream order (the flag protocol needs a fresh sequence
+ * number per step, which a replayed graph cannot have), so a captured step is correct but does not overlap. */
 int ftl_step(ftl_handle h, const void* actions_dev, const FtlOutputs* out_dev, void* cuda_stream);
+/* Optional per-step inputs of ftl_step_ex (any pointer may be NULL = the plain ftl_step behaviour):
+ *   frames_per_step  int32[N]: how many frames THIS step runs in each env, 1..FtlConfig.frames_per_step (which is then
+ *                    the capacity).  Replaces `random_frames_per_step` (ENV:405, 939-940: the reference redraws
+ *                    self.frames_per_step with np.random.randint after every step); the caller does the drawing.
+ *   regime_draws     double[N][FtlConfig.frames_per_step]: u in [0, 1) for frame j of each env, consumed where the
+ *                    reference calls random.uniform(a, b) = a + (b - a) * random() for a list-valued
+ *                    leader_speed_regime entry (ENV:1155-1156).  NULL: Philox keyed by (global env id, episode, frame).
+ *                    Lets a recorded reference episode be replayed bit for bit. */
+typedef struct FtlStepInputs {
+    const int32_t* frames_per_step;
+    const double* regime_draws;
+} FtlStepInputs;
+int ftl_step_ex(ftl_handle h, const void* actions_dev, const FtlStepInputs* in_dev, const FtlOutputs* out_dev,
+                void* cuda_stream);
+int ftl_step_host_ex(ftl_handle h, const void* actions_host, const FtlStepInputs* in_host, const FtlOutputs* out_host,
+                     void* cuda_stream);
 /* Same call with HOST buffers (pinned or pageable): copies actions in, steps, copies outputs back,
  * and synchronises the stream.  This is the end-to-end path a gym-style caller sees. */
 int ftl_step_host(ftl_handle h, const void* actions_host, const FtlOutputs* out_host, void* cuda_stream);
@@ -301,11 +321,13 @@ int ftl_set_state(ftl_handle h, int32_t first_env, int32_t n, const FtlStateBuff
 int ftl_stats(ftl_handle h, double* stats_dev, int32_t reset_after, void* cuda_stream);
 /* Number of kernel launches issued by this handle so far (for bench.py's gpu_launches). */
 int64_t ftl_launch_count(ftl_handle h);
-/* Per-kernel device timing: while enabled, ftl_step records CUDA events on the launching stream around
- * its two kernels; ftl_profile_read synchronises and returns the accumulated milliseconds of the fused
- * step kernel and of the ray kernel over `steps` steps, then clears the accumulation. */
+/* Per-kernel device timing: while enabled, ftl_step records CUDA events on the launching stream between its kernels
+ * (which makes them run in plain stream order instead of overlapping); ftl_profile_read synchronises and returns the
+ * accumulated milliseconds of the step kernels (kinematics + bookkeeping) and of the ray kernels (casting + finishing)
+ * over `steps` steps, then clears the accumulation; ftl_profile_read_kernels gives kinematics and bookkeeping apart. */
 int ftl_profile(ftl_handle h, int32_t enable);
 int ftl_profile_read(ftl_handle h, double* step_kernel_ms, double* ray_kernel_ms, int64_t* steps);
+int ftl_profile_read_kernels(ftl_handle h, double* kin_ms, double* book_ms, double* rays_ms, int64_t* steps);
 
 /* Diagnostic for the roofline report: FP32 FMA throughput of `device` measured with a
  * register-resident kernel of independent fused multiply-add chains (2 flop per FMA), in TFLOP/s.  No handle needed. */

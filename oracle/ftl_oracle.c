@@ -72,6 +72,9 @@ typedef struct FtlOracle {
     int rays_per_env;
     double stats[FTL_STAT_COUNT];
     char err[256];
+    /* optional per-step inputs (FtlStepInputs of include/ftl.h), valid during one ftl_oracle_step_ex call */
+    const int32_t* in_frames;   /* [N]     frames of this step per env (ENV:939-940), NULL = cfg.frames_per_step */
+    const double* in_draws;     /* [N][F]  the random() behind random.uniform of list-valued speed regimes (ENV:1155-1156) */
 } FtlOracle;
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -407,14 +410,15 @@ static void bear_target(const FtlOracle* o, FtlEnvState* e, int idx) {
 /* ------------------------------------------------------------------------------------------------ */
 /* leader speed / acceleration regimes                                                               */
 /* ------------------------------------------------------------------------------------------------ */
-static double leader_speed(const FtlOracle* o, FtlEnvState* e, int env_index) { /* ENV:1143-1157 */
+static double leader_speed(const FtlOracle* o, FtlEnvState* e, int env_index, const double* draw) { /* ENV:1143-1157 */
     const FtlConfig* cfg = &o->cfg;
     int sel = -1;
     for (int k = 0; k < cfg->n_speed_regime; k++)
         if (cfg->speed_regime_key[k] <= e->step_count) sel = k;
     if (sel >= 0) {
         if (cfg->speed_regime_is_range[sel]) {
-            double u = regime_uniform(o->env_id_base + env_index, e->episode_count, e->step_count);
+            /* random.uniform(a, b) = a + (b - a) * random(): the caller's recorded draw, or Philox */
+            double u = draw ? *draw : regime_uniform(o->env_id_base + env_index, e->episode_count, e->step_count);
             e->cur_speed_multiplier = cfg->speed_regime_lo[sel] + (cfg->speed_regime_hi[sel] - cfg->speed_regime_lo[sel]) * u;
         } else {
             e->cur_speed_multiplier = cfg->speed_regime_lo[sel];
@@ -461,7 +465,7 @@ static double reward(const FtlConfig* cfg, const FtlEnvState* e) { /* ENV:1869-1
 /* ------------------------------------------------------------------------------------------------ */
 /* one frame                                                                                         */
 /* ------------------------------------------------------------------------------------------------ */
-static void frame_step(FtlOracle* o, int env_index) { /* ENV:947-1141 */
+static void frame_step(FtlOracle* o, int env_index, int fps, const double* draw) { /* ENV:947-1141; fps = self.frames_per_step */
     const FtlConfig* cfg = &o->cfg;
     FtlEnvState* e = &o->env[env_index];
     float* trail = o->trail + (size_t)env_index * cfg->trail_cap * 2;
@@ -498,8 +502,8 @@ static void frame_step(FtlOracle* o, int env_index) { /* ENV:947-1141 */
     }
     /* leader, ENV:1048-1065 */
     if (!e->leader_finished) {
-        double speed = cfg->n_speed_regime > 0 ? leader_speed(o, e, env_index) : cfg->leader.max_speed;
-        double accel = cfg->n_accel_regime > 0 ? leader_accel(o, e) / cfg->frames_per_step : 0;
+        double speed = cfg->n_speed_regime > 0 ? leader_speed(o, e, env_index, draw) : cfg->leader.max_speed;
+        double accel = cfg->n_accel_regime > 0 ? leader_accel(o, e) / fps : 0;
         int tid = e->cur_target_id;
         move_to_the_point(&e->leader, &cfg->leader, (double)route[2 * tid], (double)route[2 * tid + 1], 1, speed + accel);
     } else {
@@ -528,7 +532,7 @@ static void frame_step(FtlOracle* o, int env_index) { /* ENV:947-1141 */
             e->finish_timer = 0;
         } else {
             e->finish_timer += 1;
-            if (e->finish_timer > cfg->frames_per_step * 20) {
+            if (e->finish_timer > fps * 20) {
                 mission = FTL_MISSION_SUCCESS;
                 leader_st = FTL_LEADER_FINISHED;
                 agent = FTL_AGENT_FINISHED;
@@ -1080,7 +1084,14 @@ static void env_step(FtlOracle* o, int i, const void* actions, const FtlOutputs*
         command_turn(&e->follower, &cfg->follower, a1, 1);
     else
         command_turn(&e->follower, &cfg->follower, 0, 0);
-    for (int f = 0; f < cfg->frames_per_step; f++) frame_step(o, i);
+    int fps = cfg->frames_per_step;
+    if (o->in_frames) {   /* random_frames_per_step: the caller drew this step's count, ENV:939-940 */
+        fps = o->in_frames[i];
+        if (fps < 1) fps = 1;
+        if (fps > cfg->frames_per_step) fps = cfg->frames_per_step;
+    }
+    const double* draws = o->in_draws ? o->in_draws + (size_t)i * cfg->frames_per_step : NULL;
+    for (int f = 0; f < fps; f++) frame_step(o, i, fps, draws ? draws + f : NULL);
     use_sensors(o, i, out);
     if (out) write_outputs(o, i, out);
 }
@@ -1181,6 +1192,15 @@ int ftl_oracle_step(FtlOracle* o, const void* actions, const FtlOutputs* out) {
         }
     }
     return FTL_OK;
+}
+
+int ftl_oracle_step_ex(FtlOracle* o, const void* actions, const int32_t* frames, const double* draws, const FtlOutputs* out) {
+    o->in_frames = frames;
+    o->in_draws = draws;
+    int rc = ftl_oracle_step(o, actions, out);
+    o->in_frames = NULL;
+    o->in_draws = NULL;
+    return rc;
 }
 
 int ftl_oracle_get_state(FtlOracle* o, int first, int n, const FtlStateBuffers* b) {

@@ -153,16 +153,26 @@ def run_trace(name, env_id, kwargs, seed, policy, max_env_steps, action_seed=0, 
     recs = [capture(env, obs, 0.0, False, info0, ray_names, n_bears, gc)]
     actions = []
     pol = POLICIES[policy]
+    # traces whose steps consume the reference's global RNGs also store what was drawn (FtlStepInputs of a replay)
+    list_regime = any(isinstance(v, (list, tuple)) for v in (kwargs.get("leader_speed_regime") or {}).values())
+    recorder = rh.StepInputRecorder(env, gc.c.frames_per_step) if (list_regime or gc.random_frames_per_step) else None
     for t in range(max_env_steps):
         if switch is not None and t == switch[0]:
             pol = POLICIES[switch[1]]
         a = pol(rng, env, lo, hi)
+        if recorder is not None:
+            recorder.begin_step()
         obs, reward, done, info = rh.step(env, a)
+        if recorder is not None:
+            recorder.end_step()
         actions.append(a)
         recs.append(capture(env, obs, reward, done, info, ray_names, n_bears, gc))
         if until_done and done:
             break
     out = {"actions": np.array(actions, np.float32)}
+    if recorder is not None:
+        out["step_frames"] = np.array(recorder.frames, np.int32)
+        out["step_draws"] = np.array(recorder.draws, np.float64)
     for k in recs[0]:
         out["t_" + k] = np.stack([r[k] for r in recs])
     for k, v in scen.items():
@@ -232,6 +242,13 @@ TRACES = [
          kwargs=dict(TEST_GAME_MANUAL_GAZEBO_KWARGS, leader_speed_regime={0: 1}, leader_acceleration_regime=None,
                      early_stopping={"max_distance_coef": 1.5, "low_reward": -40}),
          seed=4, policy="random", max_env_steps=400, until_done=True),
+    # configs[3] as the preset ships it: list-valued speed regimes (random.uniform per frame, ENV:1155-1156) and
+    # random_frames_per_step (np.random.randint per step, ENV:939-940); the draws are stored with the trace
+    dict(name="gazebo_list_regimes_random_frames_seed3", env_id="Test-Cont-Env-Auto-v0",
+         kwargs=dict(TEST_GAME_MANUAL_GAZEBO_KWARGS, max_steps=3000, random_frames_per_step=[2, 8],
+                     leader_speed_regime={0: [0.2, 1], 100: 1, 180: [0.5, 1], 260: 0.75, 330: [0.0, 0.5], 400: [0.4, 1]},
+                     leader_acceleration_regime={0: 0, 200: 0.03, 300: 0}),
+         seed=3, policy="follow", max_env_steps=700, until_done=True),
     # the sensors without history on the same ray engine (LeaderCorridor_lasers_v2 = rays at k*360/R,
     # LeaderCorridor_lasers = the fixed 7-ray fan), FollowerInfo and LeaderTrackDetector_vector ("new")
     dict(name="flat_sensors_seed9", env_id="Test-Cont-Env-Auto-v0",

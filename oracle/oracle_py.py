@@ -33,6 +33,7 @@ def lib():
         L.ftl_oracle_upload_scenarios.argtypes = [C.c_void_p, C.POINTER(abi.FtlScenarioPool)]
         L.ftl_oracle_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(abi.FtlOutputs)]
         L.ftl_oracle_step.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(abi.FtlOutputs)]
+        L.ftl_oracle_step_ex.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(abi.FtlOutputs)]
         L.ftl_oracle_get_state.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(abi.FtlStateBuffers)]
         L.ftl_oracle_set_state.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(abi.FtlStateBuffers)]
         L.ftl_oracle_rays_per_env.argtypes = [C.c_void_p]
@@ -79,12 +80,19 @@ class OracleEnv:
             raise RuntimeError("oracle reset failed: %d" % rc)
         return self.out
 
-    def step(self, actions):
+    def step(self, actions, frames=None, regime_draws=None):
+        """frames: int32[N] frames of this step per env; regime_draws: float64[N, frames_per_step] (FtlStepInputs)."""
         if self.cfg.action_mode == abi.ACTION_DISCRETE:
             a = np.ascontiguousarray(actions, np.int32)
         else:
             a = np.ascontiguousarray(actions, np.float32)
-        rc = self._L.ftl_oracle_step(self._h, abi.ptr(a), C.byref(self.out.c))
+        if frames is not None or regime_draws is not None:
+            f = None if frames is None else np.ascontiguousarray(frames, np.int32)
+            d = None if regime_draws is None else np.ascontiguousarray(regime_draws, np.float64)
+            assert d is None or d.shape == (self.n, self.cfg.frames_per_step)
+            rc = self._L.ftl_oracle_step_ex(self._h, abi.ptr(a), abi.ptr(f), abi.ptr(d), C.byref(self.out.c))
+        else:
+            rc = self._L.ftl_oracle_step(self._h, abi.ptr(a), C.byref(self.out.c))
         if rc:
             raise RuntimeError("oracle step failed: %d" % rc)
         return self.out

@@ -84,6 +84,44 @@ def make_env(env_id="Test-Cont-Env-Auto-v0", **kwargs):
         return gym.make(env_id, **kwargs)
 
 
+class StepInputRecorder:
+    """Records, per env.step, what the reference drew from its global RNGs inside the step: the frames_per_step the step
+    ran with (random_frames_per_step, ENV:939-940) and, per frame, the random() behind random.uniform of a list-valued
+    leader_speed_regime entry (ENV:1155-1156) -- the FtlStepInputs a replay needs (include/ftl.h)."""
+
+    def __init__(self, env, frames_cap):
+        self.env, self.cap = env, int(frames_cap)
+        self.frames, self.draws = [], []
+        self._frame = 0
+        self._cur = None
+        inner_frame_step = env.frame_step
+
+        def frame_step(action):
+            out = inner_frame_step(action)
+            self._frame += 1
+            return out
+
+        env.frame_step = frame_step
+        rec = self
+
+        def uniform(a, b):   # CPython: a + (b - a) * self.random()
+            u = random.random()
+            if rec._cur is not None and rec._frame < rec.cap:
+                rec._cur[rec._frame] = u
+            return a + (b - a) * u
+
+        random.uniform = uniform
+
+    def begin_step(self):
+        self._frame = 0
+        self._cur = np.zeros(self.cap, np.float64)
+        self.frames.append(int(self.env.frames_per_step))
+
+    def end_step(self):
+        self.draws.append(self._cur)
+        self._cur = None
+
+
 def py_action(a):
     """Action as python floats holding exactly the float32 values the GPU path receives."""
     return [float(np.float32(x)) for x in a]

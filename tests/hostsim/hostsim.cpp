@@ -220,8 +220,20 @@ int ftl_reset_host(ftl_handle h, const uint8_t* mask, const int32_t* ids, const 
     rays_all(h, o.rays);
     return FTL_OK;
 }
+int ftl_step_host_ex(ftl_handle h, const void* actions, const FtlStepInputs* in, const FtlOutputs* out, void*);
 int ftl_step_host(ftl_handle h, const void* actions, const FtlOutputs* out, void*) {
+    return ftl_step_host_ex(h, actions, nullptr, out, nullptr);
+}
+int ftl_step_host_ex(ftl_handle h, const void* actions, const FtlStepInputs* in, const FtlOutputs* out, void*) {
     DevOutputs o = dev_out(out);
+    struct Scope {   // the per-step inputs are visible to the device functions through the DevState, for this step only
+        DevState& st;
+        Scope(DevState& s, const FtlStepInputs* in) : st(s) {
+            st.in_frames = in ? in->frames_per_step : nullptr;
+            st.in_draws = in ? in->regime_draws : nullptr;
+        }
+        ~Scope() { st.in_frames = nullptr; st.in_draws = nullptr; }
+    } scope(h->st, in);
     switch (h->cfg.c.n_bears) {
         case 0: step_all<0>(h, actions, o); break;
         case 1: step_all<1>(h, actions, o); break;

@@ -10,7 +10,8 @@ _DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim")
 
 # the host build only has the host-buffer entry points; it is bound here, by the tests, and never by the package
 _HOST_ENTRY_POINTS = ("ftl_abi_version", "ftl_last_error", "ftl_create", "ftl_destroy", "ftl_rays_per_env", "ftl_num_envs",
-                      "ftl_upload_scenarios", "ftl_reset_host", "ftl_step_host", "ftl_get_state", "ftl_set_state")
+                      "ftl_upload_scenarios", "ftl_reset_host", "ftl_step_host", "ftl_step_host_ex", "ftl_get_state",
+                      "ftl_set_state")
 _LIBS = {}
 
 

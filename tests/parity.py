@@ -201,9 +201,14 @@ def replay(stepper, d, gc, env_index=0, float_rtol=0.0, ray_rtol=RTOL, ray_outli
     outliers = check_record(0, d, gc, out, st, env_index, float_rtol, ray_rtol, ray_outlier_budget)
     acts = d["actions"]
     T = len(acts) if max_steps is None else min(len(acts), max_steps)
+    has_inputs = "step_frames" in d
     for t in range(T):
         a = np.repeat(acts[t][None, :], n, axis=0)
-        out = stepper.step(a)
+        if has_inputs:   # what the reference drew from its global RNGs inside this step (FtlStepInputs)
+            out = stepper.step(a, frames=np.full(n, d["step_frames"][t], np.int32),
+                               regime_draws=np.repeat(d["step_draws"][t][None, :], n, axis=0))
+        else:
+            out = stepper.step(a)
         st = stepper.get_state()
         outliers += check_record(t + 1, d, gc, out, st, env_index, float_rtol, ray_rtol, ray_outlier_budget)
     if ray_outlier_budget is not None and outliers > ray_outlier_budget:

@@ -27,14 +27,17 @@ def _cuda_env(gc, n, **kw):
 def test_cuda_reproduces_reference_trace(path):
     d, meta = parity.load_trace(path)
     gc = parity.config_for(meta, _route_len=len(d["scen_route"]), _n_static=len(d["scen_static_rects"]))
-    env = _cuda_env(gc, 33)   # 33 copies: more than a warp, all must agree
-    env.upload_scenarios(parity.pool_for(d, gc))
     budget = 0     # hit / no-hit decisions are the reference's by construction (float64 fallback), values within 1e-4
     for idx in (0, 32):
+        # a fresh handle per replay: like the reference's env object, a handle never restores the keys of
+        # leader_acceleration_regime it has consumed (ENV:1170), so a second episode on it is a different episode
+        env = _cuda_env(gc, 33)   # 33 copies: more than a warp, all must agree
+        env.upload_scenarios(parity.pool_for(d, gc))
         T, outliers = parity.replay(env, d, gc, env_index=idx, float_rtol=parity.RTOL, ray_rtol=parity.RTOL,
                                     ray_outlier_budget=budget)
         assert T == meta["n_env_steps"]
-    parity.check_final_arrays(env.get_state(), d, gc, env_index=32)
+        parity.check_final_arrays(env.get_state(), d, gc, env_index=idx)
+        env.close()
 
 
 def _compare_states(a, b, gc, n, float_rtol):

@@ -217,3 +217,51 @@ def test_device_rollout_matches_a_manual_loop_and_stays_on_the_device():
     assert adv.shape == (T, n) and bool(torch.isfinite(adv).all())
     env.close()
     ro.close()
+
+
+def _per_step_inputs_case():
+    from continiousenvironment_follower_leader_b200.config import TEST_GAME_MANUAL_GAZEBO_KWARGS
+    return dict(TEST_GAME_MANUAL_GAZEBO_KWARGS, max_steps=700, auto_reset=True, random_frames_per_step=[1, 9],
+                leader_speed_regime={0: [0.2, 1], 60: 1, 120: [0.5, 1], 200: 0.75, 260: [0.0, 0.5], 330: [0.4, 1]},
+                leader_acceleration_regime={0: 0, 150: 0.03, 250: 0})
+
+
+def run_per_step_inputs_case(make_env, n, steps, float_rtol):
+    """FtlStepInputs on a batch: every env runs its own number of frames in every step (random_frames_per_step,
+    ENV:939-940) and takes its list-valued speed-regime draws (ENV:1155-1156) from the caller; the stepper under test and
+    the oracle receive the same inputs.  Shared by the CPU (host build) and GPU suites."""
+    import warnings
+    from oracle_py import OracleEnv
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        gc = GameConfig(**_per_step_inputs_case())
+    assert gc.c.frames_per_step == 8 and gc.random_frames_per_step == (1, 9)
+    pool = synthetic_pool(gc, 32, seed=9)
+    sim, orc = make_env(gc, n), OracleEnv(gc, n, n_threads=8)
+    sim.upload_scenarios(pool)
+    orc.upload_scenarios(pool)
+    ids = (np.arange(n) % pool.n).astype(np.int32)
+    sim.reset(scenario_ids=ids)
+    orc.reset(scenario_ids=ids)
+    rng = np.random.RandomState(23)
+    bad, dones = 0, 0
+    for t in range(steps):
+        a = parity.sample_actions(gc, rng, n, t)
+        frames = rng.randint(1, 9, size=n).astype(np.int32)
+        draws = rng.random_sample((n, gc.c.frames_per_step))
+        oc, oo = sim.step(a, frames=frames, regime_draws=draws), orc.step(a, frames=frames, regime_draws=draws)
+        assert np.array_equal(oc.done, oo.done), "done differs at step %d" % t
+        assert np.array_equal(oc.status, oo.status), "status differs at step %d" % t
+        assert np.allclose(oc.reward, oo.reward, rtol=1e-5, atol=1e-5)
+        assert np.allclose(oc.numerical_features, oo.numerical_features, rtol=max(float_rtol, 1e-12), atol=1e-4 if float_rtol else 0)
+        bad += _ray_outliers(oc.rays, oo.rays)
+        dones += int(oo.done.sum())
+        if t % 10 == 9 or t == steps - 1:
+            _compare_states(sim.get_state(), orc.get_state(), gc, n, float_rtol)
+    assert bad <= 2 and dones > 0
+    st = orc.get_state()
+    assert len(np.unique(st.env["step_count"])) > 4    # the envs really ran different numbers of frames
+
+
+def test_per_step_inputs_on_the_gpu():
+    run_per_step_inputs_case(lambda gc, n: capi.HostEnv(gc, n, lib=capi.load()), 1024, 120, parity.RTOL)

@@ -141,3 +141,9 @@ def test_fused_sensor_prev_output_is_the_wrapper_applied_to_the_oracle(pad):
         a = rng.uniform(bounds[0], bounds[1], size=(n, 2)).astype(np.float32)
         a[: n // 2, 0], a[: n // 2, 1] = bounds[1][0], 0.0
         o_s, o_r, o_o = sim.step(a), sim_raw.step(a), orc.step(a)
+
+
+def test_per_step_inputs_random_frames_and_regime_draws():
+    """FtlStepInputs (include/ftl.h) through the host build: per-env frames per step and caller-supplied regime draws."""
+    from test_gpu_parity_gaps import run_per_step_inputs_case
+    run_per_step_inputs_case(make_env, 64, 150, 0.0)

@@ -10,7 +10,8 @@ CODE = r'''
 import sys; sys.path.insert(0,'tools'); sys.path.insert(0,'.')
 import sweep_f, torch, hashlib
 a,b,h = sweep_f.run(65536,10,ref_pool=True,checksum=True)
-print('k_step %.4f k_rays %.4f sum %.4f  step(no events) %.4f  %s' % (a,b,a+b,sweep_f.run.last_total_ms,h))
+k=sweep_f.run.last_kernels
+print('k_kin %.4f k_book %.4f k_rays %.4f sum %.4f  step(no events) %.4f  %s' % (k['k_kin'],k['k_book'],k['k_rays'],a+b,sweep_f.run.last_total_ms,h))
 '''
 for rep in range(int(os.environ.get("AB_REPS", "1"))):
     for lib in libs:

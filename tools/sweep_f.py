@@ -21,7 +21,9 @@ def run(n, F, rays=(12, 36), steps=200, warm=100, auto_reset=True, max_steps=500
     for k in range(warm): env.step_raw(acts[k % 8])
     env.profile(True)
     for k in range(steps): env.step_raw(acts[k % 8])
-    a, b, c = env.profile_read()
+    km, c = env.profile_read_kernels()
+    a, b = km["k_kin"] + km["k_book"], km["k_rays"]
+    run.last_kernels = {k: v / c for k, v in km.items()}
     env.profile(False)
     # whole steps without per-kernel events: the ray kernel may overlap the tail of the step kernel
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
