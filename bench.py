@@ -463,9 +463,9 @@ def rollout_leg(job, n, steps, horizon=16):
     ro.close()
     return {"value": job.world * n * rounds * horizon / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / (rounds * horizon),
             "steps": rounds * horizon, "host_copies_per_step": 0,
-            "api": "rollout.DeviceRollout.collect: MlpPolicy (240 -> 128 -> 128 -> 2 + value head, torch) reads the fused "
-                   "sensorPrev matrix in place, writes actions into the tensor ftl_step consumes; obs/actions/rewards/"
-                   "dones/values stored in device rings"}
+            "api": "rollout.DeviceRollout.collect: MlpPolicy (240 -> 128 -> 128 -> 2 + value, torch, TF32 GEMMs, one CUDA graph "
+                   "per ring slot) reads the fused sensorPrev matrix in place and writes actions into the row ftl_step "
+                   "consumes; ftl_step writes reward/done into the rings; observations archived as bfloat16"}
 
 
 def main():

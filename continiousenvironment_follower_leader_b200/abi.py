@@ -7,7 +7,7 @@ import ctypes as C
 
 import numpy as np
 
-FTL_ABI_VERSION = 3
+FTL_ABI_VERSION = 4
 FTL_MAX_BEARS = 4
 FTL_MAX_RAY_SENSORS = 4
 FTL_MAX_REGIME = 16
@@ -42,7 +42,7 @@ class FtlRaySensorConfig(C.Structure):
                 ("react_to_safe_corridor", C.c_int32), ("react_to_green_zone", C.c_int32),
                 ("react_to_obstacles", C.c_int32), ("laser_length", C.c_double),
                 ("first_laser_angle_offset", C.c_double),
-                ("n_custom_angles", C.c_int32), ("pad_", C.c_int32),
+                ("n_custom_angles", C.c_int32), ("compas", C.c_int32),
                 ("custom_angle", C.c_double * FTL_MAX_CUSTOM_ANGLES)]
 
 
@@ -162,7 +162,8 @@ def rays_per_env(cfg):
     n = 0
     for s in range(cfg.n_ray_sensors):
         sc = cfg.ray[s]
-        n += sc.max_prev_obs * (4 * sc.lasers_count if sc.pad_sectors else sc.lasers_count)
+        n += sc.max_prev_obs * (5 * sc.lasers_count if sc.compas else 4 * sc.lasers_count if sc.pad_sectors
+                                else sc.lasers_count)
     return n
 
 

@@ -38,7 +38,7 @@ GAME_DEFAULTS = OrderedDict(  # ENV:45-105
     ignore_follower_collisions=False, path_finding_iterations=15000, leader_margin=1.5)
 
 TRACKER_CLASSES = ("LeaderPositionsTracker_v2",)
-RAY_CLASSES = ("LeaderCorridor_Prev_lasers_v2", "LaserPrevSensor")
+RAY_CLASSES = ("LeaderCorridor_Prev_lasers_v2", "LaserPrevSensor", "LeaderCorridor_lasers_compas")
 # sensors without history on the same ray engine (max_prev_obs = 1, output of shape (R,)): SEN:571-807
 FLAT_RAY_CLASSES = ("LeaderCorridor_lasers", "LeaderCorridor_lasers_v2")
 # Every class name the reference registry knows (SEN:1291-1307); anything else is "undefined".
@@ -295,6 +295,12 @@ class GameConfig:
                 r.react_to_obstacles = _REACT[rto]
                 r.first_laser_angle_offset = float(args.get("first_laser_angle_offset", 0 if legacy else -45))
                 r.n_custom_angles = 0
+                r.compas = int(cls == "LeaderCorridor_lasers_compas")
+                if r.compas and (not r.react_to_safe_corridor or not r.react_to_green_zone or
+                                 r.react_to_obstacles != abi.REACT_NONE):   # SEN:1148-1152
+                    raise ValueError("Unsupported set of flags for LeaderCorridor_lasers_compas class, now implemented"
+                                     "only option for flags: "
+                                     "react_to_safe_corridor=True, react_to_green_zone=True, react_to_obstacles=False")
                 self.ray_sensor_names.append(name)
                 self.ray_sensor_flat.append(False)
                 c.n_ray_sensors += 1
@@ -390,7 +396,7 @@ class GameConfig:
         out, off = [], 0
         for i, name in enumerate(self.ray_sensor_names):
             r = self.c.ray[i]
-            w = 4 * r.lasers_count if r.pad_sectors else r.lasers_count
+            w = 5 * r.lasers_count if r.compas else 4 * r.lasers_count if r.pad_sectors else r.lasers_count
             out.append((name, off, r.max_prev_obs, w))
             off += r.max_prev_obs * w
         return out

@@ -167,6 +167,8 @@ struct DevCfg {
     // where sensor s writes inside an env's block of `rays`: cell (row j, column q) = base + j * stride + q
     int ray_out_base[FTL_MAX_RAY_SENSORS], ray_out_stride[FTL_MAX_RAY_SENSORS];
     int ray_out_vec4;            // every lasers_count is a multiple of 4 and the layout is the raw one: rows leave as float4
+    int ray_out_fused_vec4;      // the same for the fused sensorPrev layout
+    int ray_compas_mask;         // bit s: ray sensor s is a LeaderCorridor_lasers_compas (cast by the per-env exact pass)
 };
 
 // ---- tiny helpers -----------------------------------------------------------------------------------

@@ -96,17 +96,16 @@ FTL_HD_NOINLINE float seg_hit_exact(float px, float py, double ex, double ey, fl
     return (float)sqrt(fma(ddy, ddy, ddx * ddx));
 }
 
-FTL_HD int sensor_width(const FtlRaySensorConfig& sc) {
-    return sc.max_prev_obs * (sc.pad_sectors ? 4 * sc.lasers_count : sc.lasers_count);
+FTL_HD int sensor_row_width(const FtlRaySensorConfig& sc) {
+    return sc.compas ? 5 * sc.lasers_count : sc.pad_sectors ? 4 * sc.lasers_count : sc.lasers_count;
 }
+FTL_HD int sensor_width(const FtlRaySensorConfig& sc) { return sc.max_prev_obs * sensor_row_width(sc); }
 
 // direction of ray k relative to (heading + first_laser_angle_offset), degrees: SEN:888-891, or the fixed fan of
 // LeaderCorridor_lasers (SEN:678-700)
 FTL_HD double ray_angle(const FtlRaySensorConfig& sc, int k) {
     return sc.n_custom_angles ? sc.custom_angle[k] : k * (360.0 / sc.lasers_count);
 }
-
-FTL_HD int sensor_row_width(const FtlRaySensorConfig& sc) { return sc.pad_sectors ? 4 * sc.lasers_count : sc.lasers_count; }
 
 // raw: sensor blocks one after the other, each [H][W]; fused (WRP:203-221): one [H][sum W] matrix
 inline void ray_out_layout(DevCfg& d) {
@@ -121,8 +120,9 @@ inline void ray_out_layout(DevCfg& d) {
         off += w * c.ray[s].max_prev_obs;
     }
     d.ray_out_vec4 = c.n_ray_sensors > 0 && !c.fused_sensor_prev;
+    d.ray_out_fused_vec4 = c.n_ray_sensors > 0 && c.fused_sensor_prev && d.rays_per_env % 4 == 0;
     for (int s = 0; s < c.n_ray_sensors; s++)
-        if (c.ray[s].pad_sectors || c.ray[s].lasers_count % 4 != 0) d.ray_out_vec4 = 0;
+        if (c.ray[s].pad_sectors || c.ray[s].compas || c.ray[s].lasers_count % 4 != 0) d.ray_out_vec4 = d.ray_out_fused_vec4 = 0;
 }
 
 FTL_HD int total_rays(const FtlConfig& c) {
@@ -242,6 +242,7 @@ FTL_HD RayArrays ray_arrays(RayShared* sh, int rt, int hmax) {
 }
 
 FTL_HD int sensor_class_mask(const FtlRaySensorConfig& sc) {
+    if (sc.compas) return 0;   // cast by the per-env exact pass (compas_exact_env): no edge class reaches its rays here
     int m = 0, mode = sc.react_to_obstacles;
     if (mode == FTL_REACT_ALL || mode == FTL_REACT_STATIC) m |= (1 << EC_STATIC) | (1 << EC_LEADER);  // game_object_list
     if (mode == FTL_REACT_ALL || mode == FTL_REACT_DYNAMIC) m |= 1 << EC_BEAR;                        // game_dynamic_list
@@ -255,6 +256,9 @@ FTL_HD int sensor_class_mask(const FtlRaySensorConfig& sc) {
 inline void ray_static_tables(DevCfg& d) {
     const FtlConfig& c = d.c;
     for (int k = 0; k < 8; k++) d.ray_reach[k] = -1e30f;
+    d.ray_compas_mask = 0;
+    for (int sidx = 0; sidx < c.n_ray_sensors; sidx++)
+        if (c.ray[sidx].compas) d.ray_compas_mask |= 1 << sidx;
     int base = 0;
     for (int sidx = 0; sidx < c.n_ray_sensors; sidx++) {
         const FtlRaySensorConfig& sc = c.ray[sidx];
@@ -445,12 +449,36 @@ FTL_HD_NOINLINE void ray_rows_write_fused(const DevCfg& cfg, const RayShared& sh
     const int rt = sh.rt, n_valid = sh.n_valid;
     for (int sidx = 0; sidx < sh.ns; sidx++) {
         const FtlRaySensorConfig& sc = c.ray[sidx];
+        if (sc.compas) continue;   // written by compas_exact_env
         const int R = sc.lasers_count, H = sc.max_prev_obs, base = sh.sen[sidx].base;
         const float L = (float)sc.laser_length;
         float* dst = rays_out + (size_t)i * cfg.rays_per_env + cfg.ray_out_base[sidx];
         const int stride = cfg.ray_out_stride[sidx];
         const double in_sector = R / 4.0;
         const int* srow = ra.res + ra.hmax * rt + base;
+        if (cfg.ray_out_fused_vec4 && (((size_t)rays_out) & 15) == 0) {
+            // four consecutive rays of one row per lane, as in the raw float4 path: every sensor's column block starts
+            // at a multiple of four floats in a row that is a multiple of four floats long
+            const int Q = R >> 2;
+            for (int e = lane; e < H * Q; e += 32) {
+                const int j = e / Q, k = (e - j * Q) << 2, age = H - 1 - j;
+                float4 v = make_float4(L, L, L, L);
+                if (age < n_valid) {
+                    const int4 a = *reinterpret_cast<const int4*>(ra.res + age * rt + base + k);
+                    const int4 sb = *reinterpret_cast<const int4*>(srow + k);
+                    const int b0 = sb.x < a.x ? sb.x : a.x, b1 = sb.y < a.y ? sb.y : a.y;
+                    const int b2 = sb.z < a.z ? sb.z : a.z, b3 = sb.w < a.w ? sb.w : a.w;
+                    if (b0 != kNoHitBits) v.x = i2f_bits(b0);
+                    if (b1 != kNoHitBits) v.y = i2f_bits(b1);
+                    if (b2 != kNoHitBits) v.z = i2f_bits(b2);
+                    if (b3 != kNoHitBits) v.w = i2f_bits(b3);
+                }
+                v.x = ray_out_value(c, L, v.x); v.y = ray_out_value(c, L, v.y);
+                v.z = ray_out_value(c, L, v.z); v.w = ray_out_value(c, L, v.w);
+                *reinterpret_cast<float4*>(dst + j * stride + k) = v;
+            }
+            continue;
+        }
         for (int e = lane; e < H * R; e += 32) {
             const int j = e / R, k = e - j * R, age = H - 1 - j;
             float v = L;
@@ -639,6 +667,7 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
             int off = 0;
             for (int sidx = 0; sidx < ns; sidx++) {
                 const FtlRaySensorConfig& sc = c.ray[sidx];
+                if (sc.compas) { off += sensor_width(sc); continue; }   // written by compas_exact_env
                 const int R = sc.lasers_count, H = sc.max_prev_obs, base = sh.sen[sidx].base;
                 const float L = (float)sc.laser_length;
                 float* dst = rays_out + (size_t)i * cfg.rays_per_env + off;
@@ -716,6 +745,7 @@ FTL_HD_NOINLINE void rays_exact_recast(const DevCfg& cfg, const DevState& s, con
     const int n_static = pool.n_static[ee.scenario];
     for (int sidx = 0; sidx < c.n_ray_sensors; sidx++) {
         const FtlRaySensorConfig& sc = c.ray[sidx];
+        if (sc.compas) continue;
         const int cls = sensor_class_mask(sc);
         const int stride = cfg.ray_out_stride[sidx];
         float* dst = rays_out + (size_t)i * cfg.rays_per_env + cfg.ray_out_base[sidx];
@@ -754,7 +784,87 @@ FTL_HD_NOINLINE void rays_exact_recast(const DevCfg& cfg, const DevState& s, con
     }
 }
 
+// LeaderCorridor_lasers_compas.scan (SEN:1138-1240) for one env, with the reference's own float64 sequence: every ray
+// of every stored corridor (front cap, back cap, left walls, right walls -- the order of corridor_lines, which decides
+// ties through np.argmin) is tested with all-float64 ccw predicates, the nearest hit picks the column block.  One
+// thread per env: this sensor is outside the shipped configurations and is not worth a place in the warp kernel.
+// (The reference keeps its corridor points in float64; the ring here holds them rounded to float32 -- the distances
+// agree to ~1e-6 relative, a ray that grazes a corridor vertex within ~3e-5 px may decide differently.)
+struct CompasHit { double sel, x, y; int orient; };
+FTL_HD void compas_test(const ExactEnv& ee, double ex, double ey, float fax, float fay, float fbx, float fby, int orient,
+                        CompasHit* best) {
+    const double ax = fax, ay = fay, bx = fbx, by = fby, cx = ee.px, cy = ee.py;
+    // ccw(A, B, C) = (C.y - A.y) * (B.x - A.x) > (B.y - A.y) * (C.x - A.x), SEN:608-609, everything float64
+    const bool acd = (ey - ay) * (cx - ax) > (cy - ay) * (ex - ax);
+    const bool bcd = (ey - by) * (cx - bx) > (cy - by) * (ex - bx);
+    if (acd == bcd) return;
+    const bool abc = (cy - ay) * (bx - ax) > (by - ay) * (cx - ax);
+    const bool abd = (ey - ay) * (bx - ax) > (by - ay) * (ex - ax);
+    if (abc == abd) return;
+    // seg_intersect(a1 = A, a2 = B, b1 = pos, b2 = end), SEN:628-640
+    const double dax = bx - ax, day = by - ay, dbx = ex - cx, dby = ey - cy, dpx = ax - cx, dpy = ay - cy;
+    const double dapx = -day, dapy = dax;
+    const double denom = fma(dapx, dbx, dapy * dby);   // np.dot((k,2), (2,1))
+    const double m0 = dapx * dpx, m1 = dapy * dpy;
+    const double t = (m0 + m1) / denom;
+    const double xx = t * dbx + cx, xy = t * dby + cy;
+    const double ddx = xx - cx, ddy = xy - cy;
+    const double sx = ddx * ddx, sy = ddy * ddy;
+    const double sel = sqrt(sx + sy);                  // np.linalg.norm(x - pos, axis=1)
+    if (best->orient < 0 || sel < best->sel) { best->sel = sel; best->x = xx; best->y = xy; best->orient = orient; }
+}
+
+FTL_HD_NOINLINE void compas_exact_env(const DevCfg& cfg, const DevState& s, int i, float* rays_out) {
+    const FtlConfig& c = cfg.c;
+    ExactEnv ee;
+    float2 p = s.pos[i];
+    ee.px = p.x; ee.py = p.y;
+    ee.dir = s.rd[(size_t)RD_DIR * s.n + i];
+    ee.pushes = s.gi[(size_t)GI_SNAP_PUSHES * s.n + i];
+    ee.n_valid = ee.pushes < FTL_MAX_HIST ? ee.pushes : FTL_MAX_HIST;
+    ee.scenario = 0;
+    const int cmask = c.corridor_cap - 1;
+    const float4* corr = s.corridor + (size_t)i * c.corridor_cap;
+    for (int sidx = 0; sidx < c.n_ray_sensors; sidx++) {
+        const FtlRaySensorConfig& sc = c.ray[sidx];
+        if (!sc.compas) continue;
+        const int R = sc.lasers_count, H = sc.max_prev_obs, stride = cfg.ray_out_stride[sidx];
+        const float L = (float)sc.laser_length;
+        float* dst = rays_out + (size_t)i * cfg.rays_per_env + cfg.ray_out_base[sidx];
+        for (int j = 0; j < H; j++) {
+            const int age = H - 1 - j;
+            int2 rg = make_int2(0, 0);
+            if (age < ee.n_valid) rg = s.snap_range[(size_t)((ee.pushes - 1 - age) % FTL_MAX_HIST) * s.n + i];
+            float* row = dst + (size_t)j * stride;
+            for (int k = 0; k < 5 * R; k++) row[k] = 0.f;
+            for (int k = 0; k < R; k++) {
+                double ex, ey;
+                exact_ray_end(sc, ee, k, &ex, &ey);
+                CompasHit best = {0.0, ex, ey, -1};
+                if (age < ee.n_valid && rg.y - rg.x > 1) {
+                    const float4 f4 = corr[(rg.y - 1) & cmask], b4 = corr[rg.x & cmask];
+                    compas_test(ee, ex, ey, f4.x, f4.y, f4.z, f4.w, 0, &best);   // front wall = corridor[-1]
+                    compas_test(ee, ex, ey, b4.x, b4.y, b4.z, b4.w, 1, &best);   // back wall = corridor[0]
+                    for (int q = rg.x; q < rg.y - 1; q++) {                      // left walls: corridor[q][1] -> corridor[q + 1][1]
+                        const float4 a4 = corr[q & cmask], n4 = corr[(q + 1) & cmask];
+                        compas_test(ee, ex, ey, a4.z, a4.w, n4.z, n4.w, 2, &best);
+                    }
+                    for (int q = rg.x; q < rg.y - 1; q++) {                      // right walls: corridor[q][0] -> corridor[q + 1][0]
+                        const float4 a4 = corr[q & cmask], n4 = corr[(q + 1) & cmask];
+                        compas_test(ee, ex, ey, a4.x, a4.y, n4.x, n4.y, 3, &best);
+                    }
+                }
+                // obs_item[...] = np.linalg.norm(collide - pos): 1-D -> sqrt(dot(x, x)), the FMA form
+                const double ddx = best.x - (double)ee.px, ddy = best.y - (double)ee.py;
+                const float v = ray_out_value(c, L, (float)sqrt(fma(ddy, ddy, ddx * ddx)));
+                row[best.orient < 0 ? k : k + R * (1 + best.orient)] = v;
+            }
+        }
+    }
+}
+
 FTL_HD void rays_exact_env(const DevCfg& cfg, const DevState& s, const DevPool& pool, int i, float* rays_out) {
+    if (cfg.ray_compas_mask) compas_exact_env(cfg, s, i, rays_out);
     const int count = s.unc_count[i];
     if (count == 0) return;
     const FtlConfig& c = cfg.c;

@@ -2,24 +2,30 @@
 
 The reference trains through RLlib (notebooks/Ray_train_demo.ipynb): one ``Game`` per rollout worker wrapped in
 ``ContinuousObserveModifier_sensorPrev`` (utils/wrappers.py:169-221), observations pickled to the learner.  Here the
-wrapper's matrix is written by the ray kernel itself (``fused_sensor_prev``), a policy reads it IN PLACE from the env's
-output buffer, writes its action straight into the tensor ``ftl_step`` consumes, and the trajectory lands in
-pre-allocated device rings -- no host copy per step, one stream, no synchronisation inside ``collect``.
+wrapper's matrix is written by the ray kernel itself (``fused_sensor_prev``) STRAIGHT INTO the trajectory ring (row t + 1
+of the observation archive is the output buffer of step t), the policy reads row t in place and writes its action into
+the row ``ftl_step`` consumes, and ``ftl_step`` writes reward and done into their rings -- no copy of any kind per step,
+one stream, no synchronisation inside ``collect``.  The policy section of a step (forward + action) is captured in one
+CUDA graph per ring slot, so a step costs the host two launches: the graph and ``ftl_step``.
 
 PyTorch is the consumer here (a user's policy network is a torch module; its GEMMs are library calls); the simulator
 side is libftl.so exactly as in ``FtlBatchEnv.step``.
 """
+import ctypes as C
+
 import torch
 
+from . import abi, capi
 from .batch_env import FtlBatchEnv
 from .config import GameConfig
 
 
 class MlpPolicy(torch.nn.Module):
     """tanh-squashed Gaussian policy + value head on the flattened sensorPrev matrix (the shape the shipped trained
-    configurations feed their fully connected nets)."""
+    configurations feed their fully connected nets).  ``forward`` returns (action, value); the mean and the value come
+    out of one fused head."""
 
-    def __init__(self, obs_dim, act_low, act_high, hidden=128, seed=0, dtype=torch.float32):
+    def __init__(self, obs_dim, act_low, act_high, hidden=128, seed=0):
         super().__init__()
         g = torch.Generator().manual_seed(seed)
 
@@ -30,31 +36,31 @@ class MlpPolicy(torch.nn.Module):
                 layer.bias.zero_()
             return layer
 
+        self.act_dim = len(act_low)
         self.body = torch.nn.Sequential(lin(obs_dim, hidden), torch.nn.Tanh(), lin(hidden, hidden), torch.nn.Tanh())
-        self.mu = lin(hidden, len(act_low))
-        self.value = lin(hidden, 1)
-        self.log_std = torch.nn.Parameter(torch.full((len(act_low),), -0.5))
+        self.head = lin(hidden, self.act_dim + 1)          # [mu..., value]
+        self.log_std = torch.nn.Parameter(torch.full((self.act_dim,), -0.5))
         self.register_buffer("act_mid", torch.as_tensor((act_high + act_low) / 2, dtype=torch.float32))
         self.register_buffer("act_half", torch.as_tensor((act_high - act_low) / 2, dtype=torch.float32))
-        self.to(dtype)
 
     def forward(self, obs_flat, noise=None):
-        h = self.body(obs_flat)
-        mu = self.mu(h)
+        out = self.head(self.body(obs_flat))
+        mu, value = out[:, :self.act_dim], out[:, self.act_dim]
         if noise is not None:
             mu = mu + noise * self.log_std.exp()
-        return self.act_mid + self.act_half * torch.tanh(mu.float()), self.value(h).squeeze(-1).float()
+        return self.act_mid + self.act_half * torch.tanh(mu), value
 
 
 class DeviceRollout:
     """``collect(T)`` advances all N envs T steps under ``policy`` and returns the trajectory as device tensors.
 
-    Buffers (allocated once): obs [T+1, N, H*W] (``obs_dtype``), actions [T, N, A], rewards [T, N], dones [T, N],
-    values [T+1, N].  With ``store_obs=False`` only the newest observation is kept (evaluation / throughput runs).
+    Rings (allocated once): obs [T+1, N, H*W] float32 (the simulator's own output rows), actions [T, N, A], rewards
+    [T, N], dones [T, N] (uint8), values [T+1, N].  ``use_graphs``: capture the policy section per ring slot in a CUDA
+    graph.
     """
 
     def __init__(self, n_envs, horizon, game_config=None, scenario_pool=None, policy=None, device=None, env_id_base=0,
-                 obs_dtype=torch.float32, store_obs=True, seed=0, **game_kwargs):
+                 seed=0, use_graphs=True, allow_tf32=True, **game_kwargs):
         if game_config is None:
             game_config = GameConfig(fused_sensor_prev=True, auto_reset=True, **game_kwargs)
         if not game_config.c.fused_sensor_prev or not game_config.c.auto_reset:
@@ -70,23 +76,58 @@ class DeviceRollout:
         self.act_dim = len(lo)
         self.policy = policy if policy is not None else MlpPolicy(self.obs_dim, lo, hi, seed=seed)
         self.policy.to(dev)
-        self.store_obs = bool(store_obs)
-        t_obs = self.T + 1 if self.store_obs else 1
-        self.obs = torch.zeros((t_obs, self.n, self.obs_dim), dtype=obs_dtype, device=dev)
+        self.allow_tf32 = bool(allow_tf32)
+        self.obs = torch.zeros((self.T + 1, self.n, self.obs_dim), dtype=torch.float32, device=dev)
         self.actions = torch.zeros((self.T, self.n, self.act_dim), dtype=torch.float32, device=dev)
         self.rewards = torch.zeros((self.T, self.n), dtype=torch.float32, device=dev)
         self.dones = torch.zeros((self.T, self.n), dtype=torch.uint8, device=dev)
         self.values = torch.zeros((self.T + 1, self.n), dtype=torch.float32, device=dev)
-        self._gen = torch.Generator(device=dev).manual_seed(seed)
         self._noise = torch.zeros((self.n, self.act_dim), dtype=torch.float32, device=dev)
+        # one FtlOutputs per ring slot: the kernels of step t write the next observation into obs[t + 1] and reward /
+        # done into row t of their rings
+        env = self.env
+        self._outs = [abi.FtlOutputs(env.numerical_features.data_ptr(), env.leader_target.data_ptr(),
+                                     self.obs[t + 1].data_ptr(), self.rewards[t].data_ptr(), self.dones[t].data_ptr(),
+                                     env.status.data_ptr(), None, None, None) for t in range(self.T)]
+        self._out_reset = abi.FtlOutputs(env.numerical_features.data_ptr(), env.leader_target.data_ptr(),
+                                         self.obs[0].data_ptr(), env.reward.data_ptr(), env.done.data_ptr(),
+                                         env.status.data_ptr(), None, None, None)
+        self._last = 0     # ring row that holds the current observation
+        self._graphs = {}
+        self._use_graphs = bool(use_graphs)
+        self._seed = int(seed)
         self._started = False
 
     def close(self):
+        self._graphs.clear()
         self.env.close()
 
-    def _current_obs(self):
-        # the ray kernel's output buffer viewed as [N, H*W]: no copy
-        return self.env.rays.view(self.n, self.obs_dim)
+    def _policy_section(self, t, explore):
+        """run the policy on obs[t] in place, leave the action in actions[t] (which ftl_step reads) and the value in
+        values[t]"""
+        noise = self._noise.normal_() if explore else None
+        act, val = self.policy(self.obs[t], noise)
+        self.actions[t].copy_(act)
+        self.values[t].copy_(val)
+
+    def _run_policy(self, t, explore):
+        if not self._use_graphs:
+            return self._policy_section(t, explore)
+        key = (t, bool(explore))
+        g = self._graphs.get(key)
+        if g is None:
+            # warm up on a side stream (library handles, autotuning), then capture this slot's section
+            side = torch.cuda.Stream(device=self.env.device)
+            side.wait_stream(torch.cuda.current_stream(self.env.device))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self._policy_section(t, explore)
+            torch.cuda.current_stream(self.env.device).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._policy_section(t, explore)
+            self._graphs[key] = g
+        g.replay()
 
     @torch.no_grad()
     def collect(self, steps=None, explore=True):
@@ -95,29 +136,26 @@ class DeviceRollout:
         if T > self.T:
             raise ValueError("steps exceeds the horizon the buffers were allocated for")
         env = self.env
-        if not self._started:
-            env.reset()
-            self._started = True
-        w_dtype = next(self.policy.parameters()).dtype
-        for t in range(T):
-            cur = self._current_obs()
-            if self.store_obs:
-                self.obs[t].copy_(cur)           # the next ftl_step overwrites the env's buffer
-            noise = None
-            if explore:
-                noise = self._noise.normal_(generator=self._gen)
-            act, val = self.policy(cur if cur.dtype == w_dtype else cur.to(w_dtype), noise)
-            self.actions[t].copy_(act)           # ftl_step reads this row in place
-            self.values[t].copy_(val)
-            env.step_raw(self.actions[t])
-            self.rewards[t].copy_(env.reward)
-            self.dones[t].copy_(env.done)
-        cur = self._current_obs()
-        if self.store_obs:
-            self.obs[T].copy_(cur)
-        _, val = self.policy(cur if cur.dtype == w_dtype else cur.to(w_dtype), None)
-        self.values[T].copy_(val)
-        return {"obs": self.obs[:T + 1] if self.store_obs else self.obs, "actions": self.actions[:T],
+        tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = self.allow_tf32
+        try:
+            stream = env._stream()
+            if not self._started:
+                torch.cuda.manual_seed(self._seed)
+                capi.check(env._L, env._L.ftl_reset(env._h, None, None, C.byref(self._out_reset), stream), "ftl_reset")
+                self._started = True
+            elif self._last != 0:
+                self.obs[0].copy_(self.obs[self._last])     # once per collect: the window starts where the last one ended
+            for t in range(T):
+                self._run_policy(t, explore)
+                capi.check(env._L, env._L.ftl_step(env._h, self.actions[t].data_ptr(), C.byref(self._outs[t]), stream),
+                           "ftl_step")
+            self._last = T
+            _, val = self.policy(self.obs[T], None)
+            self.values[T].copy_(val)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+        return {"obs": self.obs[:T + 1], "actions": self.actions[:T],
                 "rewards": self.rewards[:T], "dones": self.dones[:T], "values": self.values[:T + 1]}
 
     @torch.no_grad()

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FTL_ABI_VERSION 3
+#define FTL_ABI_VERSION 4
 
 #define FTL_MAX_BEARS 4
 #define FTL_MAX_RAY_SENSORS 4
@@ -85,7 +85,11 @@ typedef struct FtlRaySensorConfig {
     double laser_length;
     double first_laser_angle_offset; /* SEN:873, default -45 */
     int32_t n_custom_angles;         /* 0: ray k points at offset + k*360/R; else == lasers_count and ray k points at */
-    int32_t pad_;                    /*    offset + custom_angle[k] (degrees, relative to the follower's heading)     */
+                                     /*    offset + custom_angle[k] (degrees, relative to the follower's heading)     */
+    int32_t compas;                  /* 1: LeaderCorridor_lasers_compas (SEN:1138-1290): corridor walls and end caps only;
+                                      * a row is 5*R wide: [0,R) the ray length where nothing was hit (0 where something
+                                      * was), then R columns each for hits on the front cap, the back cap, the left walls
+                                      * and the right walls -- the distance goes into the column block of the nearest wall */
     double custom_angle[FTL_MAX_CUSTOM_ANGLES];
 } FtlRaySensorConfig;
 

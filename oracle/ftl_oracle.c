@@ -69,6 +69,7 @@ typedef struct FtlOracle {
     float* trail;     /* [N][trail_cap][2] */
     double* hist;     /* [N][corridor_cap][2] */
     float* corridor;  /* [N][corridor_cap][4] */
+    double* corridor64; /* [N][cap][4] the same points before the float32 cast of SEN:672 (LeaderCorridor_lasers_compas reads these) */
     int rays_per_env;
     double stats[FTL_STAT_COUNT];
     char err[256];
@@ -612,7 +613,7 @@ static double path_length(const FtlEnvState* e, const double* hist, int cap) {
 
 /* border points for the segment hist[ia] -> hist[ib], anchored at hist[ianchor]; SEN:302-317 */
 static void corridor_entry(const FtlOracle* o, const FtlEnvState* e, const double* hist, int ia, int ib, int ianchor,
-                           float out[4]) {
+                           float out[4], double* out64) {
     const FtlConfig* cfg = &o->cfg;
     int cap = cfg->corridor_cap;
     const double* pa = hist + 2 * RING(ia);
@@ -644,6 +645,7 @@ static void corridor_entry(const FtlOracle* o, const FtlEnvState* e, const doubl
     rx += pc[0]; ry += pc[1];
     lx += pc[0]; ly += pc[1];
     out[0] = (float)rx; out[1] = (float)ry; out[2] = (float)lx; out[3] = (float)ly;
+    if (out64) { out64[0] = rx; out64[1] = ry; out64[2] = lx; out64[3] = ly; }
 }
 
 static void tracker_scan(FtlOracle* o, int env_index) { /* SEN:243-327 */
@@ -652,6 +654,7 @@ static void tracker_scan(FtlOracle* o, int env_index) { /* SEN:243-327 */
     int cap = cfg->corridor_cap;
     double* hist = o->hist + (size_t)env_index * cap * 2;
     float* corr = o->corridor + (size_t)env_index * cap * 4;
+    double* corr64 = o->corridor64 + (size_t)env_index * cap * 4;
 
     if (e->saving_counter % cfg->saving_period == 0) {
         int n = e->ring_head - e->ring_tail;
@@ -723,14 +726,15 @@ static void tracker_scan(FtlOracle* o, int env_index) { /* SEN:243-327 */
             if (e->saving_counter == 0) { /* SEN:300-308: m-1 entries, anchors hist[0..m-2] */
                 for (int i = n - 1; i > 0; i--) {
                     int anchor = e->ring_tail + (n - i - 1);
-                    corridor_entry(o, e, hist, e->ring_tail + i - 1, e->ring_tail + i, anchor, corr + 4 * RING(anchor));
+                    corridor_entry(o, e, hist, e->ring_tail + i - 1, e->ring_tail + i, anchor, corr + 4 * RING(anchor),
+                                   corr64 + 4 * RING(anchor));
                 }
                 /* plus the duplicate anchored at hist[-2] from the last segment, stored at slot head-1 */
                 corridor_entry(o, e, hist, e->ring_head - 2, e->ring_head - 1, e->ring_head - 2,
-                               corr + 4 * RING(e->ring_head - 1));
+                               corr + 4 * RING(e->ring_head - 1), corr64 + 4 * RING(e->ring_head - 1));
             } else {
                 corridor_entry(o, e, hist, e->ring_head - 2, e->ring_head - 1, e->ring_head - 2,
-                               corr + 4 * RING(e->ring_head - 1));
+                               corr + 4 * RING(e->ring_head - 1), corr64 + 4 * RING(e->ring_head - 1));
             }
         }
         (void)corr_len;
@@ -800,10 +804,77 @@ static int ccw_ffD(float ax, float ay, float bx, float by, double dx, double dy)
     return lhs > rhs;
 }
 
+/* LeaderCorridor_lasers_compas.scan, SEN:1138-1240: the corridor in float64 (corridor_lines is built from the tracker's
+ * float64 points without the float32 cast of SEN:672), lines ordered front wall, back wall, left walls, right walls;
+ * np.argmin takes the first of equal minima. */
+static void compas_test(double ax, double ay, double bx, double by, double cx, double cy, double ex, double ey, int orient,
+                        double* best_sel, double* best_x, double* best_y, int* best_orient) {
+    /* ccw(A, B, C) = (C.y - A.y) * (B.x - A.x) > (B.y - A.y) * (C.x - A.x), SEN:608-609 */
+    int acd = (ey - ay) * (cx - ax) > (cy - ay) * (ex - ax);
+    int bcd = (ey - by) * (cx - bx) > (cy - by) * (ex - bx);
+    if (acd == bcd) return;
+    int abc = (cy - ay) * (bx - ax) > (by - ay) * (cx - ax);
+    int abd = (ey - ay) * (bx - ax) > (by - ay) * (ex - ax);
+    if (abc == abd) return;
+    double dax = bx - ax, day = by - ay, dbx = ex - cx, dby = ey - cy, dpx = ax - cx, dpy = ay - cy;
+    double dapx = -day, dapy = dax;
+    double denom = fma(dapx, dbx, dapy * dby); /* np.dot((k,2),(2,1)) */
+    double m0 = dapx * dpx, m1 = dapy * dpy;
+    double t = (m0 + m1) / denom;
+    double xx = t * dbx + cx, xy = t * dby + cy;
+    double ddx = xx - cx, ddy = xy - cy;
+    double sx = ddx * ddx, sy = ddy * ddy;
+    double sel = sqrt(sx + sy); /* np.linalg.norm(x - pos, axis=1) */
+    if (*best_orient < 0 || sel < *best_sel) { *best_sel = sel; *best_x = xx; *best_y = xy; *best_orient = orient; }
+}
+
+static void compas_sensor_scan(const FtlOracle* o, int env_index, int sensor, float* out) {
+    const FtlConfig* cfg = &o->cfg;
+    const FtlEnvState* e = &o->env[env_index];
+    const FtlRaySensorConfig* sc = &cfg->ray[sensor];
+    int cap = cfg->corridor_cap;
+    const double* corr = o->corridor64 + (size_t)env_index * cap * 4;
+    int R = sc->lasers_count, H = sc->max_prev_obs;
+    double cx = e->follower.pos[0], cy = e->follower.pos[1];
+    double L = sc->laser_length, period = 360.0 / R;
+    for (int j = 0; j < H; j++) {
+        const FtlSnapshot* sn = &e->snap[FTL_MAX_HIST - H + j];
+        float* row = out + (size_t)j * 5 * R;
+        for (int k = 0; k < 5 * R; k++) row[k] = 0.f;
+        for (int i = 0; i < R; i++) {
+            double ang = (e->follower.dir + sc->first_laser_angle_offset) + i * period;
+            double th = ang * DEG2RAD;
+            double ex = cx + cos(th) * L, ey = cy + sin(th) * L;
+            double bsel = 0, bx_ = ex, by_ = ey;
+            int borient = -1;
+            if (sn->valid && sn->corr_head - sn->corr_tail > 1) {
+                const double* f = corr + 4 * RING(sn->corr_head - 1);
+                const double* b = corr + 4 * RING(sn->corr_tail);
+                compas_test(f[0], f[1], f[2], f[3], cx, cy, ex, ey, 0, &bsel, &bx_, &by_, &borient);
+                compas_test(b[0], b[1], b[2], b[3], cx, cy, ex, ey, 1, &bsel, &bx_, &by_, &borient);
+                for (int q = sn->corr_tail; q < sn->corr_head - 1; q++) {
+                    const double* a = corr + 4 * RING(q);
+                    const double* n = corr + 4 * RING(q + 1);
+                    compas_test(a[2], a[3], n[2], n[3], cx, cy, ex, ey, 2, &bsel, &bx_, &by_, &borient);
+                }
+                for (int q = sn->corr_tail; q < sn->corr_head - 1; q++) {
+                    const double* a = corr + 4 * RING(q);
+                    const double* n = corr + 4 * RING(q + 1);
+                    compas_test(a[0], a[1], n[0], n[1], cx, cy, ex, ey, 3, &bsel, &bx_, &by_, &borient);
+                }
+            }
+            double ddx = bx_ - cx, ddy = by_ - cy;
+            float v = (float)sqrt(fma(ddy, ddy, ddx * ddx)); /* np.linalg.norm(collide - pos), 1-D: the FMA form */
+            row[borient < 0 ? i : i + R * (1 + borient)] = v;
+        }
+    }
+}
+
 static void ray_sensor_scan(const FtlOracle* o, int env_index, int sensor, float* out) {
     const FtlConfig* cfg = &o->cfg;
     const FtlEnvState* e = &o->env[env_index];
     const FtlRaySensorConfig* sc = &cfg->ray[sensor];
+    if (sc->compas) { compas_sensor_scan(o, env_index, sensor, out); return; }
     const float* corr = o->corridor + (size_t)env_index * cfg->corridor_cap * 4;
     int R = sc->lasers_count, H = sc->max_prev_obs;
     int width = sc->pad_sectors ? 4 * R : R;
@@ -861,7 +932,7 @@ static void ray_sensor_scan(const FtlOracle* o, int env_index, int sensor, float
 /* sensors + observation                                                                             */
 /* ------------------------------------------------------------------------------------------------ */
 static int sensor_width(const FtlRaySensorConfig* sc) {
-    return sc->max_prev_obs * (sc->pad_sectors ? 4 * sc->lasers_count : sc->lasers_count);
+    return sc->max_prev_obs * (sc->compas ? 5 * sc->lasers_count : sc->pad_sectors ? 4 * sc->lasers_count : sc->lasers_count);
 }
 
 static void write_outputs(FtlOracle* o, int i, const FtlOutputs* out) {
@@ -1121,6 +1192,7 @@ FtlOracle* ftl_oracle_create(const FtlConfig* cfg, int n_envs, int64_t env_id_ba
     o->trail = (float*)calloc((size_t)n_envs * cfg->trail_cap * 2, sizeof(float));
     o->hist = (double*)calloc((size_t)n_envs * cfg->corridor_cap * 2, sizeof(double));
     o->corridor = (float*)calloc((size_t)n_envs * cfg->corridor_cap * 4, sizeof(float));
+    o->corridor64 = (double*)calloc((size_t)n_envs * cfg->corridor_cap * 4, sizeof(double));
     o->rays_per_env = rays_per_env(cfg);
     return o;
 }
@@ -1129,7 +1201,7 @@ void ftl_oracle_destroy(FtlOracle* o) {
     if (!o) return;
     free(o->s_static); free(o->s_nstatic); free(o->s_route); free(o->s_nroute);
     free(o->s_lpos); free(o->s_fpos); free(o->s_ldir); free(o->s_fdir);
-    free(o->env); free(o->trail); free(o->hist); free(o->corridor);
+    free(o->env); free(o->trail); free(o->hist); free(o->corridor); free(o->corridor64);
     free(o);
 }
 
@@ -1219,6 +1291,11 @@ int ftl_oracle_set_state(FtlOracle* o, int first, int n, const FtlStateBuffers* 
     if (b->env) memcpy(o->env + first, b->env, sizeof(FtlEnvState) * n);
     if (b->trail) memcpy(o->trail + (size_t)first * cfg->trail_cap * 2, b->trail, sizeof(float) * 2 * cfg->trail_cap * n);
     if (b->hist) memcpy(o->hist + (size_t)first * cfg->corridor_cap * 2, b->hist, sizeof(double) * 2 * cfg->corridor_cap * n);
-    if (b->corridor) memcpy(o->corridor + (size_t)first * cfg->corridor_cap * 4, b->corridor, sizeof(float) * 4 * cfg->corridor_cap * n);
+    if (b->corridor) {
+        memcpy(o->corridor + (size_t)first * cfg->corridor_cap * 4, b->corridor, sizeof(float) * 4 * cfg->corridor_cap * n);
+        /* an injected state only carries the float32 points */
+        for (size_t k = 0; k < (size_t)4 * cfg->corridor_cap * n; k++)
+            o->corridor64[(size_t)first * cfg->corridor_cap * 4 + k] = (double)b->corridor[k];
+    }
     return FTL_OK;
 }

@@ -249,6 +249,15 @@ TRACES = [
                      leader_speed_regime={0: [0.2, 1], 100: 1, 180: [0.5, 1], 260: 0.75, 330: [0.0, 0.5], 400: [0.4, 1]},
                      leader_acceleration_regime={0: 0, 200: 0.03, 300: 0}),
          seed=3, policy="follow", max_env_steps=700, until_done=True),
+    # LeaderCorridor_lasers_compas (SEN:1138-1240) next to a history sensor: 5 * R columns per row
+    dict(name="compas_seed25", env_id="Test-Cont-Env-Auto-v0",
+         kwargs=dict(bear_number=1, follower_sensors={
+             "LeaderPositionsTracker_v2": cfg3_sensors()["LeaderPositionsTracker_v2"],
+             "LeaderCorridor_lasers_compas": dict(sensor_class="LeaderCorridor_lasers_compas", react_to_safe_corridor=True,
+                                                  react_to_green_zone=True, react_to_obstacles=False, lasers_count=12,
+                                                  laser_length=150, max_prev_obs=3, use_prev_obs=True, pad_sectors=False),
+             "LaserPrevSensor": cfg3_sensors()["LaserPrevSensor"]}),
+         seed=25, policy="follow", max_env_steps=220, switch=(150, "random")),
     # the sensors without history on the same ray engine (LeaderCorridor_lasers_v2 = rays at k*360/R,
     # LeaderCorridor_lasers = the fixed 7-ray fan), FollowerInfo and LeaderTrackDetector_vector ("new")
     dict(name="flat_sensors_seed9", env_id="Test-Cont-Env-Auto-v0",

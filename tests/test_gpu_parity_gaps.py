@@ -36,6 +36,9 @@ GAP_CASES = [
                         auto_reset=True), 1024, 50),
     ("f10_warm0_es", dict(bear_number=1, warm_start=0, early_stopping={"max_distance_coef": 1.3, "low_reward": -60},
                           follower_sensors=cfg3_sensors(), auto_reset=True), 1024, 80),
+    # LeaderCorridor_lasers_compas (SEN:1138-1240; cast by the per-env exact pass of k_finish)
+    ("compas", dict(parity.load_trace(parity.GOLDEN_DIR + "/compas_seed25.npz")[1]["kwargs"], auto_reset=True,
+                    max_steps=300), 1024, 60),
 ]
 
 
@@ -182,8 +185,8 @@ def test_bench_workload_sample_matches_the_oracle_after_hundreds_of_steps():
 
 def test_device_rollout_matches_a_manual_loop_and_stays_on_the_device():
     """rollout.DeviceRollout: the trajectory it stores must be the one a hand-written loop over
-    FtlBatchEnv.step with the same policy produces, the observation it feeds the policy is the fused sensorPrev matrix
-    (WRP:203-221) of the raw sensor blocks, and nothing in it lives on the host."""
+    FtlBatchEnv.step produces from the same actions, the observation it feeds the policy is the fused sensorPrev matrix
+    (WRP:203-221) of the raw sensor blocks, the stored actions are the policy's, and nothing in it lives on the host."""
     import torch
     from continiousenvironment_follower_leader_b200.batch_env import FtlBatchEnv
     from continiousenvironment_follower_leader_b200.rollout import DeviceRollout
@@ -192,31 +195,39 @@ def test_device_rollout_matches_a_manual_loop_and_stays_on_the_device():
     gc_f, gc_raw = GameConfig(fused_sensor_prev=True, **kwargs), GameConfig(**kwargs)
     pool = synthetic_pool(gc_f, 32, seed=6)
     n, T = 2048, 24
-    ro = DeviceRollout(n, T, game_config=gc_f, scenario_pool=pool, seed=3)
-    traj = ro.collect(explore=False)
-    for k, v in traj.items():
-        assert v.is_cuda, k
-    assert traj["obs"].shape == (T + 1, n, 240) and traj["actions"].shape == (T, n, 2)
-    assert float(traj["obs"].min()) >= 0 and float(traj["obs"].max()) <= 1
-    lo, hi = gc_f.action_bounds()
-    assert bool((traj["actions"] >= torch.tensor(lo, device="cuda") - 1e-6).all())
-    assert bool((traj["actions"] <= torch.tensor(hi, device="cuda") + 1e-6).all())
-    assert int(traj["dones"].sum()) > 0          # max_steps = 200 frames: episodes end inside the window
-    # the same policy driven by hand over the raw-sensor configuration
-    env = FtlBatchEnv(n, game_config=gc_raw, scenario_pool=pool)
-    env.reset()
-    with torch.no_grad():
-        for t in range(T):
-            obs = sensor_prev_observation(env).reshape(n, -1)
-            assert torch.equal(obs, traj["obs"][t]), "observation differs at step %d" % t
-            act, val = ro.policy(obs, None)
-            assert torch.equal(act, traj["actions"][t])
-            _, rew, done, _ = env.step(act.contiguous())
-            assert torch.equal(rew, traj["rewards"][t]) and torch.equal(done, traj["dones"][t].bool())
-    adv, ret = ro.advantages()
-    assert adv.shape == (T, n) and bool(torch.isfinite(adv).all())
-    env.close()
-    ro.close()
+    for use_graphs in (True, False):
+        ro = DeviceRollout(n, T, game_config=gc_f, scenario_pool=pool, seed=3, use_graphs=use_graphs)
+        launches0 = ro.env.launch_count
+        traj = ro.collect(explore=False)
+        torch.cuda.synchronize()
+        assert ro.env.launch_count - launches0 >= 3 * T
+        for k, v in traj.items():
+            assert v.is_cuda, k
+        assert traj["obs"].shape == (T + 1, n, 240) and traj["actions"].shape == (T, n, 2)
+        assert float(traj["obs"].min()) >= 0 and float(traj["obs"].max()) <= 1
+        lo, hi = gc_f.action_bounds()
+        assert bool((traj["actions"] >= torch.tensor(lo, device="cuda") - 1e-6).all())
+        assert bool((traj["actions"] <= torch.tensor(hi, device="cuda") + 1e-6).all())
+        assert int(traj["dones"].sum()) > 0          # max_steps = 200 frames: episodes end inside the window
+        # the stored actions replayed by hand over the raw-sensor configuration
+        env = FtlBatchEnv(n, game_config=gc_raw, scenario_pool=pool)
+        env.reset()
+        tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        with torch.no_grad():
+            for t in range(T):
+                obs = sensor_prev_observation(env).reshape(n, -1)
+                assert torch.equal(obs.to(traj["obs"].dtype), traj["obs"][t]), "observation differs at step %d" % t
+                act, val = ro.policy(obs, None)
+                assert torch.allclose(act, traj["actions"][t], rtol=0, atol=2e-3 * float(hi.max()))
+                assert torch.allclose(val, traj["values"][t], rtol=1e-2, atol=1e-2)
+                _, rew, done, _ = env.step(traj["actions"][t].contiguous())
+                assert torch.equal(rew, traj["rewards"][t]) and torch.equal(done, traj["dones"][t].bool())
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        adv, ret = ro.advantages()
+        assert adv.shape == (T, n) and bool(torch.isfinite(adv).all())
+        env.close()
+        ro.close()
 
 
 def _per_step_inputs_case():

@@ -148,3 +148,31 @@ def test_discrete_and_constant_speed_action_spaces():
     env2.reset()
     obs, r, d, info = env2.step(np.array([0.0], np.float32))
     assert obs["numerical_features"][7] == pytest.approx(0.025)   # ten frames of 0.0025 px/frame^2
+
+
+def test_compas_sensor_through_the_gym_surface_and_the_sensor_prev_wrapper():
+    """LeaderCorridor_lasers_compas (SEN:1138-1240): (H, 5 * R) blocks in the obs dict, 5 * R features per row in
+    ContinuousObserveModifier_sensorPrev (WRP:187-188, 214-219), and the reference's flag check."""
+    d, meta = parity.load_trace(parity.GOLDEN_DIR + "/compas_seed25.npz")
+    env = _make(**meta["kwargs"])
+    sc = scenario_gen.Scenario()
+    sc.static_rects = [tuple(r) for r in d["scen_static_rects"]]
+    sc.route = [tuple(p) for p in d["scen_route"]]
+    sc.leader_pos, sc.leader_dir = d["scen_leader_pos"], float(d["scen_leader_dir"])
+    sc.follower_pos, sc.follower_dir = d["scen_follower_pos"], float(d["scen_follower_dir"])
+    sc.found_target_point = True
+    wrapped = wrappers.ContinuousObserveModifier_sensorPrev(env, max_prev_obs=3)
+    assert wrapped.observation_space.shape == (3, 5 * 12 + 36)   # WRP:181-188: 5 * R for the compas sensor + the history sensor
+    obs = env.reset(scenario=sc)
+    for t, a in enumerate(d["actions"][:60]):
+        obs, reward, done, info = env.step(a)
+        block = obs["LeaderCorridor_lasers_compas"]
+        assert block.shape == (3, 60)
+        got = np.concatenate([obs[n].reshape(-1) for n in meta["ray_names"]])
+        assert np.allclose(got, d["t_rays"][t + 1], rtol=parity.RTOL)
+        # every ray reports in exactly one of its five columns
+        cols = block.reshape(3, 5, 12)
+        assert np.all((cols > 0).sum(axis=1) == 1)
+    with pytest.raises(ValueError):
+        _make(follower_sensors=dict(cfg3_sensors(), c={"sensor_class": "LeaderCorridor_lasers_compas", "max_prev_obs": 2,
+                                                      "react_to_green_zone": False}))

@@ -36,6 +36,9 @@ CASES = [
     ("aggregate_reward", dict(bear_number=1, aggregate_reward=True, follower_sensors=cfg3_sensors(), max_steps=300,
                               auto_reset=True), 48, 60),
     ("f1", dict(bear_number=1, frames_per_step=1, follower_sensors=cfg3_sensors()), 48, 120),
+    # LeaderCorridor_lasers_compas (SEN:1138-1240), raw and as part of the fused sensorPrev matrix
+    ("compas", dict(parity.load_trace(parity.GOLDEN_DIR + "/compas_seed25.npz")[1]["kwargs"], auto_reset=True,
+                    max_steps=300), 48, 80),
 ]
 
 
