@@ -34,7 +34,7 @@ def main():
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     head, units = rows[0], rows[1]
-    traffic, lines = {}, [sys.argv[4] if len(sys.argv) > 4 else "ncu --set full --clock-control none, bench.py cfg3 workload"]
+    traffic, lines = {"warp_inst": {}, "lanes_per_inst": {}}, [sys.argv[4] if len(sys.argv) > 4 else "ncu --set full --clock-control none, bench.py cfg3 workload"]
     seen = set()
     for row in rows[2:]:
         d = dict(zip(head, row))
@@ -48,8 +48,11 @@ def main():
         for m in METRICS:
             if m in d and d[m] != "":
                 lines.append("  %-86s %s %s" % (m, d[m], u.get(m, "")))
-        traffic[short.split("<")[0]] = to_bytes(d["dram__bytes_read.sum"], u["dram__bytes_read.sum"]) + \
+        key = {"k_kin": "k_step"}.get(short.split("<")[0], short.split("<")[0])   # bench.py's kernel groups
+        traffic[key] = to_bytes(d["dram__bytes_read.sum"], u["dram__bytes_read.sum"]) + \
             to_bytes(d["dram__bytes_write.sum"], u["dram__bytes_write.sum"])
+        traffic["warp_inst"][key] = float(d["smsp__inst_executed.sum"].replace(",", ""))
+        traffic["lanes_per_inst"][key] = float(d["smsp__thread_inst_executed_per_inst_executed.ratio"].replace(",", ""))
     open(out_txt, "w").write("\n".join(lines) + "\n")
     json.dump(traffic, open(out_json, "w"), indent=1, sort_keys=True)
     print(json.dumps(traffic))
