@@ -81,7 +81,9 @@ class FtlConfig(C.Structure):
         ("fused_sensor_prev", C.c_int32),
         ("track_vector_len", C.c_int32), ("track_vector_mode", C.c_int32),
         ("radar_sectors", C.c_int32), ("radar_len", C.c_int32), ("radar_mode", C.c_int32),
-        ("reserved", C.c_int32 * 1),
+        ("laser_points", C.c_int32), ("laser_beams", C.c_int32), ("laser_only_distances", C.c_int32),
+        ("laser_available_angle", C.c_double), ("laser_angle_step", C.c_double),
+        ("laser_range", C.c_double), ("laser_reach_extra", C.c_double),
     ]
 
 
@@ -147,7 +149,8 @@ class FtlStateBuffers(C.Structure):
 class FtlOutputs(C.Structure):
     _fields_ = [("numerical_features", C.c_void_p), ("leader_target", C.c_void_p), ("rays", C.c_void_p),
                 ("reward", C.c_void_p), ("done", C.c_void_p), ("status", C.c_void_p),
-                ("follower_info", C.c_void_p), ("track_vectors", C.c_void_p), ("radar", C.c_void_p)]
+                ("follower_info", C.c_void_p), ("track_vectors", C.c_void_p), ("radar", C.c_void_p),
+                ("laser", C.c_void_p)]
 
 
 class FtlStepInputs(C.Structure):
@@ -156,6 +159,15 @@ class FtlStepInputs(C.Structure):
 
 
 ENV_STATE_DTYPE = np.dtype(FtlEnvState)
+
+
+def laser_beam_count(available_angle, angle_step):
+    """Beams of a LaserSensor: -direction, then +-k * angle_step while the running offset is below int(angle / 2), SEN:86-98."""
+    border, diff, n = int(min(360, available_angle) / 2), 0, 1
+    while diff < border:
+        diff += angle_step
+        n += 2
+    return n
 
 
 def rays_per_env(cfg):

@@ -12,6 +12,7 @@ action spaces), the return value is ``(obs, reward, done, info)`` with CUDA tens
     obs[<FollowerInfo>]        float32 [N, 2]                       SEN:834-842
     obs[<LeaderTrackDetector_vector>] float32 [N, P, 2]            SEN:365-380
     obs[<LeaderTrackDetector_radar>]  float32 [N, sectors]         SEN:425-461
+    obs[<LaserSensor>]         float32 [N, beams, 2] (or [N, beams])   SEN:63-136
     obs["sensor_prev"]         float32 [N, H, sum of widths]        WRP:203-221, instead of the sensor entries when the
                                                                     config was built with fused_sensor_prev=True
     reward float32 [N], done bool [N]
@@ -53,12 +54,15 @@ class FtlBatchEnv:
             if self.cfg.track_vector_len else None
         self.radar = torch.zeros((n, self.cfg.radar_sectors), dtype=torch.float32, device=dev) \
             if self.cfg.radar_sectors else None
+        self.laser = torch.zeros((n,) + tuple(self.gc.laser_shape), dtype=torch.float32, device=dev) \
+            if self.gc.laser_shape else None
         self._out = abi.FtlOutputs(self.numerical_features.data_ptr(), self.leader_target.data_ptr(),
                                    self.rays.data_ptr() if rpe else None, self.reward.data_ptr(),
                                    self.done.data_ptr(), self.status.data_ptr(),
                                    None if self.follower_info is None else self.follower_info.data_ptr(),
                                    None if self.track_vectors is None else self.track_vectors.data_ptr(),
-                                   None if self.radar is None else self.radar.data_ptr())
+                                   None if self.radar is None else self.radar.data_ptr(),
+                                   None if self.laser is None else self.laser.data_ptr())
         self._stats = torch.zeros(abi.STAT_COUNT, dtype=torch.float64, device=dev)
         self._ray_layout = self.gc.ray_layout()
         self._env_id_base = int(env_id_base)
@@ -98,6 +102,8 @@ class FtlBatchEnv:
             obs[self.gc.track_vector_name] = self.track_vectors
         if self.radar is not None:
             obs[self.gc.radar_name] = self.radar
+        if self.laser is not None:
+            obs[self.gc.laser_name] = self.laser
         if self.cfg.fused_sensor_prev:   # one [N, H, sum of widths] matrix, already clip(v / laser_length, 0, 1)
             obs["sensor_prev"] = self.sensor_prev()
             return obs

@@ -38,6 +38,7 @@ SIGNATURES = {
     "ftl_destroy": ([_vp], C.c_int),
     "ftl_rays_per_env": ([_vp], C.c_int),
     "ftl_num_envs": ([_vp], C.c_int),
+    "ftl_laser_beam_count": ([C.c_double, C.c_double], C.c_int),
     "ftl_upload_scenarios": ([_vp, C.POINTER(abi.FtlScenarioPool)], C.c_int),
     "ftl_reset": ([_vp, _vp, _vp, C.POINTER(abi.FtlOutputs), _vp], C.c_int),
     "ftl_step": ([_vp, _vp, C.POINTER(abi.FtlOutputs), _vp], C.c_int),
@@ -112,7 +113,8 @@ def check(L, rc, what):
 class HostOutputs:
     """numpy buffers laid out as FtlOutputs."""
 
-    def __init__(self, n, rays_per_env, alloc=None, follower_info=False, track_vector_len=0, radar_sectors=0):
+    def __init__(self, n, rays_per_env, alloc=None, follower_info=False, track_vector_len=0, radar_sectors=0,
+                 laser_shape=None):
         alloc = alloc or (lambda shape, dtype: np.zeros(shape, dtype))
         self.numerical_features = alloc((n, 10), np.float32)
         self.leader_target = alloc((n, 2), np.int32)
@@ -124,15 +126,17 @@ class HostOutputs:
         self.follower_info = alloc((n, 2), np.float32) if follower_info else None
         self.track_vectors = alloc((n, track_vector_len, 2), np.float32) if track_vector_len else None
         self.radar = alloc((n, radar_sectors), np.float32) if radar_sectors else None
+        self.laser = alloc((n,) + tuple(laser_shape), np.float32) if laser_shape else None   # LaserSensor, SEN:63-136
         self.c = abi.FtlOutputs(abi.ptr(self.numerical_features), abi.ptr(self.leader_target), abi.ptr(self.rays),
                                 abi.ptr(self.reward), abi.ptr(self.done), abi.ptr(self.status),
                                 None if self.follower_info is None else abi.ptr(self.follower_info),
                                 None if self.track_vectors is None else abi.ptr(self.track_vectors),
-                                None if self.radar is None else abi.ptr(self.radar))
+                                None if self.radar is None else abi.ptr(self.radar),
+                                None if self.laser is None else abi.ptr(self.laser))
 
     def nbytes(self):
         return sum(a.nbytes for a in (self.numerical_features, self.leader_target, self.rays, self.reward, self.done,
-                                      self.status, self.follower_info, self.track_vectors, self.radar) if a is not None)
+                                      self.status, self.follower_info, self.track_vectors, self.radar, self.laser) if a is not None)
 
 
 class HostState:
@@ -178,7 +182,8 @@ class HostEnv:
                 return a
         self.out = HostOutputs(self.n, abi.rays_per_env(self.cfg), alloc,
                                follower_info=getattr(game_config, "follower_info_name", None) is not None,
-                               track_vector_len=self.cfg.track_vector_len, radar_sectors=self.cfg.radar_sectors)
+                               track_vector_len=self.cfg.track_vector_len, radar_sectors=self.cfg.radar_sectors,
+                               laser_shape=getattr(game_config, "laser_shape", None))
         if self.cfg.action_mode == abi.ACTION_CONTINUOUS:
             shape, dt = (self.n, 2), np.float32
         elif self.cfg.action_mode == abi.ACTION_CONST_SPEED:

@@ -243,6 +243,9 @@ class GameConfig:
         c.track_vector_len = 0
         c.radar_sectors = 0
         self.radar_name = None             # dict key of the LeaderTrackDetector_radar sensor, if any
+        self.laser_name = None             # dict key of the LaserSensor, if any
+        self.laser_shape = None            # per-env shape of its output: (beams, 2) or (beams,)
+        c.laser_points = 0
         self.ray_sensor_flat = []          # True: the sensor returns (R,), not (H, R)
         self.follower_info_name = None     # dict key of the FollowerInfo sensor, if any
         self.track_vector_name = None      # dict key of the LeaderTrackDetector_vector sensor, if any
@@ -261,10 +264,13 @@ class GameConfig:
                     # use_sensors only looks the tracker up under these literal keys (CLS:257, 263);
                     # under any other key the reference dies with an unbound leader_corridor.
                     raise ValueError("the tracker must be registered under the key 'LeaderPositionsTracker_v2'")
-                if args.get("eat_close_points", True):
-                    raise NotImplementedError("eat_close_points=True is not supported (trained configs use False)")
+                # eat_close_points is accepted and ignored, as upstream: only the deprecated LeaderPositionsTracker reads
+                # it (SEN:207); LeaderPositionsTracker_v2.scan (SEN:243-327) never does
                 if not args.get("generate_corridor", True):
-                    raise NotImplementedError("generate_corridor=False is not supported")
+                    # upstream this configuration dies with IndexError at the first trim of the history: scan pops the
+                    # (empty) corridor deque together with the history (SEN:292-293)
+                    raise NotImplementedError("generate_corridor=False is not supported (the reference itself raises "
+                                              "IndexError once the history exceeds corridor_length, SEN:292-293)")
                 c.tracker_enabled = 1
                 c.saving_period = int(args.get("saving_period", 5))
                 c.start_corridor_behind_follower = int(bool(args.get("start_corridor_behind_follower", False)))
@@ -366,6 +372,24 @@ class GameConfig:
                     raise ValueError("position_sequence_length and radar_sectors_number must be positive")
                 c.radar_mode = {"new": 0, "old": 1, "near": 2}[mode]
                 self.radar_name = name
+            elif cls == "LaserSensor":                 # SEN:18-136
+                if self.laser_name is not None:
+                    raise NotImplementedError("one LaserSensor at most")
+                if args.get("return_all_points", False):
+                    raise NotImplementedError("LaserSensor: return_all_points=True is not supported")
+                c.laser_available_angle = float(min(360, args.get("available_angle", 360)))
+                c.laser_angle_step = float(args.get("angle_step", 10))
+                if c.laser_angle_step <= 0:
+                    raise ValueError("LaserSensor: angle_step must be positive")
+                c.laser_points = int(args.get("points_number", 20))
+                if c.laser_points < 1:
+                    raise ValueError("LaserSensor: points_number must be positive")
+                c.laser_range = float(args.get("sensor_range", 5) * self.kwargs["pixels_to_meter"])
+                c.laser_reach_extra = float(3 * self.kwargs["pixels_to_meter"])
+                c.laser_only_distances = int(bool(args.get("return_only_distances", False)))
+                c.laser_beams = abi.laser_beam_count(c.laser_available_angle, c.laser_angle_step)
+                self.laser_name = name
+                self.laser_shape = (c.laser_beams,) if c.laser_only_distances else (c.laser_beams, 2)
             else:
                 raise NotImplementedError(
                     "sensor class %s is outside the accelerated path (SURVEY.md section 8(f)3)" % cls)

@@ -119,9 +119,9 @@ __global__ void k_pack_state(const DevState s, int first, int count, FtlEnvState
 }
 
 // FollowerInfo / LeaderTrackDetector_vector outputs from the stored state (launched only when requested)
-__global__ void k_optional_sensors(const __grid_constant__ DevCfg cfg, const DevState s, const DevOutputs out) {
+__global__ void k_optional_sensors(const __grid_constant__ DevCfg cfg, const DevState s, const DevPool pool, const DevOutputs out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < out.n) write_optional_sensors(cfg.c, s, out, i);
+    if (i < out.n) write_optional_sensors(cfg.c, s, pool, out, i);
 }
 
 __global__ void k_unpack_state(const __grid_constant__ DevCfg cfg, const DevState s, int first, int count,
@@ -216,6 +216,17 @@ static std::vector<double2> ray_rotation_table(const FtlConfig& c) {
             rot.push_back(make_double2(std::cos(th), std::sin(th)));
         }
     return rot;
+}
+
+static size_t laser_floats(const FtlConfig& c) {   // floats per env of FtlOutputs.laser
+    return c.laser_points > 0 ? (size_t)c.laser_beams * (c.laser_only_distances ? 1 : 2) : 0;
+}
+static int laser_beam_count(double available_angle, double angle_step) {   // SEN:86-98
+    const int border = (int)((available_angle < 360 ? available_angle : 360) / 2);
+    double diff = 0;
+    int n = 1;
+    while (diff < border) { diff += angle_step; n += 2; }
+    return n;
 }
 
 static float sq_threshold(double limit) {
@@ -319,6 +330,9 @@ static int validate(const FtlConfig* c, int n_envs) {
         return fail(FTL_ERR_INVALID, "LeaderTrackDetector_vector needs LeaderPositionsTracker_v2 (CLS:240-244)");
     if (c->radar_sectors < 0 || (c->radar_sectors > 0 && (!c->tracker_enabled || c->radar_len < 1 || c->radar_mode < 0 || c->radar_mode > 2)))
         return fail(FTL_ERR_INVALID, "LeaderTrackDetector_radar needs LeaderPositionsTracker_v2, a positive length and mode 0..2 (CLS:240-244, SEN:402-421)");
+    if (c->laser_points < 0 || (c->laser_points > 0 && (!(c->laser_angle_step > 0) || c->static_cap > 64 ||
+                                                         c->laser_beams != laser_beam_count(c->laser_available_angle, c->laser_angle_step))))
+        return fail(FTL_ERR_INVALID, "LaserSensor: points_number, angle_step must be positive and laser_beams = ftl_laser_beam_count(...)");
     return FTL_OK;
 }
 
@@ -330,6 +344,7 @@ static DevOutputs to_dev_outputs(const FtlOutputs* o, int n_real) {
         d.reward = o->reward; d.done = o->done; d.status = o->status;
         d.follower_info = o->follower_info; d.track_vectors = o->track_vectors;
         d.radar = o->radar;
+        d.laser = o->laser;
     }
     return d;
 }
@@ -348,13 +363,13 @@ static void launch_reset(FtlHandle_* h, const DevState& s, const uint8_t* mask, 
 static int flush_pending_resets(ftl_handle h, cudaStream_t st);
 static int launch_optional_sensors(ftl_handle h, const DevOutputs& o, cudaStream_t st) {
     if (!o.follower_info && !(o.track_vectors && h->cfg.c.track_vector_len > 0) &&
-        !(o.radar && h->cfg.c.radar_sectors > 0))
+        !(o.radar && h->cfg.c.radar_sectors > 0) && !(o.laser && h->cfg.c.laser_points > 0))
         return FTL_OK;
     // FollowerInfo / LeaderTrackDetector_* read the stored state, which for an env that just finished must already be
     // the first state of its next episode, like the rest of the observation
     int rc = flush_pending_resets(h, st);
     if (rc) return rc;
-    k_optional_sensors<<<(h->n + 127) / 128, 128, 0, st>>>(h->cfg, h->st, o);
+    k_optional_sensors<<<(h->n + 127) / 128, 128, 0, st>>>(h->cfg, h->st, h->pool, o);
     h->launches++;
     CUDA_TRY(cudaGetLastError());
     return FTL_OK;
@@ -421,6 +436,8 @@ static int copy_outputs_to_host(ftl_handle h, const FtlOutputs* o, cudaStream_t 
         CUDA_TRY(cudaMemcpyAsync(o->track_vectors, d.track_vectors, 8 * n * h->cfg.c.track_vector_len, cudaMemcpyDeviceToHost, st));
     if (o->radar && h->cfg.c.radar_sectors)
         CUDA_TRY(cudaMemcpyAsync(o->radar, d.radar, 4 * n * h->cfg.c.radar_sectors, cudaMemcpyDeviceToHost, st));
+    if (o->laser && h->cfg.c.laser_points)
+        CUDA_TRY(cudaMemcpyAsync(o->laser, d.laser, laser_floats(h->cfg.c) * 4 * n, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     return FTL_OK;
 }
@@ -439,6 +456,7 @@ static FtlOutputs staged_outputs(ftl_handle h, const FtlOutputs* want) {
         if (want->follower_info) o.follower_info = d.follower_info;
         if (want->track_vectors && h->cfg.c.track_vector_len) o.track_vectors = d.track_vectors;
         if (want->radar && h->cfg.c.radar_sectors) o.radar = d.radar;
+        if (want->laser && h->cfg.c.laser_points) o.laser = d.laser;
     }
     return o;
 }
@@ -540,6 +558,7 @@ int ftl_create(const FtlConfig* cfg, int32_t n_envs, int32_t device, int64_t env
     ok(dalloc(h, &h->d_out.follower_info, 2 * n));
     ok(dalloc(h, &h->d_out.track_vectors, (size_t)(c.track_vector_len > 0 ? c.track_vector_len : 1) * 2 * n));
     ok(dalloc(h, &h->d_out.radar, (size_t)(c.radar_sectors > 0 ? c.radar_sectors : 1) * n));
+    ok(dalloc(h, &h->d_out.laser, (laser_floats(c) ? laser_floats(c) : 1) * n));
     if (e != cudaSuccess) {
         for (void* p : h->allocs) cudaFree(p);
         delete h;
@@ -565,6 +584,7 @@ int ftl_destroy(ftl_handle h) {
 }
 
 int ftl_rays_per_env(ftl_handle h) { return h ? h->cfg.rays_per_env : 0; }
+int ftl_laser_beam_count(double available_angle, double angle_step) { return angle_step > 0 ? laser_beam_count(available_angle, angle_step) : 0; }
 int ftl_num_envs(ftl_handle h) { return h ? h->n : 0; }
 int64_t ftl_launch_count(ftl_handle h) { return h ? h->launches : 0; }
 
@@ -876,6 +896,8 @@ static int step_host_begin(ftl_handle h, const void* actions_host, const FtlStep
             CUDA_TRY(cudaMemcpyAsync(out_host->track_vectors, d.track_vectors, 8 * n * h->cfg.c.track_vector_len, cudaMemcpyDeviceToHost, cs));
         if (out_host->radar && h->cfg.c.radar_sectors)
             CUDA_TRY(cudaMemcpyAsync(out_host->radar, d.radar, 4 * n * h->cfg.c.radar_sectors, cudaMemcpyDeviceToHost, cs));
+        if (out_host->laser && h->cfg.c.laser_points)
+            CUDA_TRY(cudaMemcpyAsync(out_host->laser, d.laser, laser_floats(h->cfg.c) * 4 * n, cudaMemcpyDeviceToHost, cs));
     }
     h->pending = true;
     return FTL_OK;

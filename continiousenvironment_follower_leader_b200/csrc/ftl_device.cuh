@@ -137,6 +137,7 @@ struct DevOutputs {
     float* follower_info;   // [N][2] or NULL
     float* track_vectors;   // [N][track_vector_len][2] or NULL
     float* radar;           // [N][radar_sectors] or NULL
+    float* laser;           // [N][laser_beams][2] (or [N][laser_beams]) or NULL
 };
 
 // per-sensor constants of the ray pass that do not depend on the env (filled by ray_static_tables, ftl_rays.cuh)

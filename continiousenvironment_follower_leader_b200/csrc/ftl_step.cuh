@@ -292,8 +292,81 @@ FTL_HD void radar_scan(const FtlConfig& c, const double2* hist, int mask, int ta
     }
 }
 
-FTL_HD void write_optional_sensors(const FtlConfig& c, const DevState& s, const DevOutputs& out, int i) {
+// LaserSensor.scan (SEN:63-136; distance_to_rect MSC:29-44).  The reference's operand types under numpy >= 2 (the
+// follower position is a float32 array, everything else python floats, which are "weak"): beam angles and their
+// cos / sin in float64, the beam end and the sample points in float32.  Hit boxes are tested with pygame's collidepoint
+// on the truncated coordinates.
+FTL_HD bool laser_in_range(int4 q, float px, float py, double limit) {   // nearest of the 4 corners + 4 edge midpoints
+    const int xs[3] = {q.x, q.x + (q.z >> 1), q.x + q.z}, ys[3] = {q.y, q.y + (q.w >> 1), q.y + q.w};
+    double best = 1e300;
+    for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++) {
+            if (a == 1 && b == 1) continue;
+            const double dx = (double)px - xs[a], dy = (double)py - ys[b];
+            const double sx = dx * dx, sy = dy * dy;
+            const double d = sqrt(sx + sy);
+            if (d < best) best = d;
+        }
+    return best <= limit;
+}
+FTL_HD bool laser_collidepoint(int4 q, float px, float py) {
+    const int x = (int)px, y = (int)py;
+    return x >= q.x && x < q.x + q.z && y >= q.y && y < q.y + q.w;
+}
+FTL_HD_NOINLINE void laser_scan(const FtlConfig& c, const DevState& s, const DevPool& pool, int i, float* out) {
+    const float2 fp = s.pos[i];
+    const double dir = s.rd[(size_t)RD_DIR * s.n + i];
+    const int scen = s.gi[(size_t)GI_SCENARIO * s.n + i];
+    const int4* statics = pool.static_rects + (size_t)scen * c.static_cap;
+    const int n_static = pool.n_static[scen], nb = s.n_bears;
+    // objects_in_range: the leader, walls and rocks, bears (SEN:77-84); at most 1 + 64 + 4 objects in two masks
+    const double limit = c.laser_range + c.laser_reach_extra;
+    uint64_t smask = 0;
+    unsigned dmask = 0;
+    for (int k = 0; k < n_static; k++)
+        if (laser_in_range(statics[k], fp.x, fp.y, limit)) smask |= (uint64_t)1 << k;
+    for (int k = 0; k < 1 + nb; k++)
+        if (laser_in_range(s.rect[(size_t)(1 + k) * s.n + i], fp.x, fp.y, limit)) dmask |= 1u << k;
+    const int border = (int)(c.laser_available_angle / 2), P = c.laser_points;
+    double diff = 0;
+    for (int beam = 0; beam < c.laser_beams; beam++) {
+        double angle;   // SEN:93-98: -direction, then alternately +diff and -diff
+        if (beam == 0) angle = -dir;
+        else {
+            if (beam & 1) diff += c.laser_angle_step;
+            angle = angle_correction((beam & 1) ? -dir + diff : -dir - diff);
+        }
+        (void)border;
+        double sn, cs;
+        sincos_deg(angle, &sn, &cs);
+        const float x2 = fp.x + (float)(c.laser_range * cs), y2 = fp.y - (float)(c.laser_range * sn);
+        float hx = x2, hy = y2;
+        for (int k = 0; k < P; k++) {
+            const double u = (double)k / P;
+            const float uf = (float)u, vf = (float)(1 - u);
+            const float ax = x2 * uf, bx = fp.x * vf, ay = y2 * uf, by = fp.y * vf;
+            const float cx = ax + bx, cy = ay + by;
+            bool hit = false;
+            for (uint64_t m = smask; m && !hit; m &= m - 1) hit = laser_collidepoint(statics[first_bit64(m)], cx, cy);
+            for (int q = 0; q < 1 + nb && !hit; q++)
+                if (dmask & (1u << q)) hit = laser_collidepoint(s.rect[(size_t)(1 + q) * s.n + i], cx, cy);
+            if (hit) { hx = cx; hy = cy; break; }
+        }
+        const float dx = hx - fp.x, dy = hy - fp.y;
+        if (c.laser_only_distances) {
+            const float sx = dx * dx, sy = dy * dy;
+            out[beam] = sqrtf(sx + sy);           // np.linalg.norm(points - position, axis=1) on float32
+        } else {
+            out[2 * beam] = dx;
+            out[2 * beam + 1] = dy;
+        }
+    }
+}
+
+FTL_HD void write_optional_sensors(const FtlConfig& c, const DevState& s, const DevPool& pool, const DevOutputs& out, int i) {
     const float2 fp = s.pos[i];   // robot 0 = follower
+    if (out.laser && c.laser_points > 0)
+        laser_scan(c, s, pool, i, out.laser + (size_t)i * c.laser_beams * (c.laser_only_distances ? 1 : 2));
     if (out.follower_info) {
         const double fspeed = s.rd[(size_t)RD_SPEED * s.n + i], fdir = s.rd[(size_t)RD_DIR * s.n + i];
         out.follower_info[2 * (size_t)i] = (float)(fspeed / c.follower.max_speed);

@@ -259,6 +259,8 @@ class Game(Env):
             obs[self.gc.track_vector_name] = out.track_vectors[0].copy()
         if self.gc.radar_name is not None:           # SEN:425-461
             obs[self.gc.radar_name] = out.radar[0].copy()
+        if self.gc.laser_name is not None:           # SEN:63-136
+            obs[self.gc.laser_name] = out.laser[0].copy()
         return obs
 
     def _tracker_obs(self):

@@ -88,10 +88,10 @@ class DeviceRollout:
         env = self.env
         self._outs = [abi.FtlOutputs(env.numerical_features.data_ptr(), env.leader_target.data_ptr(),
                                      self.obs[t + 1].data_ptr(), self.rewards[t].data_ptr(), self.dones[t].data_ptr(),
-                                     env.status.data_ptr(), None, None, None) for t in range(self.T)]
+                                     env.status.data_ptr(), None, None, None, None) for t in range(self.T)]
         self._out_reset = abi.FtlOutputs(env.numerical_features.data_ptr(), env.leader_target.data_ptr(),
                                          self.obs[0].data_ptr(), env.reward.data_ptr(), env.done.data_ptr(),
-                                         env.status.data_ptr(), None, None, None)
+                                         env.status.data_ptr(), None, None, None, None)
         self._last = 0     # ring row that holds the current observation
         self._graphs = {}
         self._use_graphs = bool(use_graphs)

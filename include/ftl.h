@@ -154,7 +154,16 @@ typedef struct FtlConfig {
     int32_t radar_sectors;
     int32_t radar_len;
     int32_t radar_mode;
-    int32_t reserved[1];
+    /* LaserSensor (SEN:18-136): a point-sampling lidar.  Beams at -direction, then +-k*angle_step (k = 1, 2, ... while
+     * (k - 1)*angle_step < int(available_angle / 2)), each sampled at laser_points positions i/points of its length; a
+     * beam reports its first sample inside a hit box (pygame collidepoint on the leader, walls, rocks and bears whose
+     * nearest corner / edge midpoint is within laser_range + laser_reach_extra) or its end point -- as the vector from
+     * the follower, or only its length (laser_only_distances).  laser_points = 0: sensor absent. */
+    int32_t laser_points;
+    int32_t laser_beams;               /* number of beams, ftl_laser_beam_count(available_angle, angle_step) */
+    int32_t laser_only_distances;
+    double laser_available_angle, laser_angle_step;   /* degrees */
+    double laser_range, laser_reach_extra;            /* pixels: sensor_range * PIXELS_TO_METER, 3 * PIXELS_TO_METER */
 } FtlConfig;
 
 /* Scenario pool = what Game.reset() builds (ENV:434-543) before the first sensor scan, as data.
@@ -250,6 +259,8 @@ typedef struct FtlOutputs {
     float* follower_info;      /* [N][2]   FollowerInfo.scan: speed / max_speed, direction / 360 (SEN:834-842); may be NULL */
     float* track_vectors;      /* [N][track_vector_len][2]  LeaderTrackDetector_vector.scan (SEN:365-380); may be NULL */
     float* radar;              /* [N][radar_sectors]  LeaderTrackDetector_radar.scan (SEN:425-461); may be NULL */
+    float* laser;              /* [N][laser_beams][2] (or [N][laser_beams] with laser_only_distances)  LaserSensor.scan
+                                  (SEN:63-136); may be NULL */
 } FtlOutputs;
 
 /* Episode statistics accumulated on the device (summed over envs), the vector reduced with NCCL. */
@@ -269,6 +280,7 @@ const char* ftl_last_error(void);
 int ftl_create(const FtlConfig* cfg, int32_t n_envs, int32_t device, int64_t env_id_base, ftl_handle* out);
 int ftl_destroy(ftl_handle h);
 int ftl_rays_per_env(ftl_handle h);      /* floats per env in FtlOutputs.rays */
+int ftl_laser_beam_count(double available_angle, double angle_step);   /* beams of a LaserSensor, SEN:86-98 */
 int ftl_num_envs(ftl_handle h);
 
 /* ---- scenarios + reset: replaces Game.reset (ENV:434-543) ------------------------------------- */

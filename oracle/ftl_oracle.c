@@ -1015,6 +1015,78 @@ static void radar_scan(FtlOracle* o, int i, float* radar) {
     }
 }
 
+/* LaserSensor.scan, SEN:63-136, with distance_to_rect of MSC:29-44.  Operand types as numpy >= 2 sees them: the follower
+ * position is a float32 array element, every other operand a python float (weak): beam end and sample points are float32. */
+static int laser_rect_in_range(const int32_t* r, float px, float py, double limit) {
+    /* topleft, bottomleft, topright, bottomright, midtop, midleft, midbottom, midright (pygame: mid = x + w // 2) */
+    int cx = r[0] + (r[2] >> 1), cy = r[1] + (r[3] >> 1);
+    int pts[8][2] = {{r[0], r[1]}, {r[0], r[1] + r[3]}, {r[0] + r[2], r[1]}, {r[0] + r[2], r[1] + r[3]},
+                     {cx, r[1]}, {r[0], cy}, {cx, r[1] + r[3]}, {r[0] + r[2], cy}};
+    double best = INFINITY;
+    for (int k = 0; k < 8; k++) {
+        double d = dist_f64((double)px, (double)py, (double)pts[k][0], (double)pts[k][1]); /* scipy euclidean */
+        if (d < best) best = d;
+    }
+    return best <= limit;
+}
+static int laser_collidepoint(const int32_t* r, float px, float py) { /* pygame.Rect.collidepoint on truncated ints */
+    int x = (int)px, y = (int)py;
+    return x >= r[0] && x < r[0] + r[2] && y >= r[1] && y < r[1] + r[3];
+}
+static void laser_scan(FtlOracle* o, int i, float* out) {
+    const FtlConfig* cfg = &o->cfg;
+    const FtlEnvState* e = &o->env[i];
+    float x1 = e->follower.pos[0], y1 = e->follower.pos[1];
+    /* objects_in_range: game_object_list minus the follower (leader, walls, rocks) + game_dynamic_list (bears) */
+    const int32_t* objs[1 + 64 + FTL_MAX_BEARS];
+    int no = 0;
+    double limit = cfg->laser_range + cfg->laser_reach_extra;
+    if (laser_rect_in_range(e->leader.rect, x1, y1, limit)) objs[no++] = e->leader.rect;
+    const int32_t* sr = o->s_static + (size_t)e->scenario_id * cfg->static_cap * 4;
+    for (int k = 0; k < o->s_nstatic[e->scenario_id]; k++)
+        if (laser_rect_in_range(sr + 4 * k, x1, y1, limit)) objs[no++] = sr + 4 * k;
+    for (int b = 0; b < cfg->n_bears; b++)
+        if (laser_rect_in_range(e->bear[b].rect, x1, y1, limit)) objs[no++] = e->bear[b].rect;
+    int border = (int)(cfg->laser_available_angle / 2);
+    int beam = 0;
+    double diff = 0;
+    while (beam < cfg->laser_beams) {
+        double angles[2];
+        int na = 1;
+        if (beam == 0) {
+            angles[0] = -e->follower.dir;
+        } else {
+            if (!(diff < border)) break;
+            diff += cfg->laser_angle_step;
+            angles[0] = angle_correction(-e->follower.dir + diff);
+            angles[1] = angle_correction(-e->follower.dir - diff);
+            na = 2;
+        }
+        for (int a = 0; a < na; a++, beam++) {
+            double th = angles[a] * DEG2RAD; /* math.radians */
+            float x2 = x1 + (float)(cfg->laser_range * cos(th)), y2 = y1 - (float)(cfg->laser_range * sin(th));
+            float hx = x2, hy = y2;
+            for (int k = 0; k < cfg->laser_points; k++) {
+                double u = (double)k / cfg->laser_points;
+                float uf = (float)u, vf = (float)(1 - u);
+                float ax = x2 * uf, bx = x1 * vf, ay = y2 * uf, by = y1 * vf;
+                float cx = ax + bx, cy = ay + by;
+                int hit = 0;
+                for (int q = 0; q < no && !hit; q++) hit = laser_collidepoint(objs[q], cx, cy);
+                if (hit) { hx = cx; hy = cy; break; }
+            }
+            float dx = hx - x1, dy = hy - y1;
+            if (cfg->laser_only_distances) {
+                float sx = dx * dx, sy = dy * dy;
+                out[beam] = sqrtf(sx + sy);
+            } else {
+                out[2 * beam] = dx;
+                out[2 * beam + 1] = dy;
+            }
+        }
+    }
+}
+
 static void use_sensors(FtlOracle* o, int i, const FtlOutputs* out) { /* CLS:255-288 */
     const FtlConfig* cfg = &o->cfg;
     FtlEnvState* e = &o->env[i];
@@ -1038,6 +1110,8 @@ static void use_sensors(FtlOracle* o, int i, const FtlOutputs* out) { /* CLS:255
         }
     }
     if (out && out->radar && cfg->radar_sectors > 0) radar_scan(o, i, out->radar + (size_t)i * cfg->radar_sectors);
+    if (out && out->laser && cfg->laser_points > 0)
+        laser_scan(o, i, out->laser + (size_t)i * cfg->laser_beams * (cfg->laser_only_distances ? 1 : 2));
     if (cfg->n_ray_sensors > 0) {
         /* history_obstacles_list.pop(0); append(current), SEN:894-895 (one shared ring: every sensor
          * snapshots the same world at the same instants) */

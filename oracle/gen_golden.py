@@ -112,6 +112,8 @@ def capture(env, obs, reward, done, info, ray_names, n_bears, gc=None):
         rec["track_vectors"] = np.asarray(obs[gc.track_vector_name], np.float32)
     if gc is not None and getattr(gc, "radar_name", None) is not None:
         rec["radar"] = np.asarray(obs[gc.radar_name], np.float32)
+    if gc is not None and getattr(gc, "laser_name", None) is not None:
+        rec["laser"] = np.asarray(obs[gc.laser_name], np.float32)
     return rec
 
 
@@ -249,6 +251,18 @@ TRACES = [
                      leader_speed_regime={0: [0.2, 1], 100: 1, 180: [0.5, 1], 260: 0.75, 330: [0.0, 0.5], 400: [0.4, 1]},
                      leader_acceleration_regime={0: 0, 200: 0.03, 300: 0}),
          seed=3, policy="follow", max_env_steps=700, until_done=True),
+    # LaserSensor (SEN:18-136): the point-sampling lidar, default fan (37 beams) and a narrow distance-only fan, 3 bears
+    dict(name="laser_sensor_seed27", env_id="Test-Cont-Env-Auto-v0",
+         kwargs=dict(bear_number=3, follower_sensors={
+             "LaserSensor": dict(sensor_class="LaserSensor", available_angle=360, angle_step=10, points_number=20,
+                                 sensor_range=5)}),
+         seed=27, policy="random", max_env_steps=150),
+    dict(name="laser_distances_seed29", env_id="Test-Cont-Env-Auto-v0",
+         kwargs=dict(bear_number=1, frames_per_step=5, follower_sensors={
+             "LeaderPositionsTracker_v2": cfg3_sensors()["LeaderPositionsTracker_v2"],
+             "lidar": dict(sensor_class="LaserSensor", available_angle=150, angle_step=7.5, points_number=30,
+                           sensor_range=6, return_only_distances=True)}),
+         seed=29, policy="follow", max_env_steps=150),
     # LeaderCorridor_lasers_compas (SEN:1138-1240) next to a history sensor: 5 * R columns per row
     dict(name="compas_seed25", env_id="Test-Cont-Env-Auto-v0",
          kwargs=dict(bear_number=1, follower_sensors={

@@ -57,7 +57,8 @@ class OracleEnv:
             raise ValueError("oracle rejected the configuration")
         self.out = HostOutputs(n_envs, abi.rays_per_env(self.cfg),
                                follower_info=getattr(game_config, "follower_info_name", None) is not None,
-                               track_vector_len=self.cfg.track_vector_len, radar_sectors=self.cfg.radar_sectors)
+                               track_vector_len=self.cfg.track_vector_len, radar_sectors=self.cfg.radar_sectors,
+                               laser_shape=getattr(game_config, "laser_shape", None))
 
     def close(self):
         if self._h:

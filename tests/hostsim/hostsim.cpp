@@ -86,8 +86,8 @@ static void reset_all(FtlHandle_* h, const uint8_t* mask, const int* ids, const 
     }
 }
 static void optional_all(FtlHandle_* h, const DevOutputs& out) {
-    if (!out.follower_info && !out.track_vectors && !out.radar) return;
-    for (int i = 0; i < h->n; i++) write_optional_sensors(h->cfg.c, h->st, out, i);
+    if (!out.follower_info && !out.track_vectors && !out.radar && !out.laser) return;
+    for (int i = 0; i < h->n; i++) write_optional_sensors(h->cfg.c, h->st, h->pool, out, i);
 }
 static void rays_all(FtlHandle_* h, float* rays) {
     if (!rays || !h->rays_total) return;
@@ -103,7 +103,7 @@ static DevOutputs dev_out(const FtlOutputs* o) {
     if (o) {
         d.numerical_features = o->numerical_features; d.leader_target = o->leader_target; d.rays = o->rays;
         d.reward = o->reward; d.done = o->done; d.status = o->status;
-        d.follower_info = o->follower_info; d.track_vectors = o->track_vectors; d.radar = o->radar;
+        d.follower_info = o->follower_info; d.track_vectors = o->track_vectors; d.radar = o->radar; d.laser = o->laser;
     }
     return d;
 }

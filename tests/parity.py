@@ -174,6 +174,16 @@ def check_record(t, d, gc, out, st, env_index=0, float_rtol=0.0, ray_rtol=RTOL, 
             err = np.abs(got.astype(np.float64) - want) > float_rtol * np.maximum(1.0, np.abs(want))
             if err.sum() > max(2, 0.02 * err.size):
                 raise Mismatch("step %d: LeaderTrackDetector_radar differs in %d of %d sectors" % (t, err.sum(), err.size))
+    # ---- LaserSensor (SEN:63-136): sample points are discrete, so within tolerance means equal up to float rounding --
+    if "t_laser" in d:
+        want = d["t_laser"][t]
+        got = out.laser[env_index]
+        if float_rtol == 0.0:
+            _equal(got, want, "LaserSensor", t)
+        else:
+            err = np.abs(got.astype(np.float64) - want) > float_rtol * np.maximum(1.0, np.abs(want))
+            if err.sum() > max(2, 0.02 * err.size):   # a sample on a hit-box edge may fall either way
+                raise Mismatch("step %d: LaserSensor differs in %d of %d values" % (t, err.sum(), err.size))
     # ---- rays -----------------------------------------------------------------------------------
     bad = 0
     if c.n_ray_sensors:

@@ -39,6 +39,11 @@ GAP_CASES = [
     # LeaderCorridor_lasers_compas (SEN:1138-1240; cast by the per-env exact pass of k_finish)
     ("compas", dict(parity.load_trace(parity.GOLDEN_DIR + "/compas_seed25.npz")[1]["kwargs"], auto_reset=True,
                     max_steps=300), 1024, 60),
+    # LaserSensor (SEN:18-136; k_optional_sensors)
+    ("laser_points", dict(parity.load_trace(parity.GOLDEN_DIR + "/laser_sensor_seed27.npz")[1]["kwargs"], auto_reset=True,
+                          max_steps=300), 1024, 60),
+    ("laser_distances", dict(parity.load_trace(parity.GOLDEN_DIR + "/laser_distances_seed29.npz")[1]["kwargs"],
+                             auto_reset=True, max_steps=300), 1024, 60),
 ]
 
 
@@ -54,7 +59,7 @@ def test_cuda_matches_oracle_on_the_uncovered_step_options(name, kwargs, n, step
     cuda.reset(scenario_ids=ids)
     orc.reset(scenario_ids=ids)
     rng = np.random.RandomState(17)
-    bad, total, dones = 0, 0, 0
+    bad, total, dones, laser_bad, laser_total = 0, 0, 0, 0, 0
     for t in range(steps):
         a = sample_actions(gc, rng, n, t)
         oc, oo = cuda.step(a), orc.step(a)
@@ -66,9 +71,13 @@ def test_cuda_matches_oracle_on_the_uncovered_step_options(name, kwargs, n, step
         bad += _ray_outliers(oc.rays, oo.rays)
         total += oc.rays.size
         dones += int(oo.done.sum())
+        if oc.laser is not None:   # discrete sample points: equal up to float rounding, or a sample on a hit-box edge
+            laser_bad += _ray_outliers(oc.laser, oo.laser)
+            laser_total += oc.laser.size
         if t % 10 == 9 or t == steps - 1:
             _compare_states(cuda.get_state(), orc.get_state(), gc, n, parity.RTOL)
     assert bad <= 2, "%d of %d ray values outside tolerance" % (bad, total)
+    assert laser_bad <= 1e-4 * max(laser_total, 1), "%d of %d LaserSensor values outside tolerance" % (laser_bad, laser_total)
     if gc.c.aggregate_reward:   # the returned reward is the running total (ENV:1136), not the last frame's
         live = ~oo.done.astype(bool)
         assert live.sum() > n // 2

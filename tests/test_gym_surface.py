@@ -176,3 +176,23 @@ def test_compas_sensor_through_the_gym_surface_and_the_sensor_prev_wrapper():
     with pytest.raises(ValueError):
         _make(follower_sensors=dict(cfg3_sensors(), c={"sensor_class": "LeaderCorridor_lasers_compas", "max_prev_obs": 2,
                                                       "react_to_green_zone": False}))
+
+
+def test_laser_sensor_through_the_gym_surface():
+    """LaserSensor (SEN:18-136): 1 + 2 * ceil(180 / 10) = 37 beams of 20 samples; the dict entry is the (37, 2) array of
+    vectors from the follower, equal to the reference trace."""
+    d, meta = parity.load_trace(parity.GOLDEN_DIR + "/laser_sensor_seed27.npz")
+    env = _make(**meta["kwargs"])
+    sc = scenario_gen.Scenario()
+    sc.static_rects = [tuple(r) for r in d["scen_static_rects"]]
+    sc.route = [tuple(p) for p in d["scen_route"]]
+    sc.leader_pos, sc.leader_dir = d["scen_leader_pos"], float(d["scen_leader_dir"])
+    sc.follower_pos, sc.follower_dir = d["scen_follower_pos"], float(d["scen_follower_dir"])
+    sc.found_target_point = True
+    obs = env.reset(scenario=sc)
+    assert obs["LaserSensor"].shape == (37, 2) and np.array_equal(obs["LaserSensor"], d["t_laser"][0])
+    for t, a in enumerate(d["actions"][:80]):
+        obs, reward, done, info = env.step(a)
+        assert np.array_equal(obs["LaserSensor"], d["t_laser"][t + 1]), t
+    with pytest.raises(NotImplementedError):
+        _make(follower_sensors={"LaserSensor": {"return_all_points": True}})

@@ -39,6 +39,11 @@ CASES = [
     # LeaderCorridor_lasers_compas (SEN:1138-1240), raw and as part of the fused sensorPrev matrix
     ("compas", dict(parity.load_trace(parity.GOLDEN_DIR + "/compas_seed25.npz")[1]["kwargs"], auto_reset=True,
                     max_steps=300), 48, 80),
+    # LaserSensor (SEN:18-136): points and distances
+    ("laser_points", dict(parity.load_trace(parity.GOLDEN_DIR + "/laser_sensor_seed27.npz")[1]["kwargs"], auto_reset=True,
+                          max_steps=300), 48, 60),
+    ("laser_distances", dict(parity.load_trace(parity.GOLDEN_DIR + "/laser_distances_seed29.npz")[1]["kwargs"],
+                             auto_reset=True, max_steps=300), 48, 60),
 ]
 
 
@@ -72,6 +77,8 @@ def test_hostsim_matches_oracle(name, kwargs, n, steps):
             assert np.array_equal(os_.track_vectors, oo.track_vectors)
         if os_.radar is not None:
             assert np.array_equal(os_.radar, oo.radar), "radar differs at step %d" % t
+        if os_.laser is not None:
+            assert np.array_equal(os_.laser, oo.laser), "LaserSensor differs at step %d" % t
         _compare_states(sim.get_state(), orc.get_state(), gc, n, 0.0)
     assert bad == 0, "%d of %d ray values outside tolerance" % (bad, total)
     assert int(sim.get_state().env["overflow"].max()) == 0
