@@ -158,6 +158,13 @@ class FtlStepInputs(C.Structure):
     _fields_ = [("frames_per_step", C.c_void_p), ("regime_draws", C.c_void_p)]
 
 
+class FtlMlpWeights(C.Structure):
+    """Device pointers of the fused policy kernel's weights (ftl_policy_mlp, include/ftl.h)."""
+    _fields_ = [("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p), ("w3", C.c_void_p),
+                ("b3", C.c_void_p), ("noise_scale", C.c_void_p), ("act_mid", C.c_void_p), ("act_half", C.c_void_p),
+                ("obs_dim", C.c_int32), ("act_dim", C.c_int32)]
+
+
 ENV_STATE_DTYPE = np.dtype(FtlEnvState)
 
 

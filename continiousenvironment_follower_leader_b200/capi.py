@@ -57,6 +57,7 @@ SIGNATURES = {
     "ftl_profile_read": ([_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i64)], C.c_int),
     "ftl_profile_read_kernels": ([_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i64)],
                                  C.c_int),
+    "ftl_policy_mlp": ([C.POINTER(abi.FtlMlpWeights), _vp, _i32, _vp, _i32, _vp, _vp, _vp], C.c_int),
     "ftl_measure_fp32_peak": ([_i32, C.POINTER(C.c_double)], C.c_int),
     "ftl_generate_scenarios": ([C.POINTER(abi.FtlScenarioGenConfig), _vp, _i32, C.POINTER(abi.FtlScenarioPool), _i32],
                                C.c_int),

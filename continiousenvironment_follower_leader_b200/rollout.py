@@ -5,8 +5,10 @@ The reference trains through RLlib (notebooks/Ray_train_demo.ipynb): one ``Game`
 wrapper's matrix is written by the ray kernel itself (``fused_sensor_prev``) STRAIGHT INTO the trajectory ring (row t + 1
 of the observation archive is the output buffer of step t), the policy reads row t in place and writes its action into
 the row ``ftl_step`` consumes, and ``ftl_step`` writes reward and done into their rings -- no copy of any kind per step,
-one stream, no synchronisation inside ``collect``.  The policy section of a step (forward + action) is captured in one
-CUDA graph per ring slot, so a step costs the host two launches: the graph and ``ftl_step``.
+one stream, no synchronisation inside ``collect``.  The built-in ``MlpPolicy`` runs as ONE fused tensor-core kernel of
+libftl.so (``ftl_policy_mlp``, csrc/ftl_policy.cu: bfloat16 ``mma``, activations in shared memory, the action written
+where ``ftl_step`` reads it), so a step costs two launches; any other torch module runs through torch, its section of a
+step captured in one CUDA graph per ring slot.
 
 PyTorch is the consumer here (a user's policy network is a torch module; its GEMMs are library calls); the simulator
 side is libftl.so exactly as in ``FtlBatchEnv.step``.
@@ -60,7 +62,7 @@ class DeviceRollout:
     """
 
     def __init__(self, n_envs, horizon, game_config=None, scenario_pool=None, policy=None, device=None, env_id_base=0,
-                 seed=0, use_graphs=True, allow_tf32=True, **game_kwargs):
+                 seed=0, use_graphs=True, allow_tf32=True, fused_policy=True, **game_kwargs):
         if game_config is None:
             game_config = GameConfig(fused_sensor_prev=True, auto_reset=True, **game_kwargs)
         if not game_config.c.fused_sensor_prev or not game_config.c.auto_reset:
@@ -93,6 +95,12 @@ class DeviceRollout:
                                          self.obs[0].data_ptr(), env.reward.data_ptr(), env.done.data_ptr(),
                                          env.status.data_ptr(), None, None, None, None)
         self._last = 0     # ring row that holds the current observation
+        self._fused = None
+        if fused_policy and isinstance(self.policy, MlpPolicy) and self.policy.head.in_features == 128 \
+                and self.obs_dim % 16 == 0 and self.obs_dim <= 288 and self.act_dim <= 7:
+            self._noise_ring = torch.zeros((self.T, self.n, self.act_dim), dtype=torch.float32, device=dev)
+            self._scratch_act = torch.zeros((self.n, self.act_dim), dtype=torch.float32, device=dev)
+            self.sync_policy()
         self._graphs = {}
         self._use_graphs = bool(use_graphs)
         self._seed = int(seed)
@@ -101,6 +109,26 @@ class DeviceRollout:
     def close(self):
         self._graphs.clear()
         self.env.close()
+
+    def sync_policy(self):
+        """(Re-)export the MlpPolicy's parameters for the fused kernel: bfloat16 weights in torch.nn.Linear layout,
+        float32 biases.  Call after every optimiser step on the policy."""
+        p = self.policy
+        l1, l2 = p.body[0], p.body[2]
+        keep = {"w1": l1.weight.detach().to(torch.bfloat16).contiguous(), "b1": l1.bias.detach().float().contiguous(),
+                "w2": l2.weight.detach().to(torch.bfloat16).contiguous(), "b2": l2.bias.detach().float().contiguous(),
+                "w3": p.head.weight.detach().to(torch.bfloat16).contiguous(), "b3": p.head.bias.detach().float().contiguous(),
+                "noise_scale": p.log_std.detach().float().exp().contiguous(),
+                "act_mid": p.act_mid.float().contiguous(), "act_half": p.act_half.float().contiguous()}
+        self._fused = (abi.FtlMlpWeights(*[keep[k].data_ptr() for k in ("w1", "b1", "w2", "b2", "w3", "b3", "noise_scale",
+                                                                         "act_mid", "act_half")],
+                                         self.obs_dim, self.act_dim), keep)
+
+    def _fused_policy(self, obs_row, noise_row, actions_row, values_row, stream):
+        env = self.env
+        capi.check(env._L, env._L.ftl_policy_mlp(C.byref(self._fused[0]), obs_row.data_ptr(), self.obs_dim,
+                                                 None if noise_row is None else noise_row.data_ptr(), self.n,
+                                                 actions_row.data_ptr(), values_row.data_ptr(), stream), "ftl_policy_mlp")
 
     def _policy_section(self, t, explore):
         """run the policy on obs[t] in place, leave the action in actions[t] (which ftl_step reads) and the value in
@@ -146,13 +174,22 @@ class DeviceRollout:
                 self._started = True
             elif self._last != 0:
                 self.obs[0].copy_(self.obs[self._last])     # once per collect: the window starts where the last one ended
+            if self._fused is not None and explore:
+                self._noise_ring[:T].normal_()          # one kernel per collect
             for t in range(T):
-                self._run_policy(t, explore)
+                if self._fused is not None:
+                    self._fused_policy(self.obs[t], self._noise_ring[t] if explore else None, self.actions[t],
+                                       self.values[t], stream)
+                else:
+                    self._run_policy(t, explore)
                 capi.check(env._L, env._L.ftl_step(env._h, self.actions[t].data_ptr(), C.byref(self._outs[t]), stream),
                            "ftl_step")
             self._last = T
-            _, val = self.policy(self.obs[T], None)
-            self.values[T].copy_(val)
+            if self._fused is not None:
+                self._fused_policy(self.obs[T], None, self._scratch_act, self.values[T], stream)
+            else:
+                _, val = self.policy(self.obs[T], None)
+                self.values[T].copy_(val)
         finally:
             torch.backends.cuda.matmul.allow_tf32 = tf32
         return {"obs": self.obs[:T + 1], "actions": self.actions[:T],

@@ -345,6 +345,30 @@ int ftl_profile(ftl_handle h, int32_t enable);
 int ftl_profile_read(ftl_handle h, double* step_kernel_ms, double* ray_kernel_ms, int64_t* steps);
 int ftl_profile_read_kernels(ftl_handle h, double* kin_ms, double* book_ms, double* rays_ms, int64_t* steps);
 
+/* ---- a consumer: the rollout's policy as one fused kernel (no reference analogue -- the
+ * reference hands its observations to RLlib) ------------------------------------------------------------------------
+ * A tanh MLP obs_dim -> 128 -> 128 -> act_dim + 1 on rows of the fused sensorPrev matrix (FtlConfig.fused_sensor_prev):
+ * action[c] = act_mid[c] + act_half[c] * tanh(mu[c] + noise[c] * noise_scale[c]), value = the last output.  Tensor cores
+ * (mma.sync, bfloat16 operands, float32 accumulation); weights are bfloat16 in torch.nn.Linear layout ([out][in]).
+ * All pointers are device pointers. */
+typedef struct FtlMlpWeights {
+    const uint16_t* w1;  /* [128][obs_dim] bfloat16 */
+    const float* b1;     /* [128] */
+    const uint16_t* w2;  /* [128][128] */
+    const float* b2;     /* [128] */
+    const uint16_t* w3;  /* [act_dim + 1][128]: rows 0..act_dim-1 the action mean, row act_dim the value */
+    const float* b3;     /* [act_dim + 1] */
+    const float* noise_scale;  /* [act_dim] (exp(log_std)); may be NULL when no noise is given */
+    const float* act_mid;      /* [act_dim] */
+    const float* act_half;     /* [act_dim] */
+    int32_t obs_dim;     /* multiple of 16, <= 288 (weights + a tile of rows must fit the SM's shared memory) */
+    int32_t act_dim;     /* 1..7 */
+} FtlMlpWeights;
+/* obs_dev: float32 [n][obs_stride] (first obs_dim of every row are read; rows 16-byte aligned); noise_dev: float32
+ * [n][act_dim] standard normal draws or NULL; actions_dev [n][act_dim], values_dev [n]. */
+int ftl_policy_mlp(const FtlMlpWeights* w, const float* obs_dev, int32_t obs_stride, const float* noise_dev, int32_t n,
+                   float* actions_dev, float* values_dev, void* cuda_stream);
+
 /* Diagnostic for the roofline report: FP32 FMA throughput of `device` measured with a
  * register-resident kernel of independent fused multiply-add chains (2 flop per FMA), in TFLOP/s.  No handle needed. */
 int ftl_measure_fp32_peak(int32_t device, double* tflops_out);

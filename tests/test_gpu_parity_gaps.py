@@ -204,8 +204,12 @@ def test_device_rollout_matches_a_manual_loop_and_stays_on_the_device():
     gc_f, gc_raw = GameConfig(fused_sensor_prev=True, **kwargs), GameConfig(**kwargs)
     pool = synthetic_pool(gc_f, 32, seed=6)
     n, T = 2048, 24
-    for use_graphs in (True, False):
-        ro = DeviceRollout(n, T, game_config=gc_f, scenario_pool=pool, seed=3, use_graphs=use_graphs)
+    for fused_policy, use_graphs in ((True, False), (False, True), (False, False)):
+        ro = DeviceRollout(n, T, game_config=gc_f, scenario_pool=pool, seed=3, use_graphs=use_graphs,
+                           fused_policy=fused_policy)
+        assert (ro._fused is not None) == fused_policy
+        # the fused kernel computes in bfloat16: ~3 digits on the pre-activation values
+        atol_a, tol_v = (3e-2, 6e-2) if fused_policy else (2e-3, 1e-2)
         launches0 = ro.env.launch_count
         traj = ro.collect(explore=False)
         torch.cuda.synchronize()
@@ -228,8 +232,9 @@ def test_device_rollout_matches_a_manual_loop_and_stays_on_the_device():
                 obs = sensor_prev_observation(env).reshape(n, -1)
                 assert torch.equal(obs.to(traj["obs"].dtype), traj["obs"][t]), "observation differs at step %d" % t
                 act, val = ro.policy(obs, None)
-                assert torch.allclose(act, traj["actions"][t], rtol=0, atol=2e-3 * float(hi.max()))
-                assert torch.allclose(val, traj["values"][t], rtol=1e-2, atol=1e-2)
+                assert torch.allclose(act, traj["actions"][t], rtol=0, atol=atol_a * float(hi.max())), \
+                    float((act - traj["actions"][t]).abs().max())
+                assert torch.allclose(val, traj["values"][t], rtol=tol_v, atol=tol_v), float((val - traj["values"][t]).abs().max())
                 _, rew, done, _ = env.step(traj["actions"][t].contiguous())
                 assert torch.equal(rew, traj["rewards"][t]) and torch.equal(done, traj["dones"][t].bool())
         torch.backends.cuda.matmul.allow_tf32 = tf32
@@ -285,3 +290,40 @@ def run_per_step_inputs_case(make_env, n, steps, float_rtol):
 
 def test_per_step_inputs_on_the_gpu():
     run_per_step_inputs_case(lambda gc, n: capi.HostEnv(gc, n, lib=capi.load()), 1024, 120, parity.RTOL)
+
+
+def test_fused_policy_kernel_against_torch():
+    """ftl_policy_mlp (csrc/ftl_policy.cu, bfloat16 mma) against the same MLP in torch float32 on bfloat16-rounded
+    inputs and weights: what is left is the accumulation order and the bfloat16 rounding of the hidden activations."""
+    import ctypes as C
+    import torch
+    from continiousenvironment_follower_leader_b200 import abi
+    from continiousenvironment_follower_leader_b200.rollout import MlpPolicy
+    L = capi.load()
+    torch.manual_seed(0)
+    for n, D, A in ((1000, 240, 2), (131, 48, 1), (4096, 288, 7)):
+        lo, hi = -np.arange(1, A + 1, dtype=np.float32), np.arange(1, A + 1, dtype=np.float32) * 2
+        pol = MlpPolicy(D, lo, hi, seed=1).cuda()
+        with torch.no_grad():
+            for lin in (pol.body[0], pol.body[2], pol.head):
+                lin.bias.normal_(0, 0.3)
+        obs = torch.rand(n, D, device="cuda")
+        noise = torch.randn(n, A, device="cuda")
+        keep = {"w1": pol.body[0].weight.detach().to(torch.bfloat16).contiguous(), "b1": pol.body[0].bias.detach().contiguous(),
+                "w2": pol.body[2].weight.detach().to(torch.bfloat16).contiguous(), "b2": pol.body[2].bias.detach().contiguous(),
+                "w3": pol.head.weight.detach().to(torch.bfloat16).contiguous(), "b3": pol.head.bias.detach().contiguous(),
+                "ns": pol.log_std.detach().exp().contiguous(), "mid": pol.act_mid.contiguous(), "half": pol.act_half.contiguous()}
+        w = abi.FtlMlpWeights(*[keep[k].data_ptr() for k in ("w1", "b1", "w2", "b2", "w3", "b3", "ns", "mid", "half")], D, A)
+        act, val = torch.zeros(n, A, device="cuda"), torch.zeros(n, device="cuda")
+        capi.check(L, L.ftl_policy_mlp(C.byref(w), obs.data_ptr(), D, noise.data_ptr(), n, act.data_ptr(), val.data_ptr(), None),
+                   "ftl_policy_mlp")
+        torch.cuda.synchronize()
+        with torch.no_grad():   # the same arithmetic in float32 on the rounded operands
+            x = obs.to(torch.bfloat16).float()
+            h = torch.tanh(x @ keep["w1"].float().T + keep["b1"]).to(torch.bfloat16).float()
+            h = torch.tanh(h @ keep["w2"].float().T + keep["b2"]).to(torch.bfloat16).float()
+            o = h @ keep["w3"].float().T + keep["b3"]
+            want_a = keep["mid"] + keep["half"] * torch.tanh(o[:, :A] + noise * keep["ns"])
+            want_v = o[:, A]
+        assert torch.allclose(val, want_v, rtol=2e-3, atol=2e-3), float((val - want_v).abs().max())
+        assert torch.allclose(act, want_a, rtol=2e-3, atol=2e-3 * float(hi.max())), float((act - want_a).abs().max())
