@@ -34,7 +34,8 @@ __device__ __forceinline__ void add_stat(double* stats, int which, double v) { a
 // and, for an env that finished and is renewed, the first observation of its next episode.  All 32 lanes of a warp call
 // this together (the exact green-zone scans are warp collectives).
 __device__ __forceinline__ void book_env(const DevCfg& cfg, const DevState& s, const DevOutputs& img_out, const DevOutputs& out,
-                                         double* __restrict__ stats, int n_scenarios, int i) {
+                                         double* __restrict__ stats, int n_scenarios, int i,
+                                         const FrameRec* rec_from = nullptr) {
     const FtlConfig& c = cfg.c;
     Episode e;
     episode_load_book(s, i, e);
@@ -45,7 +46,12 @@ __device__ __forceinline__ void book_env(const DevCfg& cfg, const DevState& s, c
     GreenCache gc;
     green_load(s, i, gc);
     green_cache_hydrate(trail, trail_s, e.trail_len, gc);
-    const FrameRec rec = {s.rec_f + i, s.rec_l + i, s.rec_bits + i, s.rec_lbits + i, (size_t)s.n};
+#ifdef FTL_PF_WINDOW
+    // the window start moves when the trail grows (green_window_update reads trail_s[g_lo - g_unc ...]): ask for that line now
+    if (gc.g_lo - gc.g_unc >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(trail_s + (gc.g_lo - gc.g_unc)));
+#endif
+    // the kinematics' records: where the caller put them (k_kin with the bookkeeping fused: shared memory), else HBM
+    const FrameRec rec = rec_from ? *rec_from : FrameRec{s.rec_f + i, s.rec_l + i, s.rec_bits + i, s.rec_lbits + i, (size_t)s.n};
     const int fps = env_frames(cfg, s, i);
     // the warp's trip count: every lane joins the collectives of the exact scans (fps only differs between envs when the
     // caller passes FtlStepInputs.frames_per_step)

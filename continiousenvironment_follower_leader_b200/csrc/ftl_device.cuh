@@ -40,7 +40,10 @@ static inline int2 make_int2(int x, int y) { return int2{x, y}; }
 static inline int4 make_int4(int x, int y, int z, int w) { return int4{x, y, z, w}; }
 #endif
 
-#if defined(FTL_COUNT_RESCANS) && !defined(__CUDA_ARCH__)
+#if defined(FTL_COUNT_HOOK) && !defined(__CUDA_ARCH__)
+void ftl_count_hook(int k, long long v);   // diagnostic host build only (tools/scan_stats.py): one event per call
+#define FTL_COUNT(k, v) ftl_count_hook(k, v)
+#elif defined(FTL_COUNT_RESCANS) && !defined(__CUDA_ARCH__)
 extern long long g_ftl_counters[8];   // test-only instrumentation (tests/hostsim)
 #define FTL_COUNT(k, v) (g_ftl_counters[k] += (v))
 #else
@@ -561,6 +564,11 @@ FTL_HD int green_lo_exact(const float* trail_d, int n, float max_distance_f32) {
     int lo = n - 1;  // empty
     float acc = 0.f;
     FTL_COUNT(2, 1);
+#if defined(__CUDA_ARCH__) && !defined(FTL_NO_WALK_PREFETCH)
+    // the walk below is a chain of ~20 dependent batches of loads over ~640 bytes: ask for all of its cache lines first,
+    // so that only the first batch pays the DRAM round trip
+    for (int k = n - 1; k > 0 && k > n - 1 - 256; k -= 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(trail_d + k));
+#endif
     // same additions in the same order; the loads are issued eight at a time so that the walk is not one
     // memory round trip per point
     for (int i = n - 2; i >= 0; i -= 8) {
@@ -640,6 +648,9 @@ struct ScanMin { float best; int arg; };
 #ifndef FTL_SCAN_UNROLL
 #define FTL_SCAN_UNROLL 4
 #endif
+#if !defined(FTL_SCAN_WIDE) && !defined(FTL_SCAN_NARROW)
+#define FTL_SCAN_WIDE 8   // measured (profiles/r02_ab_log.txt): k_kin 0.164 -> 0.158 ms
+#endif
 #ifndef FTL_OUTLINE_SCAN   // measured: out of line is 2% slower (k_step 0.2045 -> 0.2091 ms)
 FTL_HD ScanMin warp_scan_min_impl(bool need, const float2* trail, int lo, int hi, float fx, float fy) {
 #else
@@ -662,6 +673,24 @@ FTL_HD_NOINLINE ScanMin warp_scan_min_impl(bool need, const float2* trail, int l
         float best = 3.0e38f;
         int bi = -1;
         int k = bhi - lane;
+#if defined(FTL_SCAN_WIDE)
+        // FTL_SCAN_WIDE loads in flight per lane, predicated, so that a scan of up to 32 * FTL_SCAN_WIDE points is ONE
+        // memory round trip (the unrolled-then-serial loop below pays one per remainder iteration); same visiting order
+        for (; k >= blo; k -= 32 * FTL_SCAN_WIDE) {
+            float2 p[FTL_SCAN_WIDE];
+#pragma unroll
+            for (int u = 0; u < FTL_SCAN_WIDE; u++) {
+                const int kk = k - 32 * u;
+                p[u] = t[kk >= blo ? kk : k];
+            }
+#pragma unroll
+            for (int u = 0; u < FTL_SCAN_WIDE; u++) {
+                const int kk = k - 32 * u;
+                float d2 = d2_f32(p[u].x, p[u].y, bfx, bfy);
+                if (kk >= blo && d2 < best) { best = d2; bi = kk; }
+            }
+        }
+#else
 #if FTL_SCAN_UNROLL > 1
         // several loads in flight per lane (the scan is a chain of DRAM round trips otherwise); same visiting order
         for (; k - 32 * (FTL_SCAN_UNROLL - 1) >= blo; k -= 32 * FTL_SCAN_UNROLL) {
@@ -680,6 +709,7 @@ FTL_HD_NOINLINE ScanMin warp_scan_min_impl(bool need, const float2* trail, int l
             float d2 = d2_f32(p.x, p.y, bfx, bfy);
             if (d2 < best) { best = d2; bi = k; }
         }
+#endif
 #pragma unroll
         for (int off = 16; off; off >>= 1) {
             float ob = __shfl_xor_sync(full, best, off);
@@ -718,6 +748,54 @@ FTL_HD void green_resolve(const DevCfg& cfg, const float* trail_d, int n, GreenC
     gc.g_lo = green_lo_exact_nv(trail_d, n, cfg.max_distance_f32);
     gc.g_unc = 0;
 }
+// The same walk as a warp collective (every lane of the warp calls it; `need` = this lane wants its window resolved).
+// In one lane the walk is a chain of ~20 memory round trips (eight loads each); here the warp loads the newest
+// 32 * kWalkWide segment lengths of the requesting env at once, coalesced, and every lane replays the reference's
+// additions in the reference's order from shuffled values -- same float32 sums, one round trip per 192 points.
+#ifndef FTL_WALK_WIDE
+#define FTL_WALK_WIDE 6
+#endif
+FTL_HD void warp_green_resolve(bool need, const DevCfg& cfg, const float* trail_d, int n, GreenCache& gc) {
+#if defined(__CUDA_ARCH__) && defined(FTL_COOP_WALK)
+    const unsigned full = 0xffffffffu;
+    unsigned pending = __ballot_sync(full, need);
+    if (pending == 0u) return;
+    const int lane = (int)(threadIdx.x & 31);
+    const float maxd = cfg.max_distance_f32;
+    while (pending) {
+        const int src = __ffs((int)pending) - 1;
+        pending &= pending - 1;
+        const float* td = (const float*)(uintptr_t)__shfl_sync(full, (unsigned long long)(uintptr_t)trail_d, src);
+        const int bn = __shfl_sync(full, n, src);
+        int lo = bn - 1;     // green_lo_exact: term t (t = 0, 1, ...) is trail_d[bn - 1 - t], accepted index bn - 2 - t
+        float acc = 0.f;
+        bool done = bn < 2;
+        for (int t0 = 0; !done && t0 <= bn - 2; t0 += 32 * FTL_WALK_WIDE) {
+            float d[FTL_WALK_WIDE];
+#pragma unroll
+            for (int u = 0; u < FTL_WALK_WIDE; u++) {
+                const int idx = bn - 1 - (t0 + 32 * u + lane);
+                d[u] = td[idx > 1 ? idx : 1];
+            }
+#pragma unroll
+            for (int u = 0; u < FTL_WALK_WIDE; u++) {
+                if (done) break;
+                for (int l = 0; l < 32; l++) {
+                    const float v = __shfl_sync(full, d[u], l);
+                    const int t = t0 + 32 * u + l;
+                    if (t > bn - 2) { done = true; break; }
+                    acc = acc + v;
+                    if (acc <= maxd) lo = bn - 2 - t;
+                    else { done = true; break; }
+                }
+            }
+        }
+        if (lane == src) { gc.g_lo = lo; gc.g_unc = 0; }
+    }
+#else
+    if (need) green_resolve(cfg, trail_d, n, gc);
+#endif
+}
 
 // `active` = false: the lane has no frame to evaluate (fewer frames this step than its warp's longest env) and only
 // takes part in the warp's collectives.
@@ -726,7 +804,7 @@ FTL_HD void green_flags(const DevCfg& cfg, const float2* trail, const float* tra
     FTL_COUNT(3, 1);
     const int hi = n - 2;
     // len(green) > 2 ?  (only ambiguous in the first frames of an episode)
-    if (active && gc.g_unc > 0 && hi - gc.g_lo + 1 <= 2 && hi - gc.g_lo + 1 + gc.g_unc > 2) green_resolve(cfg, trail_d, n, gc);
+    warp_green_resolve(active && gc.g_unc > 0 && hi - gc.g_lo + 1 <= 2 && hi - gc.g_lo + 1 + gc.g_unc > 2, cfg, trail_d, n, gc);
     const bool have_green = active && hi - gc.g_lo + 1 > 2;
     int le_eps = 0, le_dev = 0;
     bool need = false;
@@ -745,15 +823,18 @@ FTL_HD void green_flags(const DevCfg& cfg, const float2* trail, const float* tra
     {
         int arg;
         float m = warp_scan_min(need, trail, gc.g_lo, hi, fx, fy, &arg);
+        float m_low = m;   // lower bound material: certain and uncertain points together
         if (need) {
-            float m_low = m;   // lower bound material: certain and uncertain points together
             for (int u = gc.g_lo - gc.g_unc; u < gc.g_lo; u++) {
                 float2 p = trail[u];
                 m_low = fminf(m_low, d2_f32(p.x, p.y, fx, fy));
             }
-            if (m_low < m) {   // an undecided point would be the nearest one: now its membership matters
-                int old_lo = gc.g_lo;
-                green_resolve(cfg, trail_d, n, gc);
+        }
+        const int old_lo = gc.g_lo;
+        const bool resolve = need && m_low < m;   // an undecided point would be the nearest one: now its membership matters
+        warp_green_resolve(resolve, cfg, trail_d, n, gc);
+        if (need) {
+            if (resolve) {
                 for (int u = gc.g_lo; u < old_lo; u++) {
                     float2 p = trail[u];
                     float d2 = d2_f32(p.x, p.y, fx, fy);
@@ -989,6 +1070,56 @@ FTL_HD void tracker_seg_store(const double2* hist, double* seg_d, float* seg_f, 
     seg_f[k & mask] = sqrtf(d2_f32((float)a.x, (float)a.y, (float)b.x, (float)b.y));
 }
 
+#ifndef FTL_INLINE_NPSUM   // measured (profiles/r02_ab_log.txt): k_kin 0.1585 -> 0.1538 ms
+// Compact form of the same sums: inlined in the tracker's trim loop, np_sum's six blocked cases (each unrolled by the
+// compiler), twice, are 145 KB of the step kernel's 300 KB of code -- for a function that runs two or three times per
+// step.  One rolled, out-of-line block sum per type instead; np_sum's splitting is kept literally.
+template <typename T>
+FTL_HD_NOINLINE T ring_block_sum(const T* a, int start, int mask, int n) {   // numpy pairwise_sum for n <= 128, ring-indexed
+    if (n < 8) {
+        T r = 0;
+#pragma unroll 1
+        for (int i = 0; i < n; i++) r += a[(start + i) & mask];
+        return r;
+    }
+    T r0 = a[(start + 0) & mask], r1 = a[(start + 1) & mask], r2 = a[(start + 2) & mask], r3 = a[(start + 3) & mask],
+      r4 = a[(start + 4) & mask], r5 = a[(start + 5) & mask], r6 = a[(start + 6) & mask], r7 = a[(start + 7) & mask];
+    int i;
+#pragma unroll 1
+    for (i = 8; i < n - (n % 8); i += 8) {
+        r0 += a[(start + i) & mask]; r1 += a[(start + i + 1) & mask]; r2 += a[(start + i + 2) & mask]; r3 += a[(start + i + 3) & mask];
+        r4 += a[(start + i + 4) & mask]; r5 += a[(start + i + 5) & mask]; r6 += a[(start + i + 6) & mask]; r7 += a[(start + i + 7) & mask];
+    }
+    T res = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+#pragma unroll 1
+    for (; i < n; i++) res += a[(start + i) & mask];
+    return res;
+}
+template <typename T>
+FTL_HD T ring_np_sum(const T* a, int start, int mask, int n) {   // np_sum over a[(start + k) & mask], k < n <= 512
+    if (n <= 128) return ring_block_sum<T>(a, start, mask, n);
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    T x, y;
+    if (n2 <= 128) x = ring_block_sum<T>(a, start, mask, n2);
+    else { int m = n2 / 2; m -= m % 8; x = ring_block_sum<T>(a, start, mask, m) + ring_block_sum<T>(a, start + m, mask, n2 - m); }
+    int nr = n - n2;
+    if (nr <= 128) y = ring_block_sum<T>(a, start + n2, mask, nr);
+    else { int m = nr / 2; m -= m % 8; y = ring_block_sum<T>(a, start + n2, mask, m) + ring_block_sum<T>(a, start + n2 + m, mask, nr - m); }
+    return x + y;
+}
+FTL_HD bool tracker_len_exceeds(const double* seg_d, const float* seg_f, int tail, int n, int mask, bool f64,
+                                double limit_d, float limit_f) {
+    if (f64) return ring_np_sum<double>(seg_d, tail, mask, n - 1) > limit_d;
+    return ring_np_sum<float>(seg_f, tail, mask, n - 1) > limit_f;
+}
+FTL_HD bool tracker_too_long(const DevCfg& cfg, const Tracker& t, const double* seg_d, const float* seg_f, int cap) {
+    int n = t.ring_head - t.ring_tail;
+    if (n < 2) return false;
+    return tracker_len_exceeds(seg_d, seg_f, t.ring_tail, n, cap - 1, t.ring_tail < t.hist_f64_end, cfg.c.corridor_length,
+                               cfg.corridor_length_f32);
+}
+#else
 FTL_HD bool tracker_too_long(const DevCfg& cfg, const Tracker& t, const double* seg_d, const float* seg_f, int cap) {
     int n = t.ring_head - t.ring_tail;
     if (n < 2) return false;
@@ -1001,6 +1132,8 @@ FTL_HD bool tracker_too_long(const DevCfg& cfg, const Tracker& t, const double* 
         return len > cfg.corridor_length_f32;
     }
 }
+
+#endif
 
 FTL_HD float4 corridor_entry(const DevCfg& cfg, const Tracker& t, const double2* hist, int cap, int ia, int ib,
                              int ianchor) {  // SEN:302-317

@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(FTL_STEP_THREADS, FTL_STEP_MINBLOCKS)
 k_kin(const __grid_constant__ DevCfg cfg, const __grid_constant__ DevState s, const __grid_constant__ DevPool pool,
       const __grid_constant__ DevState img, const __grid_constant__ DevOutputs img_out,
       const void* __restrict__ actions, const __grid_constant__ DevOutputs out, double* __restrict__ stats, int seq,
-      int fused_book) {
+      int fused_book, int rec_in_smem) {
     // k_book, k_rays and k_finish are launched as programmatic dependents of this kernel and of each other: their blocks
     // may start as soon as every block of the kernel in front is running, take the SM resources that finished blocks
     // free, and wait per group of 32 envs on kin_flag / book_flag.
@@ -68,7 +68,19 @@ k_kin(const __grid_constant__ DevCfg cfg, const __grid_constant__ DevState s, co
     decode_action(cfg.c, actions, i, s.n_real, &a0, &a1);
     KinCtx k;
     kin_begin<NB>(cfg, pool, a0, a1, w, e, k);
-    const FrameRec rec = {s.rec_f + i, s.rec_l + i, s.rec_bits + i, s.rec_lbits + i, (size_t)s.n};
+    // per-frame records: in shared memory when the bookkeeping runs in this thread (a record is read back ~0.05 ms after
+    // it was written: from HBM that is a DRAM round trip per frame on the bookkeeping's dependent chain), in HBM for k_book
+    extern __shared__ __align__(16) unsigned char rec_smem[];
+    FrameRec rec = {s.rec_f + i, s.rec_l + i, s.rec_bits + i, s.rec_lbits + i, (size_t)s.n};
+#if FTL_FUSED_BOOK && !defined(FTL_REC_GLOBAL)
+    if (rec_in_smem) {
+        const int T = blockDim.x, F = cfg.c.frames_per_step;
+        float2* rf = reinterpret_cast<float2*>(rec_smem);
+        float2* rl = rf + (size_t)F * T;
+        unsigned char* rb = reinterpret_cast<unsigned char*>(rl + (size_t)F * T);
+        rec = FrameRec{rf + threadIdx.x, rl + threadIdx.x, rb + threadIdx.x, nullptr, (size_t)T};
+    }
+#endif
     const int fps = env_frames(cfg, s, i);
     kin_frames<NB>(cfg, pool, i, w, e, k, rec, e.step_count, 0, fps, fps, env_draws(cfg, s, i));
     Tracker t;
@@ -83,10 +95,10 @@ k_kin(const __grid_constant__ DevCfg cfg, const __grid_constant__ DevState s, co
     // group's state
     publish_group_flag(s.kin_flag, i >> 5, seq);
 #if FTL_FUSED_BOOK   // the bookkeeping in the same thread instead of k_book (build option, A/B in profiles/r02_ab_log.txt)
-    book_env(cfg, s, img_out, out, stats, pool.n_scenarios, i);
+    book_env(cfg, s, img_out, out, stats, pool.n_scenarios, i, &rec);
     publish_group_flag(s.book_flag, i >> 5, seq);
 #else
-    (void)fused_book; (void)stats;
+    (void)fused_book; (void)stats; (void)rec_in_smem;
 #endif
 }
 
@@ -121,7 +133,12 @@ void FTL_CAT(ftl_launch_kin_nb, FTL_NB)(const DevCfg& cfg, const DevState& s, co
     int threads = FTL_STEP_THREADS;
 #endif
     int blocks = (s.n + threads - 1) / threads;
-    k_kin<FTL_NB><<<blocks, threads, 0, st>>>(cfg, s, pool, img, img_out, actions, out, stats, seq, fused_book);
+    // 17 bytes of record per frame and env; shared memory while that stays small (the ray blocks that move in beside
+    // this kernel's last blocks need theirs), HBM otherwise
+    size_t rec_bytes = (size_t)17 * cfg.c.frames_per_step * threads;
+    const int rec_in_smem = (FTL_FUSED_BOOK && fused_book && rec_bytes <= 16 * 1024) ? 1 : 0;
+    k_kin<FTL_NB><<<blocks, threads, rec_in_smem ? rec_bytes : 0, st>>>(cfg, s, pool, img, img_out, actions, out, stats, seq,
+                                                                        fused_book, rec_in_smem);
 }
 void FTL_CAT(ftl_launch_reset_nb, FTL_NB)(const DevCfg& cfg, const DevState& s, const DevPool& pool, const uint8_t* mask,
                                            const int* ids, const DevOutputs& out, int reset_filler, cudaStream_t st) {
