@@ -158,6 +158,15 @@ class FtlBatchEnv:
         """step() without building the python-side views (what bench.py times)."""
         capi.check(self._L, self._L.ftl_step(self._h, actions.data_ptr(), C.byref(self._out), self._stream()), "ftl_step")
 
+    def render(self, first=0, n=1, scale=4):
+        """rgb_array frames of envs [first, first + n) as a uint8 device tensor [n, H, W, 3] (ftl_render, ENV:1196-1302;
+        H = ceil(game_height / scale)): a debugging / video view drawn from the state on the device."""
+        W, H = -(-self.cfg.game_width // scale), -(-self.cfg.game_height // scale)
+        img = torch.empty((n, H, W, 3), dtype=torch.uint8, device=self.device)
+        capi.check(self._L, self._L.ftl_render(self._h, int(first), int(n), int(scale), img.data_ptr(), self._stream()),
+                   "ftl_render")
+        return img
+
     # ---- state / statistics ----------------------------------------------------------------------------
     def get_state(self, first=0, n=None):
         n = self.n - first if n is None else n

@@ -52,6 +52,8 @@ SIGNATURES = {
     "ftl_get_state": ([_vp, _i32, _i32, C.POINTER(abi.FtlStateBuffers)], C.c_int),
     "ftl_set_state": ([_vp, _i32, _i32, C.POINTER(abi.FtlStateBuffers)], C.c_int),
     "ftl_stats": ([_vp, _vp, _i32, _vp], C.c_int),
+    "ftl_render": ([_vp, _i32, _i32, _i32, _vp, _vp], C.c_int),
+    "ftl_render_host": ([_vp, _i32, _i32, _i32, _vp], C.c_int),
     "ftl_launch_count": ([_vp], _i64),
     "ftl_profile": ([_vp, _i32], C.c_int),
     "ftl_profile_read": ([_vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i64)], C.c_int),
@@ -249,6 +251,14 @@ class HostEnv:
     def step_wait(self):
         check(self._L, self._L.ftl_step_host_wait(self._h), "ftl_step_host_wait")
         return self.out
+
+    def render(self, first=0, n=None, scale=1):
+        """rgb_array of envs [first, first + n): uint8 [n, H, W, 3], H = ceil(game_height / scale) (ftl_render_host)."""
+        n = self.n - first if n is None else n
+        W, H = -(-self.cfg.game_width // scale), -(-self.cfg.game_height // scale)
+        img = np.zeros((n, H, W, 3), np.uint8)
+        check(self._L, self._L.ftl_render_host(self._h, int(first), int(n), int(scale), abi.ptr(img)), "ftl_render_host")
+        return img
 
     def get_state(self, first=0, n=None):
         n = self.n - first if n is None else n

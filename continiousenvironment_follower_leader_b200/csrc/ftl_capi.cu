@@ -992,6 +992,160 @@ int ftl_set_state(ftl_handle h, int32_t first, int32_t count, const FtlStateBuff
     return FTL_OK;
 }
 
+// ---- rgb_array rasteriser (Game.render / _show_tick, ENV:1196-1302) -----------------------
+// One thread per output pixel, one block per 16 x 16 tile of one env's image; the primitives are read straight from the
+// SoA state (broadcast loads: every thread of a block walks the same lists).  Layer order as _show_tick: background, the
+// leader's route + finish point, the green zone, the min-distance ring, the objects (hit boxes instead of sprites: the
+// image files are not part of the simulator), the tracker's history and corridor (LeaderPositionsTracker_v2.show,
+// SEN:329-339), the current target ring.  Text is not drawn.
+namespace {
+struct Rgb { unsigned char r, g, b; };
+__device__ __forceinline__ float seg_dist2(float px, float py, float ax, float ay, float bx, float by) {
+    const float vx = bx - ax, vy = by - ay, wx = px - ax, wy = py - ay;
+    const float vv = vx * vx + vy * vy;
+    float t = vv > 0.f ? (wx * vx + wy * vy) / vv : 0.f;
+    t = fminf(fmaxf(t, 0.f), 1.f);
+    const float dx = wx - t * vx, dy = wy - t * vy;
+    return dx * dx + dy * dy;
+}
+__device__ __forceinline__ bool in_rect(float px, float py, int4 q) {   // pygame.Rect: [x, x + w) x [y, y + h)
+    return px >= (float)q.x && px < (float)(q.x + q.z) && py >= (float)q.y && py < (float)(q.y + q.w);
+}
+
+__global__ void __launch_bounds__(256)
+k_render(const __grid_constant__ DevCfg cfg, const DevState s, const DevPool pool, int first, int scale, int W, int H,
+         unsigned char* __restrict__ rgb) {
+    const FtlConfig& c = cfg.c;
+    const int env = first + blockIdx.z;
+    const int x = blockIdx.x * 16 + (threadIdx.x & 15), y = blockIdx.y * 16 + (threadIdx.x >> 4);
+    if (x >= W || y >= H) return;
+    const float px = ((float)x + 0.5f) * (float)scale, py = ((float)y + 0.5f) * (float)scale;   // world coordinates
+    const float thin = 0.5f * (float)scale;   // half width of a one-pixel line, in world units
+    const size_t n = s.n;
+    const int scen = s.gi[(size_t)GI_SCENARIO * n + env], trail_len = s.gi[(size_t)GI_TRAIL_LEN * n + env];
+    const int flags = s.gi[(size_t)GI_FLAGS * n + env];
+    Rgb col = {255, 255, 255};
+    const Rgb red = {255, 0, 0}, green = {0, 255, 0}, gray = {30, 30, 30}, blue = {0, 0, 255};
+    // (1) the leader's route (show_leader_path_flag) and its finish point, ENV:1233-1238
+    const int n_route = pool.n_route[scen];
+    const int2* route = pool.route + (size_t)scen * c.route_cap;
+    if (n_route > 2) {
+        for (int k = 0; k + 1 < n_route; k++) {
+            const int2 a = route[k], b = route[k + 1];
+            if (seg_dist2(px, py, (float)a.x, (float)a.y, (float)b.x, (float)b.y) <= thin * thin) { col = red; break; }
+        }
+    }
+    if (n_route > 0) {
+        const int2 f = route[n_route - 1];
+        const float dx = px - (float)f.x, dy = py - (float)f.y, r = fmaxf(5.f, thin);
+        if (dx * dx + dy * dy <= r * r) col = red;
+    }
+    // (2) the green zone: a disc of radius max_dev around every green trail point, ENV:1246-1250 (the points whose
+    //     membership the step kernel left undecided -- at most a handful at the window's far end -- are drawn too)
+    {
+        const float2* trail = s.trail + (size_t)env * c.trail_cap;
+        const int g_lo = s.gi[(size_t)GI_G_LO * n + env] - s.gi[(size_t)GI_G_UNC * n + env], hi = trail_len - 2;
+        if (hi - g_lo + 1 > 5) {
+            const float r2 = cfg.dev_f32 * cfg.dev_f32;
+            for (int k = g_lo < 0 ? 0 : g_lo; k <= hi; k++) {
+                const float2 p = trail[k];
+                const float dx = px - p.x, dy = py - p.y;
+                if (dx * dx + dy * dy <= r2) { col = green; break; }
+            }
+        }
+    }
+    // (3) the min-distance ring around the leader, two pixels wide while the follower is too close, ENV:1251-1259
+    const float2 lp = s.pos[(size_t)1 * n + env];
+    {
+        const float d = sqrtf((px - lp.x) * (px - lp.x) + (py - lp.y) * (py - lp.y));
+        const float half = ((flags & FL_TOO_CLOSE) ? 2.f : 1.f) * thin;
+        if (fabsf(d - (float)c.min_distance) <= half) col = red;
+    }
+    // (4) objects, ENV:1266-1272: static obstacles, then leader, follower, bears (their integer hit boxes)
+    {
+        const int4* statics = pool.static_rects + (size_t)scen * c.static_cap;
+        const int n_static = pool.n_static[scen];
+        for (int k = 0; k < n_static; k++)
+            if (in_rect(px, py, statics[k])) { col = gray; break; }
+        if (in_rect(px, py, s.rect[(size_t)1 * n + env])) col = blue;
+        if (in_rect(px, py, s.rect[(size_t)0 * n + env])) col = Rgb{255, 140, 0};
+        for (int b = 0; b < s.n_bears; b++)
+            if (in_rect(px, py, s.rect[(size_t)(2 + b) * n + env])) col = Rgb{139, 69, 19};
+    }
+    // (5) the tracker: history points and the corridor's two walls + end caps, SEN:329-339
+    if (c.tracker_enabled) {
+        const int tail = s.gi[(size_t)GI_RING_TAIL * n + env], head = s.gi[(size_t)GI_RING_HEAD * n + env];
+        const int mask = c.corridor_cap - 1;
+        const double2* hist = s.hist + (size_t)env * c.corridor_cap;
+        const float4* corr = s.corridor + (size_t)env * c.corridor_cap;
+        const float rp = fmaxf(3.f, thin), hw = fmaxf(1.5f, thin);
+        bool wall = false, point = false;
+        for (int k = tail; k < head && !point; k++) {
+            const double2 h = hist[k & mask];
+            const float dx = px - (float)h.x, dy = py - (float)h.y;
+            point = dx * dx + dy * dy <= rp * rp;
+        }
+        if (head - tail > 1) {
+            for (int k = tail; k + 1 < head && !wall; k++) {
+                const float4 a = corr[k & mask], b = corr[(k + 1) & mask];
+                wall = seg_dist2(px, py, a.x, a.y, b.x, b.y) <= hw * hw || seg_dist2(px, py, a.z, a.w, b.z, b.w) <= hw * hw;
+            }
+            const float4 a = corr[tail & mask], b = corr[(head - 1) & mask];
+            wall = wall || seg_dist2(px, py, a.x, a.y, a.z, a.w) <= hw * hw || seg_dist2(px, py, b.x, b.y, b.z, b.w) <= hw * hw;
+        }
+        if (point) col = Rgb{80, 10, 10};
+        if (wall) col = Rgb{150, 120, 50};
+    }
+    // (6) the leader's current target: a ring of radius 10, two pixels wide, ENV:1279
+    {
+        int tid = s.gi[(size_t)GI_TARGET_ID * n + env];
+        tid = tid < n_route ? tid : n_route - 1;
+        if (tid >= 0) {
+            const int2 t = route[tid];
+            const float d = sqrtf((px - (float)t.x) * (px - (float)t.x) + (py - (float)t.y) * (py - (float)t.y));
+            if (fabsf(d - 10.f) <= fmaxf(1.f, thin)) col = red;
+        }
+    }
+    unsigned char* o = rgb + (((size_t)blockIdx.z * H + y) * W + x) * 3;
+    o[0] = col.r; o[1] = col.g; o[2] = col.b;
+}
+}  // namespace
+
+int ftl_render(ftl_handle h, int32_t first, int32_t count, int32_t scale, uint8_t* rgb_dev, void* cuda_stream) {
+    if (!h || !rgb_dev) return fail(FTL_ERR_INVALID, "NULL argument");
+    if (first < 0 || count < 0 || first + count > h->n) return fail(FTL_ERR_INVALID, "env range out of bounds");
+    if (scale < 1) return fail(FTL_ERR_INVALID, "scale must be >= 1");
+    if (!h->have_pool || !h->was_reset) return fail(FTL_ERR_STATE, "ftl_render needs an uploaded scenario pool and a reset");
+    if (count == 0) return FTL_OK;
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    int rc = flush_pending_resets(h, st);   // a finished env is drawn as the first frame of its next episode
+    if (rc) return rc;
+    const int W = (h->cfg.c.game_width + scale - 1) / scale, H = (h->cfg.c.game_height + scale - 1) / scale;
+    k_render<<<dim3((W + 15) / 16, (H + 15) / 16, count), 256, 0, st>>>(h->cfg, h->st, h->pool, first, scale, W, H, rgb_dev);
+    h->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return FTL_OK;
+}
+
+int ftl_render_host(ftl_handle h, int32_t first, int32_t count, int32_t scale, uint8_t* rgb_host) {
+    if (!h || !rgb_host) return fail(FTL_ERR_INVALID, "NULL argument");
+    if (scale < 1) return fail(FTL_ERR_INVALID, "scale must be >= 1");
+    if (count <= 0) return count == 0 ? FTL_OK : fail(FTL_ERR_INVALID, "env range out of bounds");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t W = (h->cfg.c.game_width + scale - 1) / scale, H = (h->cfg.c.game_height + scale - 1) / scale;
+    const size_t bytes = W * H * 3 * (size_t)count;
+    uint8_t* d = nullptr;
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMalloc((void**)&d, bytes));
+    int rc = ftl_render(h, first, count, scale, d, nullptr);
+    cudaError_t e = rc == FTL_OK ? cudaMemcpy(rgb_host, d, bytes, cudaMemcpyDeviceToHost) : cudaSuccess;
+    cudaFree(d);
+    if (rc) return rc;
+    CUDA_TRY(e);
+    return FTL_OK;
+}
+
 int ftl_stats(ftl_handle h, double* stats_dev, int32_t reset_after, void* cuda_stream) {
     if (!h || !stats_dev) return fail(FTL_ERR_INVALID, "NULL argument");
     CUDA_TRY(cudaSetDevice(h->device));

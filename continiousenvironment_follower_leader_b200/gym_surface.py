@@ -202,8 +202,16 @@ class Game(Env):
         self.done = bool(out.done[0])
         return self._obs(out), float(out.reward[0]), self.done, info
 
-    def render(self, *a, **k):
-        raise NotImplementedError("rendering needs pygame and is outside the accelerated path (SURVEY.md section 2, row 13)")
+    def render(self, mode="rgb_array", scale=1, **kwargs):
+        """ENV:1196-1202 with ``return_render_matrix=True``: the frame as uint8 [game_height, game_width, 3] (the layout
+        of ``np.transpose(surfarray.array3d(display), (1, 0, 2))``), rasterised on the device by ``ftl_render`` -- the
+        layers and colours of ``_show_tick`` (ENV:1229-1302) with hit boxes instead of sprites and without the text
+        lines.  There is no window: ``mode="human"`` raises."""
+        if mode != "rgb_array":
+            raise NotImplementedError("only mode='rgb_array' is rendered (no pygame window in the accelerated path)")
+        if self._env is None:
+            raise RuntimeError("render() before reset()")
+        return self._env.render(0, 1, scale=scale)[0]
 
     def close(self):
         if self._env is not None:

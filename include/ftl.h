@@ -332,6 +332,17 @@ void* ftl_host_stream(ftl_handle h);
 int ftl_get_state(ftl_handle h, int32_t first_env, int32_t n, const FtlStateBuffers* host_out);
 int ftl_set_state(ftl_handle h, int32_t first_env, int32_t n, const FtlStateBuffers* host_in);
 
+/* ---- rgb_array: Game.render(return_render_matrix=True), ENV:1196-1202 / _show_tick ENV:1229-1302 -------------------
+ * Rasterises envs [first_env, first_env + n) on the device: rgb_dev is uint8 [n][H][W][3] (row-major, the layout of
+ * np.transpose(surfarray.array3d(display), (1, 0, 2))) with W = ceil(game_width / scale), H = ceil(game_height / scale);
+ * scale = 1 is the reference's resolution, larger values sample every scale-th world pixel.  Layers and colours follow
+ * _show_tick (route and finish point, green zone discs, min-distance ring, objects, tracker history and corridor,
+ * current target ring); objects are drawn as their integer hit boxes instead of the sprite images and no text is drawn,
+ * so the picture is a debugging view, not a pixel copy of pygame's. */
+int ftl_render(ftl_handle h, int32_t first_env, int32_t n, int32_t scale, uint8_t* rgb_dev, void* cuda_stream);
+/* The same into a host buffer (synchronous; what gym_surface.Game.render("rgb_array") calls). */
+int ftl_render_host(ftl_handle h, int32_t first_env, int32_t n, int32_t scale, uint8_t* rgb_host);
+
 /* ---- statistics -------------------------------------------------------------------------------- */
 /* Copies the FTL_STAT_COUNT running sums (double) to stats_dev; optionally zeroes them. */
 int ftl_stats(ftl_handle h, double* stats_dev, int32_t reset_after, void* cuda_stream);

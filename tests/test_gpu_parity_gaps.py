@@ -327,3 +327,51 @@ def test_fused_policy_kernel_against_torch():
             want_v = o[:, A]
         assert torch.allclose(val, want_v, rtol=2e-3, atol=2e-3), float((val - want_v).abs().max())
         assert torch.allclose(act, want_a, rtol=2e-3, atol=2e-3 * float(hi.max())), float((act - want_a).abs().max())
+
+
+def test_rgb_array_rasteriser_against_its_numpy_specification():
+    """ftl_render / ftl_render_host (ENV:1196-1302) against tests/render_ref.py on envs in mid-episode: every pixel equal,
+    except where a float32 distance sits on a boundary (a handful per frame) and inside the discs of the few trail points
+    whose green-zone membership the step kernel leaves undecided."""
+    import torch
+    import render_ref
+    from continiousenvironment_follower_leader_b200.batch_env import FtlBatchEnv
+    gc = GameConfig(bear_number=1, follower_sensors=cfg3_sensors(), auto_reset=True)
+    pool = synthetic_pool(gc, 16, seed=4)
+    n = 64
+    env = FtlBatchEnv(n, game_config=gc, scenario_pool=pool)
+    env.reset()
+    rng = np.random.default_rng(0)
+    lo, hi = gc.action_bounds()
+    for _ in range(70):
+        env.step(torch.as_tensor(rng.uniform(lo, hi, size=(n, 2)).astype(np.float32), device="cuda"))
+    st = env.get_state()
+    for scale in (4, 3):
+        img = env.render(first=0, n=8, scale=scale).cpu().numpy()
+        assert img.shape == (8, -(-gc.c.game_height // scale), -(-gc.c.game_width // scale), 3) and img.dtype == np.uint8
+        for k in range(8):
+            want, maybe_green = render_ref.render_env(gc.c, pool, st.env[k], st.trail[k], st.hist[k], st.corridor[k], scale)
+            diff = (img[k] != want).any(axis=2)
+            green_extra = diff & maybe_green & (img[k] == (0, 255, 0)).all(axis=2)
+            bad = diff & ~green_extra
+            assert bad.sum() <= 1e-3 * bad.size, "env %d scale %d: %d of %d pixels differ" % (k, scale, bad.sum(), bad.size)
+            # what the picture is for: the follower's hit box is where the state says, in its colour
+            r = st.env[k]["follower"]["rect"]
+            cx, cy = (r[0] + r[2] // 2) // scale, (r[1] + r[3] // 2) // scale
+            if 0 <= cx < img.shape[2] and 0 <= cy < img.shape[1] and r[2] >= 2 * scale and r[3] >= 2 * scale:
+                assert tuple(img[k, cy, cx]) in ((255, 140, 0), (139, 69, 19), (80, 10, 10), (150, 120, 50), (255, 0, 0))
+            assert (img[k] == 255).all(axis=2).mean() > 0.3      # mostly background
+    env.close()
+    # the host entry point behind gym_surface.Game.render("rgb_array"): full resolution, same picture as the device one
+    host = capi.HostEnv(gc, 2, lib=capi.load())
+    host.upload_scenarios(pool)
+    host.reset(scenario_ids=np.array([1, 2], np.int32))
+    for _ in range(5):
+        host.step(rng.uniform(lo, hi, size=(2, 2)).astype(np.float32))
+    full = host.render(0, 2, scale=1)
+    assert full.shape == (2, gc.c.game_height, gc.c.game_width, 3)
+    hs = host.get_state()
+    want, maybe_green = render_ref.render_env(gc.c, pool, hs.env[0], hs.trail[0], hs.hist[0], hs.corridor[0], 1)
+    bad = (full[0] != want).any(axis=2) & ~maybe_green
+    assert bad.sum() <= 1e-3 * bad.size
+    host.close()
