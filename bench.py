@@ -53,7 +53,7 @@ from continiousenvironment_follower_leader_b200.scenario import ScenarioPool, sy
 
 METRIC = "env-steps/sec (device-timed, whole box)"
 UNIT = "env-steps/s"
-TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r02_traffic.json")
+TRAFFIC_FILES = [os.path.join(ROOT, "profiles", f) for f in ("r02b_traffic.json", "r02_traffic.json")]   # newest capture first
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -121,10 +121,12 @@ def algorithmic_bytes(gc):
 
 def measured_traffic():
     """Per-launch DRAM bytes / warp instructions of each kernel from the committed ncu --set full capture."""
-    try:
-        return json.load(open(TRAFFIC_FILE))
-    except Exception:
-        return {}
+    for f in TRAFFIC_FILES:
+        try:
+            return json.load(open(f))
+        except Exception:
+            continue
+    return {}
 
 
 def measured_peaks():
@@ -463,9 +465,11 @@ def rollout_leg(job, n, steps, horizon=16):
     ro.close()
     return {"value": job.world * n * rounds * horizon / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / (rounds * horizon),
             "steps": rounds * horizon, "host_copies_per_step": 0,
-            "api": "rollout.DeviceRollout.collect: MlpPolicy (240 -> 128 -> 128 -> 2 + value, torch, TF32 GEMMs, one CUDA graph "
-                   "per ring slot) reads the fused sensorPrev matrix in place and writes actions into the row ftl_step "
-                   "consumes; ftl_step writes reward/done into the rings; observations archived as bfloat16"}
+            "api": "rollout.DeviceRollout.collect: MlpPolicy (240 -> 128 -> 128 -> 2 + value) as ONE fused kernel of libftl.so "
+                   "(ftl_policy_mlp: bfloat16 mma.sync, cp.async staging, activations in registers) reads the fused sensorPrev "
+                   "matrix in place and writes actions into the row ftl_step consumes; ftl_step writes the next observation, "
+                   "reward and done into the trajectory rings; 4 kernel launches per step, no copies",
+            "policy_kernel": "k_policy_mlp"}
 
 
 def main():
