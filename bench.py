@@ -285,7 +285,19 @@ class Job:
         self.dev = torch.device("cuda", self.local_rank)
         if self.world > 1:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-            dist.init_process_group("nccl", device_id=self.dev)
+            # NCCL prints its version banner on stdout when the communicator is made: keep stdout for the one JSON line
+            sys.stdout.flush()
+            saved = os.dup(1)
+            os.dup2(2, 1)
+            try:
+                dist.init_process_group("nccl", device_id=self.dev)
+                t = torch.zeros(1, device=self.dev)
+                dist.all_reduce(t)
+                torch.cuda.synchronize(self.dev)
+            finally:
+                sys.stdout.flush()
+                os.dup2(saved, 1)
+                os.close(saved)
 
     def barrier(self):
         self.torch.cuda.synchronize(self.dev)
@@ -444,14 +456,16 @@ def e2e_leg(job, gc, pool, n, actions, steps):
             "numa_binding": {k: v for k, v in binding.items() if k != "cpus"}}
 
 
-def rollout_leg(job, n, steps, horizon=16):
-    """Device-resident consumer: rollout.DeviceRollout on the cfg3 workload with the fused sensorPrev output."""
+def rollout_leg(job, n, steps, horizon=16, settle=160):
+    """Device-resident consumer: rollout.DeviceRollout on the cfg3 workload with the fused sensorPrev output.  `settle` =
+    untimed steps since the common reset before the timed ones: the same window of episode ages as the device-timed
+    value (the step time of this workload swings by a few percent with the 501-step episode limit)."""
     from continiousenvironment_follower_leader_b200.rollout import DeviceRollout
     torch = job.torch
     gc = workload_config(True, fused_sensor_prev=True)
     pool, _ = workload_pool(gc)
     ro = DeviceRollout(n, horizon, game_config=gc, scenario_pool=pool, device=job.dev, env_id_base=job.rank * n)
-    for _ in range(max(1, 160 // horizon)):   # settle + warm-up
+    for _ in range(max(1, settle // horizon)):   # settle + warm-up
         ro.collect()
     rounds = max(1, steps // horizon)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -530,7 +544,8 @@ def main():
         e2e = e2e_leg(job, gc, pool, n, actions, args.e2e_steps)
     rollout = None
     if args.rollout_steps > 0 and args.config == "cfg3":
-        rollout = rollout_leg(job, n, args.rollout_steps)
+        # same window of step indices since the common reset as the device-timed value above
+        rollout = rollout_leg(job, n, max(args.rollout_steps, min(args.steps, 256)), settle=args.settle + args.warmup)
         rollout["frac_of_value"] = rollout["value"] / value
 
     if rank == 0:
