@@ -44,6 +44,7 @@ def build(force=False, verbose=False, ptxas_info=False):
         jobs.append(("ftl_step_nb.cu", os.path.join(objdir, "ftl_step_nb%d.o" % nb), ["-DFTL_NB=%d" % nb] + extra_v))
     jobs.append(("ftl_capi.cu", os.path.join(objdir, "ftl_capi.o"), extra_v))
     jobs.append(("ftl_policy.cu", os.path.join(objdir, "ftl_policy.o"), extra_v))   # the rollout's fused policy kernel
+    jobs.append(("ftl_policy_tc.cu", os.path.join(objdir, "ftl_policy_tc.o"), extra_v))   # ... on tcgen05 / tensor memory
     jobs.append(("ftl_scenario_gen.cpp", os.path.join(objdir, "ftl_scenario_gen.o"), []))   # host-only C++
     todo = [j for j in jobs if force or _mtime(j[1]) < max(hdr_time, _mtime(os.path.join(CSRC, j[0])))]
     logs = []

@@ -5,31 +5,40 @@
 // ~0.09 ms per step -- a quarter of the simulator's own step -- and they are serial with it by data dependence.  Here:
 //   * one persistent block per SM keeps the three weight matrices in shared memory (bfloat16, ~100 KB, rows padded by
 //     16 bytes so that ldmatrix is conflict-free);
-//   * every warp owns tiles of 16 observation rows end to end, so there is no block barrier after the prologue: the rows
-//     arrive as float32 through cp.async (coalesced 16-byte chunks, no registers) into the warp's private staging slab,
-//     are converted to bfloat16 A fragments on the fly, and the next tile's copy is issued as soon as layer 1 has read
-//     the slab -- layer 2 and the head of this tile run while it is in flight, and the other warps of the SM cover the rest;
-//   * the three layers run on the tensor cores (mma.sync m16n8k16, bfloat16 operands, float32 accumulators; B fragments by
-//     ldmatrix.x4); the hidden activations never leave the registers -- the accumulator fragment of one layer, after bias +
-//     tanh + bfloat16 rounding, IS the A fragment of the next;
+//   * every warp owns tiles of 16 observation rows end to end, so there is no block barrier after the prologue.  The
+//     rows are read as float4 (coalesced, eight loads in flight per lane), rounded to bfloat16 and parked in the warp's
+//     private slab [16][max(obs_dim, 128) + 8]; at 7.9 KB per slab SIXTEEN warps fit beside the weights (a float32 slab filled by
+//     cp.async allowed eight: the kernel was latency-bound at two warps per scheduler, 0.039 ms), and the other warps'
+//     tensor-core work covers a warp's loads;
+//   * the three layers run on the tensor cores (mma.sync m16n8k16, bfloat16 operands, float32 accumulators; A and B
+//     fragments by ldmatrix.x4); a layer's activations (bias + tanh.approx + bfloat16 rounding) go back into the slab,
+//     which is the next layer's A operand;
 //   * the epilogue writes the action (mid + half * tanh(mu + noise * scale)) straight into the row ftl_step consumes, plus
 //     the value.
+// mma.sync runs on the legacy HMMA path of sm_100 (measured: ~10.6 cycles of tensor pipe per HMMA.16816 and SM
+// sub-partition, a floor of 14 us for this shape; 37-39 us whatever the number of warps).  ftl_policy_tc.cu is the same
+// network on tcgen05 / tensor memory (33.5 us) and is what ftl_policy_mlp launches whenever the shape fits it
+// (obs_dim <= 256); this kernel serves the rest (and FTL_POLICY_IMPL=mma).
 // Build: part of libftl.so (nvcc -gencode arch=compute_100a,code=sm_100a).
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <string>
 
 #include "../../include/ftl.h"
 
 void ftl_set_error_message(const char* msg);
+int ftl_policy_mlp_tc_launch(const FtlMlpWeights* w, const float* obs_dev, int32_t obs_stride, const float* noise_dev, int32_t n,
+                             float* actions_dev, float* values_dev, cudaStream_t stream);   // ftl_policy_tc.cu
 
 namespace {
 
 constexpr int kHid = 128;          // hidden width of both layers
-constexpr int kWarps = 8;          // warps per block (fewer when obs_dim is so large that eight slabs do not fit); each owns 16-row tiles
+constexpr int kWarps = 16;         // warps per block (fewer when obs_dim is so large that the slabs do not fit); each owns 16-row tiles
 constexpr int kHidStride = kHid + 8;   // bf16 elements per shared-memory row of W2 / W3 (16 bytes of padding)
+constexpr int kStageBatch = 8;     // float4 loads in flight per lane while a tile is staged
 
 __device__ __forceinline__ void mma_bf16(float c[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -43,6 +52,10 @@ __device__ __forceinline__ void ldmatrix_x4(uint32_t& r0, uint32_t& r1, uint32_t
 }
 __device__ __forceinline__ void ldmatrix_x2(uint32_t& r0, uint32_t& r1, uint32_t a) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(a));
+}
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts64(uint32_t a, uint32_t v0, uint32_t v1) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a), "r"(v0), "r"(v1) : "memory");
 }
 __device__ __forceinline__ void cp_async16(uint32_t a, const void* gptr) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a), "l"(gptr) : "memory");
@@ -73,19 +86,33 @@ __device__ __forceinline__ void copy_rows_async(__nv_bfloat16* dst, int dst_stri
     }
 }
 
-// the warp's next tile of 16 observation rows -> its float32 staging slab [16][D + 8]: row by row, lane l copies the
-// 16-byte chunks l, l + 32, ... of the row (coalesced); rows past the end of the batch repeat the last one
-__device__ __forceinline__ void stage_rows_async(uint32_t slab_lane, int slab_stride_bytes, const float* obs, int obs_stride, int row0,
-                                                 int n, int per_row, int lane) {
+// a tile of 16 observation rows -> the warp's bfloat16 slab [16][xs]: the tile is walked as 16 * per_row chunks of four
+// floats (chunk q = row q / per_row, column 4 * (q % per_row)), lane l takes chunks l, l + 32, ...: consecutive lanes read
+// consecutive 16 bytes.  Rows past the end of the batch repeat the last one (their results are never written).
+__device__ __forceinline__ void stage_rows(uint32_t slab, int xs, const float* obs, int obs_stride, int row0, int n, int per_row,
+                                           int lane) {
     const int last = n - 1 - row0;     // >= 0
-    const float* src = obs + (size_t)row0 * obs_stride + lane * 4;
+    const int total = 16 * per_row;
+    int r = 0, c = lane;               // chunk `lane`
+    while (c >= per_row) { c -= per_row; r++; }
+    const int dr = 32 / per_row, dc = 32 - dr * per_row;
+    for (int q0 = lane; q0 < total; q0 += 32 * kStageBatch) {
+        float4 v[kStageBatch];
+        uint32_t dst[kStageBatch];
 #pragma unroll
-    for (int r = 0; r < 16; r++) {
-        const float* s = src + (size_t)(r < last ? r : last) * obs_stride;
-        const uint32_t d = slab_lane + r * slab_stride_bytes;
-        for (int c = lane, o = 0; c < per_row; c += 32, o += 128) cp_async16(d + o * 4, s + o);
+        for (int u = 0; u < kStageBatch; u++) {
+            const bool live = q0 + 32 * u < total;
+            const int rr = r < last ? r : last;
+            dst[u] = live ? slab + (uint32_t)(r * xs + c * 4) * 2 : 0xffffffffu;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live) v[u] = __ldg(reinterpret_cast<const float4*>(obs + (size_t)(row0 + rr) * obs_stride + c * 4));
+            r += dr; c += dc;
+            if (c >= per_row) { c -= per_row; r++; }
+        }
+#pragma unroll
+        for (int u = 0; u < kStageBatch; u++)
+            if (dst[u] != 0xffffffffu) sts64(dst[u], pack_bf16(v[u].x, v[u].y), pack_bf16(v[u].z, v[u].w));
     }
-    cp_async_commit();
 }
 
 __global__ void __launch_bounds__(32 * kWarps, 1)
@@ -93,23 +120,27 @@ k_policy_mlp(const FtlMlpWeights w, const float* __restrict__ obs, const float* 
              float* __restrict__ actions, float* __restrict__ values, int obs_stride) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int D = w.obs_dim, xs = D + 8;
+    const int ss = (D > kHid ? D : kHid) + 8;   // slab row stride: the slab also holds the 128 hidden activations of a row
     __nv_bfloat16* W1 = reinterpret_cast<__nv_bfloat16*>(smem);                 // [128][xs]
     __nv_bfloat16* W2 = W1 + (size_t)kHid * xs;                                 // [128][136]
     __nv_bfloat16* W3 = W2 + (size_t)kHid * kHidStride;                         // [8][136]
     float* B1 = reinterpret_cast<float*>(W3 + (size_t)8 * kHidStride);          // [128], [128], [8]
     float* B2 = B1 + kHid;
     float* B3 = B2 + kHid;
-    float* slabs = B3 + 8;                                                      // kWarps x [16][xs] float32
+    __nv_bfloat16* slabs = reinterpret_cast<__nv_bfloat16*>(B3 + 8);            // n_warps x [16][ss] bfloat16
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const int n_out = w.act_dim + 1;
-    float* slab = slabs + (size_t)warp * 16 * xs;
-    const uint32_t slab_lane = smem_addr(slab + lane * 4);
+    const int n_warps = blockDim.x >> 5;
+    const uint32_t slab = smem_addr(slabs + (size_t)warp * 16 * ss);
     const int per_row = D / 4;
-    // per-lane ldmatrix addresses of the B fragments: lanes 0-7 / 8-15 / 16-23 / 24-31 address the rows of the four 8x8
-    // matrices (column tile nt at k0, nt at k0 + 8, nt + 1 at k0, nt + 1 at k0 + 8)
+    // per-lane ldmatrix addresses.  B fragments: lanes 0-7 / 8-15 / 16-23 / 24-31 address the rows of the four 8x8 matrices
+    // (column tile nt at k0, nt at k0 + 8, nt + 1 at k0, nt + 1 at k0 + 8).  A fragments: rows 0-7 at k0, rows 8-15 at k0,
+    // rows 0-7 at k0 + 8, rows 8-15 at k0 + 8 (= a0, a1, a2, a3 of mma.m16n8k16).
     const uint32_t w1_lane = smem_addr(W1 + (size_t)((lane >> 4) * 8 + (lane & 7)) * xs + ((lane >> 3) & 1) * 8);
     const uint32_t w2_lane = smem_addr(W2 + (size_t)((lane >> 4) * 8 + (lane & 7)) * kHidStride + ((lane >> 3) & 1) * 8);
     const uint32_t w3_lane = smem_addr(W3 + (size_t)(lane & 7) * kHidStride + ((lane >> 3) & 1) * 8);
+    const uint32_t a_lane = slab + (uint32_t)((((lane >> 3) & 1) * 8 + (lane & 7)) * ss + (lane >> 4) * 8) * 2;
+    const uint32_t h_lane = slab + (uint32_t)(g * ss + 2 * t) * 2;   // where this lane's accumulator columns go (row g; row g + 8: + 8 * xs)
     const uint32_t w1_pair = 16 * xs * 2;     // bytes between column-tile pairs of W1
     // epilogue constants of this lane's two output columns
     float e_scale[2], e_mid[2], e_half[2];
@@ -121,11 +152,8 @@ k_policy_mlp(const FtlMlpWeights w, const float* __restrict__ obs, const float* 
         e_half[j] = c < w.act_dim ? w.act_half[c] : 0.f;
     }
     const int n_tiles = (n + 15) / 16;
-    const int n_warps = blockDim.x >> 5;
-    int tile = blockIdx.x * n_warps + warp;
-    const int tile_step = gridDim.x * n_warps;
-    // ---- prologue: the warp's first tile and the weights, all asynchronous -------------------------------------------
-    if (tile < n_tiles) stage_rows_async(slab_lane, xs * 4, obs, obs_stride, tile * 16, n, per_row, lane);
+    // tiles are dealt round-robin to the blocks and, inside a block, to its warps: every SM gets the same number (+-1)
+    // ---- prologue: the weights, asynchronously, while every warp stages its first tile ----------------------------------
     copy_rows_async(W1, xs, w.w1, D, kHid, D, tid, blockDim.x);
     copy_rows_async(W2, kHidStride, w.w2, kHid, kHid, kHid, tid, blockDim.x);
     cp_async_commit();
@@ -137,6 +165,9 @@ k_policy_mlp(const FtlMlpWeights w, const float* __restrict__ obs, const float* 
     }
     for (int e = tid; e < kHid; e += blockDim.x) { B1[e] = w.b1[e]; B2[e] = w.b2[e]; }
     if (tid < 8) B3[tid] = tid < n_out ? w.b3[tid] : 0.f;
+    int tile = blockIdx.x + gridDim.x * warp;
+    const int tile_step = gridDim.x * n_warps;
+    if (tile < n_tiles) stage_rows(slab, ss, obs, obs_stride, tile * 16, n, per_row, lane);
     cp_async_wait_all();
     __syncthreads();   // the only block barrier: the weights are in place
     for (; tile < n_tiles; tile += tile_step) {
@@ -152,18 +183,14 @@ k_policy_mlp(const FtlMlpWeights w, const float* __restrict__ obs, const float* 
                     if (row < n && c < w.act_dim) e_noise[half][j] = noise[(size_t)row * w.act_dim + c];
                 }
         }
-        cp_async_wait_all();
-        __syncwarp();      // every lane's chunks of this tile have landed
-        // ---- layer 1: [16 x D] x [D x 128]; A fragments converted from the float32 slab -----------------------------
+        __syncwarp();      // every lane's part of the tile is in the slab
+        // ---- layer 1: [16 x D] x [D x 128] -----------------------------------------------------------------------------
         float acc[kHid / 8][4];
 #pragma unroll
         for (int nt = 0; nt < kHid / 8; nt++) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
-        const float* x0 = slab + (size_t)g * xs + 2 * t;
-        const float* x1 = x0 + (size_t)8 * xs;
         for (int k0 = 0; k0 < D; k0 += 16) {
-            const float2 v0 = *reinterpret_cast<const float2*>(x0 + k0), v1 = *reinterpret_cast<const float2*>(x1 + k0);
-            const float2 v2 = *reinterpret_cast<const float2*>(x0 + k0 + 8), v3 = *reinterpret_cast<const float2*>(x1 + k0 + 8);
-            const uint32_t a0 = pack_bf16(v0.x, v0.y), a1 = pack_bf16(v1.x, v1.y), a2 = pack_bf16(v2.x, v2.y), a3 = pack_bf16(v3.x, v3.y);
+            uint32_t a0, a1, a2, a3;
+            ldmatrix_x4(a0, a1, a2, a3, a_lane + k0 * 2);
             uint32_t wa = w1_lane + k0 * 2;
 #pragma unroll
             for (int nt = 0; nt < kHid / 8; nt += 2, wa += w1_pair) {
@@ -173,51 +200,49 @@ k_policy_mlp(const FtlMlpWeights w, const float* __restrict__ obs, const float* 
                 mma_bf16(acc[nt + 1], a0, a1, a2, a3, b[2], b[3]);
             }
         }
-        __syncwarp();      // the slab has been read by every lane: the next tile may overwrite it
-        if (tile + tile_step < n_tiles) stage_rows_async(slab_lane, xs * 4, obs, obs_stride, (tile + tile_step) * 16, n, per_row, lane);
-        // bias + tanh + bfloat16: the accumulator fragments become layer 2's A fragments (k-step ks <- column tiles 2ks, 2ks+1)
-        uint32_t h[kHid / 16][4];
+        __syncwarp();      // the slab has been read by every lane: the activations may overwrite it
+        // bias + tanh + bfloat16 -> the slab's first 128 columns: layer 2's A operand
 #pragma unroll
-        for (int ks = 0; ks < kHid / 16; ks++) {
-#pragma unroll
-            for (int half = 0; half < 2; half++) {
-                const int nt = 2 * ks + half;
-                const float2 bb = *reinterpret_cast<const float2*>(B1 + nt * 8 + 2 * t);
-                h[ks][2 * half] = pack_bf16(tanh_fast(acc[nt][0] + bb.x), tanh_fast(acc[nt][1] + bb.y));       // row g
-                h[ks][2 * half + 1] = pack_bf16(tanh_fast(acc[nt][2] + bb.x), tanh_fast(acc[nt][3] + bb.y));   // row g + 8
-            }
+        for (int nt = 0; nt < kHid / 8; nt++) {
+            const float2 bb = *reinterpret_cast<const float2*>(B1 + nt * 8 + 2 * t);
+            sts32(h_lane + nt * 16, pack_bf16(tanh_fast(acc[nt][0] + bb.x), tanh_fast(acc[nt][1] + bb.y)));                // row g
+            sts32(h_lane + nt * 16 + 8 * ss * 2, pack_bf16(tanh_fast(acc[nt][2] + bb.x), tanh_fast(acc[nt][3] + bb.y)));   // row g + 8
         }
+        __syncwarp();
         // ---- layer 2: [16 x 128] x [128 x 128] ------------------------------------------------------------------------
 #pragma unroll
         for (int nt = 0; nt < kHid / 8; nt++) acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
 #pragma unroll
         for (int ks = 0; ks < kHid / 16; ks++) {
+            uint32_t a0, a1, a2, a3;
+            ldmatrix_x4(a0, a1, a2, a3, a_lane + ks * 32);
 #pragma unroll
             for (int nt = 0; nt < kHid / 8; nt += 2) {
                 uint32_t b[4];
                 ldmatrix_x4(b[0], b[1], b[2], b[3], w2_lane + (nt * 8 * kHidStride + ks * 16) * 2);
-                mma_bf16(acc[nt], h[ks][0], h[ks][1], h[ks][2], h[ks][3], b[0], b[1]);
-                mma_bf16(acc[nt + 1], h[ks][0], h[ks][1], h[ks][2], h[ks][3], b[2], b[3]);
+                mma_bf16(acc[nt], a0, a1, a2, a3, b[0], b[1]);
+                mma_bf16(acc[nt + 1], a0, a1, a2, a3, b[2], b[3]);
             }
         }
+        __syncwarp();      // every lane has read layer 1's activations
 #pragma unroll
-        for (int ks = 0; ks < kHid / 16; ks++) {
-#pragma unroll
-            for (int half = 0; half < 2; half++) {
-                const int nt = 2 * ks + half;
-                const float2 bb = *reinterpret_cast<const float2*>(B2 + nt * 8 + 2 * t);
-                h[ks][2 * half] = pack_bf16(tanh_fast(acc[nt][0] + bb.x), tanh_fast(acc[nt][1] + bb.y));
-                h[ks][2 * half + 1] = pack_bf16(tanh_fast(acc[nt][2] + bb.x), tanh_fast(acc[nt][3] + bb.y));
-            }
+        for (int nt = 0; nt < kHid / 8; nt++) {
+            const float2 bb = *reinterpret_cast<const float2*>(B2 + nt * 8 + 2 * t);
+            sts32(h_lane + nt * 16, pack_bf16(tanh_fast(acc[nt][0] + bb.x), tanh_fast(acc[nt][1] + bb.y)));
+            sts32(h_lane + nt * 16 + 8 * ss * 2, pack_bf16(tanh_fast(acc[nt][2] + bb.x), tanh_fast(acc[nt][3] + bb.y)));
         }
+        __syncwarp();
         // ---- head: [16 x 128] x [128 x 8]; columns < act_dim are the action mean, column act_dim the value -------------
         float out[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int ks = 0; ks < kHid / 16; ks++) {
-            uint32_t b0, b1;
+            uint32_t a0, a1, a2, a3, b0, b1;
+            ldmatrix_x4(a0, a1, a2, a3, a_lane + ks * 32);
             ldmatrix_x2(b0, b1, w3_lane + ks * 16 * 2);
-            mma_bf16(out, h[ks][0], h[ks][1], h[ks][2], h[ks][3], b0, b1);
+            mma_bf16(out, a0, a1, a2, a3, b0, b1);
         }
+        __syncwarp();      // the slab is free for the next tile
+        if (tile + tile_step < n_tiles) stage_rows(slab, ss, obs, obs_stride, (tile + tile_step) * 16, n, per_row, lane);
 #pragma unroll
         for (int half = 0; half < 2; half++) {
             const int row = row0 + g + 8 * half;
@@ -231,7 +256,6 @@ k_policy_mlp(const FtlMlpWeights w, const float* __restrict__ obs, const float* 
             }
         }
     }
-    cp_async_wait_all();
 }
 
 }  // namespace
@@ -246,9 +270,16 @@ extern "C" int ftl_policy_mlp(const FtlMlpWeights* w, const float* obs_dev, int3
         return FTL_ERR_INVALID;
     }
     if (n == 0) return FTL_OK;
+    {   // the tcgen05 kernel (ftl_policy_tc.cu) takes every shape it has room for; FTL_POLICY_IMPL=mma keeps the mma.sync one
+        const char* impl = getenv("FTL_POLICY_IMPL");
+        if (!(impl && impl[0] == 'm')) {
+            const int rc = ftl_policy_mlp_tc_launch(w, obs_dev, obs_stride, noise_dev, n, actions_dev, values_dev, (cudaStream_t)cuda_stream);
+            if (rc <= 0) return rc;
+        }
+    }
     const int xs = w->obs_dim + 8;
     const size_t fixed = sizeof(__nv_bfloat16) * ((size_t)kHid * xs + (size_t)kHid * kHidStride + 8 * kHidStride) + sizeof(float) * (2 * kHid + 8);
-    const size_t slab = sizeof(float) * (size_t)16 * xs;
+    const size_t slab = sizeof(__nv_bfloat16) * (size_t)16 * ((w->obs_dim > kHid ? w->obs_dim : kHid) + 8);
     static int s_dev = -1, s_sms = 0, s_optin = 0;   // per-device attributes, looked up once (the rollout calls this every step)
     static size_t s_smem_set = 0;
     int dev = 0;
@@ -272,9 +303,9 @@ extern "C" int ftl_policy_mlp(const FtlMlpWeights* w, const float* obs_dev, int3
         if (e == cudaSuccess) s_smem_set = smem;
     }
     if (e == cudaSuccess) {
-        const int tiles = (n + 15) / 16, blocks = (tiles + warps - 1) / warps;
-        k_policy_mlp<<<blocks < s_sms ? blocks : s_sms, 32 * warps, smem, (cudaStream_t)cuda_stream>>>(*w, obs_dev, noise_dev, n,
-                                                                                                      actions_dev, values_dev, obs_stride);
+        const int tiles = (n + 15) / 16;
+        k_policy_mlp<<<tiles < s_sms ? tiles : s_sms, 32 * warps, smem, (cudaStream_t)cuda_stream>>>(*w, obs_dev, noise_dev, n,
+                                                                                                  actions_dev, values_dev, obs_stride);
         e = cudaGetLastError();
     }
     if (e != cudaSuccess) {

@@ -301,7 +301,10 @@ def test_fused_policy_kernel_against_torch():
     from continiousenvironment_follower_leader_b200.rollout import MlpPolicy
     L = capi.load()
     torch.manual_seed(0)
-    for n, D, A in ((1000, 240, 2), (131, 48, 1), (4096, 288, 7)):
+    # both kernels behind ftl_policy_mlp: tcgen05 / tensor memory (ftl_policy_tc.cu; obs_dim <= 256) and mma.sync (ftl_policy.cu)
+    for impl, n, D, A in (("tcgen05", 1000, 240, 2), ("tcgen05", 131, 48, 1), ("tcgen05", 70000, 240, 2), ("tcgen05", 4096, 256, 7),
+                          ("mma", 1000, 240, 2), ("mma", 131, 48, 1), ("mma", 4096, 288, 7), ("tcgen05", 4096, 288, 7)):
+        os.environ["FTL_POLICY_IMPL"] = impl
         lo, hi = -np.arange(1, A + 1, dtype=np.float32), np.arange(1, A + 1, dtype=np.float32) * 2
         pol = MlpPolicy(D, lo, hi, seed=1).cuda()
         with torch.no_grad():
@@ -325,8 +328,9 @@ def test_fused_policy_kernel_against_torch():
             o = h @ keep["w3"].float().T + keep["b3"]
             want_a = keep["mid"] + keep["half"] * torch.tanh(o[:, :A] + noise * keep["ns"])
             want_v = o[:, A]
-        assert torch.allclose(val, want_v, rtol=2e-3, atol=2e-3), float((val - want_v).abs().max())
-        assert torch.allclose(act, want_a, rtol=2e-3, atol=2e-3 * float(hi.max())), float((act - want_a).abs().max())
+        assert torch.allclose(val, want_v, rtol=3e-3, atol=3e-3), (impl, n, D, A, float((val - want_v).abs().max()))
+        assert torch.allclose(act, want_a, rtol=2e-3, atol=2e-3 * float(hi.max())), (impl, n, D, A, float((act - want_a).abs().max()))
+    os.environ.pop("FTL_POLICY_IMPL", None)
 
 
 def test_rgb_array_rasteriser_against_its_numpy_specification():

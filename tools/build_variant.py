@@ -13,6 +13,7 @@ def main():
     jobs = [("ftl_step_nb.cu", os.path.join(objdir, "nb%d.o" % nb), ["-DFTL_NB=%d" % nb] + flags) for nb in range(B.MAX_BEARS + 1)]
     jobs.append(("ftl_capi.cu", os.path.join(objdir, "capi.o"), flags))
     jobs.append(("ftl_policy.cu", os.path.join(objdir, "policy.o"), flags))
+    jobs.append(("ftl_policy_tc.cu", os.path.join(objdir, "policy_tc.o"), flags))
     jobs.append(("ftl_scenario_gen.cpp", os.path.join(objdir, "gen.o"), []))
     with concurrent.futures.ThreadPoolExecutor(max_workers=8) as ex:
         for src, rc, log in ex.map(B._compile, jobs):
