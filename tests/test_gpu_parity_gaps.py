@@ -34,6 +34,9 @@ GAP_CASES = [
     ("f2_120rays", dict(bear_number=1, frames_per_step=2, follower_sensors=cfg3_sensors(12, 120, 5)), 512, 90),
     ("f13_2bears", dict(bear_number=2, frames_per_step=13, follower_sensors=cfg3_sensors(), max_steps=400,
                         auto_reset=True), 1024, 50),
+    # 60 frames per step: the per-frame records no longer fit k_kin's shared memory and go through HBM
+    ("f60_records_in_hbm", dict(bear_number=1, frames_per_step=60, follower_sensors=cfg3_sensors(), max_steps=2000,
+                                auto_reset=True), 512, 40),
     ("f10_warm0_es", dict(bear_number=1, warm_start=0, early_stopping={"max_distance_coef": 1.3, "low_reward": -60},
                           follower_sensors=cfg3_sensors(), auto_reset=True), 1024, 80),
     # LeaderCorridor_lasers_compas (SEN:1138-1240; cast by the per-env exact pass of k_finish)
