@@ -84,6 +84,9 @@ __global__ void __launch_bounds__(128, 12)   // 40 registers: its blocks are res
 k_finish(const __grid_constant__ DevCfg cfg, const __grid_constant__ DevState s, const __grid_constant__ DevPool pool,
          const __grid_constant__ DevOutputs img_out, float* __restrict__ rays_out, int first_env, int end_env, int wait_seq,
          int renew, int pdl) {
+#ifdef FTL_KIN_PDL
+    asm volatile("griddepcontrol.launch_dependents;");            // the next step's k_kin may be scheduled behind this grid
+#endif
     if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");   // launched early: wait for all of k_rays
     const int i = first_env + blockIdx.x * blockDim.x + threadIdx.x;   // first_env is a multiple of 32: a warp = one group
     const int lane = threadIdx.x & 31;
@@ -719,13 +722,13 @@ int ftl_reset(ftl_handle h, const uint8_t* mask_dev, const int32_t* scenario_ids
     return launch_optional_sensors(h, o, st);
 }
 
-static void launch_kin(FtlHandle_* h, const void* actions, const DevOutputs& o, int seq, cudaStream_t st) {
+static void launch_kin(FtlHandle_* h, const void* actions, const DevOutputs& o, int seq, int pdl, cudaStream_t st) {
     switch (h->cfg.c.n_bears) {
-        case 0: ftl_launch_kin_nb0(h->cfg, h->st, h->pool, h->image, h->image_out, actions, o, h->d_stats, seq, FTL_FUSED_BOOK, st); break;
-        case 1: ftl_launch_kin_nb1(h->cfg, h->st, h->pool, h->image, h->image_out, actions, o, h->d_stats, seq, FTL_FUSED_BOOK, st); break;
-        case 2: ftl_launch_kin_nb2(h->cfg, h->st, h->pool, h->image, h->image_out, actions, o, h->d_stats, seq, FTL_FUSED_BOOK, st); break;
-        case 3: ftl_launch_kin_nb3(h->cfg, h->st, h->pool, h->image, h->image_out, actions, o, h->d_stats, seq, FTL_FUSED_BOOK, st); break;
-        default: ftl_launch_kin_nb4(h->cfg, h->st, h->pool, h->image, h->image_out, actions, o, h->d_stats, seq, FTL_FUSED_BOOK, st); break;
+        case 0: ftl_launch_kin_nb0(h->cfg, h->st, h->pool, h->image, h->image_out, actions, o, h->d_stats, seq, FTL_FUSED_BOOK, pdl, st); break;
+        case 1: ftl_launch_kin_nb1(h->cfg, h->st, h->pool, h->image, h->image_out, actions, o, h->d_stats, seq, FTL_FUSED_BOOK, pdl, st); break;
+        case 2: ftl_launch_kin_nb2(h->cfg, h->st, h->pool, h->image, h->image_out, actions, o, h->d_stats, seq, FTL_FUSED_BOOK, pdl, st); break;
+        case 3: ftl_launch_kin_nb3(h->cfg, h->st, h->pool, h->image, h->image_out, actions, o, h->d_stats, seq, FTL_FUSED_BOOK, pdl, st); break;
+        default: ftl_launch_kin_nb4(h->cfg, h->st, h->pool, h->image, h->image_out, actions, o, h->d_stats, seq, FTL_FUSED_BOOK, pdl, st); break;
     }
     h->launches++;
 }
@@ -740,7 +743,7 @@ static int launch_step_front(ftl_handle h, const void* actions_dev, const DevOut
     const bool overlap = !h->profiling && !FTL_NO_PDL && cap == cudaStreamCaptureStatusNone;
     const int seq = h->step_seq = (h->step_seq % 0x3fffffff) + 1;   // never 0
     if (h->profiling) prof_event(h, st);
-    launch_kin(h, actions_dev, o, seq, st);
+    launch_kin(h, actions_dev, o, seq, overlap ? 1 : 0, st);
     CUDA_TRY(cudaGetLastError());
     if (h->profiling) prof_event(h, st);
     if (!FTL_FUSED_BOOK) {

@@ -6,7 +6,7 @@
 
 #define FTL_DECLARE_NB(NB)                                                                                            \
     void ftl_launch_kin_nb##NB(const ftl::DevCfg&, const ftl::DevState&, const ftl::DevPool&, const ftl::DevState&,  \
-                               const ftl::DevOutputs&, const void*, const ftl::DevOutputs&, double*, int, int,       \
+                               const ftl::DevOutputs&, const void*, const ftl::DevOutputs&, double*, int, int, int,  \
                                cudaStream_t);                                                                         \
     void ftl_launch_reset_nb##NB(const ftl::DevCfg&, const ftl::DevState&, const ftl::DevPool&, const uint8_t*,      \
                                  const int*, const ftl::DevOutputs&, int, cudaStream_t);

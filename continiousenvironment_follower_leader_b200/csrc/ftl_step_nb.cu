@@ -50,10 +50,16 @@ __global__ void __launch_bounds__(FTL_STEP_THREADS, FTL_STEP_MINBLOCKS)
 k_kin(const __grid_constant__ DevCfg cfg, const __grid_constant__ DevState s, const __grid_constant__ DevPool pool,
       const __grid_constant__ DevState img, const __grid_constant__ DevOutputs img_out,
       const void* __restrict__ actions, const __grid_constant__ DevOutputs out, double* __restrict__ stats, int seq,
-      int fused_book, int rec_in_smem) {
+      int fused_book, int rec_in_smem, int kin_pdl) {
     // k_book, k_rays and k_finish are launched as programmatic dependents of this kernel and of each other: their blocks
     // may start as soon as every block of the kernel in front is running, take the SM resources that finished blocks
     // free, and wait per group of 32 envs on kin_flag / book_flag.
+#ifdef FTL_KIN_PDL
+    // this kernel is itself a programmatic dependent of whatever is in front of it in the stream (the previous step's
+    // k_finish calls launch_dependents at its top): its blocks are scheduled while that kernel drains and wait here
+    // until it -- and everything before it -- has completed and flushed
+    if (kin_pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
     asm volatile("griddepcontrol.launch_dependents;");
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= s.n) return;   // whole warps: n is padded to a multiple of 32
@@ -126,7 +132,7 @@ k_reset(const __grid_constant__ DevCfg cfg, const DevState s, const DevPool pool
 
 void FTL_CAT(ftl_launch_kin_nb, FTL_NB)(const DevCfg& cfg, const DevState& s, const DevPool& pool, const DevState& img,
                                          const DevOutputs& img_out, const void* actions, const DevOutputs& out,
-                                         double* stats, int seq, int fused_book, cudaStream_t st) {
+                                         double* stats, int seq, int fused_book, int pdl, cudaStream_t st) {
 #ifdef FTL_STEP_LAUNCH_THREADS
     int threads = FTL_STEP_LAUNCH_THREADS;
 #else
@@ -137,8 +143,18 @@ void FTL_CAT(ftl_launch_kin_nb, FTL_NB)(const DevCfg& cfg, const DevState& s, co
     // this kernel's last blocks need theirs), HBM otherwise
     size_t rec_bytes = (size_t)17 * cfg.c.frames_per_step * threads;
     const int rec_in_smem = (FTL_FUSED_BOOK && fused_book && rec_bytes <= 16 * 1024) ? 1 : 0;
-    k_kin<FTL_NB><<<blocks, threads, rec_in_smem ? rec_bytes : 0, st>>>(cfg, s, pool, img, img_out, actions, out, stats, seq,
-                                                                        fused_book, rec_in_smem);
+#ifdef FTL_KIN_PDL
+    const int kin_pdl = pdl ? 1 : 0;   // 0: per-kernel timing or a stream that is being captured: plain stream order (ftl_capi.cu)
+#else
+    const int kin_pdl = 0;
+#endif
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(blocks); lc.blockDim = dim3(threads); lc.dynamicSmemBytes = rec_in_smem ? rec_bytes : 0; lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at; lc.numAttrs = kin_pdl ? 1 : 0;
+    cudaLaunchKernelEx(&lc, k_kin<FTL_NB>, cfg, s, pool, img, img_out, actions, out, stats, seq, fused_book, rec_in_smem, kin_pdl);
 }
 void FTL_CAT(ftl_launch_reset_nb, FTL_NB)(const DevCfg& cfg, const DevState& s, const DevPool& pool, const uint8_t* mask,
                                            const int* ids, const DevOutputs& out, int reset_filler, cudaStream_t st) {
