@@ -196,3 +196,14 @@ def test_laser_sensor_through_the_gym_surface():
         assert np.array_equal(obs["LaserSensor"], d["t_laser"][t + 1]), t
     with pytest.raises(NotImplementedError):
         _make(follower_sensors={"LaserSensor": {"return_all_points": True}})
+
+
+def test_render_modes():
+    """Game.render: only "rgb_array" exists (ftl_render_host, GPU test in test_gpu_parity_gaps.py); "human" needs a pygame
+    window and raises, and so does rendering before the first reset."""
+    env = _make(follower_sensors=cfg3_sensors(), bear_number=1)
+    assert env.metadata["render.modes"] == ["rgb_array"]
+    with pytest.raises(NotImplementedError):
+        env.render(mode="human")
+    with pytest.raises(RuntimeError):
+        env.render(mode="rgb_array")
