@@ -819,6 +819,9 @@ FTL_HD void green_flags(const DevCfg& cfg, const float2* trail, const float* tra
         le_eps = bound_decide(ub2, gc.lb_g, disp2, cfg.eps_f32, cfg.eps2_f32);
         le_dev = le_eps == 1 ? 1 : bound_decide(ub2, gc.lb_g, disp2, cfg.dev_f32, cfg.dev2_f32);
         need = le_eps < 0 || (le_eps == 0 && le_dev < 0);
+#ifdef FTL_TIMING_NOSCAN   // timing experiment only (results differ): what the exact scans cost
+        if (need) { need = false; le_eps = le_eps < 0 ? 0 : le_eps; le_dev = le_dev < 0 ? 0 : le_dev; }
+#endif
     }
     {
         int arg;
@@ -861,6 +864,9 @@ FTL_HD void green_flags(const DevCfg& cfg, const float2* trail, const float* tra
         le = bound_decide(ub2a, gc.lb_all, disp2a, cfg.eps_f32, cfg.eps2_f32);
         FTL_COUNT(4, 1);
         need = le < 0;
+#ifdef FTL_TIMING_NOSCAN
+        if (need) { need = false; le = 0; }
+#endif
     }
     {
         int arg;
