@@ -359,9 +359,11 @@ int ftl_profile_read_kernels(ftl_handle h, double* kin_ms, double* book_ms, doub
 /* ---- a consumer: the rollout's policy as one fused kernel (no reference analogue -- the
  * reference hands its observations to RLlib) ------------------------------------------------------------------------
  * A tanh MLP obs_dim -> 128 -> 128 -> act_dim + 1 on rows of the fused sensorPrev matrix (FtlConfig.fused_sensor_prev):
- * action[c] = act_mid[c] + act_half[c] * tanh(mu[c] + noise[c] * noise_scale[c]), value = the last output.  Tensor cores
- * (mma.sync, bfloat16 operands, float32 accumulation); weights are bfloat16 in torch.nn.Linear layout ([out][in]).
- * All pointers are device pointers. */
+ * action[c] = act_mid[c] + act_half[c] * tanh(mu[c] + noise[c] * noise_scale[c]), value = the last output.  Tensor cores,
+ * bfloat16 operands, float32 accumulation: tcgen05.mma with the accumulators in tensor memory when obs_dim <= 256
+ * (csrc/ftl_policy_tc.cu), mma.sync otherwise or when the environment variable FTL_POLICY_IMPL=mma is set
+ * (csrc/ftl_policy.cu); hidden activations go through tanh.approx and bfloat16.  Weights are bfloat16 in
+ * torch.nn.Linear layout ([out][in]).  All pointers are device pointers. */
 typedef struct FtlMlpWeights {
     const uint16_t* w1;  /* [128][obs_dim] bfloat16 */
     const float* b1;     /* [128] */
