@@ -756,7 +756,7 @@ FTL_HD void green_resolve(const DevCfg& cfg, const float* trail_d, int n, GreenC
 #define FTL_WALK_WIDE 6
 #endif
 FTL_HD void warp_green_resolve(bool need, const DevCfg& cfg, const float* trail_d, int n, GreenCache& gc) {
-#if defined(__CUDA_ARCH__) && defined(FTL_COOP_WALK)
+#if defined(__CUDA_ARCH__) && !defined(FTL_SERIAL_WALK)   // measured (r02_ab_log.txt (16)): k_kin 0.1449 -> 0.1349 ms
     const unsigned full = 0xffffffffu;
     unsigned pending = __ballot_sync(full, need);
     if (pending == 0u) return;
