@@ -456,7 +456,7 @@ def e2e_leg(job, gc, pool, n, actions, steps):
             "numa_binding": {k: v for k, v in binding.items() if k != "cpus"}}
 
 
-def rollout_leg(job, n, steps, horizon=16, settle=160):
+def rollout_leg(job, n, steps, horizon=64, settle=160):
     """Device-resident consumer: rollout.DeviceRollout on the cfg3 workload with the fused sensorPrev output.  `settle` =
     untimed steps since the common reset before the timed ones: the same window of episode ages as the device-timed
     value (the step time of this workload swings by a few percent with the 501-step episode limit)."""
@@ -478,7 +478,7 @@ def rollout_leg(job, n, steps, horizon=16, settle=160):
     ms = job.all_max(e0.elapsed_time(e1))
     ro.close()
     return {"value": job.world * n * rounds * horizon / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / (rounds * horizon),
-            "steps": rounds * horizon, "host_copies_per_step": 0,
+            "steps": rounds * horizon, "horizon": horizon, "host_copies_per_step": 0,
             "api": "rollout.DeviceRollout.collect: MlpPolicy (240 -> 128 -> 128 -> 2 + value) as ONE fused kernel of libftl.so "
                    "(ftl_policy_mlp: bfloat16 mma.sync, cp.async staging, activations in registers) reads the fused sensorPrev "
                    "matrix in place and writes actions into the row ftl_step consumes; ftl_step writes the next observation, "

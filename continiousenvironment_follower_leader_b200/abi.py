@@ -165,6 +165,8 @@ class FtlMlpWeights(C.Structure):
                 ("obs_dim", C.c_int32), ("act_dim", C.c_int32)]
 
 
+OPT_KIN_PDL = 1   # ftl_set_option
+
 ENV_STATE_DTYPE = np.dtype(FtlEnvState)
 
 

@@ -52,6 +52,7 @@ SIGNATURES = {
     "ftl_get_state": ([_vp, _i32, _i32, C.POINTER(abi.FtlStateBuffers)], C.c_int),
     "ftl_set_state": ([_vp, _i32, _i32, C.POINTER(abi.FtlStateBuffers)], C.c_int),
     "ftl_stats": ([_vp, _vp, _i32, _vp], C.c_int),
+    "ftl_set_option": ([_vp, _i32, _i32], C.c_int),
     "ftl_render": ([_vp, _i32, _i32, _i32, _vp, _vp], C.c_int),
     "ftl_render_host": ([_vp, _i32, _i32, _i32, _vp], C.c_int),
     "ftl_launch_count": ([_vp], _i64),

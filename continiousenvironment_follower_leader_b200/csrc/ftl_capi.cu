@@ -84,9 +84,7 @@ __global__ void __launch_bounds__(128, 12)   // 40 registers: its blocks are res
 k_finish(const __grid_constant__ DevCfg cfg, const __grid_constant__ DevState s, const __grid_constant__ DevPool pool,
          const __grid_constant__ DevOutputs img_out, float* __restrict__ rays_out, int first_env, int end_env, int wait_seq,
          int renew, int pdl) {
-#ifdef FTL_KIN_PDL
-    asm volatile("griddepcontrol.launch_dependents;");            // the next step's k_kin may be scheduled behind this grid
-#endif
+    asm volatile("griddepcontrol.launch_dependents;");            // a programmatic dependent (the rollout's policy kernel) may be scheduled behind this grid
     if (pdl) asm volatile("griddepcontrol.wait;" ::: "memory");   // launched early: wait for all of k_rays
     const int i = first_env + blockIdx.x * blockDim.x + threadIdx.x;   // first_env is a multiple of 32: a warp = one group
     const int lane = threadIdx.x & 31;
@@ -185,6 +183,7 @@ struct FtlHandle_ {
     int state_stage_cap = 0;
     int64_t launches = 0;
     int step_seq = 0;          // sequence number of the last ftl_step (kin_flag / book_flag protocol)
+    bool kin_pdl = false;      // FTL_OPT_KIN_PDL: k_kin launched as a programmatic dependent of the kernel in front of it
     int rays_total = 0;
     bool rays_smem_opted = false;
     double2* d_rot = nullptr;   // (cos, sin)(k * 360/R) per flat ray
@@ -743,7 +742,7 @@ static int launch_step_front(ftl_handle h, const void* actions_dev, const DevOut
     const bool overlap = !h->profiling && !FTL_NO_PDL && cap == cudaStreamCaptureStatusNone;
     const int seq = h->step_seq = (h->step_seq % 0x3fffffff) + 1;   // never 0
     if (h->profiling) prof_event(h, st);
-    launch_kin(h, actions_dev, o, seq, overlap ? 1 : 0, st);
+    launch_kin(h, actions_dev, o, seq, (overlap && h->kin_pdl) ? 1 : 0, st);
     CUDA_TRY(cudaGetLastError());
     if (h->profiling) prof_event(h, st);
     if (!FTL_FUSED_BOOK) {
@@ -1113,6 +1112,14 @@ k_render(const __grid_constant__ DevCfg cfg, const DevState s, const DevPool poo
     o[0] = col.r; o[1] = col.g; o[2] = col.b;
 }
 }  // namespace
+
+int ftl_set_option(ftl_handle h, int32_t option, int32_t value) {
+    if (!h) return fail(FTL_ERR_INVALID, "NULL handle");
+    switch (option) {
+        case FTL_OPT_KIN_PDL: h->kin_pdl = value != 0; return FTL_OK;
+        default: return fail(FTL_ERR_INVALID, "unknown option");
+    }
+}
 
 int ftl_render(ftl_handle h, int32_t first, int32_t count, int32_t scale, uint8_t* rgb_dev, void* cuda_stream) {
     if (!h || !rgb_dev) return fail(FTL_ERR_INVALID, "NULL argument");

@@ -152,6 +152,7 @@ k_policy_mlp(const FtlMlpWeights w, const float* __restrict__ obs, const float* 
         e_half[j] = c < w.act_dim ? w.act_half[c] : 0.f;
     }
     const int n_tiles = (n + 15) / 16;
+    asm volatile("griddepcontrol.launch_dependents;");   // ftl_step's k_kin (FTL_OPT_KIN_PDL) waits for this grid on the device
     // tiles are dealt round-robin to the blocks and, inside a block, to its warps: every SM gets the same number (+-1)
     // ---- prologue: the weights, asynchronously, while every warp stages its first tile ----------------------------------
     copy_rows_async(W1, xs, w.w1, D, kHid, D, tid, blockDim.x);
@@ -167,6 +168,7 @@ k_policy_mlp(const FtlMlpWeights w, const float* __restrict__ obs, const float* 
     if (tid < 8) B3[tid] = tid < n_out ? w.b3[tid] : 0.f;
     int tile = blockIdx.x + gridDim.x * warp;
     const int tile_step = gridDim.x * n_warps;
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // launched as a programmatic dependent: the observations are complete from here on
     if (tile < n_tiles) stage_rows(slab, ss, obs, obs_stride, tile * 16, n, per_row, lane);
     cp_async_wait_all();
     __syncthreads();   // the only block barrier: the weights are in place
@@ -304,9 +306,15 @@ extern "C" int ftl_policy_mlp(const FtlMlpWeights* w, const float* obs_dev, int3
     }
     if (e == cudaSuccess) {
         const int tiles = (n + 15) / 16;
-        k_policy_mlp<<<tiles < s_sms ? tiles : s_sms, 32 * warps, smem, (cudaStream_t)cuda_stream>>>(*w, obs_dev, noise_dev, n,
-                                                                                                  actions_dev, values_dev, obs_stride);
-        e = cudaGetLastError();
+        cudaLaunchConfig_t lc{};
+        lc.gridDim = dim3(tiles < s_sms ? tiles : s_sms); lc.blockDim = dim3(32 * warps); lc.dynamicSmemBytes = smem;
+        lc.stream = (cudaStream_t)cuda_stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = at; lc.numAttrs = 1;
+        e = cudaLaunchKernelEx(&lc, k_policy_mlp, *w, obs_dev, noise_dev, n, actions_dev, values_dev, obs_stride);
+        if (e == cudaSuccess) e = cudaGetLastError();
     }
     if (e != cudaSuccess) {
         ftl_set_error_message((std::string("ftl_policy_mlp: ") + cudaGetErrorString(e)).c_str());

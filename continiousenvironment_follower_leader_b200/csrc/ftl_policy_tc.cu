@@ -226,7 +226,8 @@ k_policy_mlp_tc(const FtlMlpWeights w, const float* __restrict__ obs, const floa
     const int n_tiles = (n + kRows - 1) / kRows;
     TR_DECL
 
-    // ---- setup -------------------------------------------------------------------------------------------------------
+    // ---- setup (before the wait for the kernel in front: weights and barriers do not depend on it) -------------------------
+    asm volatile("griddepcontrol.launch_dependents;");   // ftl_step's k_kin (FTL_OPT_KIN_PDL) waits for this grid on the device
     if (warp == kIssuerWarp) {   // one warp allocates the tensor memory (and frees it at the end)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(base + L.tmem_slot), "n"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -264,6 +265,7 @@ k_policy_mlp_tc(const FtlMlpWeights w, const float* __restrict__ obs, const floa
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // the observations (and whatever else the kernel in front wrote) are complete
     TR(0);
 
     if (warp >= kFirstLoadWarp) {
@@ -443,8 +445,14 @@ int ftl_policy_mlp_tc_launch(const FtlMlpWeights* w, const float* obs_dev, int32
         s_smem_set = L.total;
     }
     const int tiles = (n + kRows - 1) / kRows;
-    k_policy_mlp_tc<<<tiles < s_sms ? tiles : s_sms, kThreads, L.total, stream>>>(*w, obs_dev, noise_dev, n, actions_dev, values_dev, obs_stride);
-    e = cudaGetLastError();
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(tiles < s_sms ? tiles : s_sms); lc.blockDim = dim3(kThreads); lc.dynamicSmemBytes = L.total; lc.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // scheduled while the kernel in front drains; waits on the device
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    e = cudaLaunchKernelEx(&lc, k_policy_mlp_tc, *w, obs_dev, noise_dev, n, actions_dev, values_dev, obs_stride);
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) { ftl_set_error_message((std::string("ftl_policy_mlp: ") + cudaGetErrorString(e)).c_str()); return FTL_ERR_CUDA; }
     return 0;
 }

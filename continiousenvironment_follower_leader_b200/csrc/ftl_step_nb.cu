@@ -54,12 +54,12 @@ k_kin(const __grid_constant__ DevCfg cfg, const __grid_constant__ DevState s, co
     // k_book, k_rays and k_finish are launched as programmatic dependents of this kernel and of each other: their blocks
     // may start as soon as every block of the kernel in front is running, take the SM resources that finished blocks
     // free, and wait per group of 32 envs on kin_flag / book_flag.
-#ifdef FTL_KIN_PDL
-    // this kernel is itself a programmatic dependent of whatever is in front of it in the stream (the previous step's
-    // k_finish calls launch_dependents at its top): its blocks are scheduled while that kernel drains and wait here
-    // until it -- and everything before it -- has completed and flushed
+    // Optionally (FTL_OPT_KIN_PDL, ftl_set_option) this kernel is itself a programmatic dependent of whatever is in front
+    // of it in the stream: its blocks are scheduled while that kernel drains and wait here until it -- and everything
+    // before it -- has completed and flushed.  Off by default: behind the previous step's k_finish the early blocks take
+    // what the last ray blocks would have used (+2.5 % per step), behind the rollout's policy kernel +1.6 %
+    // (profiles/r02_ab_log.txt (14), (17)).
     if (kin_pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
-#endif
     asm volatile("griddepcontrol.launch_dependents;");
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= s.n) return;   // whole warps: n is padded to a multiple of 32
@@ -143,11 +143,7 @@ void FTL_CAT(ftl_launch_kin_nb, FTL_NB)(const DevCfg& cfg, const DevState& s, co
     // this kernel's last blocks need theirs), HBM otherwise
     size_t rec_bytes = (size_t)17 * cfg.c.frames_per_step * threads;
     const int rec_in_smem = (FTL_FUSED_BOOK && fused_book && rec_bytes <= 16 * 1024) ? 1 : 0;
-#ifdef FTL_KIN_PDL
-    const int kin_pdl = pdl ? 1 : 0;   // 0: per-kernel timing or a stream that is being captured: plain stream order (ftl_capi.cu)
-#else
-    const int kin_pdl = 0;
-#endif
+    const int kin_pdl = pdl ? 1 : 0;   // FTL_OPT_KIN_PDL and neither per-kernel timing nor a stream that is being captured
     cudaLaunchConfig_t lc{};
     lc.gridDim = dim3(blocks); lc.blockDim = dim3(threads); lc.dynamicSmemBytes = rec_in_smem ? rec_bytes : 0; lc.stream = st;
     cudaLaunchAttribute at[1];

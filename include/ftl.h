@@ -332,6 +332,14 @@ void* ftl_host_stream(ftl_handle h);
 int ftl_get_state(ftl_handle h, int32_t first_env, int32_t n, const FtlStateBuffers* host_out);
 int ftl_set_state(ftl_handle h, int32_t first_env, int32_t n, const FtlStateBuffers* host_in);
 
+/* ---- launch options of a handle (no reference analogue) ---------------------------------------------------------------
+ * FTL_OPT_KIN_PDL = 1: ftl_step launches its first kernel as a programmatic dependent of the kernel in front of it in the
+ * stream (its blocks are scheduled while that kernel drains and wait for its completion on the device).  Default 0:
+ * measured slower both between back-to-back steps (+2.5 %) and behind the rollout's policy kernel (+1.6 %) -- the early
+ * blocks take what the kernel in front still uses (profiles/r02_ab_log.txt (14), (17)). */
+enum { FTL_OPT_KIN_PDL = 1 };
+int ftl_set_option(ftl_handle h, int32_t option, int32_t value);
+
 /* ---- rgb_array: Game.render(return_render_matrix=True), ENV:1196-1202 / _show_tick ENV:1229-1302 -------------------
  * Rasterises envs [first_env, first_env + n) on the device: rgb_dev is uint8 [n][H][W][3] (row-major, the layout of
  * np.transpose(surfarray.array3d(display), (1, 0, 2))) with W = ceil(game_width / scale), H = ceil(game_height / scale);
@@ -363,7 +371,9 @@ int ftl_profile_read_kernels(ftl_handle h, double* kin_ms, double* book_ms, doub
  * bfloat16 operands, float32 accumulation: tcgen05.mma with the accumulators in tensor memory when obs_dim <= 256
  * (csrc/ftl_policy_tc.cu), mma.sync otherwise or when the environment variable FTL_POLICY_IMPL=mma is set
  * (csrc/ftl_policy.cu); hidden activations go through tanh.approx and bfloat16.  Weights are bfloat16 in
- * torch.nn.Linear layout ([out][in]).  All pointers are device pointers. */
+ * torch.nn.Linear layout ([out][in]).  All pointers are device pointers.  The kernels are launched as programmatic
+ * dependents of the kernel in front of them and stage the weights before they wait for it: the weights must not be
+ * written by a kernel that triggers its dependents early (none of this library's kernels writes them). */
 typedef struct FtlMlpWeights {
     const uint16_t* w1;  /* [128][obs_dim] bfloat16 */
     const float* b1;     /* [128] */
