@@ -382,3 +382,31 @@ def test_rgb_array_rasteriser_against_its_numpy_specification():
     bad = (full[0] != want).any(axis=2) & ~maybe_green
     assert bad.sum() <= 1e-3 * bad.size
     host.close()
+
+
+def test_kin_pdl_option_changes_nothing_but_the_launch():
+    """ftl_set_option(FTL_OPT_KIN_PDL): k_kin launched as a programmatic dependent of the kernel in front of it must give
+    the same states and observations as plain stream order (it is off by default because it is slower, not because it
+    differs)."""
+    import torch
+    from continiousenvironment_follower_leader_b200.batch_env import FtlBatchEnv
+    gc = GameConfig(bear_number=1, follower_sensors=cfg3_sensors(), auto_reset=True, max_steps=300)
+    pool = synthetic_pool(gc, 32, seed=9)
+    n, steps = 4096, 40
+    rng = np.random.default_rng(3)
+    lo, hi = gc.action_bounds()
+    acts = [torch.as_tensor(rng.uniform(lo, hi, size=(n, 2)).astype(np.float32), device="cuda") for _ in range(steps)]
+    results = []
+    for opt in (0, 1):
+        env = FtlBatchEnv(n, game_config=gc, scenario_pool=pool)
+        capi.check(env._L, env._L.ftl_set_option(env._h, abi.OPT_KIN_PDL, opt), "ftl_set_option")
+        env.reset()
+        for a in acts:
+            env.step_raw(a)
+        torch.cuda.synchronize()
+        st = env.get_state()
+        results.append((st.env.tobytes(), env.rays.cpu().numpy().copy(), env.reward.cpu().numpy().copy()))
+        assert env._L.ftl_set_option(env._h, 99, 1) != 0     # unknown options are refused
+        env.close()
+    assert results[0][0] == results[1][0]
+    assert np.array_equal(results[0][1], results[1][1]) and np.array_equal(results[0][2], results[1][2])
