@@ -305,7 +305,7 @@ def test_fused_policy_kernel_against_torch():
     L = capi.load()
     torch.manual_seed(0)
     # both kernels behind ftl_policy_mlp: tcgen05 / tensor memory (ftl_policy_tc.cu; obs_dim <= 256) and mma.sync (ftl_policy.cu)
-    for impl, n, D, A in (("tcgen05", 1000, 240, 2), ("tcgen05", 131, 48, 1), ("tcgen05", 70000, 240, 2), ("tcgen05", 4096, 256, 7),
+    for impl, n, D, A in (("tcgen05", 1000, 240, 2), ("tcgen05", 131, 48, 1), ("tcgen05", 70000, 240, 2), ("tcgen05", 4096, 256, 7), ("tcgen05", 1, 240, 2), ("tcgen05", 129, 16, 3),
                           ("mma", 1000, 240, 2), ("mma", 131, 48, 1), ("mma", 4096, 288, 7), ("tcgen05", 4096, 288, 7)):
         os.environ["FTL_POLICY_IMPL"] = impl
         lo, hi = -np.arange(1, A + 1, dtype=np.float32), np.arange(1, A + 1, dtype=np.float32) * 2
