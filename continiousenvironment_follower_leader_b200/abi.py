@@ -165,7 +165,7 @@ class FtlMlpWeights(C.Structure):
                 ("obs_dim", C.c_int32), ("act_dim", C.c_int32)]
 
 
-OPT_KIN_PDL = 1   # ftl_set_option
+OPT_KIN_PDL, OPT_STEP_PHASE, OPT_NO_OVERLAP = 1, 2, 3   # ftl_set_option
 
 ENV_STATE_DTYPE = np.dtype(FtlEnvState)
 

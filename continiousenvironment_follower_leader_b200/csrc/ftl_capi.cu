@@ -183,6 +183,9 @@ struct FtlHandle_ {
     int state_stage_cap = 0;
     int64_t launches = 0;
     int step_seq = 0;          // sequence number of the last ftl_step (kin_flag / book_flag protocol)
+    int step_phase = 0;        // FTL_OPT_STEP_PHASE: 0 = a whole step per call, 1 = k_kin only, 2 = the ray kernels of the step begun before
+    int pending_wait_seq = 0;  // ... the sequence number the second half waits for
+    bool no_overlap = false;   // FTL_OPT_NO_OVERLAP: plain stream order between the kernels of a step
     bool kin_pdl = false;      // FTL_OPT_KIN_PDL: k_kin launched as a programmatic dependent of the kernel in front of it
     int rays_total = 0;
     bool rays_smem_opted = false;
@@ -739,7 +742,7 @@ static int launch_step_front(ftl_handle h, const void* actions_dev, const DevOut
     // previous replay's flags already equal to it and skip the wait.  Captured steps therefore use plain stream order.
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     CUDA_TRY(cudaStreamIsCapturing(st, &cap));
-    const bool overlap = !h->profiling && !FTL_NO_PDL && cap == cudaStreamCaptureStatusNone;
+    const bool overlap = !h->profiling && !FTL_NO_PDL && !h->no_overlap && cap == cudaStreamCaptureStatusNone;
     const int seq = h->step_seq = (h->step_seq % 0x3fffffff) + 1;   // never 0
     if (h->profiling) prof_event(h, st);
     launch_kin(h, actions_dev, o, seq, (overlap && h->kin_pdl) ? 1 : 0, st);
@@ -775,8 +778,15 @@ int ftl_step_ex(ftl_handle h, const void* actions_dev, const FtlStepInputs* in_d
     DevOutputs o = to_dev_outputs(out_dev, h->n);
     StepInputsScope scope(h, in_dev);
     int wait_seq = 0;
-    int rc = launch_step_front(h, actions_dev, o, st, &wait_seq);
-    if (rc) return rc;
+    int rc = FTL_OK;
+    if (h->step_phase != 2) {
+        rc = launch_step_front(h, actions_dev, o, st, &wait_seq);
+        if (rc) return rc;
+        h->pending_wait_seq = wait_seq;
+        if (h->step_phase == 1) return FTL_OK;
+    } else {
+        wait_seq = h->pending_wait_seq;
+    }
     rc = launch_rays_and_finish(h, h->st, o, st, 0, h->n, wait_seq, true);
     if (h->profiling) prof_event(h, st);
     if (rc) return rc;
@@ -1117,6 +1127,8 @@ int ftl_set_option(ftl_handle h, int32_t option, int32_t value) {
     if (!h) return fail(FTL_ERR_INVALID, "NULL handle");
     switch (option) {
         case FTL_OPT_KIN_PDL: h->kin_pdl = value != 0; return FTL_OK;
+        case FTL_OPT_STEP_PHASE: if (value < 0 || value > 2) return fail(FTL_ERR_INVALID, "FTL_OPT_STEP_PHASE: 0, 1 or 2"); h->step_phase = value; return FTL_OK;
+        case FTL_OPT_NO_OVERLAP: h->no_overlap = value != 0; return FTL_OK;
         default: return fail(FTL_ERR_INVALID, "unknown option");
     }
 }

@@ -710,12 +710,22 @@ FTL_HD_NOINLINE ScanMin warp_scan_min_impl(bool need, const float2* trail, int l
             if (d2 < best) { best = d2; bi = k; }
         }
 #endif
+#ifndef FTL_SCAN_SHUFFLE   // arg-min in two hardware reductions (squared distances are non-negative floats: they order like
+                           // their bits; among equal minima the largest index wins, as in the shuffle tree below); measured
+                           // (r02_ab_log.txt (21)): k_kin 0.1342 -> 0.1328 ms
+        {
+            const unsigned mbits = __reduce_min_sync(full, __float_as_uint(best));
+            const int widx = __reduce_max_sync(full, __float_as_uint(best) == mbits ? bi : -1);
+            best = __uint_as_float(mbits); bi = widx;
+        }
+#else
 #pragma unroll
         for (int off = 16; off; off >>= 1) {
             float ob = __shfl_xor_sync(full, best, off);
             int oi = __shfl_xor_sync(full, bi, off);
             if (ob < best || (ob == best && oi > bi)) { best = ob; bi = oi; }
         }
+#endif
         if (lane == src) { my_best = best; my_arg = bi; }
     }
     *arg = my_arg;

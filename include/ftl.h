@@ -336,8 +336,15 @@ int ftl_set_state(ftl_handle h, int32_t first_env, int32_t n, const FtlStateBuff
  * FTL_OPT_KIN_PDL = 1: ftl_step launches its first kernel as a programmatic dependent of the kernel in front of it in the
  * stream (its blocks are scheduled while that kernel drains and wait for its completion on the device).  Default 0:
  * measured slower both between back-to-back steps (+2.5 %) and behind the rollout's policy kernel (+1.6 %) -- the early
- * blocks take what the kernel in front still uses (profiles/r02_ab_log.txt (14), (17)). */
-enum { FTL_OPT_KIN_PDL = 1 };
+ * blocks take what the kernel in front still uses (profiles/r02_ab_log.txt (14), (17)).
+ * FTL_OPT_STEP_PHASE = 2: 0 (default) ftl_step issues a whole step; 1: only its first half (k_kin: kinematics, bookkeeping,
+ * reward / done / numerical outputs); 2: only the second half (the ray kernels) of the step begun by the last phase-1 call,
+ * possibly on another stream that the caller has ordered behind the first.  For callers that interleave the halves of
+ * several handles; results are those of whole steps.  The per-step inputs of ftl_step_ex belong to the phase-1 call.
+ * FTL_OPT_NO_OVERLAP = 3: 1 = the kernels of a step run in plain stream order (no dependent launches, no flag waits),
+ * as they do under stream capture.  Both measured in profiles/r02_ab_log.txt (22) (two ordered half-batches: slower than
+ * one whole batch). */
+enum { FTL_OPT_KIN_PDL = 1, FTL_OPT_STEP_PHASE = 2, FTL_OPT_NO_OVERLAP = 3 };
 int ftl_set_option(ftl_handle h, int32_t option, int32_t value);
 
 /* ---- rgb_array: Game.render(return_render_matrix=True), ENV:1196-1202 / _show_tick ENV:1229-1302 -------------------

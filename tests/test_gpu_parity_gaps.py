@@ -410,3 +410,37 @@ def test_kin_pdl_option_changes_nothing_but_the_launch():
         env.close()
     assert results[0][0] == results[1][0]
     assert np.array_equal(results[0][1], results[1][1]) and np.array_equal(results[0][2], results[1][2])
+
+
+def test_step_phase_options_split_a_step_without_changing_it():
+    """ftl_set_option(FTL_OPT_STEP_PHASE): a step issued as its kinematics half (1) and its ray half (2) -- with and
+    without the dependent-launch overlap (FTL_OPT_NO_OVERLAP) -- gives the states, rays and rewards of whole steps."""
+    import torch
+    from continiousenvironment_follower_leader_b200.batch_env import FtlBatchEnv
+    gc = GameConfig(bear_number=1, follower_sensors=cfg3_sensors(), auto_reset=True, max_steps=300)
+    pool = synthetic_pool(gc, 32, seed=9)
+    n, steps = 4096, 40
+    rng = np.random.default_rng(5)
+    lo, hi = gc.action_bounds()
+    acts = [torch.as_tensor(rng.uniform(lo, hi, size=(n, 2)).astype(np.float32), device="cuda") for _ in range(steps)]
+    results = []
+    for split, no_overlap in ((False, 0), (True, 0), (True, 1)):
+        env = FtlBatchEnv(n, game_config=gc, scenario_pool=pool)
+        capi.check(env._L, env._L.ftl_set_option(env._h, abi.OPT_NO_OVERLAP, no_overlap), "ftl_set_option")
+        env.reset()
+        for a in acts:
+            if split:
+                for phase in (1, 2):
+                    capi.check(env._L, env._L.ftl_set_option(env._h, abi.OPT_STEP_PHASE, phase), "ftl_set_option")
+                    env.step_raw(a)
+            else:
+                env.step_raw(a)
+        torch.cuda.synchronize()
+        capi.check(env._L, env._L.ftl_set_option(env._h, abi.OPT_STEP_PHASE, 0), "ftl_set_option")
+        assert env._L.ftl_set_option(env._h, abi.OPT_STEP_PHASE, 3) != 0
+        st = env.get_state()
+        results.append((st.env.tobytes(), env.rays.cpu().numpy().copy(), env.reward.cpu().numpy().copy()))
+        env.close()
+    for r in results[1:]:
+        assert r[0] == results[0][0]
+        assert np.array_equal(r[1], results[0][1]) and np.array_equal(r[2], results[0][2])
