@@ -106,7 +106,7 @@ class FtlScenarioGenConfig(C.Structure):
                 ("leader_width_f", C.c_double), ("leader_height_f", C.c_double),
                 ("add_obstacles", C.c_int32), ("obstacle_number", C.c_int32), ("step_grid", C.c_int32),
                 ("bridge_size", C.c_int32 * 2), ("leader_margin", C.c_double),
-                ("path_finding", C.c_int32), ("pad_", C.c_int32)]
+                ("path_finding", C.c_int32), ("multiple_end_points", C.c_int32)]
 
 
 class FtlRobotState(C.Structure):

@@ -194,7 +194,8 @@ class GameConfig:
         if corridor_cap & (corridor_cap - 1) or corridor_cap > 512:
             raise ValueError("corridor_cap must be a power of two <= 512")
         c.corridor_cap = int(corridor_cap)
-        c.route_cap = int(route_cap) if route_cap else 128
+        # three D* legs across the field (multiple_end_points) are up to ~4 x a single route
+        c.route_cap = int(route_cap) if route_cap else (512 if g["multiple_end_points"] else 128)
         c.static_cap = int(static_cap) if static_cap else max(2 + int(g["obstacle_number"]) if g["add_obstacles"] else 0, 1)
         c.auto_reset = int(bool(auto_reset))
         self.c = c

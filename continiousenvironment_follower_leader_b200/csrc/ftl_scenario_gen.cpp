@@ -166,8 +166,10 @@ bool shortest_path(const std::vector<uint8_t>& blocked, int nx, int ny, Cell sta
 
 struct Route { std::vector<Cell> pts; bool found; };
 
-// the map generate_trajectory_dstar builds (ENV:1493-1507), searched for a shortest path
-Route plan_dstar_grid(const FtlScenarioGenConfig& g, long sx_px, long sy_px, long gx_px, long gy_px,
+// the map generate_trajectory_dstar builds (ENV:1493-1507), searched for a shortest path to the first goal; with
+// multiple_end_points two more legs, goal to goal on the same map, are appended (ENV:1552-1587)
+struct Px { long x, y; };
+Route plan_dstar_grid(const FtlScenarioGenConfig& g, long sx_px, long sy_px, const std::vector<Px>& goals_px,
                       const std::vector<Rect>& statics) {
     const int sg = g.step_grid, nx = g.game_width / sg, ny = g.game_height / sg;
     const int margin = (int)std::floor(g.leader_margin * std::max(g.leader_width_f, g.leader_height_f) / sg);
@@ -180,12 +182,13 @@ Route plan_dstar_grid(const FtlScenarioGenConfig& g, long sx_px, long sy_px, lon
             for (int j = pmy - hh; j < pmy + hh; j++)
                 if (0 <= i && i < nx && 0 <= j && j < ny) blocked[(size_t)i * ny + j] = 1;
     }
-    Cell start = {(int)(sx_px / (double)sg), (int)(sy_px / (double)sg)}, goal = {(int)(gx_px / (double)sg), (int)(gy_px / (double)sg)};
+    auto cell_of = [&](long px, long py) { return Cell{(int)(px / (double)sg), (int)(py / (double)sg)}; };
+    auto is_blocked = [&](Cell c) { return 0 <= c.x && c.x < nx && 0 <= c.y && c.y < ny && blocked[(size_t)c.x * ny + c.y]; };
+    Cell start = cell_of(sx_px, sy_px), goal = cell_of(goals_px[0].x, goals_px[0].y);
     if (0 <= start.x && start.x < nx && 0 <= start.y && start.y < ny) blocked[(size_t)start.x * ny + start.y] = 0;
     Route out;
     std::vector<Cell> path;
-    const bool goal_blocked = 0 <= goal.x && goal.x < nx && 0 <= goal.y && goal.y < ny && blocked[(size_t)goal.x * ny + goal.y];
-    if (goal_blocked || !shortest_path(blocked, nx, ny, start, goal, &path)) {
+    if (is_blocked(goal) || !shortest_path(blocked, nx, ny, start, goal, &path)) {
         // unreachable target: the reference reports found_target_point=False (dstar.py:183-188) and SkipBadSeeds
         // re-resets; a short stub route keeps the episode well defined
         out.pts = {{start.x * sg, start.y * sg}, {std::max(start.x - 1, 0) * sg, start.y * sg}};
@@ -196,6 +199,16 @@ Route plan_dstar_grid(const FtlScenarioGenConfig& g, long sx_px, long sy_px, lon
     size_t count = path.size() > 2 ? path.size() - 1 : path.size();
     for (size_t k = 0; k < count; k++) out.pts.push_back({path[k].x * sg, path[k].y * sg});
     out.found = true;
+    for (size_t leg = 1; leg < goals_px.size(); leg++) {
+        // the next leg starts in the previous goal cell; a leg that cannot be planned adds nothing and clears the flag
+        const Cell nxt = cell_of(goals_px[leg].x, goals_px[leg].y);
+        if (is_blocked(nxt) || is_blocked(goal) || !shortest_path(blocked, nx, ny, goal, nxt, &path)) {
+            out.found = false;
+        } else {
+            for (size_t k = 0; k + 1 < path.size(); k++) out.pts.push_back({path[k].x * sg, path[k].y * sg});
+        }
+        goal = nxt;
+    }
     return out;
 }
 
@@ -301,20 +314,34 @@ int generate_one(const FtlScenarioGenConfig& g, int64_t seed, const PoolOut& out
         objects.insert(objects.end(), statics.begin(), statics.end());
     }
     if ((int)statics.size() > out.static_cap) { *why = "more static rectangles than static_cap"; return FTL_ERR_INVALID; }
-    // ---- generate_finish_point([20, 20], [W/2, H-20]), ENV:471, 1614-1630
-    long fx, fy;
-    for (;;) {
-        if (!draw(20, (double)(int)(W / 2.0), 10, &fx) || !draw(20, H - 20, 10, &fy)) return FTL_ERR_INVALID;
-        bool ok = true;
-        for (const Rect& r : objects)
-            if (collidepoint(r, fx, fy) || distance_to_rect(fx, fy, r) < g.leader_pos_epsilon) ok = false;
-        if (ok) break;
+    // ---- generate_finish_point, ENV:471-482, 1614-1630
+    auto finish_point = [&](double l0, double l1, double r0, double r1, Px* fp) {
+        for (;;) {
+            if (!draw(l0, r0, 10, &fp->x) || !draw(l1, r1, 10, &fp->y)) return false;
+            bool ok = true;
+            for (const Rect& r : objects)
+                if (collidepoint(r, fp->x, fp->y) || distance_to_rect(fp->x, fp->y, r) < g.leader_pos_epsilon) ok = false;
+            if (ok) return true;
+        }
+    };
+    std::vector<Px> goals(1);
+    if (!finish_point(20, 20, (double)(int)(W / 2.0), H - 20, &goals[0])) return FTL_ERR_INVALID;
+    if (g.multiple_end_points) {
+        if (g.path_finding != 0) { *why = "Only dstar pathfinding function supports multiple end points (ENV:239-243)"; return FTL_ERR_INVALID; }
+        for (int k = 0; k < 2; k++) {   // each in the half of the field (upper / lower) the previous one is not in
+            Px fp;
+            const bool lower = goals.back().y >= H / 2.0;
+            if (!(lower ? finish_point(20, 20, W - 20, (double)(int)(H / 2.0), &fp)
+                        : finish_point(20, (double)(int)(H / 2.0), W - 20, H - 20, &fp))) return FTL_ERR_INVALID;
+            goals.push_back(fp);
+        }
     }
+    const long fx = goals[0].x, fy = goals[0].y;
     // ---- route
     Route route;
     if (g.path_finding == 0) {
         if (!g.add_obstacles) { *why = "'Game' object has no attribute 'obstacles1' (ENV:1501: dstar needs add_obstacles)"; return FTL_ERR_INVALID; }
-        route = plan_dstar_grid(g, lx, ly, fx, fy, statics);
+        route = plan_dstar_grid(g, lx, ly, goals, statics);
     } else {
         route = plan_astar_grid(g, lx, ly, fx, fy, statics);
     }

@@ -134,6 +134,9 @@ class Game(Env):
         self.found_target_point = False
         self.trajectory = g["trajectory"]
         self.finish_point = (10, 10)
+        self.multiple_end_points = bool(g["multiple_end_points"])
+        if self.multiple_end_points:
+            self.finish_point2 = (1490, 990)          # ENV:246
         self.simulation_number = 0
         self.done = False
         if self.gc.discrete_action_space:
@@ -167,6 +170,8 @@ class Game(Env):
         sc = scenario if scenario is not None else scenario_gen.generate(self.gc, trajectory=self._trajectory_arg)
         self.trajectory = list(sc.route)
         self.finish_point = sc.finish_point
+        if self.multiple_end_points and sc.finish_points is not None:      # ENV:472-482
+            self.finish_point, self.finish_point2, self.finish_point3 = sc.finish_points
         self.found_target_point = bool(sc.found_target_point)
         self._ensure_env(len(sc.route), len(sc.static_rects))
         pool = ScenarioPool(1, self.gc.c.static_cap, self.gc.c.route_cap)

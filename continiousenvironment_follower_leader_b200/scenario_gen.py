@@ -60,6 +60,7 @@ class Scenario:
         self.follower_pos = None
         self.follower_dir = 0.0
         self.finish_point = None
+        self.finish_points = None      # multiple_end_points: the three finish points, ENV:471-482
         self.found_target_point = False
 
 
@@ -113,23 +114,31 @@ def generate(gc, trajectory=None):
         sc.found_target_point = False       # the reference only sets it inside the D* branch (ENV:1543)
         sc.finish_point = sc.route[-1]
     else:
-        # generate_finish_point([20, 20], [W/2, H-20]), ENV:471, 1614-1630
-        while True:
-            fp = (_randrange(20, int(W / 2), 10), _randrange(20, H - 20, 10))
-            ok = True
-            for r in objects:
-                if _collidepoint(r, fp) or _distance_to_rect(fp, r) < c.leader_pos_epsilon:
-                    ok = False
-            if ok:
-                break
+        def finish_point(left_top, right_bottom):       # generate_finish_point, ENV:1614-1630
+            while True:
+                fp = (_randrange(left_top[0], right_bottom[0], 10), _randrange(left_top[1], right_bottom[1], 10))
+                ok = True
+                for r in objects:
+                    if _collidepoint(r, fp) or _distance_to_rect(fp, r) < c.leader_pos_epsilon:
+                        ok = False
+                if ok:
+                    return fp
+        fp = finish_point([20, 20], [int(W / 2), H - 20])                                       # ENV:471
         sc.finish_point = fp
+        goals = [fp]
         if g["multiple_end_points"]:
-            raise NotImplementedError("multiple_end_points (three chained D* runs, ENV:1549-1612) is not supported")
+            # two more finish points, each in the half of the field (upper / lower) the previous one is not in, ENV:472-482
+            for _ in range(2):
+                if goals[-1][1] >= H / 2:
+                    goals.append(finish_point([20, 20], [W - 20, int(H / 2)]))
+                else:
+                    goals.append(finish_point([20, int(H / 2)], [W - 20, H - 20]))
+            sc.finish_points = list(goals)
         if g["path_finding_algorythm"] == "dstar":
             if not g["add_obstacles"]:
                 # the reference dereferences self.obstacles1 here (ENV:1501)
                 raise AttributeError("'Game' object has no attribute 'obstacles1'")
-            sc.route, sc.found_target_point = _plan_dstar_grid(gc, (lx, ly), fp, sc.static_rects, leader_wf, leader_hf)
+            sc.route, sc.found_target_point = _plan_dstar_grid(gc, (lx, ly), goals, sc.static_rects, leader_wf, leader_hf)
         else:
             sc.route = _plan_astar_grid(gc, (lx, ly), fp, sc.static_rects, leader_wf, leader_hf)
             sc.found_target_point = False
@@ -147,8 +156,6 @@ def gen_config(gc):
     """GameConfig -> the FtlScenarioGenConfig of include/ftl.h (what ftl_generate_scenarios needs)."""
     from . import abi
     g, c = gc.kwargs, gc.c
-    if g["multiple_end_points"]:
-        raise NotImplementedError("multiple_end_points (three chained D* runs, ENV:1549-1612) is not supported")
     if g["trajectory"] is not None:
         raise ValueError("an explicit trajectory= needs no generated route: use generate()")
     s = abi.FtlScenarioGenConfig()
@@ -162,6 +169,7 @@ def gen_config(gc):
     s.bridge_size[0], s.bridge_size[1] = int(g["bridge_size"][0]), int(g["bridge_size"][1])
     s.leader_margin = float(g["leader_margin"])
     s.path_finding = 0 if g["path_finding_algorythm"] == "dstar" else 1
+    s.multiple_end_points = int(bool(g["multiple_end_points"]))
     return s
 
 
@@ -215,8 +223,9 @@ def _shortest_path(blocked, nx, ny, start, goal, max_iter=None):
     return path[::-1]
 
 
-def _plan_dstar_grid(gc, start_px, goal_px, static_rects, leader_wf, leader_hf):
-    """The map generate_trajectory_dstar builds (ENV:1493-1507), searched for a shortest path."""
+def _plan_dstar_grid(gc, start_px, goals_px, static_rects, leader_wf, leader_hf):
+    """The map generate_trajectory_dstar builds (ENV:1493-1507), searched for a shortest path to goals_px[0]; with
+    multiple_end_points two more legs on fresh copies of the map, goal to goal, appended (ENV:1552-1587)."""
     g, c = gc.kwargs, gc.c
     sg = g["step_grid"]
     nx, ny = c.game_width // sg, c.game_height // sg
@@ -233,7 +242,8 @@ def _plan_dstar_grid(gc, start_px, goal_px, static_rects, leader_wf, leader_hf):
                 if 0 <= i < nx and 0 <= j < ny:
                     blocked.add((i, j))
     start = (int(start_px[0] / sg), int(start_px[1] / sg))
-    goal = (int(goal_px[0] / sg), int(goal_px[1] / sg))
+    cells_of = lambda p: (int(p[0] / sg), int(p[1] / sg))  # noqa: E731
+    goal = cells_of(goals_px[0])
     blocked.discard(start)
     path = None if goal in blocked else _shortest_path(blocked, nx, ny, start, goal)
     if path is None:
@@ -244,7 +254,18 @@ def _plan_dstar_grid(gc, start_px, goal_px, static_rects, leader_wf, leader_hf):
         return [(p[0] * sg, p[1] * sg) for p in stub], False
     # D* lists every cell from the start up to (not including) the goal cell (dstar.py:176-195)
     cells = path[:-1] if len(path) > 2 else path
-    return [(p[0] * sg, p[1] * sg) for p in cells], True
+    found = True
+    for nxt in goals_px[1:]:
+        # the next leg starts in the previous goal cell; a leg that cannot be planned adds nothing and clears the flag
+        # (upstream its point list is whatever the aborted parent walk left behind, ENV:1611)
+        nxt = cells_of(nxt)
+        leg = None if (nxt in blocked or goal in blocked) else _shortest_path(blocked, nx, ny, goal, nxt)
+        if leg is None:
+            found = False
+        else:
+            cells = cells + leg[:-1]
+        goal = nxt
+    return [(p[0] * sg, p[1] * sg) for p in cells], found
 
 
 def _plan_astar_grid(gc, start_px, goal_px, static_rects, leader_wf, leader_hf):

@@ -196,7 +196,7 @@ typedef struct FtlScenarioGenConfig {
     int32_t bridge_size[2];                   /* ENV:617 */
     double leader_margin;
     int32_t path_finding;                     /* 0: the D* grid (ENV:1493-1507), 1: the A* grid (ENV:1632-1712) */
-    int32_t pad_;
+    int32_t multiple_end_points;              /* 1: three finish points, three D* legs appended (ENV:472-482, 1552-1611); D* only */
 } FtlScenarioGenConfig;
 
 /* ---- canonical per-env state record used by get/set_state and by the oracle ----------------- */

@@ -207,3 +207,22 @@ def test_render_modes():
         env.render(mode="human")
     with pytest.raises(RuntimeError):
         env.render(mode="rgb_array")
+
+
+def test_multiple_end_points_through_the_gym_surface():
+    """Game(multiple_end_points=True): the three finish points the reference draws for the seed (ENV:471-482; fixture from
+    the unmodified reference, oracle/gen_multi_end_golden.py), a route through all of them, and the leader follows it."""
+    with open(parity.GOLDEN_DIR + "/multi_end_points.json") as f:
+        gold = json.load(f)
+    case = gold["cases"][0]
+    env = _make(**gold["kwargs"])
+    assert env.finish_point2 == (1490, 990)                       # ENV:246
+    env.seed(case["seed"])
+    env.reset()
+    assert [list(env.finish_point), list(env.finish_point2), list(env.finish_point3)] == case["finish_points"]
+    assert len(env.trajectory) == case["n_route"] and env.found_target_point
+    with pytest.raises(NotImplementedError):                      # ENV:239-243
+        _make(multiple_end_points=True, path_finding_algorythm="astar")
+    for _ in range(5):
+        obs, rew, done, info = env.step(np.array([0.3, 0.0], np.float32))
+    assert np.isfinite(obs["numerical_features"]).all() and not done
