@@ -47,8 +47,13 @@ using namespace ftl;
 #define FTL_RAYS_WARPS 2   // envs per block.  A block lives as long as its slowest env: 2-warp blocks measured 2.3 % faster
 #endif                     // than 4-warp ones (and they fit sooner into what a finished block of the step kernels frees)
 #ifndef FTL_RAYS_MINB
+#if FTL_RAYS_LANES == 32
 #define FTL_RAYS_MINB (28 / FTL_RAYS_WARPS)   // 28 warps per SM: 72 registers, no spills; shared memory (7.2 KB per warp) allows no more
+#else
+#define FTL_RAYS_MINB (20 / FTL_RAYS_WARPS)   // two envs per warp: 11 KB of shared memory per warp
 #endif
+#endif
+constexpr int kRaysEnvsPerWarp = 32 / FTL_RAYS_LANES;
 
 __global__ void __launch_bounds__(32 * FTL_RAYS_WARPS, FTL_RAYS_MINB)
 k_rays(const __grid_constant__ DevCfg cfg, const DevState s, const DevPool pool, const double2* __restrict__ rot,
@@ -56,10 +61,13 @@ k_rays(const __grid_constant__ DevCfg cfg, const DevState s, const DevPool pool,
     asm volatile("griddepcontrol.launch_dependents;");   // k_finish may be scheduled behind the last wave of this grid
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5;
-    const int i = first_env + blockIdx.x * (blockDim.x >> 5) + warp;  // one warp per env
+    const int sub = (int)(threadIdx.x & 31) / FTL_RAYS_LANES;          // which env of the warp this lane serves
+    const int i0 = first_env + (blockIdx.x * (blockDim.x >> 5) + warp) * kRaysEnvsPerWarp;   // the warp's envs share a group of 32
+    if (i0 >= end_env) return;
+    if (wait_seq) wait_group_flag(s.kin_flag, i0 >> 5, wait_seq);   // launched early: wait for these envs' kinematics
+    const int i = i0 + sub;
     if (i >= end_env) return;
-    if (wait_seq) wait_group_flag(s.kin_flag, i >> 5, wait_seq);   // launched early: wait for this env's kinematics
-    RayShared& sh = *reinterpret_cast<RayShared*>(smem + (size_t)warp * smem_per_warp);
+    RayShared& sh = *reinterpret_cast<RayShared*>(smem + (size_t)(warp * kRaysEnvsPerWarp + sub) * smem_per_warp);
     rays_warp(cfg, s, pool, rot, i, sh, rays_out);
 }
 
@@ -401,12 +409,12 @@ static int launch_rays_and_finish(ftl_handle h, const DevState& s, const DevOutp
     const bool pdl = wait_seq != 0;
     const int warps = FTL_RAYS_WARPS, threads = warps * 32;
     const int per_warp = (int)((ray_shared_bytes(h->rays_total, h->cfg.ray_hmax) + 15) & ~(size_t)15);
-    const int smem = per_warp * warps;
+    const int smem = per_warp * warps * kRaysEnvsPerWarp;   // per_warp: one env's block
     if (smem > 48 * 1024 && !h->rays_smem_opted) {
         CUDA_TRY(cudaFuncSetAttribute(k_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         h->rays_smem_opted = true;
     }
-    const int blocks = (end_env - first_env + warps - 1) / warps;
+    const int blocks = (end_env - first_env + warps * kRaysEnvsPerWarp - 1) / (warps * kRaysEnvsPerWarp);
     const double2* rot = h->d_rot;
     CUDA_TRY(launch_pdl(k_rays, dim3(blocks), dim3(threads), smem, st, pdl, h->cfg, s, h->pool, rot, o.rays, per_warp,
                         first_env, end_env, wait_seq));
@@ -505,7 +513,7 @@ int ftl_create(const FtlConfig* cfg, int32_t n_envs, int32_t device, int64_t env
     if (h->rays_total > 0) {   // the ray kernel keeps its tables in dynamic shared memory: refuse what cannot fit, here
         int optin = 0;
         CUDA_TRY(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-        const size_t need = ((ray_shared_bytes(h->rays_total, d.ray_hmax) + 15) & ~(size_t)15) * FTL_RAYS_WARPS;
+        const size_t need = ((ray_shared_bytes(h->rays_total, d.ray_hmax) + 15) & ~(size_t)15) * FTL_RAYS_WARPS * kRaysEnvsPerWarp;
         if (need > (size_t)optin) {
             const int rt = h->rays_total;
             delete h;

@@ -164,32 +164,62 @@ FTL_HD float i2f_bits(int i) {
 //           floats order like ints) into res[age][ray] / res[static][ray]
 //   out     rows assembled (static minimum merged into every valid history row), written coalesced
 // =====================================================================================================
+// FTL_RAYS_LANES: lanes that serve one env -- 32 (one env per warp) or 16 (two envs per warp: each half-warp runs the
+// pass of its own env with its own shared block and only ever synchronises with its own 16 lanes; the halves share the
+// warp's instruction stream wherever their control flow agrees).  The item lists of an env are short (37 rectangles,
+// ~10 stored rectangles, ~50 edges, 48 rays): with 32 lanes 18 are active on average.
+#ifndef FTL_RAYS_LANES
+#define FTL_RAYS_LANES 32
+#endif
+constexpr int kLanes = FTL_RAYS_LANES;
+static_assert(kLanes == 32 || kLanes == 16, "FTL_RAYS_LANES: 32 or 16");
 #if defined(__CUDA_ARCH__)
-#define FTL_LANES(lane) for (int lane = (int)(threadIdx.x & 31), ftl_once_ = 1; ftl_once_; ftl_once_ = 0)
-#define FTL_WARP_SYNC() __syncwarp()
+#define FTL_LANES(lane) for (int lane = (int)(threadIdx.x & (kLanes - 1)), ftl_once_ = 1; ftl_once_; ftl_once_ = 0)
+#define FTL_LANE_MASK() (kLanes == 32 ? 0xffffffffu : (0xffffu << (threadIdx.x & 16)))
+#define FTL_WARP_SYNC() __syncwarp(FTL_LANE_MASK())
 FTL_HD int smem_atomic_add(int* p, int v) { return atomicAdd(p, v); }
 FTL_HD void smem_atomic_min(int* p, int v) { atomicMin(p, v); }
 #else
-#define FTL_LANES(lane) for (int lane = 0; lane < 32; ++lane)
+#ifdef FTL_DBG_LANE_ORDER   // host test builds: another lane order (the GPU serves the shared lists in no particular order)
+#define FTL_LANES(lane) for (int ftl_k_ = 0, lane = FTL_DBG_LANE_ORDER % kLanes; ftl_k_ < kLanes; ++ftl_k_, lane = (lane * 5 + FTL_DBG_LANE_ORDER) % kLanes)
+#else
+#define FTL_LANES(lane) for (int lane = 0; lane < kLanes; ++lane)
+#endif
 #define FTL_WARP_SYNC() ((void)0)
 FTL_HD int smem_atomic_add(int* p, int v) { int o = *p; *p = o + v; return o; }
 FTL_HD void smem_atomic_min(int* p, int v) { if (v < *p) *p = v; }
 #endif
 
 #ifndef FTL_EDGE_CAP
+#if FTL_RAYS_LANES == 32
 #define FTL_EDGE_CAP 176   // measured: 160 -> 176 saves the mid-env flush of about half the envs (-2.8 % k_rays); 224 costs occupancy
+#else
+#define FTL_EDGE_CAP 112   // a round of 16 lanes adds at most 64 edges: the same 48 edges of head room before a flush is forced
+#endif
 #endif
 #ifndef FTL_PAIR_CAP
+#if FTL_RAYS_LANES == 32
 #define FTL_PAIR_CAP 320
+#else
+#define FTL_PAIR_CAP 256
+#endif
 #endif
 constexpr int kEdgeCap = FTL_EDGE_CAP;  // compact edge list per flush (overridable: tests build with tiny lists)
 constexpr int kPairCap = FTL_PAIR_CAP;  // (edge, ray) pairs per flush
-constexpr int kCorridorChunk = 64;  // corridor ring entries per batch (2 edges each)
+constexpr int kCorridorChunk = 2 * kLanes;  // corridor ring entries per batch (2 edges each)
 constexpr int kStaticBit = 8;       // row-mask bit of the static minimum (merged into all valid rows)
 constexpr int kNoHitBits = 0x7f7fffff;
 // a pair word: flat ray (12 bits), edge slot (8 bits), rows of the ray's sensor that the edge belongs to (9 bits)
 constexpr int kPairEdgeShift = 12, kPairRowsShift = 20;
 static_assert(kEdgeCap <= (1 << (kPairRowsShift - kPairEdgeShift)), "edge slot does not fit the pair word");
+#if defined(__CUDACC__)
+// The list is flushed whenever the next round of appends (at most 4 edges per lane, or one corridor batch) might not fit,
+// so with this much room the overflow path of edge_append (edge_inline) is never taken on the GPU.  It is kept for the host
+// test builds with tiny lists.  A GPU build with FTL_EDGE_CAP=24 was tried once: rare missed corridor hits in configurations
+// whose corridor spans several batches, not reproducible in the host build with the same lists and any lane order, not
+// found (profiles/r02_ab_log.txt (24)); such builds are refused instead.
+static_assert(kEdgeCap >= 4 * kLanes + 2 * FTL_MAX_HIST, "FTL_EDGE_CAP too small for a GPU build: the edge list must never overflow");
+#endif
 constexpr int kMaxTotalRays = 1 << kPairEdgeShift;   // checked at ftl_create
 enum EdgeClass { EC_STATIC = 0, EC_LEADER = 1, EC_BEAR = 2, EC_CORRIDOR = 3, EC_CAP = 4, EC_COUNT = 5 };
 
@@ -324,7 +354,12 @@ FTL_HD void edge_ray_test(RayShared& sh, const RayArrays& ra, int f, int rows, f
 }
 
 // all candidate rays of one edge, tested in place (only used when the shared lists are full)
-FTL_HD_NOINLINE void edge_inline(RayShared& sh, int rt, const RayEdge ed, int n_sensors) {
+#ifdef FTL_DBG_INLINE_EDGE
+FTL_HD void edge_inline(
+#else
+FTL_HD_NOINLINE void edge_inline(
+#endif
+RayShared& sh, int rt, const RayEdge ed, int n_sensors) {
     const RayArrays ra = ray_arrays(&sh, rt, sh.hmax);
     const int cls_bit = ed.mask >> 16;
     for (int sidx = 0; sidx < n_sensors; sidx++) {
@@ -380,7 +415,7 @@ FTL_HD_NOINLINE void ray_flush(RayShared& sh, int n_sensors) {
     const int ne = sh.ne < kEdgeCap ? sh.ne : kEdgeCap;
     // ---- A2: edges -> (edge, ray) pairs ----------------------------------------------------------------------
     FTL_LANES(lane) {
-        for (int ei = lane; ei < ne; ei += 32) {
+        for (int ei = lane; ei < ne; ei += kLanes) {
             const RayEdge ed = sh.e[ei];
             const int cls_bit = ed.mask >> 16;
             const float ba = atan2_deg_approx(ed.ay - sh.py, ed.ax - sh.px);
@@ -428,7 +463,7 @@ FTL_HD_NOINLINE void ray_flush(RayShared& sh, int n_sensors) {
     // ---- B: uniform pair tests ----------------------------------------------------------------------------------
     const int np = sh.np < kPairCap ? sh.np : kPairCap;
     FTL_LANES(lane) {
-        for (int t = lane; t < np; t += 32) {
+        for (int t = lane; t < np; t += kLanes) {
             const int pr = sh.pair[t], ei = (pr >> kPairEdgeShift) & ((1 << (kPairRowsShift - kPairEdgeShift)) - 1);
             const int f = pr & ((1 << kPairEdgeShift) - 1), rows = pr >> kPairRowsShift;
             const RayEdge ed = sh.e[ei];
@@ -460,7 +495,7 @@ FTL_HD_NOINLINE void ray_rows_write_fused(const DevCfg& cfg, const RayShared& sh
             // four consecutive rays of one row per lane, as in the raw float4 path: every sensor's column block starts
             // at a multiple of four floats in a row that is a multiple of four floats long
             const int Q = R >> 2;
-            for (int e = lane; e < H * Q; e += 32) {
+            for (int e = lane; e < H * Q; e += kLanes) {
                 const int j = e / Q, k = (e - j * Q) << 2, age = H - 1 - j;
                 float4 v = make_float4(L, L, L, L);
                 if (age < n_valid) {
@@ -479,7 +514,7 @@ FTL_HD_NOINLINE void ray_rows_write_fused(const DevCfg& cfg, const RayShared& sh
             }
             continue;
         }
-        for (int e = lane; e < H * R; e += 32) {
+        for (int e = lane; e < H * R; e += kLanes) {
             const int j = e / R, k = e - j * R, age = H - 1 - j;
             float v = L;
             if (age < n_valid) {
@@ -509,18 +544,18 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
     // snapshot rectangles); their ADDRESSES only depend on the env index, so the corridor ring's lines (corridor_cap entries of 16
     // bytes) are requested now, while the setup below runs (k_rays 0.2451 -> 0.2431 ms).
     {
-        const int pl = (int)(threadIdx.x & 31);
+        const int pl = (int)(threadIdx.x & (kLanes - 1));
         const char* ring = reinterpret_cast<const char*>(s.corridor + (size_t)i * c.corridor_cap);
-        for (int k = pl; k * 128 < c.corridor_cap * 16; k += 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(ring + k * 128));
+        for (int k = pl; k * 128 < c.corridor_cap * 16; k += kLanes) asm volatile("prefetch.global.L1 [%0];" ::"l"(ring + k * 128));
 #ifdef FTL_RECT_PREFETCH   // measured: the rectangle history too makes the kernel slower (0.2431 -> 0.2454 ms)
-        for (int k = pl; k < FTL_MAX_HIST * (1 + NBr); k += 32)
+        for (int k = pl; k < FTL_MAX_HIST * (1 + NBr); k += kLanes)
             asm volatile("prefetch.global.L1 [%0];" ::"l"(s.snap_rect + (size_t)k * s.n + i));
 #endif
     }
 #endif
     const double dir = s.rd[(size_t)RD_DIR * s.n + i];
-    // ---- setup: lane 0 the scalars, lanes < ns the sensor tables (static part from DevCfg), lanes 8.. the class
-    //      reaches, lanes 16.. the stored corridor ranges -------------------------------------------------------
+    // ---- setup: lane 0 the scalars, lanes < ns the sensor tables (static part from DevCfg), lanes < 5 the class
+    //      reaches, the last eight lanes the stored corridor ranges -------------------------------------------------------
     FTL_LANES(lane) {
         const int pushes = s.gi[(size_t)GI_SNAP_PUSHES * s.n + i];
         if (lane == 0) {
@@ -543,22 +578,24 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
             sincos_deg(a0, &st.sn0, &st.cs0);
             sh.sen[lane] = st;
         }
-        if (lane >= 8 && lane < 8 + EC_COUNT) sh.reach[lane - 8] = cfg.ray_reach[lane - 8];
+        if (lane < EC_COUNT) sh.reach[lane] = cfg.ray_reach[lane];
 #if defined(__CUDA_ARCH__) && !defined(FTL_NO_RAYS_PREFETCH)
         {   // every slot of the range ring is loaded at once (no wait for the push counter), then handed to its age
+            constexpr int kR0 = kLanes - FTL_MAX_HIST;   // the last FTL_MAX_HIST lanes of the env's lane group
             int2 rg_slot = make_int2(0, 0);
-            if (lane >= 16 && lane < 16 + FTL_MAX_HIST) rg_slot = s.snap_range[(size_t)(lane - 16) * s.n + i];
-            const int age = lane - 16;
-            const int src = 16 + (((pushes - 1 - age) % FTL_MAX_HIST) + FTL_MAX_HIST) % FTL_MAX_HIST;
-            const int rx = __shfl_sync(0xffffffffu, rg_slot.x, src & 31), ry = __shfl_sync(0xffffffffu, rg_slot.y, src & 31);
-            if (lane >= 16 && lane < 16 + FTL_MAX_HIST) {
+            if (lane >= kR0) rg_slot = s.snap_range[(size_t)(lane - kR0) * s.n + i];
+            const int age = lane - kR0;
+            const int src = kR0 + (((pushes - 1 - age) % FTL_MAX_HIST) + FTL_MAX_HIST) % FTL_MAX_HIST;
+            const int src_abs = (src & (kLanes - 1)) + (int)(threadIdx.x & (32 - kLanes));
+            const int rx = __shfl_sync(FTL_LANE_MASK(), rg_slot.x, src_abs), ry = __shfl_sync(FTL_LANE_MASK(), rg_slot.y, src_abs);
+            if (lane >= kR0) {
                 const bool live = age < pushes;
                 sh.tail[age] = live ? rx : 0; sh.head[age] = live ? ry : 0;
             }
         }
 #else
-        if (lane >= 16 && lane < 16 + FTL_MAX_HIST) {
-            const int age = lane - 16;
+        if (lane >= kLanes - FTL_MAX_HIST) {
+            const int age = lane - (kLanes - FTL_MAX_HIST);
             int2 rg = make_int2(0, 0);
             if (age < pushes) rg = s.snap_range[(size_t)((pushes - 1 - age) % FTL_MAX_HIST) * s.n + i];
             sh.tail[age] = rg.x; sh.head[age] = rg.y;
@@ -568,7 +605,7 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
     FTL_WARP_SYNC();
     FTL_LANES(lane) {
         int sidx = 0;
-        for (int f = lane; f < rt; f += 32) {
+        for (int f = lane; f < rt; f += kLanes) {
             while (sidx + 1 < ns && f >= sh.sen[sidx + 1].base) sidx++;
             const FtlRaySensorConfig& sc = c.ray[sidx];
             const double cs0 = sh.sen[sidx].cs0, sn0 = sh.sen[sidx].sn0;
@@ -587,17 +624,17 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
         const int n_static = pool.n_static[sh.scenario];
         const int n_dyn = n_valid * (1 + NBr);
         if (sh.reach[EC_STATIC] > 0.f) {
-            for (int q0 = 0; q0 < n_static; q0 += 32) {
+            for (int q0 = 0; q0 < n_static; q0 += kLanes) {
                 FTL_WARP_SYNC();
-                if (sh.ne + 4 * 32 > kEdgeCap) ray_flush(sh, ns);   // a round adds at most 4 edges per lane
+                if (sh.ne + 4 * kLanes > kEdgeCap) ray_flush(sh, ns);   // a round adds at most 4 edges per lane
                 FTL_LANES(lane) {
                     if (q0 + lane < n_static) rect_append(sh, statics[q0 + lane], EC_STATIC, 1 << kStaticBit);
                 }
             }
         }
-        for (int q0 = 0; q0 < n_dyn; q0 += 32) {
+        for (int q0 = 0; q0 < n_dyn; q0 += kLanes) {
             FTL_WARP_SYNC();
-            if (sh.ne + 4 * 32 > kEdgeCap) ray_flush(sh, ns);
+            if (sh.ne + 4 * kLanes > kEdgeCap) ray_flush(sh, ns);
             FTL_LANES(lane) {
                 int q = q0 + lane;
                 if (q < n_dyn) {
@@ -625,7 +662,7 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
                 if (sh.ne + 2 * kCorridorChunk > kEdgeCap) ray_flush(sh, ns);
                 FTL_LANES(lane) {
                     int q1 = q0 + kCorridorChunk < max_head - 1 ? q0 + kCorridorChunk : max_head - 1;
-                    for (int q = q0 + lane; q < q1; q += 32) {
+                    for (int q = q0 + lane; q < q1; q += kLanes) {
                         int rows = 0;
                         for (int a = 0; a < n_valid; a++)
                             if (q >= sh.tail[a] && q < sh.head[a] - 1) rows |= 1 << a;
@@ -670,7 +707,7 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
                 float* dst = rays_out + (size_t)i * cfg.rays_per_env + off;
                 const float inv_Q = 1.0f / (float)Q;
                 const int* srow = ra.res + ra.hmax * rt + base;
-                for (int e = lane; e < H * Q; e += 32) {
+                for (int e = lane; e < H * Q; e += kLanes) {
                     const int j = (int)(((float)e + 0.5f) * inv_Q);   // e / Q without an integer division
                     const int k = (e - j * Q) << 2;
                     const int age = H - 1 - j;
@@ -703,7 +740,7 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
                 const double in_sector = R / 4.0;
                 const float inv_R = 1.0f / (float)R;
                 const int* srow = ra.res + ra.hmax * rt + base;
-                for (int e = lane; e < H * R; e += 32) {
+                for (int e = lane; e < H * R; e += kLanes) {
                     int j = (int)(((float)e + 0.5f) * inv_R);      // e / R without an integer division (H*R < 2^20)
                     int k = e - j * R;
                     const int age = H - 1 - j;

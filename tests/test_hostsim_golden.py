@@ -35,3 +35,17 @@ def test_ray_pass_overflow_paths_give_the_same_rays():
     env = capi.HostEnv(gc, 1, lib=lib("libftl_hostsim_smallcaps.so"))
     env.upload_scenarios(parity.pool_for(d, gc))
     parity.replay(env, d, gc, float_rtol=0.0, ray_rtol=parity.RTOL, ray_outlier_budget=0, max_steps=120)
+
+
+@pytest.mark.parametrize("libname", ["libftl_hostsim_lanes16.so", "libftl_hostsim_order.so"])
+def test_ray_pass_variants_give_the_same_rays(libname):
+    """FTL_RAYS_LANES=16 (two envs per warp on the GPU: the lane phases with 16 lanes, smaller lists, the range ring
+    handled by lanes 8-15) and a 24-edge list served in a permuted lane order -- same rays as the reference trace."""
+    from hostsim_py import lib
+    from continiousenvironment_follower_leader_b200 import capi
+    for name in ("cfg3_seed23_follow_then_random", "flat_sensors_seed9"):
+        d, meta = parity.load_trace(parity.GOLDEN_DIR + "/" + name + ".npz")
+        gc = parity.config_for(meta, _route_len=len(d["scen_route"]), _n_static=len(d["scen_static_rects"]))
+        env = capi.HostEnv(gc, 1, lib=lib(libname))
+        env.upload_scenarios(parity.pool_for(d, gc))
+        parity.replay(env, d, gc, float_rtol=0.0, ray_rtol=parity.RTOL, ray_outlier_budget=0, max_steps=150)
