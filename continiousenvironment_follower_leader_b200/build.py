@@ -65,6 +65,37 @@ def build(force=False, verbose=False, ptxas_info=False):
     return OUT, "\n".join(logs)
 
 
+SMALL_LISTS_OUT = os.path.join(CSRC, "libftl_smalllists.so")
+SMALL_LISTS_FLAGS = ["-DFTL_EDGE_CAP=24", "-DFTL_PAIR_CAP=40", "-DFTL_UNC_PER_ENV=2", "-DFTL_ALLOW_EDGE_OVERFLOW"]
+
+
+def build_small_lists(force=False):
+    """csrc/libftl_smalllists.so: the same sources with tiny shared lists in the ray kernel (24 edges, 40 pairs, 2 exact-pass
+    records per env), a TEST build: every overflow path of the ray pass runs on the GPU, where the lanes really are
+    concurrent (tests/test_gpu_parity_gaps.py; the host build has the same lists in libftl_hostsim_smallcaps.so)."""
+    build(force=False)   # the policy kernels and the scenario generator do not depend on the flags: their objects are shared
+    hdr_time = max(_mtime(os.path.join(CSRC, h)) for h in HEADERS)
+    objdir = os.path.join(CSRC, "build", "smalllists")
+    os.makedirs(objdir, exist_ok=True)
+    jobs = [("ftl_step_nb.cu", os.path.join(objdir, "nb%d.o" % nb), ["-DFTL_NB=%d" % nb] + SMALL_LISTS_FLAGS)
+            for nb in range(MAX_BEARS + 1)]
+    jobs.append(("ftl_capi.cu", os.path.join(objdir, "capi.o"), SMALL_LISTS_FLAGS))
+    todo = [j for j in jobs if force or _mtime(j[1]) < max(hdr_time, _mtime(os.path.join(CSRC, j[0])))]
+    if todo:
+        with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(todo), os.cpu_count() or 4)) as ex:
+            for src, rc, log in ex.map(_compile, todo):
+                if rc != 0:
+                    raise RuntimeError("nvcc failed on %s:\n%s" % (src, log))
+    shared = [os.path.join(CSRC, "build", o) for o in ("ftl_policy.o", "ftl_policy_tc.o", "ftl_scenario_gen.o")]
+    objs = [j[1] for j in jobs] + shared
+    if todo or _mtime(SMALL_LISTS_OUT) < max(_mtime(o) for o in objs):
+        r = subprocess.run([NVCC] + ARCH + ["-shared", "-o", SMALL_LISTS_OUT] + objs, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    return SMALL_LISTS_OUT
+
+
 if __name__ == "__main__":
     out, log = build(force="--force" in sys.argv, verbose=True, ptxas_info="--ptxas-info" in sys.argv)
     print("built", out)
+    print("built", build_small_lists(force="--force" in sys.argv))

@@ -177,6 +177,12 @@ static_assert(kLanes == 32 || kLanes == 16, "FTL_RAYS_LANES: 32 or 16");
 #define FTL_LANES(lane) for (int lane = (int)(threadIdx.x & (kLanes - 1)), ftl_once_ = 1; ftl_once_; ftl_once_ = 0)
 #define FTL_LANE_MASK() (kLanes == 32 ? 0xffffffffu : (0xffffu << (threadIdx.x & 16)))
 #define FTL_WARP_SYNC() __syncwarp(FTL_LANE_MASK())
+// A decision every lane of the env must take alike, from a shared word that the lanes go on to modify: __syncwarp() orders
+// memory but does not make the lanes run in lockstep afterwards, so a lane that reads the word late may already see the
+// appends of a faster one (found with a 24-edge list, where "flush first?" sits on its boundary all the time: some lanes
+// flushed and some did not, profiles/r02_ab_log.txt (24)).  The first lane's reading is broadcast; nobody gets past the
+// shuffle before everyone has arrived.
+#define FTL_UNIFORM_INT(val_) __shfl_sync(FTL_LANE_MASK(), (val_), (int)(threadIdx.x & (32 - kLanes)))
 FTL_HD int smem_atomic_add(int* p, int v) { return atomicAdd(p, v); }
 FTL_HD void smem_atomic_min(int* p, int v) { atomicMin(p, v); }
 #else
@@ -186,6 +192,7 @@ FTL_HD void smem_atomic_min(int* p, int v) { atomicMin(p, v); }
 #define FTL_LANES(lane) for (int lane = 0; lane < kLanes; ++lane)
 #endif
 #define FTL_WARP_SYNC() ((void)0)
+#define FTL_UNIFORM_INT(val_) (val_)
 FTL_HD int smem_atomic_add(int* p, int v) { int o = *p; *p = o + v; return o; }
 FTL_HD void smem_atomic_min(int* p, int v) { if (v < *p) *p = v; }
 #endif
@@ -212,12 +219,12 @@ constexpr int kNoHitBits = 0x7f7fffff;
 // a pair word: flat ray (12 bits), edge slot (8 bits), rows of the ray's sensor that the edge belongs to (9 bits)
 constexpr int kPairEdgeShift = 12, kPairRowsShift = 20;
 static_assert(kEdgeCap <= (1 << (kPairRowsShift - kPairEdgeShift)), "edge slot does not fit the pair word");
-#if defined(__CUDACC__)
+#if defined(__CUDACC__) && !defined(FTL_ALLOW_EDGE_OVERFLOW)
 // The list is flushed whenever the next round of appends (at most 4 edges per lane, or one corridor batch) might not fit,
-// so with this much room the overflow path of edge_append (edge_inline) is never taken on the GPU.  It is kept for the host
-// test builds with tiny lists.  A GPU build with FTL_EDGE_CAP=24 was tried once: rare missed corridor hits in configurations
-// whose corridor spans several batches, not reproducible in the host build with the same lists and any lane order, not
-// found (profiles/r02_ab_log.txt (24)); such builds are refused instead.
+// so with this much room the overflow path of edge_append (edge_inline) is never taken in a product build: which edges
+// would be tested in place depends on the order the lanes get their slots in, and with it which inconclusive pairs are
+// recorded -- results would stay within tolerance but no longer be bit-reproducible.  The test build with tiny lists
+// (build.build_small_lists, libftl_hostsim_smallcaps.so) defines FTL_ALLOW_EDGE_OVERFLOW.
 static_assert(kEdgeCap >= 4 * kLanes + 2 * FTL_MAX_HIST, "FTL_EDGE_CAP too small for a GPU build: the edge list must never overflow");
 #endif
 constexpr int kMaxTotalRays = 1 << kPairEdgeShift;   // checked at ftl_create
@@ -245,6 +252,9 @@ struct alignas(16) RayShared {   // 16-byte multiple: the arrays behind it are r
     RaySensorTab sen[FTL_MAX_RAY_SENSORS];
     RayEdge e[kEdgeCap];
     int pair[kPairCap];                            // rows << 20 | edge << 12 | flat ray
+#ifdef FTL_DBG_EDGES
+    int dbg[16];                                   // diagnostic counters (appended, in place, listed, flushes, pairs, ...)
+#endif
     int nu;                                        // (edge, ray) pairs of this env whose float32 predicates were inconclusive
     UncRec* unc;                                   // this env's slice of DevState.unc_rec
     // arrays of length rays_total behind the struct: dx, dy, len (float), res[hmax + 1] (int): one row of minima per
@@ -375,6 +385,12 @@ RayShared& sh, int rt, const RayEdge ed, int n_sensors) {
 FTL_HD void edge_append(RayShared& sh, float ax, float ay, float bx, float by, int mask) {
     int slot = smem_atomic_add(&sh.ne, 1);
     RayEdge ed = {ax, ay, bx, by, mask};
+#ifdef FTL_DBG_EDGES
+    smem_atomic_add(&sh.dbg[0], 1);
+    for (int k = 0; k < EC_COUNT; k++) if (mask & (1 << (16 + k))) smem_atomic_add(&sh.dbg[8 + k], 1);
+    if (slot >= kEdgeCap) { smem_atomic_add(&sh.dbg[1], 1); smem_atomic_add(&sh.dbg[7], (int)(ax + ay + bx + by)); }
+    smem_atomic_add(&sh.dbg[6], (int)(ax + ay + bx + by));   // order-independent checksum of what was appended
+#endif
     if (slot < kEdgeCap)
         sh.e[slot] = ed;
     else
@@ -413,6 +429,12 @@ FTL_HD_NOINLINE void ray_flush(RayShared& sh, int n_sensors) {
     const RayArrays ra = ray_arrays(&sh, sh.rt, sh.hmax);
     FTL_WARP_SYNC();
     const int ne = sh.ne < kEdgeCap ? sh.ne : kEdgeCap;
+#ifdef FTL_DBG_EDGES
+    FTL_LANES(lane) {
+        if (lane == 0) { sh.dbg[2] += ne; sh.dbg[3] += 1; }
+        for (int ei = lane; ei < ne; ei += kLanes) smem_atomic_add(&sh.dbg[7], (int)(sh.e[ei].ax + sh.e[ei].ay + sh.e[ei].bx + sh.e[ei].by));
+    }
+#endif
     // ---- A2: edges -> (edge, ray) pairs ----------------------------------------------------------------------
     FTL_LANES(lane) {
         for (int ei = lane; ei < ne; ei += kLanes) {
@@ -462,6 +484,9 @@ FTL_HD_NOINLINE void ray_flush(RayShared& sh, int n_sensors) {
     FTL_WARP_SYNC();
     // ---- B: uniform pair tests ----------------------------------------------------------------------------------
     const int np = sh.np < kPairCap ? sh.np : kPairCap;
+#ifdef FTL_DBG_EDGES
+    FTL_LANES(lane) { if (lane == 0) { sh.dbg[4] += np; sh.dbg[5] += sh.np - np; } }
+#endif
     FTL_LANES(lane) {
         for (int t = lane; t < np; t += kLanes) {
             const int pr = sh.pair[t], ei = (pr >> kPairEdgeShift) & ((1 << (kPairRowsShift - kPairEdgeShift)) - 1);
@@ -566,6 +591,9 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
             sh.snap_pushes = pushes;
             sh.n_valid = pushes < FTL_MAX_HIST ? pushes : FTL_MAX_HIST;
             sh.ne = 0; sh.np = 0; sh.nu = 0; sh.rt = rt; sh.ns = ns; sh.hmax = cfg.ray_hmax;
+#ifdef FTL_DBG_EDGES
+            for (int k = 0; k < 16; k++) sh.dbg[k] = 0;
+#endif
             sh.unc = s.unc_rec + (size_t)i * kUncPerEnv;
         }
         if (lane < ns) {
@@ -626,7 +654,7 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
         if (sh.reach[EC_STATIC] > 0.f) {
             for (int q0 = 0; q0 < n_static; q0 += kLanes) {
                 FTL_WARP_SYNC();
-                if (sh.ne + 4 * kLanes > kEdgeCap) ray_flush(sh, ns);   // a round adds at most 4 edges per lane
+                if (FTL_UNIFORM_INT(sh.ne) + 4 * kLanes > kEdgeCap) ray_flush(sh, ns);   // a round adds at most 4 edges per lane
                 FTL_LANES(lane) {
                     if (q0 + lane < n_static) rect_append(sh, statics[q0 + lane], EC_STATIC, 1 << kStaticBit);
                 }
@@ -634,7 +662,7 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
         }
         for (int q0 = 0; q0 < n_dyn; q0 += kLanes) {
             FTL_WARP_SYNC();
-            if (sh.ne + 4 * kLanes > kEdgeCap) ray_flush(sh, ns);
+            if (FTL_UNIFORM_INT(sh.ne) + 4 * kLanes > kEdgeCap) ray_flush(sh, ns);
             FTL_LANES(lane) {
                 int q = q0 + lane;
                 if (q < n_dyn) {
@@ -659,7 +687,7 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
             }
             for (int q0 = min_tail; q0 < max_head - 1; q0 += kCorridorChunk) {
                 FTL_WARP_SYNC();
-                if (sh.ne + 2 * kCorridorChunk > kEdgeCap) ray_flush(sh, ns);
+                if (FTL_UNIFORM_INT(sh.ne) + 2 * kCorridorChunk > kEdgeCap) ray_flush(sh, ns);
                 FTL_LANES(lane) {
                     int q1 = q0 + kCorridorChunk < max_head - 1 ? q0 + kCorridorChunk : max_head - 1;
                     for (int q = q0 + lane; q < q1; q += kLanes) {
@@ -677,7 +705,7 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
         }
         if (sh.reach[EC_CAP] > 0.f) {
             FTL_WARP_SYNC();
-            if (sh.ne + 2 * FTL_MAX_HIST > kEdgeCap) ray_flush(sh, ns);
+            if (FTL_UNIFORM_INT(sh.ne) + 2 * FTL_MAX_HIST > kEdgeCap) ray_flush(sh, ns);
             FTL_LANES(lane) {
                 if (lane < 2 * n_valid) {   // SEN:648-650
                     int age = lane >> 1;
@@ -761,6 +789,12 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
             }
         }
         if (lane == 0) s.unc_count[i] = sh.nu;   // 0 almost always; > kUncPerEnv: recast the env exactly
+#ifdef FTL_DBG_EDGES
+        if (lane == 0 && i == FTL_DBG_EDGES)
+            printf("DBG env %d: appended %d in_place %d listed %d flushes %d pairs %d pairs_in_place %d sum_app %d sum_listed %d nu %d by class %d %d %d %d %d\n", i,
+                   sh.dbg[0], sh.dbg[1], sh.dbg[2], sh.dbg[3], sh.dbg[4], sh.dbg[5], sh.dbg[6], sh.dbg[7], sh.nu,
+                   sh.dbg[8], sh.dbg[9], sh.dbg[10], sh.dbg[11], sh.dbg[12]);
+#endif
     }
     FTL_WARP_SYNC();
 }

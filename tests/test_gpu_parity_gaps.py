@@ -16,7 +16,7 @@ import pytest
 
 import parity
 from continiousenvironment_follower_leader_b200 import abi, capi
-from continiousenvironment_follower_leader_b200.config import GameConfig, cfg3_sensors
+from continiousenvironment_follower_leader_b200.config import GameConfig, cfg3_sensors, TEST_GAME_MANUAL_GAZEBO_KWARGS
 from continiousenvironment_follower_leader_b200.scenario import ScenarioPool, synthetic_pool
 from test_gpu_parity import _compare_states, _ray_outliers
 
@@ -52,10 +52,28 @@ GAP_CASES = [
 
 @pytest.mark.parametrize("name,kwargs,n,steps", GAP_CASES, ids=[c[0] for c in GAP_CASES])
 def test_cuda_matches_oracle_on_the_uncovered_step_options(name, kwargs, n, steps):
+    _gap_case(kwargs, n, steps, capi.load())
+
+
+SMALL_LIST_CASES = [c for c in GAP_CASES if c[0] in ("f60_records_in_hbm", "f13_2bears")] + [
+    ("gazebo", dict(TEST_GAME_MANUAL_GAZEBO_KWARGS, max_steps=900, auto_reset=True), 1024, 100)]
+
+
+@pytest.mark.parametrize("name,kwargs,n,steps", SMALL_LIST_CASES, ids=[c[0] for c in SMALL_LIST_CASES])
+def test_ray_kernel_overflow_paths_on_the_gpu(name, kwargs, n, steps):
+    """csrc/libftl_smalllists.so (build.build_small_lists: 24 edges, 40 pairs, 2 exact-pass records per env) against the
+    oracle: every overflow path of the ray pass with really concurrent lanes.  Long corridors (60 frames per step, the
+    Gazebo presets) are the cases in which the lanes of a warp once disagreed on "flush the list first?" -- a decision
+    read from a shared counter that faster lanes were already incrementing (FTL_UNIFORM_INT in ftl_rays.cuh)."""
+    from continiousenvironment_follower_leader_b200 import build
+    _gap_case(kwargs, n, steps, capi.load(build.SMALL_LISTS_OUT))
+
+
+def _gap_case(kwargs, n, steps, lib):
     from oracle_py import OracleEnv
     gc = GameConfig(**kwargs)
     pool = synthetic_pool(gc, 64, seed=2)
-    cuda, orc = capi.HostEnv(gc, n, lib=capi.load()), OracleEnv(gc, n, n_threads=8)
+    cuda, orc = capi.HostEnv(gc, n, lib=lib), OracleEnv(gc, n, n_threads=8)
     cuda.upload_scenarios(pool)
     orc.upload_scenarios(pool)
     ids = (np.arange(n) % pool.n).astype(np.int32)
