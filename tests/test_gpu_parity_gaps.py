@@ -66,7 +66,8 @@ def test_ray_kernel_overflow_paths_on_the_gpu(name, kwargs, n, steps):
     Gazebo presets) are the cases in which the lanes of a warp once disagreed on "flush the list first?" -- a decision
     read from a shared counter that faster lanes were already incrementing (FTL_UNIFORM_INT in ftl_rays.cuh)."""
     from continiousenvironment_follower_leader_b200 import build
-    _gap_case(kwargs, n, steps, capi.load(build.SMALL_LISTS_OUT))
+    path = build.SMALL_LISTS_OUT if os.path.exists(build.SMALL_LISTS_OUT) else build.build_small_lists()   # built by build()
+    _gap_case(kwargs, n, steps, capi.load(path))
 
 
 def _gap_case(kwargs, n, steps, lib):
