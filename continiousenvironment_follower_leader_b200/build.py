@@ -66,13 +66,14 @@ def build(force=False, verbose=False, ptxas_info=False):
 
 
 SMALL_LISTS_OUT = os.path.join(CSRC, "libftl_smalllists.so")
-SMALL_LISTS_FLAGS = ["-DFTL_EDGE_CAP=24", "-DFTL_PAIR_CAP=40", "-DFTL_UNC_PER_ENV=2", "-DFTL_ALLOW_EDGE_OVERFLOW"]
+SMALL_LISTS_FLAGS = ["-DFTL_EDGE_CAP=24", "-DFTL_PAIR_CAP=40", "-DFTL_UNC_PER_ENV=2", "-DFTL_ALLOW_EDGE_OVERFLOW",
+                     "-DFTL_SCAN_WIDE=1", "-DFTL_WALK_WIDE=1"]   # ... and one load in flight per lane in k_kin's warp scans / walks
 
 
 def build_small_lists(force=False):
     """csrc/libftl_smalllists.so: the same sources with tiny shared lists in the ray kernel (24 edges, 40 pairs, 2 exact-pass
-    records per env), a TEST build: every overflow path of the ray pass runs on the GPU, where the lanes really are
-    concurrent (tests/test_gpu_parity_gaps.py; the host build has the same lists in libftl_hostsim_smallcaps.so)."""
+    records per env; the warp-cooperative scans and walks of k_kin in rounds of 32 points), a TEST build: every overflow path
+    of the ray pass and every loop of the warp collectives runs on the GPU, where the lanes really are concurrent (tests/test_gpu_parity_gaps.py; the host build has the same lists in libftl_hostsim_smallcaps.so)."""
     build(force=False)   # the policy kernels and the scenario generator do not depend on the flags: their objects are shared
     hdr_time = max(_mtime(os.path.join(CSRC, h)) for h in HEADERS)
     objdir = os.path.join(CSRC, "build", "smalllists")
