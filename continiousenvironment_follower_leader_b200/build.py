@@ -81,12 +81,17 @@ def build_small_lists(force=False):
     jobs = [("ftl_step_nb.cu", os.path.join(objdir, "nb%d.o" % nb), ["-DFTL_NB=%d" % nb] + SMALL_LISTS_FLAGS)
             for nb in range(MAX_BEARS + 1)]
     jobs.append(("ftl_capi.cu", os.path.join(objdir, "capi.o"), SMALL_LISTS_FLAGS))
+    stamp = os.path.join(objdir, "flags.txt")   # objects made with other flags are stale
+    if not os.path.exists(stamp) or open(stamp).read() != " ".join(SMALL_LISTS_FLAGS):
+        force = True
     todo = [j for j in jobs if force or _mtime(j[1]) < max(hdr_time, _mtime(os.path.join(CSRC, j[0])))]
     if todo:
         with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(todo), os.cpu_count() or 4)) as ex:
             for src, rc, log in ex.map(_compile, todo):
                 if rc != 0:
                     raise RuntimeError("nvcc failed on %s:\n%s" % (src, log))
+        with open(stamp, "w") as f:
+            f.write(" ".join(SMALL_LISTS_FLAGS))
     shared = [os.path.join(CSRC, "build", o) for o in ("ftl_policy.o", "ftl_policy_tc.o", "ftl_scenario_gen.o")]
     objs = [j[1] for j in jobs] + shared
     if todo or _mtime(SMALL_LISTS_OUT) < max(_mtime(o) for o in objs):
