@@ -34,6 +34,7 @@ _vp, _i32, _i64 = C.c_void_p, C.c_int32, C.c_int64
 SIGNATURES = {
     "ftl_abi_version": ([], C.c_int),
     "ftl_last_error": ([], C.c_char_p),
+    "ftl_build_info": ([], C.c_char_p),
     "ftl_create": ([C.POINTER(abi.FtlConfig), _i32, _i32, _i64, C.POINTER(_vp)], C.c_int),
     "ftl_destroy": ([_vp], C.c_int),
     "ftl_rays_per_env": ([_vp], C.c_int),

@@ -488,6 +488,12 @@ extern "C" {
 
 int ftl_abi_version(void) { return FTL_ABI_VERSION; }
 const char* ftl_last_error(void) { return g_err.c_str(); }
+#define FTL_STR2(x) #x
+#define FTL_STR(x) FTL_STR2(x)
+const char* ftl_build_info(void) {
+    return "edge_cap=" FTL_STR(FTL_EDGE_CAP) " pair_cap=" FTL_STR(FTL_PAIR_CAP) " unc_per_env=" FTL_STR(FTL_UNC_PER_ENV)
+           " rays_lanes=" FTL_STR(FTL_RAYS_LANES) " scan_wide=" FTL_STR(FTL_SCAN_WIDE) " walk_wide=" FTL_STR(FTL_WALK_WIDE);
+}
 
 int ftl_create(const FtlConfig* cfg, int32_t n_envs, int32_t device, int64_t env_id_base, ftl_handle* out) {
     if (!out) return fail(FTL_ERR_INVALID, "out handle is NULL");

@@ -274,6 +274,9 @@ typedef struct FtlHandle_* ftl_handle;
 /* ---- lifecycle: replaces Game.__init__ (ENV:45-416) ------------------------------------------ */
 int ftl_abi_version(void);
 const char* ftl_last_error(void);
+/* The compile-time sizes of this build of the kernels, as text ("edge_cap=176 pair_cap=320 unc_per_env=16 rays_lanes=32
+ * scan_wide=8 walk_wide=6"): the product build and the test build with tiny lists (csrc/libftl_smalllists.so) differ here. */
+const char* ftl_build_info(void);
 /* Validates the configuration the way check_parameters/sensor constructors do (ENV:419-427,
  * SEN:761) and allocates every device buffer for n_envs environments on CUDA device `device`.
  * env_id_base: global index of this handle's first env (rank offset for multi-GPU sharding). */

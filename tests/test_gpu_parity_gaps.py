@@ -67,7 +67,11 @@ def test_ray_kernel_overflow_paths_on_the_gpu(name, kwargs, n, steps):
     read from a shared counter that faster lanes were already incrementing (FTL_UNIFORM_INT in ftl_rays.cuh)."""
     from continiousenvironment_follower_leader_b200 import build
     path = build.SMALL_LISTS_OUT if os.path.exists(build.SMALL_LISTS_OUT) else build.build_small_lists()   # built by build()
-    _gap_case(kwargs, n, steps, capi.load(path))
+    lib = capi.load(path)
+    info = lib.ftl_build_info().decode()
+    assert "edge_cap=24 " in info and "pair_cap=40 " in info and "scan_wide=1 " in info, info
+    assert "edge_cap=176 " in capi.load().ftl_build_info().decode()
+    _gap_case(kwargs, n, steps, lib)
 
 
 def _gap_case(kwargs, n, steps, lib):
