@@ -18,8 +18,9 @@ follow_the_leader_continuous_env.py:908-945).  Workloads (BASELINE.json `configs
 
 Weak scaling at every N: each rank owns a disjoint env slice keyed by global env id; NCCL only all-reduces the
 episode-statistics vector (at least once inside the timed region).  Before the warm-up the batch is advanced `--settle`
-untimed steps (default 150) so that the timed steps see the steady-state mix of episode ages, not the first steps after a
-reset.
+untimed steps (default 2 000: four episode lengths) so that the timed steps see the stationary mix of episode ages: every env
+starts its first episode together, and the step time swings with the 501-step episode limit for about 1 500 steps before it
+settles (tools/age_curve.py: 0.345 ms right after the reset, 0.353-0.368 in between, 0.362 +- 0.001 from step 2 000 on).
 
 The printed JSON line carries
   value     device-timed whole-job env-steps/s with actions resident in HBM (CUDA events, max over ranks)
@@ -494,7 +495,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg3", choices=["cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--envs-per-gpu", type=int, default=None)
-    ap.add_argument("--settle", type=int, default=150, help="untimed steps before the warm-up (steady-state episode mix)")
+    ap.add_argument("--settle", type=int, default=2000, help="untimed steps before the warm-up (stationary episode-age mix)")
     ap.add_argument("--e2e-steps", type=int, default=30)
     ap.add_argument("--rollout-steps", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
