@@ -589,7 +589,11 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
             sh.dir = dir;
             sh.scenario = s.gi[(size_t)GI_SCENARIO * s.n + i];
             sh.snap_pushes = pushes;
+#ifdef FTL_RAYS_ALL_AGES   // measured (r02_ab_log.txt (25)): the snapshot ring keeps FTL_MAX_HIST entries, no sensor looks further back than ray_hmax
             sh.n_valid = pushes < FTL_MAX_HIST ? pushes : FTL_MAX_HIST;
+#else
+            sh.n_valid = pushes < cfg.ray_hmax ? pushes : cfg.ray_hmax;   // ages no sensor keeps are not cast at all
+#endif
             sh.ne = 0; sh.np = 0; sh.nu = 0; sh.rt = rt; sh.ns = ns; sh.hmax = cfg.ray_hmax;
 #ifdef FTL_DBG_EDGES
             for (int k = 0; k < 16; k++) sh.dbg[k] = 0;
@@ -651,6 +655,7 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
         const int4* statics = pool.static_rects + (size_t)sh.scenario * c.static_cap;
         const int n_static = pool.n_static[sh.scenario];
         const int n_dyn = n_valid * (1 + NBr);
+#ifdef FTL_RAYS_SPLIT_RECT_ROUNDS   // measured (r02_ab_log.txt (26)): static and stored rectangles in rounds of their own
         if (sh.reach[EC_STATIC] > 0.f) {
             for (int q0 = 0; q0 < n_static; q0 += kLanes) {
                 FTL_WARP_SYNC();
@@ -675,6 +680,31 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
                 }
             }
         }
+#else
+        {   // static rectangles and the stored leader / bear rectangles as ONE item list: 37 + 10 items are two rounds, not three
+            const int ns_on = sh.reach[EC_STATIC] > 0.f ? n_static : 0;
+            const int n_rect = ns_on + n_dyn;
+            for (int q0 = 0; q0 < n_rect; q0 += kLanes) {
+                FTL_WARP_SYNC();
+                if (FTL_UNIFORM_INT(sh.ne) + 4 * kLanes > kEdgeCap) ray_flush(sh, ns);   // a round adds at most 4 edges per lane
+                FTL_LANES(lane) {
+                    const int q = q0 + lane;
+                    if (q < n_rect) {
+                        const int4* src = statics + q;
+                        int cls = EC_STATIC, rows = 1 << kStaticBit;
+                        if (q >= ns_on) {
+                            const int d = q - ns_on, age = d / (1 + NBr), k = d - age * (1 + NBr);
+                            const int slot = (sh.snap_pushes - 1 - age) % FTL_MAX_HIST;
+                            cls = k == 0 ? EC_LEADER : EC_BEAR;
+                            rows = 1 << age;
+                            src = s.snap_rect + ((size_t)slot * (1 + NBr) + k) * s.n + i;
+                        }
+                        if (sh.reach[cls] > 0.f) rect_append(sh, *src, cls, rows);
+                    }
+                }
+            }
+        }
+#endif
         // ---- A1: corridor sides (union of the stored ranges) and end caps; the list is only flushed when the next
         //      batch might not fit ----------------------------------------------------------------------------------
         const float4* corr = s.corridor + (size_t)i * c.corridor_cap;
