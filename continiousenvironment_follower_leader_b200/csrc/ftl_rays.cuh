@@ -757,6 +757,39 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
 #ifndef FTL_NO_VEC4_OUT
         if (cfg.ray_out_vec4 && (((size_t)rays_out) & 15) == 0) {
             // four consecutive rays of one row per lane: two 16-byte shared loads, one 16-byte store
+#ifndef FTL_RAYS_OUT_PER_SENSOR
+            // one item list over all sensors (15 + 45 float4 items are two rounds, not three): a sensor block is [H][R] and the
+            // blocks follow each other, so item t of the env simply lands at float4 index t
+            int T = 0;
+            for (int sidx = 0; sidx < ns; sidx++) T += sh.sen[sidx].H * (sh.sen[sidx].R >> 2);
+            float* dst = rays_out + (size_t)i * cfg.rays_per_env;
+            for (int t = lane; t < T; t += kLanes) {
+                int sidx = 0, s0 = 0;
+                for (; sidx + 1 < ns; sidx++) {
+                    const int cnt = sh.sen[sidx].H * (sh.sen[sidx].R >> 2);
+                    if (t < s0 + cnt) break;
+                    s0 += cnt;
+                }
+                const RaySensorTab& st = sh.sen[sidx];
+                const int Q = st.R >> 2, e = t - s0;
+                const int j = (int)(((float)e + 0.5f) * (4.f * st.inv_R));   // e / Q without an integer division (H*Q < 2^20)
+                const int k = (e - j * Q) << 2;
+                const int age = st.H - 1 - j;
+                const float L = st.L;
+                float4 v = make_float4(L, L, L, L);
+                if (age < n_valid) {
+                    const int4 a = *reinterpret_cast<const int4*>(ra.res + age * rt + st.base + k);
+                    const int4 sb = *reinterpret_cast<const int4*>(ra.res + ra.hmax * rt + st.base + k);
+                    const int b0 = sb.x < a.x ? sb.x : a.x, b1 = sb.y < a.y ? sb.y : a.y;
+                    const int b2 = sb.z < a.z ? sb.z : a.z, b3 = sb.w < a.w ? sb.w : a.w;
+                    if (b0 != kNoHitBits) v.x = i2f_bits(b0);
+                    if (b1 != kNoHitBits) v.y = i2f_bits(b1);
+                    if (b2 != kNoHitBits) v.z = i2f_bits(b2);
+                    if (b3 != kNoHitBits) v.w = i2f_bits(b3);
+                }
+                *reinterpret_cast<float4*>(dst + 4 * t) = v;
+            }
+#else
             int off = 0;
             for (int sidx = 0; sidx < ns; sidx++) {
                 const FtlRaySensorConfig& sc = c.ray[sidx];
@@ -784,6 +817,7 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
                 }
                 off += H * R;
             }
+#endif
         } else
 #endif
         {
