@@ -350,10 +350,24 @@ FTL_HD void unc_push(RayShared& sh, float ax, float ay, float bx, float by, int 
 FTL_HD void hit_merge(const RayArrays& ra, int f, int rows, float d) {
     if (d >= kNoHit) return;
     int bits = f2i_bits(d);
+#ifndef FTL_MERGE_PREDICATED   // measured (r02_ab_log.txt (27)): k_rays 0.2245 -> 0.2205 ms
+    if (rows & (1 << kStaticBit)) smem_atomic_min(&ra.res[ra.hmax * ra.rt + f], bits);
+    rows &= (1 << kStaticBit) - 1;
+    while (rows) {   // one atomic per row the edge belongs to (bits at or above hmax are never set)
+#if defined(__CUDA_ARCH__)
+        const int a = __ffs(rows) - 1;
+#else
+        const int a = __builtin_ctz((unsigned)rows);
+#endif
+        rows &= rows - 1;
+        smem_atomic_min(&ra.res[a * ra.rt + f], bits);
+    }
+#else
     // constant trip count (unrolled, predicated): bits at or above hmax are never set, so no row beyond hmax is touched
     for (int a = 0; a < FTL_MAX_HIST; a++)
         if (rows & (1 << a)) smem_atomic_min(&ra.res[a * ra.rt + f], bits);
     if (rows & (1 << kStaticBit)) smem_atomic_min(&ra.res[ra.hmax * ra.rt + f], bits);
+#endif
 }
 
 FTL_HD void edge_ray_test(RayShared& sh, const RayArrays& ra, int f, int rows, float ax, float ay, float bx, float by) {
@@ -400,23 +414,41 @@ FTL_HD void edge_append(RayShared& sh, float ax, float ay, float bx, float by, i
 // A1 for one rectangle: reach cull + front-facing edges (edge order/orientation of SEN:668-671).  A ray from
 // outside enters through a front-facing edge; the exit through a back-facing edge is farther and never the
 // minimum the reference reports.  (inside only happens after a crash: then every edge is kept.)
+FTL_HD void edge_store(RayShared& sh, int slot, float ax, float ay, float bx, float by, int mask) {
+    RayEdge ed = {ax, ay, bx, by, mask};
+    if (slot < kEdgeCap)
+        sh.e[slot] = ed;
+    else
+        edge_inline(sh, sh.rt, ed, sh.ns);
+}
 FTL_HD void rect_append(RayShared& sh, int4 q, int cls, int rows) {
     const float l = (float)q.x, t = (float)q.y, r = (float)(q.x + q.z), b = (float)(q.y + q.w);
     const float px = sh.px, py = sh.py, reach = sh.reach[cls] + 1.f;
     if (r < px - reach || l > px + reach || b < py - reach || t > py + reach) return;
     const int mask = rows | (1 << (16 + cls));
     const bool inside = px >= l && px <= r && py >= t && py <= b;
+#ifdef FTL_APPEND_PER_EDGE   // measured (r02_ab_log.txt (28)): one atomic per edge
     if (inside || py > b) edge_append(sh, l, b, r, b, mask);
     if (inside || px > r) edge_append(sh, r, t, r, b, mask);
     if (inside || py < t) edge_append(sh, r, t, l, t, mask);
     if (inside || px < l) edge_append(sh, l, b, l, t, mask);
+#else
+    // one reservation for the rectangle's front-facing edges (two from outside), then the stores
+    const bool e0 = inside || py > b, e1 = inside || px > r, e2 = inside || py < t, e3 = inside || px < l;
+    int slot = smem_atomic_add(&sh.ne, (int)e0 + (int)e1 + (int)e2 + (int)e3);
+    if (e0) edge_store(sh, slot++, l, b, r, b, mask);
+    if (e1) edge_store(sh, slot++, r, t, r, b, mask);
+    if (e2) edge_store(sh, slot++, r, t, l, t, mask);
+    if (e3) edge_store(sh, slot++, l, b, l, t, mask);
+#endif
+}
+FTL_HD bool seg_in_reach(const RayShared& sh, float ax, float ay, float bx, float by, int cls) {
+    const float px = sh.px, py = sh.py, reach = sh.reach[cls] + 1.f;
+    return !(fmaxf(ax, bx) < px - reach || fminf(ax, bx) > px + reach || fmaxf(ay, by) < py - reach ||
+             fminf(ay, by) > py + reach);
 }
 FTL_HD void seg_append(RayShared& sh, float ax, float ay, float bx, float by, int cls, int rows) {
-    const float px = sh.px, py = sh.py, reach = sh.reach[cls] + 1.f;
-    if (fmaxf(ax, bx) < px - reach || fminf(ax, bx) > px + reach || fmaxf(ay, by) < py - reach ||
-        fminf(ay, by) > py + reach)
-        return;
-    edge_append(sh, ax, ay, bx, by, rows | (1 << (16 + cls)));
+    if (seg_in_reach(sh, ax, ay, bx, by, cls)) edge_append(sh, ax, ay, bx, by, rows | (1 << (16 + cls)));
 }
 
 // A2 + B over the current edge list, then empty it.  One out-of-line copy for the five places that may flush: the
@@ -726,7 +758,7 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
                             if (q >= sh.tail[a] && q < sh.head[a] - 1) rows |= 1 << a;
                         if (rows) {
                             float4 a4 = corr[q & cmask], b4 = corr[(q + 1) & cmask];
-                            seg_append(sh, a4.x, a4.y, b4.x, b4.y, EC_CORRIDOR, rows);
+                            seg_append(sh, a4.x, a4.y, b4.x, b4.y, EC_CORRIDOR, rows);   // (one reservation for both sides: slower)
                             seg_append(sh, a4.z, a4.w, b4.z, b4.w, EC_CORRIDOR, rows);
                         }
                     }
