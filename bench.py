@@ -54,7 +54,7 @@ from continiousenvironment_follower_leader_b200.scenario import ScenarioPool, sy
 
 METRIC = "env-steps/sec (device-timed, whole box)"
 UNIT = "env-steps/s"
-TRAFFIC_FILES = [os.path.join(ROOT, "profiles", f) for f in ("r02d_traffic.json", "r02b_traffic.json", "r02_traffic.json")]   # newest capture first
+TRAFFIC_FILES = [os.path.join(ROOT, "profiles", f) for f in ("r02f_traffic.json", "r02b_traffic.json", "r02_traffic.json")]   # newest capture first
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -677,8 +677,19 @@ FTL_HD void rays_warp(const DevCfg& cfg, const DevState& s, const DevPool& pool,
             ra.dx[f] = (float)((cs0 * r.x - sn0 * r.y) * sc.laser_length);
             ra.dy[f] = (float)((sn0 * r.x + cs0 * r.y) * sc.laser_length);
             ra.len[f] = (float)sc.laser_length;
+#ifdef FTL_RES_INIT_PER_RAY
             for (int a = 0; a <= ra.hmax; a++) ra.res[a * rt + f] = kNoHitBits;
+#endif
         }
+#ifndef FTL_RES_INIT_PER_RAY   // measured (r02_ab_log.txt (30)): the rows of minima as 16-byte stores (288 words: three rounds, not twelve stores per lane)
+        const int n_res = (ra.hmax + 1) * rt;
+        if ((rt & 3) == 0) {   // res starts 12 * rt bytes behind a 16-byte boundary
+            int4* r4 = reinterpret_cast<int4*>(ra.res);
+            for (int k = lane; k < (n_res >> 2); k += kLanes) r4[k] = make_int4(kNoHitBits, kNoHitBits, kNoHitBits, kNoHitBits);
+        } else {
+            for (int k = lane; k < n_res; k += kLanes) ra.res[k] = kNoHitBits;
+        }
+#endif
     }
     FTL_WARP_SYNC();
     const int n_valid = sh.n_valid;
