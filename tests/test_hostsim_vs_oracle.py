@@ -157,3 +157,37 @@ def test_per_step_inputs_random_frames_and_regime_draws():
     """FtlStepInputs (include/ftl.h) through the host build: per-env frames per step and caller-supplied regime draws."""
     from test_gpu_parity_gaps import run_per_step_inputs_case
     run_per_step_inputs_case(make_env, 64, 150, 0.0)
+
+
+def test_routes_through_three_finish_points_are_followed_alike():
+    """multiple_end_points (ENV:471-482, 1552-1611): scenarios from the native generator -- three chained D* legs, ~150-270
+    waypoints, route_cap 512 -- stepped by the device functions and by the oracle: the leader's waypoint logic over a route
+    several times the usual length."""
+    from continiousenvironment_follower_leader_b200 import scenario_gen
+    gc = GameConfig(multiple_end_points=True, bear_number=1, follower_sensors=cfg3_sensors(), max_steps=1500)
+    pool = scenario_gen.generate_pool_native(gc, [1, 2, 3, 4, 6, 8])
+    assert gc.c.route_cap == 512 and int(pool.n_route.max()) > 128 and bool(pool.found_target_point.all())
+    n, steps = 24, 260
+    sim, orc = make_env(gc, n), OracleEnv(gc, n, n_threads=4)
+    sim.upload_scenarios(pool)
+    orc.upload_scenarios(pool)
+    ids = (np.arange(n) % pool.n).astype(np.int32)
+    sim.reset(scenario_ids=ids)
+    orc.reset(scenario_ids=ids)
+    rng = np.random.RandomState(11)
+    lo, hi = gc.action_bounds()
+    bad = total = 0
+    for t in range(steps):
+        a = rng.uniform(lo, hi, size=(n, 2)).astype(np.float32)
+        a[: n // 2] = (0.6 * hi[0], 0.0)      # half of the batch just drives on: its leaders get far along their routes
+        os_, oo = sim.step(a), orc.step(a)
+        assert np.array_equal(os_.done, oo.done), "done differs at step %d" % t
+        assert np.array_equal(os_.status, oo.status)
+        assert np.array_equal(os_.leader_target, oo.leader_target)
+        assert np.array_equal(os_.numerical_features, oo.numerical_features)
+        bad += _ray_outliers(os_.rays, oo.rays)
+        total += os_.rays.size
+    assert bad == 0, "%d of %d ray values outside tolerance" % (bad, total)
+    st = orc.get_state()
+    _compare_states(sim.get_state(), st, gc, n, 0.0)
+    assert int(st.env["cur_target_id"].max()) > 60      # leaders are well into their routes
