@@ -467,3 +467,37 @@ def test_step_phase_options_split_a_step_without_changing_it():
     for r in results[1:]:
         assert r[0] == results[0][0]
         assert np.array_equal(r[1], results[0][1]) and np.array_equal(r[2], results[0][2])
+
+
+def test_routes_through_three_finish_points_on_the_gpu():
+    """multiple_end_points (ENV:471-482, 1552-1611): scenarios of the native generator with three chained D* legs (up to ~270
+    waypoints, route_cap 512) on the CUDA path against the oracle."""
+    from oracle_py import OracleEnv
+    from continiousenvironment_follower_leader_b200 import scenario_gen
+    gc = GameConfig(multiple_end_points=True, bear_number=1, follower_sensors=cfg3_sensors(), max_steps=1500)
+    pool = scenario_gen.generate_pool_native(gc, [1, 2, 3, 4, 6, 8])
+    assert gc.c.route_cap == 512 and int(pool.n_route.max()) > 128
+    n, steps = 768, 220
+    cuda, orc = capi.HostEnv(gc, n, lib=capi.load()), OracleEnv(gc, n, n_threads=8)
+    cuda.upload_scenarios(pool)
+    orc.upload_scenarios(pool)
+    ids = (np.arange(n) % pool.n).astype(np.int32)
+    cuda.reset(scenario_ids=ids)
+    orc.reset(scenario_ids=ids)
+    rng = np.random.RandomState(11)
+    lo, hi = gc.action_bounds()
+    bad = 0
+    for t in range(steps):
+        a = rng.uniform(lo, hi, size=(n, 2)).astype(np.float32)
+        a[: n // 2] = (0.6 * hi[0], 0.0)      # half of the batch just drives on: its leaders get far along their routes
+        oc, oo = cuda.step(a), orc.step(a)
+        assert np.array_equal(oc.done, oo.done), "done differs at step %d" % t
+        assert np.array_equal(oc.status, oo.status), "status differs at step %d" % t
+        assert np.array_equal(oc.leader_target, oo.leader_target)
+        assert np.allclose(oc.numerical_features, oo.numerical_features, rtol=parity.RTOL, atol=1e-4)
+        bad += _ray_outliers(oc.rays, oo.rays)
+        if t % 20 == 19 or t == steps - 1:
+            _compare_states(cuda.get_state(), orc.get_state(), gc, n, parity.RTOL)
+    assert bad <= 2
+    assert int(orc.get_state().env["cur_target_id"].max()) > 45      # leaders are well into their routes (56 here)
+    cuda.close()
